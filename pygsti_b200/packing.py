@@ -1,0 +1,221 @@
+"""
+Host-side packing: pyGSTi layout atoms and models -> the flat arrays the C ABI takes.
+
+Nothing here imports pyGSTi; the functions are duck-typed against the reference objects:
+
+* ``pack_atom(atom)``  reads exactly the members the reference's Cython conversion code reads
+  (``layout_atom.table.contents``, ``rho_labels``, ``op_labels``, ``full_effect_labels``,
+  ``elbl_indices_by_expcircuit``, ``elindices_by_expcircuit``; reference
+  ``pygsti/forwardsims/mapforwardsim_calc_densitymx.pyx:55-101,163-181``) and produces int32 CSR
+  tables in the reference's own row format ``[iDest, iStart, iCache, prep?, ops...]`` (pyx:55-77).
+* ``pack_model(model, atom)``  pulls the dense superoperators / superkets through
+  ``model._circuit_layer_operator(lbl, typ).to_dense('HilbertSchmidt')`` (same access path as
+  pyx:164-167; dense arrays as in ``matrixforwardsim.py:700,1039-1045``).
+* ``pack_derivs(model, atom, param_slice)``  builds the sparse "member-element -> parameter" matrix D
+  from ``member.deriv_wrt_params()`` and ``member.gpindices`` (same inputs as
+  ``matrixforwardsim.py:126-170, 1111-1136``).
+
+Index conventions ("W space", one column per dense member element):
+    op g, element (i, j)   ->  g*d*d + i*d + j          (row-major flattening, matrixforwardsim.py:114-124)
+    prep r, element i      ->  n_ops*d*d + r*d + i
+    effect e, element i    ->  n_ops*d*d + n_rho*d + e*d + i
+"""
+from dataclasses import dataclass, field
+import numpy as np
+
+
+@dataclass
+class AtomTables:
+    """Integer tables of one layout atom, in the reference's prefix-table row format."""
+    dim: int
+    n_ops: int
+    n_rho: int
+    n_eff: int
+    n_elements: int
+    cache_size: int
+    row_dest: np.ndarray      # int32 [n_rows]   expanded-circuit index (iDest)
+    row_istart: np.ndarray    # int32 [n_rows]   cache slot to start from, -1 = start from a prep
+    row_icache: np.ndarray    # int32 [n_rows]   cache slot to store the final state in, -1 = none
+    row_prep: np.ndarray      # int32 [n_rows]   prep index when row_istart == -1, else -1
+    row_ptr: np.ndarray       # int32 [n_rows+1] CSR pointer into row_ops
+    row_ops: np.ndarray       # int32 [nnz]      op indices of the row's remainder (prep label removed)
+    out_ptr: np.ndarray       # int32 [n_rows+1] CSR pointer (per ROW, in row order) into out_eff/out_el
+    out_eff: np.ndarray       # int32 [n_out]    effect index of each outcome
+    out_el: np.ndarray        # int32 [n_out]    atom-local element index of each outcome
+
+    @property
+    def n_rows(self):
+        return int(self.row_dest.shape[0])
+
+    def num_state_propagations(self):
+        """Same count as the reference's ``PrefixTable.num_state_propagations`` (prefixtable.py:106)."""
+        return int(self.row_ops.shape[0])
+
+    def to_dict(self, prefix=""):
+        d = {prefix + "meta": np.array([self.dim, self.n_ops, self.n_rho, self.n_eff, self.n_elements,
+                                        self.cache_size], dtype=np.int64)}
+        for k in ("row_dest", "row_istart", "row_icache", "row_prep", "row_ptr", "row_ops",
+                  "out_ptr", "out_eff", "out_el"):
+            d[prefix + k] = getattr(self, k)
+        return d
+
+    @classmethod
+    def from_dict(cls, d, prefix=""):
+        m = d[prefix + "meta"]
+        kw = {k: np.ascontiguousarray(d[prefix + k], dtype=np.int32)
+              for k in ("row_dest", "row_istart", "row_icache", "row_prep", "row_ptr", "row_ops",
+                        "out_ptr", "out_eff", "out_el")}
+        return cls(dim=int(m[0]), n_ops=int(m[1]), n_rho=int(m[2]), n_eff=int(m[3]),
+                   n_elements=int(m[4]), cache_size=int(m[5]), **kw)
+
+
+@dataclass
+class ModelTensors:
+    G: np.ndarray      # f64 [n_ops, d, d] row-major superoperators
+    rho: np.ndarray    # f64 [n_rho, d]
+    E: np.ndarray      # f64 [n_eff, d]
+
+
+@dataclass
+class DerivMap:
+    """Sparse D[w, p] = d(member element w)/d(parameter p), COO with duplicates already summed."""
+    n_w: int
+    n_params: int
+    rows: np.ndarray   # int32 [nnz]  W-space index
+    cols: np.ndarray   # int32 [nnz]  parameter column (relative to the requested slice)
+    vals: np.ndarray   # f64   [nnz]
+
+
+def atom_labels(atom):
+    """(rho_labels, op_labels, effect_labels) in the exact order the reference enumerates them
+    (pyx:163-167: ``enumerate(layout_atom.rho_labels)``, ``enumerate(layout_atom.op_labels)`` and
+    iteration over the ``full_effect_labels`` set object, whose order defines ``elabel_lookup``,
+    maplayout.py:104-105)."""
+    return list(atom.rho_labels), list(atom.op_labels), list(atom.full_effect_labels)
+
+
+def pack_atom(atom, dim):
+    rho_labels, op_labels, eff_labels = atom_labels(atom)
+    rho_lookup = {lbl: i for i, lbl in enumerate(rho_labels)}
+    op_lookup = {lbl: i for i, lbl in enumerate(op_labels)}
+    contents = atom.table.contents
+    n_rows = len(contents)
+    row_dest = np.empty(n_rows, np.int32)
+    row_istart = np.empty(n_rows, np.int32)
+    row_icache = np.empty(n_rows, np.int32)
+    row_prep = np.full(n_rows, -1, np.int32)
+    row_ptr = np.zeros(n_rows + 1, np.int64)
+    ops = []
+    out_ptr = np.zeros(n_rows + 1, np.int64)
+    out_eff = []
+    out_el = []
+    elbl = atom.elbl_indices_by_expcircuit
+    elind = atom.elindices_by_expcircuit
+    for k, (i_dest, i_start, remainder, i_cache) in enumerate(contents):
+        row_dest[k] = i_dest
+        row_icache[k] = -1 if i_cache is None else i_cache
+        if i_start is None:
+            row_istart[k] = -1
+            row_prep[k] = rho_lookup[remainder[0]]
+            rem = remainder[1:]
+        else:
+            row_istart[k] = i_start
+            rem = remainder
+        ops.extend(op_lookup[gl] for gl in rem)
+        row_ptr[k + 1] = len(ops)
+        out_eff.extend(elbl[i_dest])
+        out_el.extend(elind[i_dest])
+        out_ptr[k + 1] = len(out_eff)
+    if row_ptr[-1] >= 2**31 or out_ptr[-1] >= 2**31:
+        raise MemoryError("layout atom too large for int32 tables")
+    return AtomTables(
+        dim=int(dim), n_ops=len(op_labels), n_rho=len(rho_labels), n_eff=len(eff_labels),
+        n_elements=int(atom.num_elements), cache_size=int(atom.cache_size),
+        row_dest=row_dest, row_istart=row_istart, row_icache=row_icache, row_prep=row_prep,
+        row_ptr=row_ptr.astype(np.int32), row_ops=np.asarray(ops, dtype=np.int32),
+        out_ptr=out_ptr.astype(np.int32), out_eff=np.asarray(out_eff, dtype=np.int32),
+        out_el=np.asarray(out_el, dtype=np.int32))
+
+
+def _members(model, atom):
+    rho_labels, op_labels, eff_labels = atom_labels(atom)
+    M = model._circuit_layer_operator
+    ops = [M(l, 'op') for l in op_labels]
+    rhos = [M(l, 'prep') for l in rho_labels]
+    effs = [M(l, 'povm') for l in eff_labels]
+    return ops, rhos, effs
+
+
+def pack_model(model, atom, dim):
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    G = np.empty((len(ops), d, d), dtype=np.float64)
+    for i, op in enumerate(ops):
+        G[i] = np.asarray(op.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(d, d)
+    rho = np.empty((len(rhos), d), dtype=np.float64)
+    for i, r in enumerate(rhos):
+        rho[i] = np.asarray(r.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(d)
+    E = np.empty((len(effs), d), dtype=np.float64)
+    for i, e in enumerate(effs):
+        E[i] = np.asarray(e.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(d)
+    return ModelTensors(G=G, rho=rho, E=E)
+
+
+def _gp_array(gpindices):
+    if gpindices is None:
+        return np.zeros(0, dtype=np.int64)
+    if isinstance(gpindices, slice):
+        if gpindices.start is None or gpindices.stop is None:
+            return np.zeros(0, dtype=np.int64)
+        return np.arange(gpindices.start, gpindices.stop, gpindices.step or 1, dtype=np.int64)
+    return np.asarray(gpindices, dtype=np.int64)
+
+
+def param_slice_to_array(param_slice, num_params):
+    if param_slice is None:
+        return np.arange(num_params, dtype=np.int64)
+    return _gp_array(param_slice)
+
+
+def pack_derivs(model, atom, dim, param_indices=None):
+    """Sparse D restricted to ``param_indices`` (columns renumbered 0..len-1 in the given order).
+
+    With a parameter interposer (``model._param_interposer``; matrixforwardsim.py:140-152, 1089-1105)
+    D is first assembled w.r.t. *op* parameters and then multiplied by d(op_params)/d(model_params).
+    """
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    n_w = len(ops) * d * d + len(rhos) * d + len(effs) * d
+    interposer = getattr(model, '_param_interposer', None)
+    n_model_params = int(model.num_params)
+    n_op_params = int(interposer.num_op_params) if interposer is not None else n_model_params
+
+    rows, cols, vals = [], [], []
+    off = 0
+    for group, size in ((ops, d * d), (rhos, d), (effs, d)):
+        for m in group:
+            gp = _gp_array(m.gpindices)
+            if gp.size:
+                dM = np.asarray(m.deriv_wrt_params(), dtype=np.float64).reshape(size, gp.size)
+                r, c = np.nonzero(dM)
+                rows.append(off + r)
+                cols.append(gp[c])
+                vals.append(dM[r, c])
+            off += size
+    if rows:
+        rows = np.concatenate(rows); cols = np.concatenate(cols); vals = np.concatenate(vals)
+    else:
+        rows = np.zeros(0, np.int64); cols = np.zeros(0, np.int64); vals = np.zeros(0, np.float64)
+
+    import scipy.sparse as sps
+    D = sps.coo_matrix((vals, (rows, cols)), shape=(n_w, n_op_params)).tocsr()  # sums duplicates
+    if interposer is not None:
+        D = (D @ sps.csr_matrix(interposer.deriv_op_params_wrt_model_params())).tocsr()
+    pidx = param_slice_to_array(param_indices, n_model_params)
+    if not (pidx.size == n_model_params and np.array_equal(pidx, np.arange(n_model_params))):
+        D = D[:, pidx]
+    D = D.tocoo()
+    keep = D.data != 0.0
+    return DerivMap(n_w=n_w, n_params=int(pidx.size),
+                    rows=D.row[keep].astype(np.int32), cols=D.col[keep].astype(np.int32),
+                    vals=D.data[keep].astype(np.float64))
