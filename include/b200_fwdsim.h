@@ -1,0 +1,135 @@
+/*
+ * b200_fwdsim.h -- C ABI of the B200-native forward-simulation engine (libb200fwdsim.so).
+ *
+ * This is the drop-in boundary for ONE hot path of pyGSTi: bulk circuit-outcome simulation for the
+ * `densitymx` evotype.  Every entry point below names the reference interface it replaces
+ * (paths relative to the pyGSTi source tree @ 6822f14).  Plain C: opaque handles, raw pointers and
+ * sizes, no C++/torch/numpy types.  Return value: 0 = ok, negative = error (see B200_E_*), message via
+ * b200_last_error() (thread-local).  No exception crosses the boundary.  There is NO CPU fallback: with
+ * no usable CUDA device every compute entry point fails with B200_E_CUDA.
+ *
+ * Data model (mirrors what the reference's Cython conversion layer hands its C++ loop,
+ * pygsti/forwardsims/mapforwardsim_calc_densitymx.pyx:55-143):
+ *   - a layout ATOM is a prefix table: rows [iDest, iStart, iCache, (prep), ops...] (pyx:55-77) plus, per
+ *     row, the list of (effect index, element index) outcomes (pyx:179-181);
+ *   - a MODEL is the dense real superoperators G[n_ops][d][d] (row-major), superkets rho[n_rho][d] and
+ *     effect vectors E[n_eff][d], float64, in the Pauli-product basis (what OpCRep_Dense / StateCRep /
+ *     EffectCRep_Dense hold: pygsti/evotypes/densitymx/opcreps.cpp:33-54, statecreps.cpp:20-45,
+ *     effectcreps.cpp:29-45).  Non-dense reps are densified by the caller through
+ *     LinearOperator.to_dense('HilbertSchmidt');
+ *   - the parameter DERIVATIVES are a sparse matrix D[w][p] = d(member element w)/d(parameter p) in COO
+ *     form; w indexes "W space": op g element (i,j) -> g*d*d+i*d+j ; prep r element i -> n_ops*d*d+r*d+i ;
+ *     effect e element i -> n_ops*d*d+n_rho*d+e*d+i   (row-major vec as in matrixforwardsim.py:114-124;
+ *     contents from member.deriv_wrt_params()/gpindices as in matrixforwardsim.py:126-170,1111-1136).
+ */
+#ifndef B200_FWDSIM_H
+#define B200_FWDSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK            0
+#define B200_E_INVALID    -1   /* bad argument / inconsistent table                         */
+#define B200_E_CUDA       -2   /* CUDA runtime error or no device (no CPU fallback exists)  */
+#define B200_E_NOMEM      -3   /* host or device allocation failed (-> MemoryError, as
+                                  mapforwardsim.py:276-333 / resource_alloc.check_can_allocate_memory) */
+#define B200_E_STATE      -4   /* call order violated (e.g. fill before model upload)        */
+#define B200_E_UNSUPPORTED -5  /* dimension / size outside what the kernels are built for    */
+
+typedef struct b200_ctx  b200_ctx;    /* one per GPU (per process or several per process)          */
+typedef struct b200_atom b200_atom;   /* device-resident layout atom + its current model tensors   */
+
+/* ---- library / device ------------------------------------------------------------------------ */
+int         b200_version(void);
+const char* b200_last_error(void);
+int         b200_device_count(int* n_out);
+
+/* One engine context per GPU.  `stream` = 0 creates a private non-blocking stream; otherwise an
+ * existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) is adopted, so that the caller's
+ * CUDA events bracket the kernels.  Replaces: the per-rank execution context the reference gets from
+ * ResourceAllocation (pygsti/baseobjs/resourceallocation.py:28) -- one rank <-> one ctx. */
+int b200_ctx_create(int device, void* stream, b200_ctx** out);
+int b200_ctx_destroy(b200_ctx* ctx);
+int b200_ctx_sync(b200_ctx* ctx);
+/* kernels launched by this ctx since creation (the "gpu_launches" bench counter) */
+int b200_ctx_launch_count(b200_ctx* ctx, int64_t* n_out);
+
+/* ---- layout atom (one-time per layout) ---------------------------------------------------------
+ * Replaces convert_maplayout / convert_dict_of_intlists / create_rhocache (pyx:55-101), which the
+ * reference re-runs on every call; here the tables are uploaded once and live on the device.
+ *   row_ptr[n_rows+1], row_ops[row_ptr[n_rows]] : CSR of op indices of each row's remainder
+ *   row_istart[n_rows]  : cache slot the row starts from, -1 = starts from prep row_prep[k]
+ *   row_icache[n_rows]  : cache slot the row's final state is stored in, -1 = none
+ *   out_ptr[n_rows+1], out_eff[], out_el[] : CSR (per row, in row order) of outcomes:
+ *                         effect index and atom-local element index (final_indices, pyx:179-181)
+ * Rows must be in evaluation order (a row may only start from a cache slot written by an earlier row),
+ * as PrefixTable guarantees (pygsti/layouts/prefixtable.py:65-101). */
+int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, int n_eff,
+                     int64_t n_rows, const int32_t* row_ptr, const int32_t* row_ops,
+                     const int32_t* row_istart, const int32_t* row_prep, const int32_t* row_icache,
+                     int32_t cache_size,
+                     const int32_t* out_ptr, const int32_t* out_eff, const int32_t* out_el,
+                     int64_t n_elements, b200_atom** out);
+int b200_atom_free(b200_ctx* ctx, b200_atom* atom);
+/* info[0]=n_rows info[1]=n_elements info[2]=table propagations (PrefixTable.num_state_propagations,
+ * prefixtable.py:106) info[3]=expanded propagations (no prefix sharing) info[4]=max circuit depth
+ * info[5]=W-space width  info[6]=n_params of the uploaded derivative map (or -1)
+ * info[7]=1 if the derivative map is a unit partial permutation (fused fast path) */
+int b200_atom_info(b200_atom* atom, int64_t info[8]);
+
+/* ---- model tensors (every call of the reference re-reads the reps: pyx:163-167) ----------------
+ * Replaces the rep lookups `model._circuit_layer_operator(lbl, typ)._rep` (pyx:164-167) and the
+ * OpCRep_Dense / StateCRep / EffectCRep_Dense objects they wrap.  Host pointers, copied immediately. */
+int b200_atom_set_model(b200_ctx* ctx, b200_atom* atom,
+                        const double* G, const double* rho, const double* E);
+
+/* Sparse derivative map D (COO, duplicates summed by the engine), n_params = number of Jacobian
+ * columns produced (the caller has already restricted/renumbered to its param_slice,
+ * distforwardsim.py:130-144).  Replaces the per-parameter `model.set_parameter_values` loop of
+ * mapfill_dprobs_atom (pyx:362-381) and `_doperation`/`_process_wrt_filter` of the Matrix simulator
+ * (matrixforwardsim.py:89-170). */
+int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* atom, int64_t n_w, int32_t n_params,
+                         int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals);
+
+/* ---- the hot path, HOST buffers (copies inside the call) ---------------------------------------
+ * b200_fill_probs   replaces mapfill_probs_atom + dm_mapfill_probs (pyx:149-287):
+ *     out[el * out_stride] = E . G_L ... G_1 rho        for every element of the atom.
+ * b200_fill_dprobs  replaces mapfill_dprobs_atom (pyx:290-383) with the ANALYTIC Jacobian
+ *     (= MatrixForwardSimulator._dprobs_from_rho_e, matrixforwardsim.py:1059-1139):
+ *     out[el * row_stride + p] = d p_el / d theta_p ,  p in [0, n_params);  columns outside are untouched.
+ *     probs_out may be NULL; otherwise it receives the probabilities as well (pr_array_to_fill,
+ *     distforwardsim.py:127-128).  Strides are in doubles. */
+int b200_fill_probs(b200_ctx* ctx, b200_atom* atom, double* out, int64_t out_stride);
+int b200_fill_dprobs(b200_ctx* ctx, b200_atom* atom, double* out, int64_t row_stride,
+                     double* probs_out, int64_t probs_stride);
+
+/* Reference-semantics forward differences (pyx:349-378): base pass + one pass per parameter with the
+ * members perturbed to M + eps * dM/dtheta_p (exact reproduction of the reference for members linear in
+ * their parameters, first-order for the others), out = (p2 - p) / eps. */
+int b200_fill_dprobs_fd(b200_ctx* ctx, b200_atom* atom, double eps, double* out, int64_t row_stride,
+                        double* probs_out, int64_t probs_stride);
+
+/* Hessian block for members LINEAR in their parameters (d2M/dtheta2 = 0: full, TP, static members),
+ * replaces MapForwardSimulator._mapfill_hprobs_atom (mapforwardsim.py:394-438) analytically:
+ *     out[(el * n1 + a) * n2 + b] = d2 p_el / d theta_{p1[a]} d theta_{p2[b]}
+ * p1/p2 index columns of the uploaded derivative map. */
+int b200_fill_hprobs_linear(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t* p1,
+                            int32_t n2, const int32_t* p2, double* out);
+
+/* ---- the hot path, DEVICE buffers (no copies; asynchronous on the ctx stream) ------------------ */
+int b200_fill_probs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out);
+int b200_fill_dprobs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out, int64_t ld, double* d_probs);
+
+/* ---- pinned host memory for zero-staging transfers --------------------------------------------- */
+int b200_host_alloc(void** out, int64_t bytes);     /* cudaHostAlloc */
+int b200_host_free(void* p);
+int b200_host_register(void* p, int64_t bytes);     /* cudaHostRegister an existing buffer (cached) */
+int b200_host_unregister(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FWDSIM_H */

@@ -1,0 +1,679 @@
+// engine.cu -- host side of libb200fwdsim.so: contexts, atoms, the C ABI of include/b200_fwdsim.h.
+//
+// There is no CPU compute path in this library: every fill entry point launches CUDA kernels or fails.
+#include "../../include/b200_fwdsim.h"
+#include "common.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_d16.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    int code_ = (e_ == cudaErrorMemoryAllocation) ? B200_E_NOMEM : B200_E_CUDA; \
+    return fail(code_, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    DevBuf out_buf;      // device staging of host-buffer results
+    DevBuf probs_buf;
+    DevBuf w_buf;        // W matrix of the general path
+    DevBuf scratch;      // forward-state scratch of the generic kernels
+    DevBuf fd_models, fd_gt, fd_probs;
+    void* pinned = nullptr; size_t pinned_cap = 0;   // pinned staging for pageable destinations
+};
+
+struct b200_atom {
+    b200_ctx* ctx = nullptr;
+    int dim = 0, n_ops = 0, n_rho = 0, n_eff = 0;
+    int64_t n_rows = 0, n_elements = 0, n_prop_table = 0, n_prop_expanded = 0;
+    int max_depth = 0;
+    int64_t n_w = 0, off_rho = 0, off_eff = 0;
+    // device tables
+    DevBuf circ_ptr, circ_ops, circ_prep, out_ptr, out_eff, out_el;
+    // model
+    bool has_model = false;
+    DevBuf M, Gt;
+    // derivative map
+    bool has_derivs = false;
+    int32_t n_params = 0;
+    bool unit_perm = false;
+    DevBuf cptr, crow, cval;               // CSC of D
+    DevBuf colmap, spam_col, spam_w;       // fused-path maps (unit partial permutation)
+    int n_spam = 0;
+    DevBuf id_colmap, id_spam_col, id_spam_w;  // identity maps: d16 kernel writing W for the general path
+    int id_n_spam = 0;
+    std::vector<int32_t> h_cptr, h_crow; std::vector<double> h_cval;  // host copy (hessian / fd)
+};
+
+static AtomDev atom_dev(b200_atom* a) {
+    AtomDev d;
+    d.dim = a->dim; d.n_ops = a->n_ops; d.n_rho = a->n_rho; d.n_eff = a->n_eff;
+    d.n_circ = (int)a->n_rows; d.max_depth = a->max_depth; d.n_elements = a->n_elements;
+    d.circ_ptr = a->circ_ptr.as<uint32_t>(); d.circ_ops = a->circ_ops.as<int32_t>();
+    d.circ_prep = a->circ_prep.as<int32_t>(); d.out_ptr = a->out_ptr.as<int32_t>();
+    d.out_eff = a->out_eff.as<int32_t>(); d.out_el = a->out_el.as<int32_t>();
+    return d;
+}
+static ModelDev model_dev(b200_atom* a) {
+    ModelDev m;
+    m.M = a->M.as<double>(); m.Gt = a->Gt.as<double>();
+    m.n_w = a->n_w; m.off_rho = a->off_rho; m.off_eff = a->off_eff;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_version(void) { return 100; }
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200_device_count(int* n_out) {
+    if (!n_out) return fail(B200_E_INVALID, "n_out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *n_out = 0; return fail(B200_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n_out = n;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
+    if (!out) return fail(B200_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(B200_E_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(B200_E_INVALID, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    b200_ctx* c = new b200_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = c;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_destroy(b200_ctx* c) {
+    if (!c) return B200_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release();
+    c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_sync(b200_ctx* c) {
+    if (!c) return fail(B200_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_ctx_launch_count(b200_ctx* c, int64_t* n_out) {
+    if (!c || !n_out) return fail(B200_E_INVALID, "NULL argument");
+    *n_out = c->launches;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// atom upload: validate the prefix table, expand it into independent circuits (host), upload.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CU(b.ensure(bytes));
+    if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return B200_OK;
+}
+
+extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, int n_eff,
+                                int64_t n_rows, const int32_t* row_ptr, const int32_t* row_ops,
+                                const int32_t* row_istart, const int32_t* row_prep, const int32_t* row_icache,
+                                int32_t cache_size,
+                                const int32_t* out_ptr, const int32_t* out_eff, const int32_t* out_el,
+                                int64_t n_elements, b200_atom** out)
+{
+    if (!ctx || !out) return fail(B200_E_INVALID, "NULL ctx/out");
+    *out = nullptr;
+    if (dim != 4 && dim != 16 && dim != 64 && dim != 256)
+        return fail(B200_E_UNSUPPORTED, "dim=%d: kernels are built for d = 4, 16, 64, 256 (1-4 qubits)", dim);
+    if (n_rows < 0 || n_elements < 0 || n_ops < 0 || n_rho <= 0 || n_eff <= 0 || cache_size < 0)
+        return fail(B200_E_INVALID, "negative/zero size argument");
+    if (n_rows > 0 && (!row_ptr || !row_istart || !row_prep || !row_icache || !out_ptr))
+        return fail(B200_E_INVALID, "NULL table pointer");
+    if (n_rows >= (int64_t)1 << 31) return fail(B200_E_UNSUPPORTED, "too many rows");
+    CU(cudaSetDevice(ctx->device));
+
+    // ---- expand: full op sequence of every row; cache slot -> producing row -------------------
+    std::vector<int64_t> slot_row((size_t)cache_size, -1);
+    std::vector<uint64_t> xptr((size_t)n_rows + 1, 0);
+    std::vector<int32_t> xprep((size_t)n_rows);
+    // first pass: lengths
+    for (int64_t k = 0; k < n_rows; ++k) {
+        if (row_ptr[k + 1] < row_ptr[k]) return fail(B200_E_INVALID, "row_ptr not monotone at row %lld", (long long)k);
+        int64_t rem = row_ptr[k + 1] - row_ptr[k];
+        int64_t len;
+        if (row_istart[k] < 0) {
+            if (row_prep[k] < 0 || row_prep[k] >= n_rho) return fail(B200_E_INVALID, "row %lld: bad prep index %d", (long long)k, row_prep[k]);
+            len = rem; xprep[k] = row_prep[k];
+        } else {
+            if (row_istart[k] >= cache_size || slot_row[row_istart[k]] < 0)
+                return fail(B200_E_INVALID, "row %lld starts from cache slot %d which no earlier row wrote", (long long)k, row_istart[k]);
+            int64_t src = slot_row[row_istart[k]];
+            len = (int64_t)(xptr[src + 1] - xptr[src]) + rem; xprep[k] = xprep[src];
+        }
+        xptr[k + 1] = xptr[k] + (uint64_t)len;
+        if (row_icache[k] >= 0) {
+            if (row_icache[k] >= cache_size) return fail(B200_E_INVALID, "row %lld: cache slot %d >= cache_size", (long long)k, row_icache[k]);
+            slot_row[row_icache[k]] = k;
+        }
+        if (out_ptr[k + 1] < out_ptr[k]) return fail(B200_E_INVALID, "out_ptr not monotone");
+    }
+    if (xptr[n_rows] >= ((uint64_t)1 << 32)) return fail(B200_E_UNSUPPORTED, "expanded layout has >= 2^32 propagations");
+    std::vector<int32_t> xops((size_t)xptr[n_rows]);
+    std::fill(slot_row.begin(), slot_row.end(), -1);
+    int max_depth = 0;
+    for (int64_t k = 0; k < n_rows; ++k) {
+        int32_t* dst = xops.data() + xptr[k];
+        if (row_istart[k] >= 0) {
+            int64_t src = slot_row[row_istart[k]];
+            size_t n = (size_t)(xptr[src + 1] - xptr[src]);
+            if (n) memcpy(dst, xops.data() + xptr[src], n * sizeof(int32_t));
+            dst += n;
+        }
+        for (int32_t t = row_ptr[k]; t < row_ptr[k + 1]; ++t) {
+            if (row_ops[t] < 0 || row_ops[t] >= n_ops) return fail(B200_E_INVALID, "row %lld: op index %d out of range", (long long)k, row_ops[t]);
+            *dst++ = row_ops[t];
+        }
+        if (row_icache[k] >= 0) slot_row[row_icache[k]] = k;
+        max_depth = std::max<int>(max_depth, (int)(xptr[k + 1] - xptr[k]));
+    }
+    int64_t n_out = n_rows ? out_ptr[n_rows] : 0;
+    for (int64_t t = 0; t < n_out; ++t) {
+        if (out_eff[t] < 0 || out_eff[t] >= n_eff) return fail(B200_E_INVALID, "effect index %d out of range", out_eff[t]);
+        if (out_el[t] < 0 || out_el[t] >= n_elements) return fail(B200_E_INVALID, "element index %d out of range", out_el[t]);
+    }
+
+    // ---- order circuits longest-first (tail of the persistent grid = short circuits) -----------
+    std::vector<int64_t> order((size_t)n_rows);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+        return (xptr[x + 1] - xptr[x]) > (xptr[y + 1] - xptr[y]); });
+    std::vector<uint32_t> cptr((size_t)n_rows + 1, 0);
+    std::vector<int32_t> cops(xops.size()), cprep((size_t)n_rows), coptr((size_t)n_rows + 1, 0), coeff((size_t)n_out), coel((size_t)n_out);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        int64_t k = order[i];
+        size_t n = (size_t)(xptr[k + 1] - xptr[k]);
+        if (n) memcpy(cops.data() + cptr[i], xops.data() + xptr[k], n * sizeof(int32_t));
+        cptr[i + 1] = cptr[i] + (uint32_t)n;
+        cprep[i] = xprep[k];
+        int32_t no = out_ptr[k + 1] - out_ptr[k];
+        memcpy(coeff.data() + coptr[i], out_eff + out_ptr[k], (size_t)no * sizeof(int32_t));
+        memcpy(coel.data() + coptr[i], out_el + out_ptr[k], (size_t)no * sizeof(int32_t));
+        coptr[i + 1] = coptr[i] + no;
+    }
+
+    b200_atom* a = new b200_atom();
+    a->ctx = ctx; a->dim = dim; a->n_ops = n_ops; a->n_rho = n_rho; a->n_eff = n_eff;
+    a->n_rows = n_rows; a->n_elements = n_elements;
+    a->n_prop_table = n_rows ? row_ptr[n_rows] : 0;
+    a->n_prop_expanded = (int64_t)xptr[n_rows];
+    a->max_depth = max_depth;
+    a->off_rho = (int64_t)n_ops * dim * dim;
+    a->off_eff = a->off_rho + (int64_t)n_rho * dim;
+    a->n_w = a->off_eff + (int64_t)n_eff * dim;
+    int rc;
+    if ((rc = upload_vec(a->circ_ptr, cptr, ctx->stream)) || (rc = upload_vec(a->circ_ops, cops, ctx->stream)) ||
+        (rc = upload_vec(a->circ_prep, cprep, ctx->stream)) || (rc = upload_vec(a->out_ptr, coptr, ctx->stream)) ||
+        (rc = upload_vec(a->out_eff, coeff, ctx->stream)) || (rc = upload_vec(a->out_el, coel, ctx->stream))) {
+        b200_atom_free(ctx, a); return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
+    *out = a;
+    return B200_OK;
+}
+
+extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
+    if (!a) return B200_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
+                      &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
+                      &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
+    for (DevBuf* b : bufs) b->release();
+    delete a;
+    return B200_OK;
+}
+
+extern "C" int b200_atom_info(b200_atom* a, int64_t info[8]) {
+    if (!a || !info) return fail(B200_E_INVALID, "NULL argument");
+    info[0] = a->n_rows; info[1] = a->n_elements; info[2] = a->n_prop_table; info[3] = a->n_prop_expanded;
+    info[4] = a->max_depth; info[5] = a->n_w; info[6] = a->has_derivs ? a->n_params : -1;
+    info[7] = (a->has_derivs && a->unit_perm) ? 1 : 0;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model / derivative upload
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_atom_set_model(b200_ctx* ctx, b200_atom* a, const double* G, const double* rho, const double* E) {
+    if (!ctx || !a || !rho || !E || (a->n_ops > 0 && !G)) return fail(B200_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    const int d = a->dim;
+    CU(a->M.ensure((size_t)a->n_w * sizeof(double)));
+    CU(a->Gt.ensure(std::max<size_t>((size_t)a->off_rho * sizeof(double), 16)));
+    double* M = a->M.as<double>();
+    if (a->n_ops) CU(cudaMemcpyAsync(M, G, (size_t)a->off_rho * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(M + a->off_rho, rho, (size_t)a->n_rho * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(M + a->off_eff, E, (size_t)a->n_eff * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (a->n_ops) {
+        dim3 grid((unsigned)std::min<int64_t>((a->off_rho + 255) / 256, 1024), 1);
+        k_transpose_gates<<<grid, 256, 0, ctx->stream>>>(M, a->n_w, a->n_ops, d, a->Gt.as<double>());
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));   // caller may free/modify its host arrays on return
+    a->has_model = true;
+    return B200_OK;
+}
+
+extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, int32_t n_params,
+                                    int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals)
+{
+    if (!ctx || !a) return fail(B200_E_INVALID, "NULL argument");
+    if (n_w != a->n_w) return fail(B200_E_INVALID, "n_w=%lld does not match the atom's W space (%lld)", (long long)n_w, (long long)a->n_w);
+    if (n_params < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(B200_E_INVALID, "bad derivative map");
+    if (nnz >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "derivative map too large");
+    CU(cudaSetDevice(ctx->device));
+    // COO -> CSC with duplicates summed
+    std::vector<int64_t> idx((size_t)nnz);
+    std::iota(idx.begin(), idx.end(), 0);
+    for (int64_t t = 0; t < nnz; ++t) {
+        if (rows[t] < 0 || rows[t] >= n_w) return fail(B200_E_INVALID, "D row %d out of range", rows[t]);
+        if (cols[t] < 0 || cols[t] >= n_params) return fail(B200_E_INVALID, "D col %d out of range", cols[t]);
+    }
+    std::sort(idx.begin(), idx.end(), [&](int64_t x, int64_t y) {
+        return cols[x] != cols[y] ? cols[x] < cols[y] : rows[x] < rows[y]; });
+    std::vector<int32_t> cptr((size_t)n_params + 1, 0), crow; std::vector<double> cval;
+    crow.reserve((size_t)nnz); cval.reserve((size_t)nnz);
+    std::vector<int32_t> ccol; ccol.reserve((size_t)nnz);
+    for (int64_t t = 0; t < nnz; ++t) {
+        int64_t i = idx[t];
+        if (!crow.empty() && ccol.back() == cols[i] && crow.back() == rows[i]) cval.back() += vals[i];
+        else { crow.push_back(rows[i]); ccol.push_back(cols[i]); cval.push_back(vals[i]); }
+    }
+    for (size_t t = 0; t < ccol.size(); ++t) cptr[ccol[t] + 1]++;
+    for (int p = 0; p < n_params; ++p) cptr[p + 1] += cptr[p];
+
+    // unit partial permutation?  every column <= 1 entry, every row <= 1 entry, all values == 1.0
+    bool unit = true;
+    std::vector<int32_t> colmap((size_t)n_w, -1);
+    for (int p = 0; p < n_params && unit; ++p) {
+        int n = cptr[p + 1] - cptr[p];
+        if (n > 1) unit = false;
+        else if (n == 1) {
+            int t = cptr[p];
+            if (cval[t] != 1.0 || colmap[crow[t]] != -1) unit = false;
+            else colmap[crow[t]] = p;
+        }
+    }
+    a->n_params = n_params; a->unit_perm = unit;
+    a->h_cptr = cptr; a->h_crow = crow; a->h_cval = cval;
+    int rc;
+    if ((rc = upload_vec(a->cptr, cptr, ctx->stream)) || (rc = upload_vec(a->crow, crow, ctx->stream)) ||
+        (rc = upload_vec(a->cval, cval, ctx->stream))) return rc;
+    if (unit) {
+        // columns not fed by a gate element: fed by a rho/effect element (w >= off_rho) or by nothing
+        std::vector<int32_t> spam_col, spam_w;
+        std::vector<char> fed((size_t)n_params, 0);
+        for (int64_t w = 0; w < a->off_rho; ++w) if (colmap[w] >= 0) fed[colmap[w]] = 1;
+        std::vector<int32_t> src((size_t)n_params, -1);
+        for (int64_t w = a->off_rho; w < n_w; ++w) if (colmap[w] >= 0) src[colmap[w]] = (int32_t)w;
+        for (int p = 0; p < n_params; ++p) if (!fed[p]) { spam_col.push_back(p); spam_w.push_back(src[p]); }
+        a->n_spam = (int)spam_col.size();
+        if ((rc = upload_vec(a->colmap, colmap, ctx->stream)) || (rc = upload_vec(a->spam_col, spam_col, ctx->stream)) ||
+            (rc = upload_vec(a->spam_w, spam_w, ctx->stream))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    a->has_derivs = true;
+    return B200_OK;
+}
+
+// identity maps so the d16 kernel can emit W (general path)
+static int ensure_identity_maps(b200_ctx* ctx, b200_atom* a) {
+    if (a->id_colmap.p) return B200_OK;
+    std::vector<int32_t> cm((size_t)a->n_w), sc, sw;
+    for (int64_t w = 0; w < a->n_w; ++w) cm[w] = (int32_t)w;
+    for (int64_t w = a->off_rho; w < a->n_w; ++w) { sc.push_back((int32_t)w); sw.push_back((int32_t)w); }
+    a->id_n_spam = (int)sc.size();
+    int rc;
+    if ((rc = upload_vec(a->id_colmap, cm, ctx->stream)) || (rc = upload_vec(a->id_spam_col, sc, ctx->stream)) ||
+        (rc = upload_vec(a->id_spam_w, sw, ctx->stream))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int grid_for(b200_ctx* c, int64_t n_units, int per_sm) {
+    int64_t g = (int64_t)c->sm_count * per_sm;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, n_units));
+}
+
+template <int D>
+static int launch_probs_generic(b200_ctx* c, b200_atom* a, const double* M, const double* Gt, int nb,
+                                double* out, int64_t el_stride, int64_t batch_stride) {
+    if (a->n_rows == 0) return B200_OK;
+    size_t smem = (size_t)GEN_WARPS * 2 * D * sizeof(double);
+    int per_sm = nb > 1 ? 2 : 8;
+    int gx = grid_for(c, (a->n_rows + GEN_WARPS - 1) / GEN_WARPS, per_sm);
+    dim3 grid(gx, nb);
+    k_probs_generic<D><<<grid, GEN_WARPS * 32, smem, c->stream>>>(atom_dev(a), M, Gt, a->n_w, out, el_stride, batch_stride);
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+static int launch_probs(b200_ctx* c, b200_atom* a, const double* M, const double* Gt, int nb,
+                        double* out, int64_t el_stride, int64_t batch_stride) {
+    switch (a->dim) {
+        case 4: return launch_probs_generic<4>(c, a, M, Gt, nb, out, el_stride, batch_stride);
+        case 16: return launch_probs_generic<16>(c, a, M, Gt, nb, out, el_stride, batch_stride);
+        case 64: return launch_probs_generic<64>(c, a, M, Gt, nb, out, el_stride, batch_stride);
+        case 256: return launch_probs_generic<256>(c, a, M, Gt, nb, out, el_stride, batch_stride);
+    }
+    return fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
+}
+
+template <int D>
+static int launch_w_generic(b200_ctx* c, b200_atom* a, double* W, int64_t ldw, double* probs) {
+    if (a->n_rows == 0) return B200_OK;
+    int gx = grid_for(c, (a->n_rows + GEN_WARPS - 1) / GEN_WARPS, 8);
+    size_t need = (size_t)gx * GEN_WARPS * (size_t)(a->max_depth + 1) * D * sizeof(double);
+    CU(c->scratch.ensure(need));
+    size_t smem = (size_t)GEN_WARPS * 2 * D * sizeof(double);
+    k_w_generic<D><<<gx, GEN_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), W, ldw, probs, c->scratch.as<double>());
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+template <int NG>
+static int launch_d16_t(b200_ctx* c, b200_atom* a, const D16Args& args) {
+    size_t smem = d16_smem_bytes(NG, a->max_depth);
+    CU(cudaFuncSetAttribute(k_dprobs_d16<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (c->smem_optin > 0 ? (220u * 1024u) : (96u * 1024u)) / (smem + 1024)));
+    int gx = grid_for(c, a->n_rows, per_sm);
+    k_dprobs_d16<NG><<<gx, D16_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), args);
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+static bool d16_ok(b200_ctx* c, b200_atom* a) {
+    return a->dim == 16 && a->n_ops >= 1 && a->n_ops <= 8 &&
+           d16_smem_bytes(a->n_ops, a->max_depth) + 1024 <= c->smem_optin;
+}
+static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
+    if (a->n_rows == 0) return B200_OK;
+    switch (a->n_ops) {
+        case 1: return launch_d16_t<1>(c, a, args);
+        case 2: return launch_d16_t<2>(c, a, args);
+        case 3: return launch_d16_t<3>(c, a, args);
+        case 4: return launch_d16_t<4>(c, a, args);
+        case 5: return launch_d16_t<5>(c, a, args);
+        case 6: return launch_d16_t<6>(c, a, args);
+        case 7: return launch_d16_t<7>(c, a, args);
+        case 8: return launch_d16_t<8>(c, a, args);
+    }
+    return fail(B200_E_UNSUPPORTED, "d16 kernel: n_ops=%d", a->n_ops);
+}
+
+// W[el][w] for the whole atom (general path)
+static int compute_w(b200_ctx* c, b200_atom* a, double* W, double* probs) {
+    if (d16_ok(c, a)) {
+        int rc = ensure_identity_maps(c, a);
+        if (rc) return rc;
+        D16Args args;
+        args.colmap = a->id_colmap.as<int32_t>(); args.spam_col = a->id_spam_col.as<int32_t>();
+        args.spam_w = a->id_spam_w.as<int32_t>(); args.n_spam = a->id_n_spam;
+        args.J = W; args.ld = a->n_w; args.probs = probs;
+        return launch_d16(c, a, args);
+    }
+    CU(cudaMemsetAsync(W, 0, (size_t)a->n_elements * a->n_w * sizeof(double), c->stream));
+    switch (a->dim) {
+        case 4: return launch_w_generic<4>(c, a, W, a->n_w, probs);
+        case 16: return launch_w_generic<16>(c, a, W, a->n_w, probs);
+        case 64: return launch_w_generic<64>(c, a, W, a->n_w, probs);
+        case 256: return launch_w_generic<256>(c, a, W, a->n_w, probs);
+    }
+    return fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
+}
+
+extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
+    if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    CU(cudaSetDevice(c->device));
+    return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_out, 1, 0);
+}
+
+extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs) {
+    if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (ld < a->n_params) return fail(B200_E_INVALID, "ld=%lld < n_params=%d", (long long)ld, a->n_params);
+    CU(cudaSetDevice(c->device));
+    if (a->n_elements == 0 || a->n_params == 0) {
+        if (d_probs && a->n_elements) return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_probs, 1, 0);
+        return B200_OK;
+    }
+    if (a->unit_perm && d16_ok(c, a)) {
+        D16Args args;
+        args.colmap = a->colmap.as<int32_t>(); args.spam_col = a->spam_col.as<int32_t>();
+        args.spam_w = a->spam_w.as<int32_t>(); args.n_spam = a->n_spam;
+        args.J = d_out; args.ld = ld; args.probs = d_probs;
+        return launch_d16(c, a, args);
+    }
+    // general path: W then J = W . D
+    CU(c->w_buf.ensure((size_t)a->n_elements * a->n_w * sizeof(double)));
+    int rc = compute_w(c, a, c->w_buf.as<double>(), d_probs);
+    if (rc) return rc;
+    dim3 grid((a->n_params + 127) / 128, (unsigned)std::min<int64_t>(a->n_elements, 65535));
+    k_contract_csc<<<grid, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, a->n_elements, a->n_params,
+                                                 a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(), d_out, ld);
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles
+static int copy_out_2d(b200_ctx* c, const double* d_src, int64_t width, int64_t n_rows, double* h_dst, int64_t hstride) {
+    if (n_rows == 0 || width == 0) return B200_OK;
+    CU(cudaMemcpy2DAsync(h_dst, (size_t)hstride * 8, d_src, (size_t)width * 8, (size_t)width * 8, (size_t)n_rows,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    (void)is_pinned;
+    return B200_OK;
+}
+
+extern "C" int b200_fill_probs(b200_ctx* c, b200_atom* a, double* out, int64_t out_stride) {
+    if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
+    if (out_stride < 1) return fail(B200_E_INVALID, "out_stride must be >= 1");
+    CU(cudaSetDevice(c->device));
+    CU(c->probs_buf.ensure(std::max<size_t>((size_t)a->n_elements * 8, 16)));
+    int rc = b200_fill_probs_dev(c, a, c->probs_buf.as<double>());
+    if (rc) return rc;
+    return copy_out_2d(c, c->probs_buf.as<double>(), 1, a->n_elements, out, out_stride);
+}
+
+extern "C" int b200_fill_dprobs(b200_ctx* c, b200_atom* a, double* out, int64_t row_stride,
+                                double* probs_out, int64_t probs_stride) {
+    if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (row_stride < a->n_params) return fail(B200_E_INVALID, "row_stride < n_params");
+    if (probs_out && probs_stride < 1) return fail(B200_E_INVALID, "probs_stride must be >= 1");
+    CU(cudaSetDevice(c->device));
+    CU(c->out_buf.ensure(std::max<size_t>((size_t)a->n_elements * a->n_params * 8, 16)));
+    double* d_probs = nullptr;
+    if (probs_out) { CU(c->probs_buf.ensure(std::max<size_t>((size_t)a->n_elements * 8, 16))); d_probs = c->probs_buf.as<double>(); }
+    int rc = b200_fill_dprobs_dev(c, a, c->out_buf.as<double>(), a->n_params, d_probs);
+    if (rc) return rc;
+    rc = copy_out_2d(c, c->out_buf.as<double>(), a->n_params, a->n_elements, out, row_stride);
+    if (rc) return rc;
+    if (probs_out) return copy_out_2d(c, d_probs, 1, a->n_elements, probs_out, probs_stride);
+    return B200_OK;
+}
+
+extern "C" int b200_fill_dprobs_fd(b200_ctx* c, b200_atom* a, double eps, double* out, int64_t row_stride,
+                                   double* probs_out, int64_t probs_stride) {
+    if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (row_stride < a->n_params) return fail(B200_E_INVALID, "row_stride < n_params");
+    if (eps == 0.0) return fail(B200_E_INVALID, "eps must be non-zero");
+    CU(cudaSetDevice(c->device));
+    const int64_t nE = a->n_elements; const int Np = a->n_params;
+    CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * Np * 8, 16)));
+    CU(c->probs_buf.ensure(std::max<size_t>((size_t)nE * 8, 16)));
+    double* P0 = c->probs_buf.as<double>();
+    int rc = launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, P0, 1, 0);
+    if (rc) return rc;
+    // batches of perturbed models
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(Np, std::min<int64_t>(256, ((int64_t)256 << 20) / std::max<int64_t>(1, nE * 8))));
+    CU(c->fd_models.ensure((size_t)B * a->n_w * 8));
+    CU(c->fd_gt.ensure(std::max<size_t>((size_t)B * a->off_rho * 8, 16)));
+    CU(c->fd_probs.ensure(std::max<size_t>((size_t)B * nE * 8, 16)));
+    for (int p0 = 0; p0 < Np; p0 += B) {
+        const int nb = std::min(B, Np - p0);
+        dim3 g1((unsigned)std::min<int64_t>((a->n_w + 255) / 256, 256), nb);
+        k_perturb_models<<<g1, 256, 0, c->stream>>>(a->M.as<double>(), a->n_w, nb, p0, eps, a->cptr.as<int32_t>(),
+                                                    a->crow.as<int32_t>(), a->cval.as<double>(), c->fd_models.as<double>());
+        dim3 g2(4, nb);
+        k_perturb_apply<<<g2, 128, 0, c->stream>>>(a->n_w, p0, eps, a->cptr.as<int32_t>(), a->crow.as<int32_t>(),
+                                                   a->cval.as<double>(), c->fd_models.as<double>());
+        c->launches += 2;
+        if (a->n_ops) {
+            dim3 g3((unsigned)std::min<int64_t>((a->off_rho + 255) / 256, 256), nb);
+            k_transpose_gates<<<g3, 256, 0, c->stream>>>(c->fd_models.as<double>(), a->n_w, a->n_ops, a->dim, c->fd_gt.as<double>());
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+        rc = launch_probs(c, a, c->fd_models.as<double>(), c->fd_gt.as<double>(), nb, c->fd_probs.as<double>(), 1, nE);
+        if (rc) return rc;
+        if (nE) {
+            int gx = (int)std::min<int64_t>((nE + 3) / 4, 4096);
+            k_fd_finish<<<gx, 128, 0, c->stream>>>(c->fd_probs.as<double>(), P0, nE, nb, p0, eps, c->out_buf.as<double>(), Np);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    rc = copy_out_2d(c, c->out_buf.as<double>(), Np, nE, out, row_stride);
+    if (rc) return rc;
+    if (probs_out) return copy_out_2d(c, P0, 1, nE, probs_out, probs_stride);
+    return B200_OK;
+}
+
+extern "C" int b200_fill_hprobs_linear(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1,
+                                       int32_t n2, const int32_t* p2, double* out) {
+    (void)c; (void)a; (void)n1; (void)p1; (void)n2; (void)p2; (void)out;
+    return fail(B200_E_UNSUPPORTED, "b200_fill_hprobs_linear: kernel not built yet");
+}
+
+// ------------------------------------------------------------------------------------------------
+// pinned host memory
+// ------------------------------------------------------------------------------------------------
+static std::mutex g_reg_mu;
+static std::map<void*, size_t> g_registered;
+
+extern "C" int b200_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return fail(B200_E_INVALID, "bad argument");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(e == cudaErrorMemoryAllocation ? B200_E_NOMEM : B200_E_CUDA, "cudaHostAlloc(%lld): %s", (long long)bytes, cudaGetErrorString(e)); }
+    return B200_OK;
+}
+extern "C" int b200_host_free(void* p) {
+    if (!p) return B200_OK;
+    CU(cudaFreeHost(p));
+    return B200_OK;
+}
+extern "C" int b200_host_register(void* p, int64_t bytes) {
+    if (!p || bytes <= 0) return fail(B200_E_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_registered.find(p);
+    if (it != g_registered.end()) {
+        if (it->second >= (size_t)bytes) return B200_OK;
+        cudaHostUnregister(p); g_registered.erase(it);
+    }
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200_E_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    g_registered[p] = (size_t)bytes;
+    return B200_OK;
+}
+extern "C" int b200_host_unregister(void* p) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_registered.find(p);
+    if (it == g_registered.end()) return B200_OK;
+    cudaHostUnregister(p);
+    g_registered.erase(it);
+    return B200_OK;
+}

@@ -1,0 +1,221 @@
+// kernels_generic.cuh -- dimension-generic FP64 kernels (any d = 4^n, any number of gates).
+//
+// These are the correctness-first members of the kernel family: one warp owns one circuit and walks
+// its op sequence; they are used for dimensions / gate counts the specialised kernels do not cover,
+// for the forward-difference mode and for the Hessian.  Arithmetic restated from the reference:
+//   state propagation  out[i] = sum_j G[i][j] v[j]   (pygsti/evotypes/densitymx/opcreps.cpp:40-54)
+//   outcome            p = sum_i E[i] v[i]           (pygsti/evotypes/densitymx/effectcreps.cpp:39-45)
+//   circuit walk       pygsti/forwardsims/mapforwardsim_calc_densitymx.pyx:224-283
+#pragma once
+#include "common.cuh"
+
+#define GEN_WARPS 4   // warps per CTA in the generic kernels
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor_f64(v, m);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// probs: out[b*batch_stride + el*el_stride] for model b = blockIdx.y (b = 0 for the plain call;
+// b > 0 are the perturbed models of the forward-difference mode).
+// dynamic smem: GEN_WARPS * 2 * D doubles.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+k_probs_generic(AtomDev a, const double* __restrict__ Mbase, const double* __restrict__ Gtbase,
+                int64_t n_w, double* __restrict__ out, int64_t el_stride, int64_t batch_stride)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* buf0 = smem + (size_t)warp * 2 * D;
+    double* buf1 = buf0 + D;
+    const int b = blockIdx.y;
+    const double* M = Mbase + (int64_t)b * n_w;
+    const double* Gt = Gtbase + (int64_t)b * a.n_ops * D * D;
+    const double* rho = M + (int64_t)a.n_ops * D * D;
+    const double* E = rho + (int64_t)a.n_rho * D;
+    double* o = out + (int64_t)b * batch_stride;
+
+    const int gw = blockIdx.x * GEN_WARPS + warp;
+    const int nw = gridDim.x * GEN_WARPS;
+    for (int c = gw; c < a.n_circ; c += nw) {
+        const uint32_t p0 = a.circ_ptr[c], p1 = a.circ_ptr[c + 1];
+        const double* r = rho + (int64_t)a.circ_prep[c] * D;
+        double* s = buf0; double* t = buf1;
+        for (int i = lane; i < D; i += 32) s[i] = r[i];
+        __syncwarp();
+        for (uint32_t k = p0; k < p1; ++k) {
+            const double* Gg = Gt + (int64_t)a.circ_ops[k] * D * D;
+            for (int i = lane; i < D; i += 32) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < D; ++j) acc += Gg[j * D + i] * s[j];
+                t[i] = acc;
+            }
+            __syncwarp();
+            double* x = s; s = t; t = x;
+        }
+        for (int q = a.out_ptr[c]; q < a.out_ptr[c + 1]; ++q) {
+            const double* e = E + (int64_t)a.out_eff[q] * D;
+            double part = 0.0;
+            for (int i = lane; i < D; i += 32) part += e[i] * s[i];
+            part = warp_sum(part);
+            if (lane == 0) o[(int64_t)a.out_el[q] * el_stride] = part;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// W accumulate: W[el][w] = d p_el / d(member element w), W pre-zeroed, row stride ldw.
+// One warp per circuit; forward states kept in a per-warp global scratch (L2 resident).
+// Adjoint recursion (SURVEY.md App. B.2 == matrixforwardsim.py:1059-1139 for fully
+// parameterised members):
+//   s_0 = rho, s_k = G_k s_{k-1};   e_L = E_j, e_{k-1} = G_k^T e_k
+//   W[el, G_k block] += e_k (x) s_{k-1};  W[el, rho] += e_0;  W[el, E_j] += s_L
+// dynamic smem: GEN_WARPS * 2 * D doubles.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+k_w_generic(AtomDev a, ModelDev m, double* __restrict__ W, int64_t ldw, double* __restrict__ probs,
+            double* __restrict__ scratch /* [total warps][(max_depth+1)*D] */)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* eb0 = smem + (size_t)warp * 2 * D;
+    double* eb1 = eb0 + D;
+    const double* G = m.M;
+    const double* rho = m.M + m.off_rho;
+    const double* E = m.M + m.off_eff;
+    const int gw = blockIdx.x * GEN_WARPS + warp;
+    const int nw = gridDim.x * GEN_WARPS;
+    double* st = scratch + (int64_t)gw * (a.max_depth + 1) * D;
+
+    for (int c = gw; c < a.n_circ; c += nw) {
+        const uint32_t p0 = a.circ_ptr[c];
+        const int L = (int)(a.circ_ptr[c + 1] - p0);
+        const int prep = a.circ_prep[c];
+        const int32_t* ops = a.circ_ops + p0;
+        for (int i = lane; i < D; i += 32) st[i] = rho[(int64_t)prep * D + i];
+        __syncwarp();
+        for (int k = 0; k < L; ++k) {
+            const double* Gg = m.Gt + (int64_t)ops[k] * D * D;
+            const double* s = st + (int64_t)k * D;
+            double* t = st + (int64_t)(k + 1) * D;
+            for (int i = lane; i < D; i += 32) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < D; ++j) acc += Gg[j * D + i] * s[j];
+                t[i] = acc;
+            }
+            __syncwarp();
+        }
+        const double* sL = st + (int64_t)L * D;
+        for (int q = a.out_ptr[c]; q < a.out_ptr[c + 1]; ++q) {
+            const int ei = a.out_eff[q];
+            const int64_t el = a.out_el[q];
+            double* Wr = W + el * ldw;
+            const double* ev = E + (int64_t)ei * D;
+            double part = 0.0;
+            for (int i = lane; i < D; i += 32) {
+                part += ev[i] * sL[i];
+                Wr[m.off_eff + (int64_t)ei * D + i] += sL[i];
+            }
+            if (probs) { part = warp_sum(part); if (lane == 0) probs[el] = part; }
+            double* e = eb0; double* en = eb1;
+            for (int i = lane; i < D; i += 32) e[i] = ev[i];
+            __syncwarp();
+            for (int k = L - 1; k >= 0; --k) {
+                const int g = ops[k];
+                const double* s = st + (int64_t)k * D;
+                double* Wg = Wr + (int64_t)g * D * D;
+                for (int idx = lane; idx < D * D; idx += 32) {
+                    const int i = idx / D, j = idx - i * D;
+                    Wg[idx] += e[i] * s[j];
+                }
+                const double* Gg = G + (int64_t)g * D * D;
+                for (int j = lane; j < D; j += 32) {
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int i = 0; i < D; ++i) acc += Gg[i * D + j] * e[i];
+                    en[j] = acc;
+                }
+                __syncwarp();
+                double* x = e; e = en; en = x;
+            }
+            for (int i = lane; i < D; i += 32) Wr[m.off_rho + (int64_t)prep * D + i] += e[i];
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// J = W . D  with D in CSC (per parameter column p: entries [cptr[p], cptr[p+1]) of (row w, val)).
+// grid.x over column tiles of 128, grid.y over element rows; coalesced stores along p.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_contract_csc(const double* __restrict__ W, int64_t ldw, int64_t n_el, int n_params,
+               const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
+               const double* __restrict__ cval, double* __restrict__ J, int64_t ldj)
+{
+    const int p = blockIdx.x * 128 + threadIdx.x;
+    if (p >= n_params) return;
+    const int b = cptr[p], e = cptr[p + 1];
+    for (int64_t el = blockIdx.y; el < n_el; el += gridDim.y) {
+        const double* Wr = W + el * ldw;
+        double acc = 0.0;
+        for (int t = b; t < e; ++t) acc += cval[t] * Wr[crow[t]];
+        J[el * ldj + p] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward-difference helpers (reference semantics, pyx:349-378)
+// ---------------------------------------------------------------------------------------------
+// build perturbed models: Mb[b] = M + eps * D[:, p0+b]  (and their transposed gates)
+__global__ void k_perturb_models(const double* __restrict__ M, int64_t n_w, int nb, int p0, double eps,
+                                 const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
+                                 const double* __restrict__ cval, double* __restrict__ Mb)
+{
+    const int b = blockIdx.y;
+    double* dst = Mb + (int64_t)b * n_w;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_w; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = M[i];
+    (void)nb; (void)p0; (void)eps; (void)cptr; (void)crow; (void)cval;
+}
+__global__ void k_perturb_apply(int64_t n_w, int p0, double eps,
+                                const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
+                                const double* __restrict__ cval, double* __restrict__ Mb)
+{
+    const int b = blockIdx.y;
+    double* dst = Mb + (int64_t)b * n_w;
+    const int beg = cptr[p0 + b], end = cptr[p0 + b + 1];
+    for (int t = beg + blockIdx.x * blockDim.x + threadIdx.x; t < end; t += gridDim.x * blockDim.x)
+        dst[crow[t]] += eps * cval[t];   // CSC rows are unique within a column (duplicates summed at upload)
+}
+// Gt[b][g][j][i] = M[b][g][i][j]
+__global__ void k_transpose_gates(const double* __restrict__ Mb, int64_t n_w, int n_ops, int D,
+                                  double* __restrict__ Gtb)
+{
+    const int b = blockIdx.y;
+    const double* G = Mb + (int64_t)b * n_w;
+    double* Gt = Gtb + (int64_t)b * n_ops * D * D;
+    const int64_t n = (int64_t)n_ops * D * D;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = idx / (D * D); const int r = (int)(idx - g * D * D);
+        const int j = r / D, i = r - j * D;
+        Gt[idx] = G[g * D * D + (int64_t)i * D + j];
+    }
+}
+// out[el*ld + p0 + b] = (Pb[b][el] - P0[el]) / eps
+__global__ void k_fd_finish(const double* __restrict__ Pb, const double* __restrict__ P0, int64_t n_el,
+                            int nb, int p0, double eps, double* __restrict__ out, int64_t ld)
+{
+    const int b = threadIdx.x & 31;            // 32 columns per block-row for semi-coalesced stores
+    const int64_t el0 = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int bb = b; bb < nb; bb += 32)
+        for (int64_t el = el0; el < n_el; el += (int64_t)gridDim.x * (blockDim.x >> 5))
+            out[el * ld + p0 + bb] = (Pb[(int64_t)bb * n_el + el] - P0[el]) / eps;
+}

@@ -1,0 +1,197 @@
+"""Thin object layer over the C ABI: Context (one per GPU) and Atom (device-resident layout atom).
+
+Only numpy + ctypes; arrays are handed to the library as raw pointers + strides.  All compute happens in
+libb200fwdsim.so on the GPU; a missing library or device raises (no fallback).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from .packing import AtomTables, DerivMap, ModelTensors
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def device_count():
+    lib = _lib.load()
+    n = C.c_int(0)
+    rc = lib.b200_device_count(C.byref(n))
+    if rc != 0:
+        return 0
+    return n.value
+
+
+class Context:
+    """One engine context per GPU (mirrors one MPI rank's ResourceAllocation in the reference)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        h = C.c_void_p(0)
+        _lib.check(self._lib.b200_ctx_create(int(device), C.c_void_p(int(stream) if stream else 0), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200_ctx_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._lib.b200_ctx_sync(self._h))
+
+    @property
+    def launch_count(self):
+        n = C.c_int64(0)
+        _lib.check(self._lib.b200_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def upload_atom(self, t: AtomTables):
+        return Atom(self, t)
+
+
+class Atom:
+    def __init__(self, ctx: Context, t: AtomTables):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self.dim = t.dim
+        self.n_elements = t.n_elements
+        self.n_ops, self.n_rho, self.n_eff = t.n_ops, t.n_rho, t.n_eff
+        self.n_w = t.n_ops * t.dim * t.dim + (t.n_rho + t.n_eff) * t.dim
+        self.n_params = None
+        arrs = [_i32(x) for x in (t.row_ptr, t.row_ops, t.row_istart, t.row_prep, t.row_icache,
+                                  t.out_ptr, t.out_eff, t.out_el)]
+        h = C.c_void_p(0)
+        _lib.check(self._lib.b200_atom_upload(
+            ctx._h, t.dim, t.n_ops, t.n_rho, t.n_eff, t.n_rows,
+            _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]), _ptr(arrs[4]),
+            int(t.cache_size), _ptr(arrs[5]), _ptr(arrs[6]), _ptr(arrs[7]), int(t.n_elements), C.byref(h)))
+        self._h = h
+
+    def free(self):
+        if getattr(self, "_h", None) is not None and self._h.value and self.ctx._h.value:
+            self._lib.b200_atom_free(self.ctx._h, self._h)
+        self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def info(self):
+        buf = (C.c_int64 * 8)()
+        _lib.check(self._lib.b200_atom_info(self._h, buf))
+        keys = ("n_rows", "n_elements", "n_prop_table", "n_prop_expanded", "max_depth", "n_w", "n_params",
+                "fused_path")
+        return dict(zip(keys, list(buf)))
+
+    # ---- uploads -------------------------------------------------------------------------------
+    def set_model(self, G, rho=None, E=None):
+        if isinstance(G, ModelTensors):
+            G, rho, E = G.G, G.rho, G.E
+        d = self.dim
+        G = _f64(G).reshape(self.n_ops, d, d)
+        rho = _f64(rho).reshape(self.n_rho, d)
+        E = _f64(E).reshape(self.n_eff, d)
+        _lib.check(self._lib.b200_atom_set_model(self.ctx._h, self._h, _ptr(G), _ptr(rho), _ptr(E)))
+
+    def set_derivs(self, D: DerivMap):
+        rows, cols, vals = _i32(D.rows), _i32(D.cols), _f64(D.vals)
+        _lib.check(self._lib.b200_atom_set_derivs(self.ctx._h, self._h, int(D.n_w), int(D.n_params),
+                                                  int(rows.shape[0]), _ptr(rows), _ptr(cols), _ptr(vals)))
+        self.n_params = int(D.n_params)
+
+    # ---- host-buffer fills ---------------------------------------------------------------------
+    @staticmethod
+    def _vec_stride(a, n):
+        if a.dtype != np.float64 or a.ndim != 1 or a.shape[0] != n:
+            raise ValueError("expected float64 vector of length %d" % n)
+        if n > 1 and (a.strides[0] % 8 or a.strides[0] <= 0):
+            raise ValueError("unsupported stride")
+        return (a.strides[0] // 8) if n > 1 else 1
+
+    def fill_probs(self, out):
+        st = self._vec_stride(out, self.n_elements)
+        _lib.check(self._lib.b200_fill_probs(self.ctx._h, self._h, _ptr(out), st))
+        return out
+
+    def _mat_stride(self, a):
+        if a.dtype != np.float64 or a.ndim != 2 or a.shape != (self.n_elements, self.n_params):
+            raise ValueError("expected float64 array of shape (%d, %d), got %s" %
+                             (self.n_elements, self.n_params, a.shape))
+        if a.shape[1] > 1 and a.strides[1] != 8:
+            raise ValueError("Jacobian destination must be contiguous along the parameter axis")
+        if a.shape[0] > 1 and (a.strides[0] % 8 or a.strides[0] < 8 * a.shape[1]):
+            raise ValueError("unsupported row stride")
+        return (a.strides[0] // 8) if a.shape[0] > 1 else max(a.shape[1], 1)
+
+    def fill_dprobs(self, out, probs_out=None):
+        rs = self._mat_stride(out)
+        ps = self._vec_stride(probs_out, self.n_elements) if probs_out is not None else 1
+        _lib.check(self._lib.b200_fill_dprobs(self.ctx._h, self._h, _ptr(out), rs, _ptr(probs_out), ps))
+        return out
+
+    def fill_dprobs_fd(self, out, eps=1e-7, probs_out=None):
+        rs = self._mat_stride(out)
+        ps = self._vec_stride(probs_out, self.n_elements) if probs_out is not None else 1
+        _lib.check(self._lib.b200_fill_dprobs_fd(self.ctx._h, self._h, float(eps), _ptr(out), rs,
+                                                 _ptr(probs_out), ps))
+        return out
+
+    def fill_hprobs_linear(self, p1, p2, out):
+        p1, p2 = _i32(p1), _i32(p2)
+        if out.dtype != np.float64 or not out.flags.c_contiguous or \
+                out.shape != (self.n_elements, p1.shape[0], p2.shape[0]):
+            raise ValueError("expected C-contiguous float64 array (n_elements, n1, n2)")
+        _lib.check(self._lib.b200_fill_hprobs_linear(self.ctx._h, self._h, p1.shape[0], _ptr(p1),
+                                                     p2.shape[0], _ptr(p2), _ptr(out)))
+        return out
+
+    # ---- device-buffer fills (raw device pointers, e.g. torch.Tensor.data_ptr()) -----------------
+    def fill_probs_dev(self, d_out_ptr):
+        _lib.check(self._lib.b200_fill_probs_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr))))
+
+    def fill_dprobs_dev(self, d_out_ptr, ld, d_probs_ptr=0):
+        _lib.check(self._lib.b200_fill_dprobs_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr)), int(ld),
+                                                  C.c_void_p(int(d_probs_ptr))))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by cudaHostAlloc memory (freed when the array is garbage collected)."""
+    lib = _lib.load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p(0)
+    _lib.check(lib.b200_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.b200_host_free(C.c_void_p(self.ptr))
+            except Exception:
+                pass
+    _OWNERS[arr.ctypes.data] = _Owner(p.value)
+    return arr
+
+
+_OWNERS = {}

@@ -35,9 +35,11 @@ from pygsti_b200 import packing  # noqa: E402
 def _canon_perm(map_layout, other_layout, n_circuits):
     """perm such that other_array[perm] is in map-layout element order."""
     perm = np.empty(map_layout.num_elements, dtype=np.int64)
-    for i in range(n_circuits):
+    # NB: with num_atoms > 1 the Map layout re-orders circuits (SURVEY App. A trap 8), so match by circuit
+    assert len(map_layout.circuits) == n_circuits
+    for i, circ in enumerate(map_layout.circuits):
         mi, mo = map_layout.indices_and_outcomes_for_index(i)
-        oi, oo = other_layout.indices_and_outcomes_for_index(i)
+        oi, oo = other_layout.indices_and_outcomes(circ)
         mi = np.arange(mi.start, mi.stop) if isinstance(mi, slice) else np.asarray(mi)
         oi = np.arange(oi.start, oi.stop) if isinstance(oi, slice) else np.asarray(oi)
         lut = {o: int(ix) for o, ix in zip(oo, oi)}
