@@ -1,0 +1,201 @@
+"""
+``pygsti_b200.calclib`` -- a drop-in *calclib* module for pyGSTi's Map forward simulator.
+
+pyGSTi's ``SimpleMapForwardSimulator._set_evotype`` imports
+``pygsti.forwardsims.mapforwardsim_calc_<evotype>`` and calls three functions of it
+(reference: pygsti/forwardsims/mapforwardsim.py:93-102, :372-391).  This module exports the same three
+functions with the same signatures and argument meaning as the Cython original
+(pygsti/forwardsims/mapforwardsim_calc_densitymx.pyx:40, :149, :290), implemented on the B200 engine:
+
+    propagate_staterep(staterep, operationreps)
+    mapfill_probs_atom(fwdsim, array_to_fill, dest_indices, layout_atom, resource_alloc)
+    mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices, layout_atom,
+                        param_indices, resource_alloc, eps)
+
+Differences, by design:
+  * the Jacobian is ANALYTIC by default (parity target: the reference's MatrixForwardSimulator, <= 1e-10 abs);
+    ``fwdsim.derivative_mode = 'fd'`` reproduces the reference's forward differences (pyx:349-378)
+    with the given ``eps`` on the device;
+  * layout tables are converted once per atom and cached on the device (the reference converts on every
+    call, pyx:163-181); the model tensors are re-read on every call, as the reference does;
+  * there is NO CPU fallback: without the CUDA library / a GPU these functions raise.
+"""
+import os
+import weakref
+
+import numpy as np
+
+from . import engine, packing
+
+_CONTEXTS = {}
+_ATOM_CACHE = weakref.WeakKeyDictionary()   # layout atom -> {device: uploaded engine atom}; never pickled
+
+# members whose derivative w.r.t. their own parameters does not depend on the parameter values
+# (the dense array is linear in the parameters), so the derivative map can be cached per layout atom
+_LINEAR_MEMBERS = frozenset([
+    "FullArbitraryOp", "FullTPOp", "StaticArbitraryOp", "StaticUnitaryOp", "StaticCliffordOp", "StaticStandardOp",
+    "FullState", "TPState", "StaticState", "FullPOVMEffect", "StaticPOVMEffect", "ComplementPOVMEffect",
+    "ConjugatedStatePOVMEffect"])
+
+
+def get_context(device=None):
+    """Process-wide engine context for a GPU (default: LOCAL_RANK's GPU, else 0)."""
+    if device is None:
+        device = int(os.environ.get("B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        n = engine.device_count()
+        if n > 0:
+            device %= n
+    if device not in _CONTEXTS:
+        _CONTEXTS[device] = engine.Context(device)
+    return _CONTEXTS[device]
+
+
+def _device_for(fwdsim, layout_atom):
+    dev = getattr(layout_atom, "_b200_device", None)   # single-process multi-GPU: atoms are tagged
+    if dev is not None:
+        return dev
+    return getattr(fwdsim, "_b200_device", None)
+
+
+def _engine_atom(fwdsim, layout_atom):
+    """Upload (once) and return the device-resident copy of a layout atom."""
+    ctx = get_context(_device_for(fwdsim, layout_atom))
+    cache = _ATOM_CACHE.get(layout_atom)
+    if cache is None:
+        cache = _ATOM_CACHE[layout_atom] = {}
+    ent = cache.get(ctx.device)
+    if ent is None:
+        dim = fwdsim.model.dim
+        tables = packing.pack_atom(layout_atom, dim)
+        ent = {"atom": ctx.upload_atom(tables), "tables": tables, "deriv_key": None}
+        cache[ctx.device] = ent
+    return ctx, ent
+
+
+def _to_index_array(idx, n):
+    if idx is None:
+        return None
+    if isinstance(idx, slice):
+        start, stop, step = idx.indices(n)
+        return np.arange(start, stop, step, dtype=np.int64)
+    return np.asarray(idx, dtype=np.int64)
+
+
+def _is_full_range(idx, n):
+    if idx is None:
+        return True
+    if isinstance(idx, slice):
+        return idx.indices(n) == (0, n, 1)
+    idx = np.asarray(idx)
+    return idx.shape == (n,) and np.array_equal(idx, np.arange(n))
+
+
+def _contiguous_block(idx, n):
+    """(start, stop) if idx selects a contiguous ascending block of range(n), else None."""
+    if idx is None:
+        return (0, n)
+    if isinstance(idx, slice):
+        start, stop, step = idx.indices(n)
+        return (start, max(start, stop)) if step == 1 else None
+    idx = np.asarray(idx)
+    if idx.size == 0:
+        return (0, 0)
+    if np.array_equal(idx, np.arange(idx[0], idx[0] + idx.size)):
+        return (int(idx[0]), int(idx[0]) + idx.size)
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+def propagate_staterep(staterep, operationreps):
+    """Same contract as pyx:40-47 (used only by the single-circuit reference path); host-side rep objects
+    are the reference's own, so this simply chains their ``acton``."""
+    ret = staterep
+    for oprep in operationreps:
+        ret = oprep.acton(ret)
+    return ret
+
+
+def mapfill_probs_atom(fwdsim, array_to_fill, dest_indices, layout_atom, resource_alloc):
+    """array_to_fill[dest_indices] = outcome probabilities of every element of ``layout_atom``
+    (replaces pyx:149-190 + dm_mapfill_probs pyx:194-287)."""
+    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+    if not shared_mem_leader:
+        return  # same guard as pyx:158,183: only the host leader writes shared memory
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    mt = packing.pack_model(fwdsim.model, layout_atom, fwdsim.model.dim)
+    atom.set_model(mt)
+    nE = layout_atom.num_elements
+    blk = _contiguous_block(dest_indices, array_to_fill.shape[0])
+    if blk is not None and blk[1] - blk[0] == nE and array_to_fill.dtype == np.float64:
+        atom.fill_probs(array_to_fill[blk[0]:blk[1]])
+    else:
+        tmp = np.empty(nE)
+        atom.fill_probs(tmp)
+        array_to_fill[_to_index_array(dest_indices, array_to_fill.shape[0])] = tmp
+
+
+def _deriv_map(fwdsim, layout_atom, ent, param_indices):
+    """Upload the derivative map for this parameter block (cached when every member is linear in its
+    parameters, in which case D does not depend on the current parameter vector)."""
+    model = fwdsim.model
+    pidx = packing.param_slice_to_array(param_indices, model.num_params)
+    ops, rhos, effs = packing._members(model, layout_atom)
+    linear = all(type(m).__name__ in _LINEAR_MEMBERS for m in ops + rhos + effs) \
+        and getattr(model, "_param_interposer", None) is None
+    key = (pidx.tobytes(), model.num_params) if linear else None
+    if key is not None and ent["deriv_key"] == key:
+        return pidx
+    D = packing.pack_derivs(model, layout_atom, model.dim, pidx)
+    ent["atom"].set_derivs(D)
+    ent["deriv_key"] = key
+    return pidx
+
+
+def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices, layout_atom, param_indices,
+                        resource_alloc, eps):
+    """array_to_fill[dest_indices, dest_param_indices] = d(probabilities)/d(params[param_indices])
+    (replaces pyx:290-383).  ``eps`` is used only in 'fd' mode."""
+    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+    model = fwdsim.model
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    mt = packing.pack_model(model, layout_atom, model.dim)
+    atom.set_model(mt)
+    pidx = _deriv_map(fwdsim, layout_atom, ent, param_indices)
+    if not shared_mem_leader:
+        return
+    nE = layout_atom.num_elements
+    nP = int(pidx.size)
+    mode = getattr(fwdsim, "derivative_mode", "analytic")
+    fill = (lambda out: atom.fill_dprobs_fd(out, eps=eps)) if mode == "fd" else atom.fill_dprobs
+
+    rblk = _contiguous_block(dest_indices, array_to_fill.shape[0])
+    if dest_param_indices is None:
+        cblk = (0, nP)
+    else:
+        cblk = _contiguous_block(dest_param_indices, array_to_fill.shape[1])
+    direct = (rblk is not None and cblk is not None and rblk[1] - rblk[0] == nE and cblk[1] - cblk[0] == nP
+              and array_to_fill.dtype == np.float64
+              and (array_to_fill.shape[1] <= 1 or array_to_fill.strides[1] == 8))
+    if nE == 0 or nP == 0:
+        return
+    if direct:
+        fill(array_to_fill[rblk[0]:rblk[1], cblk[0]:cblk[1]])
+    else:
+        tmp = np.empty((nE, nP))
+        fill(tmp)
+        r = _to_index_array(dest_indices, array_to_fill.shape[0])
+        c = np.arange(nP) if dest_param_indices is None else _to_index_array(dest_param_indices, array_to_fill.shape[1])
+        array_to_fill[np.ix_(r, c)] = tmp
+
+
+# The reference calclib also exports six time-dependent functions (pyx:400-586).  They are OUT OF SCOPE for
+# this engine; calling them fails loudly instead of silently running on the CPU.
+def _td_unsupported(*args, **kwargs):
+    raise NotImplementedError("time-dependent mapfill_TD* functions are not implemented by the B200 engine; "
+                              "use pyGSTi's MapForwardSimulator for time-dependent objective terms")
+
+
+mapfill_TDchi2_terms = mapfill_TDloglpp_terms = mapfill_TDterms = _td_unsupported
+mapfill_TDdchi2_terms = mapfill_TDdloglpp_terms = mapfill_TDdterms = _td_unsupported

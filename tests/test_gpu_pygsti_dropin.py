@@ -1,0 +1,159 @@
+"""
+End-to-end drop-in tests on the GPU THROUGH pyGSTi's own API: ``model.sim = B200ForwardSimulator()``.
+
+These re-state the reference's own forward-simulator tests with the new simulator added to the list of
+simulators under test (pyGSTi test/unit/objects/test_forwardsim.py:278-348 ForwardSimConsistencyTester,
+:351-378 ForwardSimIntegrationTester, :58-146 smoke tests; test/unit/mpi/run_me_with_mpiexec.py:176-261
+atom / param-block equivalence).  They need the reference install (baseline/_ref, built by
+oracle/build_ref.py; it is git-ignored but travels to the GPU box) and skip when pyGSTi is not importable;
+tests/test_gpu_parity.py covers the same kernels against committed golden vectors without pyGSTi.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(REPO, "baseline", "_ref")
+if os.path.isdir(os.path.join(REF, "pygsti")) and REF not in sys.path:
+    sys.path.insert(0, REF)
+pygsti = pytest.importorskip("pygsti", reason="reference install (baseline/_ref) not present")
+
+import scipy.linalg as la  # noqa: E402
+from pygsti.modelpacks import smq1Q_XYI, smq2Q_XYCNOT  # noqa: E402
+from pygsti.forwardsims import MapForwardSimulator, MatrixForwardSimulator  # noqa: E402
+from pygsti.circuits import create_lsgst_circuit_lists  # noqa: E402
+from pygsti_b200.forwardsim import B200ForwardSimulator  # noqa: E402
+
+PROBS_TOL = 1e-14   # colinearity tolerances of the reference's own tester (test_forwardsim.py:280-281)
+JACS_TOL = 1e-10
+
+
+def _bulk_arrays(model, sim, circuits, want_jac=True):
+    m = model.copy()
+    m.sim = sim
+    pr = m.sim.bulk_probs(circuits)
+    probs = np.concatenate([np.array(list(pr[c].values())) for c in circuits])
+    jac = None
+    if want_jac:
+        dp = m.sim.bulk_dprobs(circuits)
+        jac = np.concatenate([np.array(list(dp[c].values())) for c in circuits])
+    return probs, jac
+
+
+def _colinearities(rows):
+    _, _, vt = la.svd(rows, full_matrices=False)
+    v = vt[0, :]
+    col = (rows / la.norm(rows, axis=1)[:, None]) @ v
+    if np.count_nonzero(col < 0) > col.size / 2:
+        col *= -1
+    return col
+
+
+def test_consistency_tester_with_b200_simulator_added():
+    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    circuits = create_lsgst_circuit_lists(model, smq1Q_XYI.prep_fiducials(), smq1Q_XYI.meas_fiducials(),
+                                          smq1Q_XYI.germs(), [4])[0]
+    sims = [MapForwardSimulator(), MatrixForwardSimulator(), B200ForwardSimulator(),
+            B200ForwardSimulator(derivative_mode='fd')]
+    res = [_bulk_arrays(model, s, circuits) for s in sims]
+    pcl = _colinearities(np.vstack([r[0] for r in res]))
+    assert np.all(pcl >= 1 - PROBS_TOL), pcl
+    jcl = _colinearities(np.stack([r[1].ravel() for r in res]))
+    assert np.all(jcl >= 1 - JACS_TOL), jcl
+    # and the absolute bar of BASELINE.json: 1e-10 vs the reference (probs vs Map, Jacobian vs analytic Matrix)
+    assert np.max(np.abs(res[2][0] - res[0][0])) <= 1e-10
+    assert np.max(np.abs(res[2][1] - res[1][1])) <= 1e-10
+
+
+def test_model_probabilities_known_answer():
+    """test_model.py:418-486 style: probabilities equal the explicit numpy product E^T Gy Gx rho."""
+    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    model.sim = B200ForwardSimulator()
+    c = pygsti.circuits.Circuit([('Gxpi2', 0), ('Gypi2', 0)], line_labels=(0,))
+    p = model.probabilities(c)
+    Gx = model.operations[('Gxpi2', 0)].to_dense(); Gy = model.operations[('Gypi2', 0)].to_dense()
+    rho = model.preps['rho0'].to_dense()
+    for k, E in model.povms['Mdefault'].items():
+        expect = float(E.to_dense() @ Gy @ Gx @ rho)
+        assert abs(p[(k,)] - expect) <= 1e-12
+
+
+@pytest.mark.parametrize("param", ["full", "full TP", "CPTPLND", "H+S"])
+def test_parameterizations_vs_matrix_sim(param):
+    model = smq1Q_XYI.target_model(param)
+    v = model.to_vector(); rng = np.random.default_rng(1)
+    model.from_vector(v + 5e-3 * rng.standard_normal(v.size))
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data[:150]
+    pm, jm = _bulk_arrays(model, MatrixForwardSimulator(), circuits)
+    pb, jb = _bulk_arrays(model, B200ForwardSimulator(), circuits)
+    assert np.max(np.abs(pm - pb)) <= 1e-10
+    assert np.max(np.abs(jm - jb)) <= 1e-10
+
+
+def test_atoms_and_param_blocks_equal_single_atom():
+    """run_me_with_mpiexec.py:176-261 logic without MPI: num_atoms in {1,4}, param_blk_sizes in {None,15}."""
+    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    ref = None
+    for natoms, blk in [(1, None), (4, None), (1, (15,)), (4, (15,))]:
+        m = model.copy()
+        m.sim = B200ForwardSimulator(num_atoms=natoms, param_blk_sizes=blk)
+        layout = m.sim.create_layout(circuits, array_types=('e', 'ep'))
+        p = np.empty(layout.num_elements); dp = np.full((layout.num_elements, m.num_params), np.nan)
+        m.sim.bulk_fill_dprobs(dp, layout, pr_array_to_fill=p)
+        cur = {}
+        for i, c in enumerate(layout.circuits):
+            idx, outs = layout.indices_and_outcomes_for_index(i)
+            cur[c] = (p[idx].copy(), dp[idx].copy())
+        if ref is None:
+            ref = cur
+        else:
+            for c in ref:
+                assert np.max(np.abs(ref[c][0] - cur[c][0])) <= 1e-13
+                assert np.max(np.abs(ref[c][1] - cur[c][1])) <= 1e-12
+
+
+def test_hprobs_vs_matrix_sim():
+    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data[:30]
+    mm = model.copy(); mm.sim = MatrixForwardSimulator()
+    hm = mm.sim.bulk_hprobs(circuits)
+    mb = model.copy(); mb.sim = B200ForwardSimulator()
+    hb = mb.sim.bulk_hprobs(circuits)
+    worst = 0.0
+    for c in circuits:
+        for k in hm[c]:
+            worst = max(worst, np.max(np.abs(hm[c][k] - hb[c][k])))
+    # FD (eps=1e-5) of the ANALYTIC Jacobian along one axis; the reference's own Map simulator (FD of FD)
+    # is off by ~3e-3 here
+    assert worst <= 5e-4, worst
+
+
+def test_two_qubit_full_model_vs_reference():
+    model = smq2Q_XYCNOT.target_model().depolarize(op_noise=0.01, spam_noise=0.01)
+    circuits = smq2Q_XYCNOT.create_gst_experiment_design(2).all_circuits_needing_data[::7][:120]
+    pmap, _ = _bulk_arrays(model, MapForwardSimulator(), circuits, want_jac=False)
+    pb, jb = _bulk_arrays(model, B200ForwardSimulator(), circuits)
+    assert np.max(np.abs(pmap - pb)) <= 1e-10
+    _, jm = _bulk_arrays(model, MatrixForwardSimulator(), circuits[:40])
+    n = jm.shape[0]
+    assert np.max(np.abs(jm - jb[:n])) <= 1e-10
+
+
+def test_gst_fit_reaches_reference_quality():
+    """ForwardSimIntegrationTester (test_forwardsim.py:351-378): full GST on noiseless data, 2*DeltaLogL <= 0.05."""
+    from pygsti.protocols import gst, ProtocolData
+    from pygsti.data import simulate_data
+    from pygsti.tools import two_delta_logl
+    design = smq1Q_XYI.create_gst_experiment_design(max_max_length=8)
+    datagen = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    ds = simulate_data(datagen, design.all_circuits_needing_data, 20000, sample_error='none')
+    proto = gst.GateSetTomography(smq1Q_XYI.target_model("full TP"), 'stdgaugeopt', name="testGST")
+    results = proto.run(ProtocolData(design, ds), simulator=B200ForwardSimulator())
+    mdl = results.estimates["testGST"].models['stdgaugeopt']
+    assert isinstance(results.estimates["testGST"].models['final iteration estimate'].sim, B200ForwardSimulator)
+    assert two_delta_logl(mdl, ds) <= 0.05

@@ -1,0 +1,78 @@
+"""Host-side logic of the pyGSTi plug-in (no GPU): class plumbing that the reference's traps demand
+(SURVEY.md App. A 'Boundary traps'), packing of layouts/models, and loud failure without a device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(REPO, "baseline", "_ref")
+if os.path.isdir(os.path.join(REF, "pygsti")) and REF not in sys.path:
+    sys.path.insert(0, REF)
+pygsti = pytest.importorskip("pygsti", reason="reference install (baseline/_ref) not present")
+
+from pygsti.modelpacks import smq1Q_XYI  # noqa: E402
+from pygsti_b200 import packing, engine, _lib  # noqa: E402
+from pygsti_b200.forwardsim import B200ForwardSimulator  # noqa: E402
+from oracle import oracle_np as onp  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def model():
+    return smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+
+
+def test_sim_assignment_copy_and_serialization(model):
+    m = model.copy()
+    m.sim = B200ForwardSimulator(num_atoms=2, derivative_mode='fd')
+    assert isinstance(m.sim, B200ForwardSimulator) and m.sim.model is m
+    assert m.sim.calclib.__name__ == "pygsti_b200.calclib"
+    m2 = m.copy()                      # Model.copy deep-copies the simulator through __getstate__
+    assert isinstance(m2.sim, B200ForwardSimulator) and m2.sim.model is m2
+    assert m2.sim.derivative_mode == 'fd' and m2.sim.calclib.__name__ == "pygsti_b200.calclib"
+    s = m.sim.copy()                   # MapForwardSimulator.copy hard-codes its class: must be overridden
+    assert isinstance(s, B200ForwardSimulator) and s._num_atoms == 2
+    st = m.sim.to_nice_serialization()
+    s2 = B200ForwardSimulator.from_nice_serialization(st)
+    assert isinstance(s2, B200ForwardSimulator) and s2.derivative_mode == 'fd'
+
+
+def test_layout_is_the_reference_layout_and_no_jacobian_table(model):
+    m = model.copy()
+    m.sim = B200ForwardSimulator()
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data
+    layout = m.sim.create_layout(circuits, array_types=('e', 'ep'))
+    assert type(layout).__name__ == "MapCOPALayout"
+    assert not hasattr(layout.atoms[0], "jac_table")     # trap 3: the generic calclib would build it
+
+
+def test_packing_reproduces_reference_probs_through_the_oracle(model):
+    m = model.copy()
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    m.sim = 'map'
+    layout = m.sim.create_layout(circuits, array_types=('e', 'ep'))
+    ref = np.empty(layout.num_elements); m.sim.bulk_fill_probs(ref, layout)
+    atom = layout.atoms[0]
+    t = packing.pack_atom(atom, m.dim)
+    mt = packing.pack_model(m, atom, m.dim)
+    out = onp.mapfill_probs(t, mt.G, mt.rho, mt.E)
+    assert np.max(np.abs(out - ref)) <= 1e-14
+    D = packing.pack_derivs(m, atom, m.dim, slice(10, 30))
+    assert D.n_params == 20 and D.cols.max() < 20
+    Dfull = packing.pack_derivs(m, atom, m.dim)
+    J = onp.dprobs_analytic(t, mt.G, mt.rho, mt.E, Dfull)
+    Jb = onp.dprobs_analytic(t, mt.G, mt.rho, mt.E, D)
+    assert np.max(np.abs(J[:, 10:30] - Jb)) == 0.0
+
+
+def test_fill_fails_loudly_without_gpu(model):
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = model.copy()
+    m.sim = B200ForwardSimulator()
+    circuits = smq1Q_XYI.create_gst_experiment_design(1).all_circuits_needing_data
+    with pytest.raises(_lib.B200Error):
+        m.sim.bulk_probs(circuits)
+    with pytest.raises(ValueError):
+        B200ForwardSimulator(derivative_mode='nope')

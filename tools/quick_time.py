@@ -4,14 +4,15 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pygsti_b200 import engine
-from tests.conftest import Case
+from pygsti_b200.fixtures import Case
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_full_layout"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 c = Case(name)
 a = c.atoms[0]
 torch.cuda.set_device(0)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 ctx = engine.Context(0, stream=stream.cuda_stream)
 at = ctx.upload_atom(a["tables"]); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
 print(at.info())
