@@ -108,8 +108,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(case, n_params_sample, threads):
-    """Reference algorithm (FD Jacobian, pyx:290-383) on the host cores; returns dict for the JSON line."""
+def cpu_reference_sample(case, threads, core_seconds=20.0):
+    """Reference algorithm (FD Jacobian, pyx:290-383) on the host cores; returns dict for the JSON line.
+
+    Sample = base pass (serial, as in the reference) + n FD parameter passes with n a multiple of the thread
+    count (every thread gets the same number of identical full-table passes); the full Jacobian is
+    base + Np passes, so  t_full = t_base + t_n * Np / n."""
     from oracle import oracle_c
     oracle_c.build()
     kind = "reference" if os.path.exists(oracle_c.LIB_REF) else "port"
@@ -118,18 +122,20 @@ def cpu_reference_sample(case, n_params_sample, threads):
     t = a["tables"]
     csc = oracle_c.csc_of(a["D"])
     Np = a["D"].n_params
-    # spread the sample over the parameter range (gate, prep and effect parameters)
-    n = min(n_params_sample, Np)
+    t0 = time.time()
+    orc.mapfill_probs(t, a["G"], a["rho"], a["E"])
+    t_base = time.time() - t0
+    per_thread = max(1, int(round(core_seconds / max(t_base, 1e-3) / threads)))
+    n = min(Np - 80, per_thread * threads)
     lo = 80
     t0 = time.time()
     orc.dprobs_fd(t, a["G"], a["rho"], a["E"], a["D"], p_lo=lo, p_hi=lo + n, eps=1e-7, n_threads=threads, csc=csc)
-    dt = time.time() - t0
-    # (base pass + n passes) measured; full Jacobian = base + Np passes.  With T threads the n passes run
-    # ceil(n/T) deep, so scale the per-pass throughput, not the wall clock, to Np passes.
-    full = dt * (Np + 1) / (n + 1)
+    dt = time.time() - t0 - t_base           # dprobs_fd runs its own base pass first
+    full = t_base + max(dt, 1e-6) * Np / n
     return {"value": case.n_elements / full, "unit": "circuit-outcomes/s", "cores": threads, "kind": kind,
-            "sample": "%d of %d FD parameter passes (+ base pass) over the full 68335-row prefix table, "
-                      "%.1f s wall on %d threads, extrapolated x(Np+1)/(n+1)" % (n, Np, dt, threads),
+            "sample": "base pass %.3f s + %d of %d FD parameter passes in %.2f s on %d threads over the full "
+                      "68335-row prefix table; full Jacobian = base + Np passes (extrapolated x Np/n)"
+                      % (t_base, n, Np, dt, threads),
             "seconds_full_jacobian_extrapolated": full}
 
 
@@ -139,13 +145,12 @@ def run_reference_arm(args, rank, world):
     from pygsti_b200.fixtures import Case
     case = Case(WORKLOAD)
     threads = os.cpu_count() or 1
-    n = max(threads * 16, 64)
     vals = []
     for _ in range(args.warmup):
-        cpu_reference_sample(case, min(n, 2 * threads), threads)
+        cpu_reference_sample(case, threads, core_seconds=2.0)
     t0 = time.time()
     for _ in range(args.steps):
-        vals.append(cpu_reference_sample(case, n, threads))
+        vals.append(cpu_reference_sample(case, threads, core_seconds=20.0))
     dt = time.time() - t0
     v = float(np.mean([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
@@ -168,7 +173,6 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-sample-params", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
@@ -295,7 +299,7 @@ def main():
             "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference_sample(case, args.cpu_sample_params, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_reference_sample(case, os.cpu_count() or 1, core_seconds=20.0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,124 @@
+"""
+Multi-GPU host logic: one process per GPU (torch.distributed; NCCL over NVLink on the B200 box, gloo on CPU).
+
+The path shards over independent circuits (layout atoms / circuits are independent units that
+need only the small model tensors), so there is NO collective on the data path.  The single exchange step
+the reference has -- gathering element shards when the host optimizer wants whole arrays
+(``gather_local_array`` -> ``Allgatherv``, pygsti/baseobjs/resourceallocation.py:323-329) -- is
+``allgather_rows`` below.
+
+``shard_tables`` cuts a layout atom into ``world`` independent sub-atoms balanced by propagation count.
+Prefix-cache links are resolved (every row of a shard carries its full op sequence) so a shard never
+depends on rows owned by another rank; the reference's equivalent is the prefix-tree cut of
+``PrefixTable.find_splitting_new`` (pygsti/layouts/prefixtable.py:154-290), which duplicates shared
+prefixes on both sides of a cut for the same reason.
+"""
+import numpy as np
+
+from .packing import AtomTables
+
+
+def expanded_lengths(t: AtomTables):
+    """Depth of every row after following cache links (no sequences materialised)."""
+    n = t.n_rows
+    L = np.zeros(n, dtype=np.int64)
+    slot_len = np.zeros(max(t.cache_size, 1), dtype=np.int64)
+    rem = (t.row_ptr[1:] - t.row_ptr[:-1]).astype(np.int64)
+    for k in range(n):
+        l = rem[k] + (slot_len[t.row_istart[k]] if t.row_istart[k] >= 0 else 0)
+        L[k] = l
+        if t.row_icache[k] >= 0:
+            slot_len[t.row_icache[k]] = l
+    return L
+
+
+def shard_rows(t: AtomTables, world: int):
+    """Greedy balanced assignment of rows to ranks by (depth + 1) * n_outcomes work; returns list of row-index arrays."""
+    L = expanded_lengths(t)
+    nout = (t.out_ptr[1:] - t.out_ptr[:-1]).astype(np.int64)
+    work = (L + 1) * (1 + 2 * nout)          # forward chain + per-outcome backward chain and accumulation
+    order = np.argsort(-work, kind="stable")
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.empty(t.n_rows, dtype=np.int64)
+    # longest-processing-time-first in blocks (keeps it O(n log n) and deterministic)
+    for idx in order:
+        r = int(np.argmin(load))
+        owner[idx] = r
+        load[r] += work[idx]
+    return [np.flatnonzero(owner == r) for r in range(world)]
+
+
+def shard_tables(t: AtomTables, rank: int, world: int, rows=None):
+    """Sub-atom of ``t`` owned by ``rank``: (AtomTables with locally renumbered elements, global element index
+    of every local element).  Rows are independent (no cache links)."""
+    if rows is None:
+        rows = shard_rows(t, world)[rank]
+    rows = np.asarray(rows, dtype=np.int64)
+    # expand only what is needed: follow cache links through producing rows
+    slot_row = {}
+    prep = np.empty(t.n_rows, dtype=np.int32)
+    parent = np.full(t.n_rows, -1, dtype=np.int64)
+    for k in range(t.n_rows):
+        if t.row_istart[k] >= 0:
+            parent[k] = slot_row[int(t.row_istart[k])]
+            prep[k] = prep[parent[k]]
+        else:
+            prep[k] = t.row_prep[k]
+        if t.row_icache[k] >= 0:
+            slot_row[int(t.row_icache[k])] = k
+    ops, ptr = [], [0]
+    out_eff, out_el, optr = [], [], [0]
+    for k in rows:
+        chain = []
+        r = int(k)
+        while r >= 0:
+            chain.append(t.row_ops[t.row_ptr[r]:t.row_ptr[r + 1]])
+            r = int(parent[r])
+        seq = np.concatenate(chain[::-1]) if chain else np.zeros(0, np.int32)
+        ops.append(seq)
+        ptr.append(ptr[-1] + len(seq))
+        a, b = t.out_ptr[k], t.out_ptr[k + 1]
+        out_eff.append(t.out_eff[a:b]); out_el.append(t.out_el[a:b]); optr.append(optr[-1] + (b - a))
+    glob = np.concatenate(out_el).astype(np.int64) if out_el else np.zeros(0, np.int64)
+    n_local = glob.shape[0]
+    local = AtomTables(
+        dim=t.dim, n_ops=t.n_ops, n_rho=t.n_rho, n_eff=t.n_eff, n_elements=int(n_local), cache_size=0,
+        row_dest=np.arange(len(rows), dtype=np.int32), row_istart=np.full(len(rows), -1, np.int32),
+        row_icache=np.full(len(rows), -1, np.int32), row_prep=prep[rows].astype(np.int32),
+        row_ptr=np.asarray(ptr, dtype=np.int32),
+        row_ops=(np.concatenate(ops).astype(np.int32) if ops else np.zeros(0, np.int32)),
+        out_ptr=np.asarray(optr, dtype=np.int32),
+        out_eff=(np.concatenate(out_eff).astype(np.int32) if out_eff else np.zeros(0, np.int32)),
+        out_el=np.arange(n_local, dtype=np.int32))
+    return local, glob
+
+
+def allgather_rows(local, global_index, n_total, group=None):
+    """All-gather row shards of a (n_local, ...) torch tensor into the full (n_total, ...) tensor on every rank.
+
+    ``global_index`` (int64 tensor, n_local) gives the destination row of each local row.  Shards may be
+    uneven: they are padded to the largest shard for the collective (one ``all_gather`` = one NCCL
+    allgather on the GPU box; the analogue of the reference's Allgatherv)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    nmax = max(sizes) if sizes else 0
+    tail = tuple(local.shape[1:])
+    pad = torch.zeros((nmax,) + tail, dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    ipad = torch.full((nmax,), -1, dtype=torch.int64, device=local.device)
+    ipad[:local.shape[0]] = global_index.to(local.device)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    ibufs = [torch.empty_like(ipad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    dist.all_gather(ibufs, ipad, group=group)
+    out = torch.empty((n_total,) + tail, dtype=local.dtype, device=local.device)
+    for r in range(world):
+        n = sizes[r]
+        if n:
+            out[ibufs[r][:n]] = bufs[r][:n]
+    return out

@@ -1,0 +1,62 @@
+"""Multi-GPU path on real devices (skipped with < 2 GPUs): ranks shard a layout, fill their shard on their GPU
+through the C ABI (device-buffer entry points) and reassemble it with one NCCL all-gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, q):
+    sys.path.insert(0, REPO)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pygsti_b200.fixtures import Case
+    from pygsti_b200 import dist as bd, engine
+    c = Case(name)
+    a = c.atoms[0]
+    local, glob = bd.shard_tables(a["tables"], rank, world)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    ctx = engine.Context(rank, stream=stream.cuda_stream)
+    at = ctx.upload_atom(local); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
+    Np = c.num_params
+    J = torch.empty((local.n_elements, Np), dtype=torch.float64, device="cuda")
+    P = torch.empty(local.n_elements, dtype=torch.float64, device="cuda")
+    at.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
+    gi = torch.from_numpy(glob).cuda()
+    Pf = bd.allgather_rows(P, gi, c.n_elements)
+    Jf = bd.allgather_rows(J, gi, c.n_elements)
+    torch.cuda.synchronize()
+    st = int(c["probs_map_stride"])
+    e1 = float(np.max(np.abs(Pf.cpu().numpy()[::st] - c["probs_map_sample"])))
+    rows = torch.as_tensor(c["dprobs_matrix_sample_elements"], device="cuda")
+    e2 = float(np.max(np.abs(Jf[rows].cpu().numpy() - c["dprobs_matrix_sample_rows"])))
+    q.put((rank, e1, e2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shard_fill_allgather():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, "c2_lite_layout", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, e1, e2 in res:
+        assert e1 <= 1e-12 and e2 <= 1e-10, res
