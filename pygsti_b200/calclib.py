@@ -135,6 +135,37 @@ def mapfill_probs_atom(fwdsim, array_to_fill, dest_indices, layout_atom, resourc
         array_to_fill[_to_index_array(dest_indices, array_to_fill.shape[0])] = tmp
 
 
+def all_members_linear(fwdsim, layout_atom):
+    model = fwdsim.model
+    ops, rhos, effs = packing._members(model, layout_atom)
+    return all(type(m).__name__ in _LINEAR_MEMBERS for m in ops + rhos + effs) \
+        and getattr(model, "_param_interposer", None) is None
+
+
+def mapfill_hprobs_atom_linear(fwdsim, array_to_fill, dest_param_indices1, dest_param_indices2, layout_atom,
+                               param_indices1, param_indices2, resource_alloc):
+    """array_to_fill[:, dest1, dest2] = d2 p / d theta_{p1} d theta_{p2} for members linear in their parameters
+    (replaces MapForwardSimulator._mapfill_hprobs_atom, mapforwardsim.py:394-438)."""
+    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+    model = fwdsim.model
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
+    _deriv_map(fwdsim, layout_atom, ent, None)          # full derivative map; blocks select its columns
+    if not shared_mem_leader:
+        return
+    p1 = packing.param_slice_to_array(param_indices1, model.num_params)
+    p2 = packing.param_slice_to_array(param_indices2, model.num_params)
+    nE = layout_atom.num_elements
+    if nE == 0 or p1.size == 0 or p2.size == 0:
+        return
+    tmp = np.empty((nE, p1.size, p2.size))
+    atom.fill_hprobs_linear(p1, p2, tmp)
+    d1 = np.arange(p1.size) if dest_param_indices1 is None else _to_index_array(dest_param_indices1, array_to_fill.shape[1])
+    d2 = np.arange(p2.size) if dest_param_indices2 is None else _to_index_array(dest_param_indices2, array_to_fill.shape[2])
+    array_to_fill[np.ix_(np.arange(nE), d1, d2)] = tmp
+
+
 def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     """Upload the derivative map for this parameter block (cached when every member is linear in its
     parameters, in which case D does not depend on the current parameter vector)."""

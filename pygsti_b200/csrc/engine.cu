@@ -452,9 +452,9 @@ template <int NG>
 static int launch_d16_t(b200_ctx* c, b200_atom* a, const D16Args& args) {
     size_t smem = d16_smem_bytes(NG, a->max_depth);
     CU(cudaFuncSetAttribute(k_dprobs_d16<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (c->smem_optin > 0 ? (220u * 1024u) : (96u * 1024u)) / (smem + 1024)));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(227u * 1024u) / (smem + 1024)));
     int gx = grid_for(c, a->n_rows, per_sm);
-    k_dprobs_d16<NG><<<gx, D16_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), args);
+    k_dprobs_d16<NG><<<gx, D16_THREADS, smem, c->stream>>>(atom_dev(a), model_dev(a), args);
     c->launches++;
     CU(cudaGetLastError());
     return B200_OK;
@@ -632,10 +632,74 @@ extern "C" int b200_fill_dprobs_fd(b200_ctx* c, b200_atom* a, double eps, double
     return B200_OK;
 }
 
+template <int D>
+static int launch_w_tangent(b200_ctx* c, b200_atom* a, int nb, const double* dMb, const double* dGtb, double* Wb) {
+    int gx = grid_for(c, (a->n_rows + GEN_WARPS - 1) / GEN_WARPS, 4);
+    size_t need = (size_t)nb * gx * GEN_WARPS * 2 * (size_t)(a->max_depth + 1) * D * sizeof(double);
+    CU(c->scratch.ensure(need));
+    size_t smem = (size_t)GEN_WARPS * 4 * D * sizeof(double);
+    dim3 grid(gx, nb);
+    k_w_tangent_generic<D><<<grid, GEN_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), dMb, dGtb, Wb, a->n_w,
+                                                                       c->scratch.as<double>());
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
 extern "C" int b200_fill_hprobs_linear(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1,
                                        int32_t n2, const int32_t* p2, double* out) {
-    (void)c; (void)a; (void)n1; (void)p1; (void)n2; (void)p2; (void)out;
-    return fail(B200_E_UNSUPPORTED, "b200_fill_hprobs_linear: kernel not built yet");
+    if (!c || !a || !out || (n1 > 0 && !p1) || (n2 > 0 && !p2)) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    for (int i = 0; i < n1; ++i) if (p1[i] < 0 || p1[i] >= a->n_params) return fail(B200_E_INVALID, "p1[%d] out of range", i);
+    for (int i = 0; i < n2; ++i) if (p2[i] < 0 || p2[i] >= a->n_params) return fail(B200_E_INVALID, "p2[%d] out of range", i);
+    CU(cudaSetDevice(c->device));
+    const int64_t nE = a->n_elements;
+    if (nE == 0 || n1 == 0 || n2 == 0) return B200_OK;
+    DevBuf d_p1, d_p2, d_out;
+    std::vector<int32_t> v1(p1, p1 + n1), v2(p2, p2 + n2);
+    int rc;
+    if ((rc = upload_vec(d_p1, v1, c->stream)) || (rc = upload_vec(d_p2, v2, c->stream))) return rc;
+    CU(d_out.ensure((size_t)nE * n1 * n2 * 8));
+    // batch of tangent directions bounded by ~1 GB of W scratch
+    const int64_t per = nE * a->n_w * 8;
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n1, ((int64_t)1 << 30) / std::max<int64_t>(per, 1)));
+    CU(c->w_buf.ensure((size_t)B * per));
+    CU(c->fd_models.ensure((size_t)B * a->n_w * 8));
+    CU(c->fd_gt.ensure(std::max<size_t>((size_t)B * a->off_rho * 8, 16)));
+    for (int a0 = 0; a0 < n1; a0 += B) {
+        const int nb = std::min(B, n1 - a0);
+        CU(cudaMemsetAsync(c->fd_models.p, 0, (size_t)nb * a->n_w * 8, c->stream));
+        CU(cudaMemsetAsync(c->w_buf.p, 0, (size_t)nb * per, c->stream));
+        dim3 g1(4, nb);
+        k_tangent_models<<<g1, 128, 0, c->stream>>>(a->n_w, d_p1.as<int32_t>(), a0, a->cptr.as<int32_t>(),
+                                                    a->crow.as<int32_t>(), a->cval.as<double>(), c->fd_models.as<double>());
+        c->launches++;
+        if (a->n_ops) {
+            dim3 g3((unsigned)std::min<int64_t>((a->off_rho + 255) / 256, 256), nb);
+            k_transpose_gates<<<g3, 256, 0, c->stream>>>(c->fd_models.as<double>(), a->n_w, a->n_ops, a->dim, c->fd_gt.as<double>());
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+        switch (a->dim) {
+            case 4: rc = launch_w_tangent<4>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
+            case 16: rc = launch_w_tangent<16>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
+            case 64: rc = launch_w_tangent<64>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
+            case 256: rc = launch_w_tangent<256>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
+            default: rc = fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
+        }
+        if (rc) return rc;
+        dim3 g4((n2 + 127) / 128, (unsigned)std::min<int64_t>(nE * nb, 65535));
+        k_contract_hess<<<g4, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, nb, a0, n1, n2, d_p2.as<int32_t>(),
+                                                   a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
+                                                   d_out.as<double>());
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(out, d_out.p, (size_t)nE * n1 * n2 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    d_p1.release(); d_p2.release(); d_out.release();
+    return B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

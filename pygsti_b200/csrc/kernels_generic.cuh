@@ -152,6 +152,126 @@ k_w_generic(AtomDev a, ModelDev m, double* __restrict__ W, int64_t ldw, double* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tangent W accumulate (Hessian of members LINEAR in their parameters; forward-over-reverse).
+// For the tangent direction dM = dM/dtheta_p (batch b = blockIdx.y; dM[b] = [dG | drho | dE], dGt[b] its
+// transposed gates):   ds_0 = drho, ds_k = G_k ds_{k-1} + dG_k s_{k-1};   de_L = dE_j,
+// de_{k-1} = G_k^T de_k + dG_k^T e_k;   d/dtheta_p of the W row:
+//   Wp[el, G_k block] += de_k (x) s_{k-1} + e_k (x) ds_{k-1};  Wp[el, rho] += de_0;  Wp[el, E_j] += ds_L
+// so that  H[el, p, q] = sum_w Wp[el, w] D[w, q]   (second derivatives of the members vanish).
+// Equals MatrixForwardSimulator._hprobs_from_rho_e (matrixforwardsim.py:1141-1287) for linear members.
+// Scratch per warp: 2 * (max_depth+1) * D doubles (states and tangent states).
+// dynamic smem: GEN_WARPS * 4 * D doubles.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(GEN_WARPS * 32)
+k_w_tangent_generic(AtomDev a, ModelDev m, const double* __restrict__ dMb, const double* __restrict__ dGtb,
+                    double* __restrict__ Wb, int64_t ldw, double* __restrict__ scratch)
+{
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* eb0 = smem + (size_t)warp * 4 * D;
+    double* eb1 = eb0 + D; double* db0 = eb1 + D; double* db1 = db0 + D;
+    const int b = blockIdx.y;
+    const double* dM = dMb + (int64_t)b * m.n_w;
+    const double* dGt = dGtb + (int64_t)b * a.n_ops * D * D;
+    double* W = Wb + (int64_t)b * a.n_elements * ldw;
+    const double* G = m.M; const double* rho = m.M + m.off_rho; const double* E = m.M + m.off_eff;
+    const double* dG = dM; const double* drho = dM + m.off_rho; const double* dE = dM + m.off_eff;
+    const int gw = blockIdx.x * GEN_WARPS + warp;
+    const int nw = gridDim.x * GEN_WARPS;
+    double* st = scratch + ((int64_t)b * nw + gw) * 2 * (a.max_depth + 1) * D;
+    double* dst = st + (int64_t)(a.max_depth + 1) * D;
+
+    for (int c = gw; c < a.n_circ; c += nw) {
+        const uint32_t p0 = a.circ_ptr[c];
+        const int L = (int)(a.circ_ptr[c + 1] - p0);
+        const int prep = a.circ_prep[c];
+        const int32_t* ops = a.circ_ops + p0;
+        for (int i = lane; i < D; i += 32) { st[i] = rho[(int64_t)prep * D + i]; dst[i] = drho[(int64_t)prep * D + i]; }
+        __syncwarp();
+        for (int k = 0; k < L; ++k) {
+            const double* Gg = m.Gt + (int64_t)ops[k] * D * D;
+            const double* dGg = dGt + (int64_t)ops[k] * D * D;
+            const double* s = st + (int64_t)k * D; const double* ds = dst + (int64_t)k * D;
+            for (int i = lane; i < D; i += 32) {
+                double acc = 0.0, dacc = 0.0;
+                for (int j = 0; j < D; ++j) {
+                    acc += Gg[j * D + i] * s[j];
+                    dacc += Gg[j * D + i] * ds[j] + dGg[j * D + i] * s[j];
+                }
+                st[(int64_t)(k + 1) * D + i] = acc; dst[(int64_t)(k + 1) * D + i] = dacc;
+            }
+            __syncwarp();
+        }
+        const double* dsL = dst + (int64_t)L * D;
+        for (int q = a.out_ptr[c]; q < a.out_ptr[c + 1]; ++q) {
+            const int ei = a.out_eff[q];
+            double* Wr = W + (int64_t)a.out_el[q] * ldw;
+            double* e = eb0; double* en = eb1; double* de = db0; double* den = db1;
+            for (int i = lane; i < D; i += 32) {
+                e[i] = E[(int64_t)ei * D + i]; de[i] = dE[(int64_t)ei * D + i];
+                Wr[m.off_eff + (int64_t)ei * D + i] += dsL[i];
+            }
+            __syncwarp();
+            for (int k = L - 1; k >= 0; --k) {
+                const int g = ops[k];
+                const double* s = st + (int64_t)k * D; const double* ds = dst + (int64_t)k * D;
+                double* Wg = Wr + (int64_t)g * D * D;
+                for (int idx = lane; idx < D * D; idx += 32) {
+                    const int i = idx / D, j = idx - i * D;
+                    Wg[idx] += de[i] * s[j] + e[i] * ds[j];
+                }
+                const double* Gg = G + (int64_t)g * D * D;
+                const double* dGg = dG + (int64_t)g * D * D;
+                for (int j = lane; j < D; j += 32) {
+                    double acc = 0.0, dacc = 0.0;
+                    for (int i = 0; i < D; ++i) {
+                        acc += Gg[i * D + j] * e[i];
+                        dacc += Gg[i * D + j] * de[i] + dGg[i * D + j] * e[i];
+                    }
+                    en[j] = acc; den[j] = dacc;
+                }
+                __syncwarp();
+                double* x = e; e = en; en = x; x = de; de = den; den = x;
+            }
+            for (int i = lane; i < D; i += 32) Wr[m.off_rho + (int64_t)prep * D + i] += de[i];
+            __syncwarp();
+        }
+    }
+}
+
+// dense tangent models: dMb[b][w] = D[w, cols[b0 + b]]
+__global__ void k_tangent_models(int64_t n_w, const int32_t* __restrict__ cols, int b0,
+                                 const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
+                                 const double* __restrict__ cval, double* __restrict__ dMb)
+{
+    const int b = blockIdx.y;
+    const int p = cols[b0 + b];
+    double* dst = dMb + (int64_t)b * n_w;
+    for (int t = cptr[p] + blockIdx.x * blockDim.x + threadIdx.x; t < cptr[p + 1]; t += gridDim.x * blockDim.x)
+        dst[crow[t]] = cval[t];
+}
+
+// out[((el * n1) + a0 + b) * n2 + c] = sum_t cval[t] * Wb[b][el][crow[t]]   over column cols2[c] of D
+__global__ void __launch_bounds__(128)
+k_contract_hess(const double* __restrict__ Wb, int64_t ldw, int64_t n_el, int nb, int a0, int n1, int n2,
+                const int32_t* __restrict__ cols2, const int32_t* __restrict__ cptr,
+                const int32_t* __restrict__ crow, const double* __restrict__ cval, double* __restrict__ out)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c >= n2) return;
+    const int p = cols2[c];
+    const int tb = cptr[p], te = cptr[p + 1];
+    for (int64_t r = blockIdx.y; r < n_el * nb; r += gridDim.y) {
+        const int64_t el = r / nb; const int b = (int)(r - el * nb);
+        const double* Wr = Wb + ((int64_t)b * n_el + el) * ldw;
+        double acc = 0.0;
+        for (int t = tb; t < te; ++t) acc += cval[t] * Wr[crow[t]];
+        out[(el * n1 + a0 + b) * n2 + c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // J = W . D  with D in CSC (per parameter column p: entries [cptr[p], cptr[p+1]) of (row w, val)).
 // grid.x over column tiles of 128, grid.y over element rows; coalesced stores along p.
 // ---------------------------------------------------------------------------------------------

@@ -91,9 +91,19 @@ class B200ForwardSimulator(_MapForwardSimulator):
                 atom._b200_device = devs[i % len(devs)]
         return layout
 
-    # ---- hessian: FD of the analytic Jacobian along the first parameter axis ----------------------
-    # (MapForwardSimulator._mapfill_hprobs_atom, mapforwardsim.py:394-438, drives self.calclib.mapfill_dprobs_atom
-    #  and therefore already runs on the engine; nothing to override.)
+    # ---- hessian ------------------------------------------------------------------------------------
+    def _bulk_fill_hprobs_atom(self, array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
+                               param_slice1, param_slice2, resource_alloc):
+        """Replaces mapforwardsim.py:384-391.  Members linear in their parameters (full / TP / static):
+        fully analytic second order on the device (== MatrixForwardSimulator to ~1e-13).  Otherwise the
+        reference's own driver `_mapfill_hprobs_atom` (mapforwardsim.py:394-438: finite differences along the
+        first parameter axis, `hessian_eps`) runs on top of the ANALYTIC device Jacobian."""
+        if self.derivative_mode == 'analytic' and _b200_calclib.all_members_linear(self, layout_atom):
+            _b200_calclib.mapfill_hprobs_atom_linear(self, array_to_fill, dest_param_slice1, dest_param_slice2,
+                                                     layout_atom, param_slice1, param_slice2, resource_alloc)
+        else:
+            super()._bulk_fill_hprobs_atom(array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
+                                           param_slice1, param_slice2, resource_alloc)
 
     def __getstate__(self):
         state = super().__getstate__()

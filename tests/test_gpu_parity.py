@@ -120,3 +120,21 @@ def test_full_size_layout_properties(gpu_ctx, load_case):
     # model is depolarized (not exactly TP) so only check the linear-algebra identity on a sample vs oracle
     assert np.all(np.isfinite(jsum))
     at.free()
+
+
+@pytest.mark.parametrize("name", ["c1_1q_hess", "c1_1q_tp_hess"])
+def test_hprobs_linear_vs_reference_matrix(gpu_ctx, load_case, name):
+    """Analytic Hessian for members linear in their parameters (b200_fill_hprobs_linear) against the
+    reference's MatrixForwardSimulator.bulk_fill_hprobs golden, full blocks and a rectangular sub-block."""
+    c = load_case(name)
+    a = c.atoms[0]
+    at = _atom(gpu_ctx, a)
+    Np = c.num_params
+    H = np.full((c.n_elements, Np, Np), np.nan)
+    at.fill_hprobs_linear(np.arange(Np), np.arange(Np), H)
+    assert np.max(np.abs(H - c["hprobs_matrix"])) <= 1e-10
+    p1 = np.array([3, 17, 40, 5]); p2 = np.arange(10, 31)
+    Hb = np.full((c.n_elements, len(p1), len(p2)), np.nan)
+    at.fill_hprobs_linear(p1, p2, Hb)
+    assert np.max(np.abs(Hb - c["hprobs_matrix"][:, p1][:, :, p2])) <= 1e-10
+    at.free()

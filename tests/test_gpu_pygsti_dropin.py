@@ -117,8 +117,14 @@ def test_atoms_and_param_blocks_equal_single_atom():
                 assert np.max(np.abs(ref[c][1] - cur[c][1])) <= 1e-12
 
 
-def test_hprobs_vs_matrix_sim():
-    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+@pytest.mark.parametrize("param,tol", [("full", 1e-10), ("full TP", 1e-10), ("CPTPLND", 5e-4)])
+def test_hprobs_vs_matrix_sim(param, tol):
+    """full / TP members are linear in their parameters -> fully analytic device Hessian (1e-10 vs the
+    reference's analytic Matrix simulator).  CPTPLND: the reference's FD driver (eps=1e-5) over the ANALYTIC
+    device Jacobian; the reference's own Map simulator (FD of FD) is off by ~3e-3 here."""
+    model = smq1Q_XYI.target_model(param)
+    v = model.to_vector(); rng = np.random.default_rng(2)
+    model.from_vector(v + 5e-3 * rng.standard_normal(v.size))
     circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data[:30]
     mm = model.copy(); mm.sim = MatrixForwardSimulator()
     hm = mm.sim.bulk_hprobs(circuits)
@@ -128,9 +134,20 @@ def test_hprobs_vs_matrix_sim():
     for c in circuits:
         for k in hm[c]:
             worst = max(worst, np.max(np.abs(hm[c][k] - hb[c][k])))
-    # FD (eps=1e-5) of the ANALYTIC Jacobian along one axis; the reference's own Map simulator (FD of FD)
-    # is off by ~3e-3 here
-    assert worst <= 5e-4, worst
+    assert worst <= tol, worst
+
+
+def test_hprobs_rectangles_match_full_blocks():
+    """iter_hprobs_by_rectangle (forwardsim.py:787-878) semantics used by the MLE Hessian."""
+    model = smq1Q_XYI.target_model().depolarize(op_noise=0.05, spam_noise=0.025)
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data[:20]
+    model.sim = B200ForwardSimulator()
+    layout = model.sim.create_layout(circuits, array_types=('e', 'ep', 'epp'))
+    full = np.empty((layout.num_elements, model.num_params, model.num_params))
+    model.sim.bulk_fill_hprobs(full, layout)
+    sl1, sl2 = slice(5, 25), slice(30, 60)
+    for s1, s2, hblk in model.sim.iter_hprobs_by_rectangle(layout, [(sl1, sl2)], False):
+        assert np.max(np.abs(hblk - full[:, s1, s2])) <= 1e-12
 
 
 def test_two_qubit_full_model_vs_reference():
