@@ -5,6 +5,9 @@
 #include "common.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_d16.cuh"
+#include "kernels_d16_2p.cuh"
+#include "kernels_d16_trie.cuh"
+#include <cstdlib>
 
 #include <algorithm>
 #include <cstdarg>
@@ -57,6 +60,7 @@ struct b200_ctx {
     DevBuf probs_buf;
     DevBuf w_buf;        // W matrix of the general path
     DevBuf scratch;      // forward-state scratch of the generic kernels
+    DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
     DevBuf fd_models, fd_gt, fd_probs;
     void* pinned = nullptr; size_t pinned_cap = 0;   // pinned staging for pageable destinations
 };
@@ -69,6 +73,15 @@ struct b200_atom {
     int64_t n_w = 0, off_rho = 0, off_eff = 0;
     // device tables
     DevBuf circ_ptr, circ_ops, circ_prep, out_ptr, out_eff, out_el;
+    DevBuf srow, bperm, bcnt;          // two-phase d16 path: scratch row offsets, per-circuit gate buckets
+    int64_t scratch_rows = 0;
+    // trie path (prefix + suffix sharing)
+    bool has_trie = false;
+    DevBuf tf_parent, tf_first, tf_len, tf_op, tb_parent, tb_first, tb_len, tb_op, t_fn, t_bn, t_fend, t_bend;
+    DevBuf t_S, t_H, t_ready_f, t_ready_b, t_counters, t_units, t_uidx, t_cgrp;
+    int n_units = 0;
+    int n_fchains = 0, n_bchains = 0; uint32_t n_fnodes = 0, n_bnodes = 0;
+    unsigned epoch = 0;
     // model
     bool has_model = false;
     DevBuf M, Gt;
@@ -142,7 +155,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (!c) return B200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release();
+    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -175,6 +188,73 @@ static int upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
     CU(b.ensure(bytes));
     if (!v.empty()) CU(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
     return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trie of circuits (prefix sharing) -- host side, once per atom.  Sequences are (root id, symbols...);
+// nodes are created chain by chain while scanning the circuits in lexicographic order, so a chain's parent
+// node always has a smaller id and belongs to an earlier chain (kernels_d16_trie.cuh relies on this).
+// ------------------------------------------------------------------------------------------------
+struct TrieHost {
+    std::vector<int32_t> chain_parent; std::vector<uint32_t> chain_first, chain_len, chain_depth;
+    std::vector<uint8_t> node_op;
+    std::vector<uint32_t> depth_node;   // per circuit c, depth d in [0, L_c]: node id, at offset dptr[c] + d
+    std::vector<uint64_t> dptr;
+};
+static void build_trie(int64_t n, const std::vector<int32_t>& root, const std::vector<uint32_t>& ptr,
+                       const std::vector<int32_t>& sym, bool reversed, TrieHost& T) {
+    auto at = [&](int64_t c, uint32_t d) -> int32_t {      // d-th symbol of circuit c's key
+        const uint32_t L = ptr[c + 1] - ptr[c];
+        return reversed ? sym[ptr[c] + (L - 1 - d)] : sym[ptr[c] + d];
+    };
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+        if (root[x] != root[y]) return root[x] < root[y];
+        const uint32_t lx = ptr[x + 1] - ptr[x], ly = ptr[y + 1] - ptr[y];
+        const uint32_t l = std::min(lx, ly);
+        for (uint32_t d = 0; d < l; ++d) { const int32_t a = at(x, d), b = at(y, d); if (a != b) return a < b; }
+        return lx < ly; });
+    T.dptr.assign((size_t)n + 1, 0);
+    for (int64_t c = 0; c < n; ++c) T.dptr[c + 1] = T.dptr[c] + (ptr[c + 1] - ptr[c]) + 1;
+    T.depth_node.assign((size_t)T.dptr[n], 0);
+    std::vector<uint32_t> path;
+    int64_t prev = -1;
+    for (int64_t oi = 0; oi < n; ++oi) {
+        const int64_t c = order[oi];
+        const uint32_t L = ptr[c + 1] - ptr[c];
+        uint32_t lcp = 0;
+        if (prev < 0 || root[prev] != root[c]) {
+            const uint32_t id = (uint32_t)T.node_op.size();
+            T.chain_parent.push_back(-(1 + root[c])); T.chain_first.push_back(id); T.chain_len.push_back(1);
+            T.chain_depth.push_back(0);
+            T.node_op.push_back(255);
+            path.assign(1, id);
+        } else {
+            const uint32_t Lp = ptr[prev + 1] - ptr[prev];
+            const uint32_t l = std::min(L, Lp);
+            while (lcp < l && at(prev, lcp) == at(c, lcp)) ++lcp;
+            path.resize((size_t)lcp + 1);
+        }
+        if (L > lcp) {
+            const uint32_t id0 = (uint32_t)T.node_op.size();
+            T.chain_parent.push_back((int32_t)path[lcp]); T.chain_first.push_back(id0); T.chain_len.push_back(L - lcp);
+            T.chain_depth.push_back(lcp + 1);
+            for (uint32_t d = lcp; d < L; ++d) { T.node_op.push_back((uint8_t)at(c, d)); path.push_back(id0 + (d - lcp)); }
+        }
+        for (uint32_t d = 0; d <= L; ++d) T.depth_node[T.dptr[c] + d] = path[d];
+        prev = c;
+    }
+    // work order of the chains: by start depth (a chain's parent chain starts at a smaller depth => is handed out
+    // earlier: the spin-waits in k_trie_chains cannot deadlock), long chains first within a depth
+    std::vector<uint32_t> ord(T.chain_first.size());
+    std::iota(ord.begin(), ord.end(), 0u);
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
+        if (T.chain_depth[x] != T.chain_depth[y]) return T.chain_depth[x] < T.chain_depth[y];
+        return T.chain_len[x] > T.chain_len[y]; });
+    std::vector<int32_t> cp(ord.size()); std::vector<uint32_t> cf(ord.size()), cl(ord.size());
+    for (size_t i = 0; i < ord.size(); ++i) { cp[i] = T.chain_parent[ord[i]]; cf[i] = T.chain_first[ord[i]]; cl[i] = T.chain_len[ord[i]]; }
+    T.chain_parent.swap(cp); T.chain_first.swap(cf); T.chain_len.swap(cl);
 }
 
 extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, int n_eff,
@@ -264,7 +344,29 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
         coptr[i + 1] = coptr[i] + no;
     }
 
+    // two-phase d16 tables: scratch rows per circuit = (L+1)*(1+n_out); steps of each circuit sorted by gate
+    std::vector<uint32_t> srow; std::vector<uint16_t> bperm, bcnt;
+    int64_t scratch_rows = 0;
+    if (dim == 16 && max_depth < 65535) {
+        srow.resize((size_t)n_rows + 1); bperm.resize(cops.size()); bcnt.assign((size_t)n_rows * std::max(n_ops, 1), 0);
+        uint64_t acc_rows = 0;
+        std::vector<uint32_t> off((size_t)std::max(n_ops, 1) + 1);
+        for (int64_t i = 0; i < n_rows; ++i) {
+            const uint32_t b0 = cptr[i], L = cptr[i + 1] - b0;
+            srow[i] = (uint32_t)acc_rows;
+            acc_rows += (uint64_t)(L + 1) * (1 + (uint64_t)(coptr[i + 1] - coptr[i]));
+            uint16_t* cn = bcnt.data() + (size_t)i * std::max(n_ops, 1);
+            for (uint32_t k = 0; k < L; ++k) cn[cops[b0 + k]]++;
+            off[0] = 0;
+            for (int g = 0; g < n_ops; ++g) off[g + 1] = off[g] + cn[g];
+            for (uint32_t k = 0; k < L; ++k) bperm[b0 + off[cops[b0 + k]]++] = (uint16_t)k;
+        }
+        srow[n_rows] = (uint32_t)acc_rows;
+        scratch_rows = (acc_rows < ((uint64_t)1 << 32)) ? (int64_t)acc_rows : 0;   // 0 disables the two-phase path
+    }
+
     b200_atom* a = new b200_atom();
+    a->scratch_rows = scratch_rows;
     a->ctx = ctx; a->dim = dim; a->n_ops = n_ops; a->n_rho = n_rho; a->n_eff = n_eff;
     a->n_rows = n_rows; a->n_elements = n_elements;
     a->n_prop_table = n_rows ? row_ptr[n_rows] : 0;
@@ -276,8 +378,92 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
     int rc;
     if ((rc = upload_vec(a->circ_ptr, cptr, ctx->stream)) || (rc = upload_vec(a->circ_ops, cops, ctx->stream)) ||
         (rc = upload_vec(a->circ_prep, cprep, ctx->stream)) || (rc = upload_vec(a->out_ptr, coptr, ctx->stream)) ||
-        (rc = upload_vec(a->out_eff, coeff, ctx->stream)) || (rc = upload_vec(a->out_el, coel, ctx->stream))) {
+        (rc = upload_vec(a->out_eff, coeff, ctx->stream)) || (rc = upload_vec(a->out_el, coel, ctx->stream)) ||
+        (rc = upload_vec(a->srow, srow, ctx->stream)) || (rc = upload_vec(a->bperm, bperm, ctx->stream)) ||
+        (rc = upload_vec(a->bcnt, bcnt, ctx->stream))) {
         b200_atom_free(ctx, a); return rc;
+    }
+    // trie path tables (d = 16, <= 8 effects, <= 255 ops): prefix trie of (prep, ops), suffix trie of reversed ops
+    if (dim == 16 && n_eff <= 8 && n_ops <= 255 && n_ops >= 1 && scratch_rows > 0 && xptr[n_rows] < ((uint64_t)1 << 31)) {
+        TrieHost TF, TB;
+        std::vector<int32_t> zero_root((size_t)n_rows, 0);
+        build_trie(n_rows, cprep, cptr, cops, false, TF);
+        build_trie(n_rows, zero_root, cptr, cops, true, TB);
+        if (TF.node_op.size() < ((size_t)1 << 31) && TB.node_op.size() < ((size_t)1 << 31)) {
+            std::vector<uint32_t> fn(cops.size()), bn(cops.size()), fend((size_t)n_rows), bend((size_t)n_rows);
+            for (int64_t i = 0; i < n_rows; ++i) {
+                const uint32_t b0 = cptr[i], L = cptr[i + 1] - b0;
+                for (uint32_t t = 0; t < L; ++t) {
+                    const uint32_t k = bperm[b0 + t];                       // step index in gate-bucket order
+                    fn[b0 + t] = TF.depth_node[TF.dptr[i] + k];             // s_k      : prefix of length k
+                    bn[b0 + t] = TB.depth_node[TB.dptr[i] + (L - 1 - k)];   // e_k      : suffix of length L-1-k
+                }
+                fend[i] = TF.depth_node[TF.dptr[i] + L];
+                bend[i] = TB.depth_node[TB.dptr[i] + L];
+            }
+            // phase-B units: (circuit, outcome group of <= 4, gate); padded (fwd node, bwd node) pairs
+            const uint32_t zf_node = (uint32_t)TF.node_op.size(), zb_node = (uint32_t)TB.node_op.size();   // all-zero rows
+            std::vector<uint4> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
+            bool trie_ok = true;
+            for (int64_t i = 0; i < n_rows; ++i) {
+                const uint32_t b0 = cptr[i];
+                const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
+                // padded index lists of this circuit's gates (shared by all of its outcome groups)
+                std::vector<uint32_t> goff((size_t)n_ops), gng((size_t)n_ops);
+                uint32_t tbase = 0;
+                for (int g = 0; g < n_ops; ++g) {
+                    goff[g] = (uint32_t)uidx.size(); gng[g] = (cn[g] + 3u) / 4u;
+                    for (uint32_t t = 0; t < gng[g] * 4u; ++t) {
+                        uint2 e; e.x = (t < cn[g]) ? fn[b0 + tbase + t] : zf_node; e.y = (t < cn[g]) ? bn[b0 + tbase + t] : zb_node;
+                        uidx.push_back(e);
+                    }
+                    tbase += cn[g];
+                }
+                // outcome groups by effect index block [4k, 4k+4): the H rows of a group are then contiguous
+                for (int eb = 0; eb < n_eff; eb += 4) {
+                    CGroup cgp; memset(&cgp, 0, sizeof cgp);
+                    bool any = false;
+                    for (int o = 0; o < 4; ++o) cgp.el[o] = -1;
+                    for (int32_t oq = coptr[i]; oq < coptr[i + 1]; ++oq) {
+                        const int e = coeff[oq];
+                        if (e >= eb && e < eb + 4) {
+                            if (cgp.el[e - eb] >= 0) trie_ok = false;      // same effect twice in one circuit: not representable
+                            cgp.el[e - eb] = coel[oq]; any = true;
+                        }
+                    }
+                    if (!any) continue;
+                    cgp.e_base = (uint32_t)eb; cgp.prep = (uint32_t)cprep[i]; cgp.f_end = fend[i]; cgp.b_end = bend[i];
+                    const uint32_t cgi = (uint32_t)cgrp.size();
+                    cgrp.push_back(cgp);
+                    for (int g = 0; g < n_ops; ++g) {
+                        uint4 un; un.x = goff[g]; un.y = cgi; un.z = (uint32_t)g | (gng[g] << 16); un.w = 0;
+                        units.push_back(un);
+                    }
+                }
+            }
+            for (int pad = 0; pad < 16; ++pad) uidx.push_back(make_uint2(zf_node, zb_node));   // prefetch slack
+            if (uidx.empty()) uidx.push_back(make_uint2(zf_node, zb_node));
+            a->n_units = (int)units.size();
+            if ((rc = upload_vec(a->t_units, units, ctx->stream)) || (rc = upload_vec(a->t_uidx, uidx, ctx->stream)) ||
+                (rc = upload_vec(a->t_cgrp, cgrp, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
+            a->n_fchains = (int)TF.chain_first.size(); a->n_bchains = (int)TB.chain_first.size();
+            a->n_fnodes = (uint32_t)TF.node_op.size(); a->n_bnodes = (uint32_t)TB.node_op.size();
+            std::vector<unsigned> zf((size_t)a->n_fnodes, 0u), zb((size_t)a->n_bnodes, 0u), zc(2, 0u);
+            if ((rc = upload_vec(a->tf_parent, TF.chain_parent, ctx->stream)) || (rc = upload_vec(a->tf_first, TF.chain_first, ctx->stream)) ||
+                (rc = upload_vec(a->tf_len, TF.chain_len, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
+                (rc = upload_vec(a->tb_parent, TB.chain_parent, ctx->stream)) || (rc = upload_vec(a->tb_first, TB.chain_first, ctx->stream)) ||
+                (rc = upload_vec(a->tb_len, TB.chain_len, ctx->stream)) || (rc = upload_vec(a->tb_op, TB.node_op, ctx->stream)) ||
+                (rc = upload_vec(a->t_fn, fn, ctx->stream)) || (rc = upload_vec(a->t_bn, bn, ctx->stream)) ||
+                (rc = upload_vec(a->t_fend, fend, ctx->stream)) || (rc = upload_vec(a->t_bend, bend, ctx->stream)) ||
+                (rc = upload_vec(a->t_ready_f, zf, ctx->stream)) || (rc = upload_vec(a->t_ready_b, zb, ctx->stream)) ||
+                (rc = upload_vec(a->t_counters, zc, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
+            cudaError_t e1 = a->t_S.ensure(((size_t)a->n_fnodes + 1) * 128), e2 = a->t_H.ensure(((size_t)a->n_bnodes + 2) * n_eff * 128);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) { b200_atom_free(ctx, a); return fail(B200_E_NOMEM, "trie tables: out of device memory"); }
+            CU(cudaMemsetAsync(a->t_S.p, 0, ((size_t)a->n_fnodes + 1) * 128, ctx->stream));            // incl. the zero rows
+            CU(cudaMemsetAsync(a->t_H.p, 0, ((size_t)a->n_bnodes + 2) * n_eff * 128, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            a->has_trie = trie_ok;
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));   // host vectors go out of scope
     *out = a;
@@ -288,6 +474,9 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
+                      &a->srow, &a->bperm, &a->bcnt, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
+                      &a->tb_first, &a->tb_len, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
+                      &a->t_ready_f, &a->t_ready_b, &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
     for (DevBuf* b : bufs) b->release();
@@ -459,12 +648,89 @@ static int launch_d16_t(b200_ctx* c, b200_atom* a, const D16Args& args) {
     CU(cudaGetLastError());
     return B200_OK;
 }
+static bool d16_2p_ok(b200_ctx* c, b200_atom* a);
+static int d16_mode();
 static bool d16_ok(b200_ctx* c, b200_atom* a) {
+    if (d16_mode() >= 1 && d16_2p_ok(c, a)) return true;
     return a->dim == 16 && a->n_ops >= 1 && a->n_ops <= 8 &&
            d16_smem_bytes(a->n_ops, a->max_depth) + 1024 <= c->smem_optin;
 }
+static int d16_mode() {   // 0 = fused kernel, 1 = two-phase per-circuit chains, 2 = trie (prefix+suffix sharing; default)
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("B200_D16_MODE");
+        mode = (e && !strcmp(e, "fused")) ? 0 : (e && !strcmp(e, "2p")) ? 1 : 2;
+    }
+    return mode;
+}
+static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
+    if (a->n_rows == 0) return B200_OK;
+    TrieDev t;
+    t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
+    t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
+    t.b_parent = a->tb_parent.as<int32_t>(); t.b_first = a->tb_first.as<uint32_t>(); t.b_len = a->tb_len.as<uint32_t>();
+    t.b_op = a->tb_op.as<uint8_t>(); t.n_bchains = a->n_bchains; t.n_bnodes = a->n_bnodes;
+    t.fn_b = a->t_fn.as<uint32_t>(); t.bn_b = a->t_bn.as<uint32_t>(); t.f_end = a->t_fend.as<uint32_t>(); t.b_end = a->t_bend.as<uint32_t>();
+    t.bcnt = a->bcnt.as<uint16_t>();
+    t.S = a->t_S.as<double>(); t.H = a->t_H.as<double>();
+    t.ready_f = a->t_ready_f.as<unsigned>(); t.ready_b = a->t_ready_b.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
+    const unsigned epoch = ++a->epoch;
+    CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
+    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
+    const size_t smemB = (size_t)AT_WARPS * 4 * 256 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
+    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    int gA = 2 * c->sm_count * 4;                  // even = forward trie, odd = backward trie
+    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch);
+    int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS - 1) / AT_WARPS, 8);
+    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<uint4>(), a->n_units,
+                                                               a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(),
+                                                               getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+static bool d16_2p_ok(b200_ctx* c, b200_atom* a) {
+    return a->dim == 16 && a->n_ops >= 1 && a->scratch_rows > 0 &&
+           (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin && a->n_ops <= 255;
+}
+static int launch_d16_2p(b200_ctx* c, b200_atom* a, const D16Args& args) {
+    if (a->n_rows == 0) return B200_OK;
+    CU(c->scratch2p.ensure((size_t)a->scratch_rows * 128));
+    TwoPhaseDev tp;
+    tp.srow = a->srow.as<uint32_t>(); tp.bperm = a->bperm.as<uint16_t>(); tp.bcnt = a->bcnt.as<uint16_t>();
+    tp.scratch = c->scratch2p.as<double>();
+    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)C2P_WARPS * 32 * 8;
+    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4;
+    CU(cudaFuncSetAttribute(k_chain_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    CU(cudaFuncSetAttribute(k_accum_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    static int batch_rows = -1;
+    if (batch_rows < 0) { const char* e = getenv("B200_2P_BATCH_MB"); batch_rows = e ? atoi(e) * 8192 : 0; }
+    // batches of whole circuits (longest first); 0 = single batch
+    std::vector<int> cuts; cuts.push_back(0);
+    if (batch_rows > 0) {
+        // host copy of srow is not kept: approximate equal-row batches through max_depth bound is not exact, so
+        // we split by circuit count proportionally (rows are dominated by depth; circuits are depth-sorted)
+        int nb = (int)((a->scratch_rows + batch_rows - 1) / batch_rows);
+        for (int i = 1; i < nb; ++i) cuts.push_back((int)((int64_t)a->n_rows * i / nb));
+    }
+    cuts.push_back((int)a->n_rows);
+    for (size_t bi = 0; bi + 1 < cuts.size(); ++bi) {
+        const int c0 = cuts[bi], c1 = cuts[bi + 1];
+        if (c1 <= c0) continue;
+        int gA = grid_for(c, ((int64_t)(c1 - c0) + C2P_WARPS - 1) / C2P_WARPS, 4);
+        k_chain_d16<<<gA, C2P_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), tp, args.probs, c0, c1);
+        int gB = grid_for(c, ((int64_t)(c1 - c0) + 1) / 2, 6);
+        k_accum_d16<<<gB, A2P_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), tp, args, c0, c1);
+        c->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return B200_OK;
+}
 static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (a->n_rows == 0) return B200_OK;
+    if (d16_mode() == 2 && a->has_trie && d16_2p_ok(c, a)) return launch_d16_trie(c, a, args);
+    if (d16_mode() >= 1 && d16_2p_ok(c, a)) return launch_d16_2p(c, a, args);
     switch (a->n_ops) {
         case 1: return launch_d16_t<1>(c, a, args);
         case 2: return launch_d16_t<2>(c, a, args);

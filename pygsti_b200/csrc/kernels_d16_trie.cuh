@@ -1,0 +1,366 @@
+// kernels_d16_trie.cuh -- d = 16 Jacobian with prefix AND suffix sharing.
+//
+// The reference's Map simulator shares circuit PREFIXES through its prefix table / state cache
+// (pygsti/layouts/prefixtable.py:26-101, mapforwardsim_calc_densitymx.pyx:224-283: 3 151 617 -> 189 293
+// propagations on the BASELINE layout).  The analytic Jacobian additionally needs the backward vectors
+// e_k = (G_{L-1} ... G_{k+1})^T E, which depend only on the circuit SUFFIX and the effect -- so they share
+// exactly the same way through a trie of reversed circuits (151 802 nodes x 4 effects instead of 12.6 M
+// chain steps).  Both tries are built once per layout atom on the host (engine.cu: build_trie).
+//
+//   phase A  k_trie_chains : each trie is cut into chains (maximal runs of nodes created together); warps pull
+//            chains in creation order from an atomic counter, wait (acquire) for the parent node published by an
+//            earlier chain, then walk their chain: forward chains s = G s (DFMA), backward chains
+//            E^T[8x16] <- E^T . G for all effects at once (DMMA, rows = effects).  Every node value is written to
+//            the tables S[n_fnodes][16], H[n_bnodes][n_eff][16] and published (release) for dependent chains.
+//            Critical path = deepest circuit, ~340 k mat-vecs in total at BASELINE size: tens of microseconds.
+//   phase B  k_accum_trie_d16 : one warp per (circuit, outcome), gate by gate:
+//            W_g[i][j] = sum_{t: g_t = g} e_t[i] s_t[j]  as DMMA with K = 4 time steps; the rows are gathered from
+//            the (L2-resident, ~100 MB) tables through per-step node indices stored in gate-bucket order; only one
+//            gate's 16x16 accumulator is live at a time and it is stored to the Jacobian row as soon as the gate
+//            is finished.  This kernel is the whole HBM-write-bound cost.
+#pragma once
+#include "common.cuh"
+#include "kernels_d16.cuh"   // dmma884, D16Args, D16_SPAM_MAX
+
+struct TrieDev {
+    // forward trie (node value = state after the prefix; depth 0 = the prep itself)
+    const int32_t* f_parent;   // [n_fchains] parent node id, or -(1+prep) for a root chain
+    const uint32_t* f_first;   // [n_fchains] first node id (nodes of a chain are consecutive)
+    const uint32_t* f_len;     // [n_fchains]
+    const uint8_t* f_op;       // [n_fnodes]  op applied to reach the node (255 = root copy)
+    int n_fchains; uint32_t n_fnodes;
+    // backward trie (node value = (suffix product)^T E_e for every effect e; depth 0 = E itself)
+    const int32_t* b_parent; const uint32_t* b_first; const uint32_t* b_len; const uint8_t* b_op;
+    int n_bchains; uint32_t n_bnodes;
+    // per circuit step, in gate-bucket order (same order as TwoPhaseDev.bperm): node of s_k and node of e_k
+    const uint32_t* fn_b; const uint32_t* bn_b;
+    const uint32_t* f_end;     // [n_circ] node of s_L
+    const uint32_t* b_end;     // [n_circ] node of e_0 (d p / d rho)
+    const uint16_t* bcnt;      // [n_circ][n_ops] bucket sizes
+    // value tables + synchronisation
+    double* S;                 // [n_fnodes][16]
+    double* H;                 // [n_bnodes][n_eff][16]
+    unsigned* ready_f; unsigned* ready_b;   // [n_nodes] epoch stamps
+    unsigned* counters;        // [2] chain work counters (zeroed before launch)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+#define TRIE_WARPS 4
+
+// dynamic smem: n_ops*256 doubles (backward B fragments) + n_ops*256 doubles (forward fragments)
+//               + TRIE_WARPS*2*16 doubles (forward exchange)
+__global__ void __launch_bounds__(TRIE_WARPS * 32)
+k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
+{
+    extern __shared__ __align__(16) double smt[];
+    double* bfrag = smt;
+    double* ffrag = bfrag + a.n_ops * 256;
+    double* fx_all = ffrag + a.n_ops * 256;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* G = m.M;
+    const double* rho = m.M + m.off_rho;
+    const double* E = m.M + m.off_eff;
+    for (int idx = threadIdx.x; idx < a.n_ops * 256; idx += blockDim.x) {
+        const int g = idx >> 8, r = (idx >> 5) & 7, l = idx & 31;
+        const int tt = r >> 1, u = r & 1, mr = l >> 2, q = l & 3;
+        const int kk = (tt >> 1) * 8 + 2 * q + (tt & 1);
+        bfrag[idx] = G[g * 256 + kk * 16 + 8 * u + mr];
+        ffrag[idx] = G[g * 256 + (l & 15) * 16 + (l >> 4) * 8 + r];
+    }
+    __syncthreads();
+
+    const int role = blockIdx.x & 1;      // 0: forward trie, 1: backward trie
+    if (role == 0) {
+        double* fx = fx_all + warp * 32;
+        const int half = lane >> 4;
+        for (;;) {
+            int ci = 0;
+            if (lane == 0) ci = (int)atomicAdd(t.counters + 0, 1u);
+            ci = __shfl_sync(0xffffffffu, ci, 0);
+            if (ci >= t.n_fchains) break;
+            const int parent = t.f_parent[ci];
+            const uint32_t first = t.f_first[ci], len = t.f_len[ci];
+            double v = 0.0;
+            uint32_t i0 = 0;
+            if (parent < 0) {                       // root chain: first node is the prep itself
+                if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; t.S[(size_t)first * 16 + lane] = v; }
+                __threadfence(); __syncwarp();
+                if (lane == 0) st_release_u32(t.ready_f + first, epoch);
+                i0 = 1;
+            } else {
+                if (lane == 0) { while (ld_acquire_u32(t.ready_f + parent) != epoch) __nanosleep(20); }
+                __syncwarp();
+                if (lane < 16) v = __ldcg(t.S + (size_t)parent * 16 + lane);
+            }
+            int cur = 0;
+            if (lane < 16) fx[lane] = v;
+            __syncwarp();
+            for (uint32_t i = i0; i < len; ++i) {
+                const int g = t.f_op[first + i];
+                const double2* s2 = reinterpret_cast<const double2*>(fx + cur * 16 + half * 8);
+                const double2 s0 = s2[0], s1 = s2[1], s2v = s2[2], s3 = s2[3];
+                const double* fp = ffrag + g * 256 + lane;
+                double f0 = fp[0] * s0.x, f1 = fp[32] * s0.y, f2 = fp[64] * s1.x, f3 = fp[96] * s1.y;
+                f0 = fma(fp[128], s2v.x, f0); f1 = fma(fp[160], s2v.y, f1);
+                f2 = fma(fp[192], s3.x, f2); f3 = fma(fp[224], s3.y, f3);
+                double w = (f0 + f1) + (f2 + f3);
+                w += shfl_xor_f64(w, 16);
+                cur ^= 1;
+                if (lane < 16) { fx[cur * 16 + lane] = w; t.S[(size_t)(first + i) * 16 + lane] = w; }
+                __threadfence(); __syncwarp();
+                if (lane == 0) st_release_u32(t.ready_f + first + i, epoch);
+            }
+        }
+    } else {
+        const int mrow = lane >> 2, q = lane & 3;
+        const int ne = a.n_eff;
+        const bool rowok = mrow < ne;
+        for (;;) {
+            int ci = 0;
+            if (lane == 0) ci = (int)atomicAdd(t.counters + 1, 1u);
+            ci = __shfl_sync(0xffffffffu, ci, 0);
+            if (ci >= t.n_bchains) break;
+            const int parent = t.b_parent[ci];
+            const uint32_t first = t.b_first[ci], len = t.b_len[ci];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            uint32_t i0 = 0;
+            if (parent < 0) {                       // root: E itself
+                if (rowok) {
+                    const double* Er = E + mrow * 16;
+                    a0 = Er[2 * q]; a1 = Er[2 * q + 1]; a2 = Er[8 + 2 * q]; a3 = Er[9 + 2 * q];
+                    double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
+                    *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
+                    *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
+                }
+                __threadfence(); __syncwarp();
+                if (lane == 0) st_release_u32(t.ready_b + first, epoch);
+                i0 = 1;
+            } else {
+                if (lane == 0) { while (ld_acquire_u32(t.ready_b + parent) != epoch) __nanosleep(20); }
+                __syncwarp();
+                if (rowok) {
+                    const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
+                    const double2 x = __ldcg(reinterpret_cast<const double2*>(hp));
+                    const double2 y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                    a0 = x.x; a1 = x.y; a2 = y.x; a3 = y.y;
+                }
+            }
+            for (uint32_t i = i0; i < len; ++i) {
+                const int g = t.b_op[first + i];
+                const double* bp = bfrag + g * 256 + lane;
+                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+                dmma884(d00, d01, a0, bp[0]);   dmma884(d10, d11, a0, bp[32]);
+                dmma884(x00, x01, a1, bp[64]);  dmma884(x10, x11, a1, bp[96]);
+                dmma884(d00, d01, a2, bp[128]); dmma884(d10, d11, a2, bp[160]);
+                dmma884(x00, x01, a3, bp[192]); dmma884(x10, x11, a3, bp[224]);
+                a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
+                if (rowok) {
+                    double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
+                    *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
+                    *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
+                }
+                __threadfence(); __syncwarp();
+                if (lane == 0) st_release_u32(t.ready_b + first + i, epoch);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// phase B: one warp per unit = (circuit, outcome group of <= 4, gate); the group's outcomes are stacked along M:
+//   W_g^{(o)}[i][j] = sum_t e_t^{(o)}[i] s_t[j]  ->  A = [e^{(0)}; e^{(1)}; e^{(2)}; e^{(3)}] (64 x 4 per group of
+//   4 time steps), B = s (4 x 16): 16 DMMA per 4 steps; the s rows and node indices are loaded once for the 4
+//   outcomes and the 4 effect rows of a backward node are contiguous (512 B).
+// All index work is done once on the host (engine.cu): `uidx` holds (forward node, backward node) pairs in
+// gate-bucket order, every bucket padded to a multiple of 4 with the index of an all-zero table row, so the
+// inner loop has no predication: 1 + 2 + 8 eight-byte loads and 16 DMMA per 4 steps.
+// The unit of gate 0 also writes the SPAM / unmapped columns and the probabilities of its outcomes.
+// dynamic smem: n_ops*4*32 int2 (column map fragments) + 2*SPAM_MAX ints
+// ------------------------------------------------------------------------------------------------------------
+#define AT_WARPS 8
+
+struct CGroup {            // 32 bytes: the outcomes of one circuit whose effect index lies in [e_base, e_base+4)
+    int32_t el[4];         // element (Jacobian row) of the outcome with effect e_base + i, -1 = no such outcome
+    uint32_t e_base;       // multiple of 4
+    uint32_t prep;
+    uint32_t f_end, b_end; // node of s_L, node of e_0
+};
+
+__global__ void __launch_bounds__(AT_WARPS * 32, 2)
+k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __restrict__ units, int n_units,
+                 const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, int dbg)
+{
+    extern __shared__ __align__(16) unsigned char smb[];
+    double* stage_all = reinterpret_cast<double*>(smb);                 // [warps][4 outcomes][256] TMA store staging
+    int2* cm_s = reinterpret_cast<int2*>(stage_all + AT_WARPS * 4 * 256);   // [n_ops*4][32]
+    int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
+    int* spamw_s = spamc_s + D16_SPAM_MAX;
+    int* gbase_s = spamw_s + D16_SPAM_MAX;                              // [n_ops] first J column of a fully contiguous gate block, else -1
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
+        const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
+        const int i = 8 * (tile >> 1) + (l >> 2), jc = 8 * (tile & 1) + 2 * (l & 3);
+        int2 cc = *reinterpret_cast<const int2*>(args.colmap + g * 256 + i * 16 + jc);
+        if (cc.y == cc.x + 1 && cc.x >= 0 && ((cc.x | (int)(args.ld & 1)) & 1) == 0) cc.y = -2;
+        cm_s[idx] = cc;
+    }
+    for (int g = threadIdx.x; g < a.n_ops; g += blockDim.x) {
+        // whole 16x16 block maps to 256 consecutive, 16-byte aligned columns -> one 2 KB bulk (TMA) store per outcome
+        const int b0 = args.colmap[g * 256];
+        bool ok = b0 >= 0 && (b0 & 1) == 0 && (args.ld & 1) == 0 && ((reinterpret_cast<size_t>(args.J) & 15) == 0);
+        for (int k = 1; k < 256 && ok; ++k) ok = (args.colmap[g * 256 + k] == b0 + k);
+        gbase_s[g] = ok ? b0 : -1;
+    }
+    const int n_spam_s = args.n_spam < D16_SPAM_MAX ? args.n_spam : D16_SPAM_MAX;
+    for (int tt = threadIdx.x; tt < n_spam_s; tt += blockDim.x) { spamc_s[tt] = args.spam_col[tt]; spamw_s[tt] = args.spam_w[tt]; }
+    __syncthreads();
+
+    uint64_t pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    auto ldk = [&](const double* p) -> double {
+        double v; asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol_keep)); return v; };
+    const unsigned mrow = lane >> 2, q = lane & 3;
+    const unsigned ne16 = (unsigned)a.n_eff * 16u;
+    const double* E = m.M + m.off_eff;
+    const double* Sb = t.S + mrow;
+    const double* Hb = t.H + mrow;
+    const int ustride = gridDim.x * AT_WARPS;
+    // per-gate flag: every lane of every tile can use a 16-byte store (the common, fully parameterised case)
+    for (int u = blockIdx.x * AT_WARPS + warp; u < n_units; u += ustride) {
+        const uint4 un = __ldg(units + u);
+        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y));       // el[4] by effect
+        const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y) + 1);   // e_base | prep | f_end | b_end
+        const int g = (int)(un.z & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(un.z >> 16);
+        const unsigned ebase16 = g1.x * 16u;
+        double acc[4][8];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[o][r] = 0.0;
+        // two-deep software pipeline: node indices are fetched two groups ahead, table rows one group ahead, so
+        // the L2 gathers of group gi+1 are in flight while the 16 DMMA of group gi issue
+        const uint2* ip = uidx + un.x + q;        // (uidx is padded: two groups past the end are readable)
+        uint2 nd1 = __ldg(ip + 4);
+        double r[10];
+        {
+            const uint2 nd0 = __ldg(ip);
+            const double* sp = Sb + nd0.x * 16u;
+            const double* hp = Hb + (nd0.y * ne16 + ebase16);
+            r[0] = ldk(sp); r[1] = ldk(sp + 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[2 + k] = ldk(hp + 8 * k);
+        }
+        ip += 8;
+#pragma unroll 1
+        for (int gi = 0; gi < ngroups; ++gi) {
+            const uint2 nd2 = __ldg(ip); ip += 4;
+            const double* sp = Sb + nd1.x * 16u;
+            const double* hp = Hb + (nd1.y * ne16 + ebase16);
+            double n[10];
+            n[0] = ldk(sp); n[1] = ldk(sp + 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) n[2 + k] = ldk(hp + 8 * k);
+            dmma884(acc[0][0], acc[0][1], r[2], r[0]); dmma884(acc[0][2], acc[0][3], r[2], r[1]);
+            dmma884(acc[0][4], acc[0][5], r[3], r[0]); dmma884(acc[0][6], acc[0][7], r[3], r[1]);
+            dmma884(acc[1][0], acc[1][1], r[4], r[0]); dmma884(acc[1][2], acc[1][3], r[4], r[1]);
+            dmma884(acc[1][4], acc[1][5], r[5], r[0]); dmma884(acc[1][6], acc[1][7], r[5], r[1]);
+            dmma884(acc[2][0], acc[2][1], r[6], r[0]); dmma884(acc[2][2], acc[2][3], r[6], r[1]);
+            dmma884(acc[2][4], acc[2][5], r[7], r[0]); dmma884(acc[2][6], acc[2][7], r[7], r[1]);
+            dmma884(acc[3][0], acc[3][1], r[8], r[0]); dmma884(acc[3][2], acc[3][3], r[8], r[1]);
+            dmma884(acc[3][4], acc[3][5], r[9], r[0]); dmma884(acc[3][6], acc[3][7], r[9], r[1]);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) r[k] = n[k];
+            nd1 = nd2;
+        }
+        const int2* cm = cm_s + g * 128 + lane;
+        int2 cc[4];
+#pragma unroll
+        for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
+        const int els[4] = {(int)g0.x, (int)g0.y, (int)g0.z, (int)g0.w};
+        const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+        if (dbg == 2) { if (acc[0][0] + acc[1][1] + acc[2][2] + acc[3][3] == 1.2345e300) args.J[0] = 1.0; continue; }
+        const int gb = gbase_s[g];
+        if (gb >= 0 && dbg == 4) {   // opt-in (B200_DBG=4): measured equal to the LSU path on B200 (profiles/README.md)
+            // TMA path: fragments -> shared staging (row-major 16x16 per outcome) -> cp.async.bulk to the Jacobian rows.
+            // The bulk engine drains the stores while this warp's LSU goes on gathering the next unit.
+            double* stg = stage_all + warp * (4 * 256);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // previous unit's bulk stores have read the staging
+            __syncwarp();
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int tile = 0; tile < 4; ++tile) {
+                    const int i = 8 * (tile >> 1) + (int)mrow, jc = 8 * (tile & 1) + 2 * (int)q;
+                    *reinterpret_cast<double2*>(stg + o * 256 + i * 16 + jc) = make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]);
+                }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 4 && els[lane] >= 0) {
+                double* dst = args.J + (int64_t)els[lane] * args.ld + gb;
+                const unsigned src = (unsigned)__cvta_generic_to_shared(stg + lane * 256);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(dst), "r"(src) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else if (fast) {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (els[o] >= 0) {
+                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                    for (int tile = 0; tile < 4; ++tile)
+                        __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (els[o] >= 0) {
+                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                    for (int tile = 0; tile < 4; ++tile) {
+                        const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
+                        if (cc[tile].y == -2) {
+                            *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
+                        } else {
+                            if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
+                            if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                        }
+                    }
+                }
+            }
+        }
+        if (g == 0) {
+            // SPAM / unmapped columns and probabilities of the group's outcomes
+            const int prep = (int)g1.y;
+            const double* sL = t.S + (size_t)g1.z * 16;
+            for (int o = 0; o < 4; ++o) {
+                if (els[o] < 0) continue;
+                const int ei = (int)g1.x + o;
+                double* Jr = args.J + (int64_t)els[o] * args.ld;
+                if (args.probs) {
+                    double pr = (lane < 16) ? E[ei * 16 + lane] * sL[lane] : 0.0;
+#pragma unroll
+                    for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
+                    if (lane == 0) args.probs[els[o]] = pr;
+                }
+                const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
+                const double* e0 = t.H + (size_t)g1.w * ne16 + ei * 16;
+                for (int tt = lane; tt < args.n_spam; tt += 32) {
+                    const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
+                    const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
+                    double val = 0.0;
+                    if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0];
+                    else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0];
+                    Jr[col] = val;
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
