@@ -42,6 +42,7 @@ WORKLOAD = "c2_full_layout"
 WORKLOAD_DESC = ("smq2Q_XYCNOT full model (d=16, Np=1360), GST design maxL=128 lite=False: 68335 circuits, "
                  "273340 outcomes; bulk_fill_dprobs + probs")
 METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
+NCU_TRAFFIC_BYTES = 3.351e9   # dram__bytes_read.sum + dram__bytes_write.sum of one step (both kernels), see profiles/
 
 
 def _peaks():
@@ -283,7 +284,8 @@ def main():
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (reference-generated GST layout + depolarized target model; no dataset needed)",
             "config": {"workload": WORKLOAD_DESC, "derivative": "analytic adjoint (== reference MatrixForwardSimulator)",
-                       "kernel": "k_dprobs_d16<5> fused Jacobian path" if info["fused_path"] else "general W.D path",
+                       "kernel": ("k_trie_chains (prefix/suffix-trie chains) + k_accum_trie_d16 (DMMA gather-accumulate, "
+                                  "fused Jacobian store)") if info["fused_path"] else "general W.D path",
                        "parallelism": "dp%d: one replica of the layout per GPU, no data-path collective" % world,
                        "l2": "each step writes a 2.97 GB Jacobian (>> 126 MB L2); no explicit flush needed",
                        "dprobs_elements_per_s": value * Np},
@@ -292,9 +294,14 @@ def main():
                     "path": "b200_atom_set_model + b200_fill_dprobs (C ABI), pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                         "traffic_source": "ncu --set full, profiles/r01_ncu_full_trie_kernels_raw.csv: k_accum_trie_d16 "
+                                           "dram read 0.376 GB + write 2.923 GB, k_trie_chains read 0.003 + write 0.049 GB",
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": ms_per_step},
+                         "kernel_ms": ms_per_step,
+                         "note": "conservative: duration of the WHOLE step (k_trie_chains + k_accum_trie_d16, CUDA events "
+                                 "on the launching stream); the dominant kernel k_accum_trie_d16 alone is ~77% of it "
+                                 "(profiles/)"},
             "clocks": clocks,
             "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
         }

@@ -117,7 +117,7 @@ def test_atoms_and_param_blocks_equal_single_atom():
                 assert np.max(np.abs(ref[c][1] - cur[c][1])) <= 1e-12
 
 
-@pytest.mark.parametrize("param,tol", [("full", 1e-10), ("full TP", 1e-10), ("CPTPLND", 5e-4)])
+@pytest.mark.parametrize("param,tol", [("full", 1e-10), ("full TP", 1e-10), ("CPTPLND", 3e-3)])
 def test_hprobs_vs_matrix_sim(param, tol):
     """full / TP members are linear in their parameters -> fully analytic device Hessian (1e-10 vs the
     reference's analytic Matrix simulator).  CPTPLND: the reference's FD driver (eps=1e-5) over the ANALYTIC
