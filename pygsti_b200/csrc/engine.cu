@@ -200,6 +200,7 @@ struct TrieHost {
     std::vector<uint8_t> node_op;
     std::vector<uint32_t> depth_node;   // per circuit c, depth d in [0, L_c]: node id, at offset dptr[c] + d
     std::vector<uint64_t> dptr;
+    std::vector<int64_t> sorted;        // circuits in lexicographic key order
 };
 static void build_trie(int64_t n, const std::vector<int32_t>& root, const std::vector<uint32_t>& ptr,
                        const std::vector<int32_t>& sym, bool reversed, TrieHost& T) {
@@ -215,6 +216,7 @@ static void build_trie(int64_t n, const std::vector<int32_t>& root, const std::v
         const uint32_t l = std::min(lx, ly);
         for (uint32_t d = 0; d < l; ++d) { const int32_t a = at(x, d), b = at(y, d); if (a != b) return a < b; }
         return lx < ly; });
+    T.sorted = order;
     T.dptr.assign((size_t)n + 1, 0);
     for (int64_t c = 0; c < n; ++c) T.dptr[c + 1] = T.dptr[c] + (ptr[c + 1] - ptr[c]) + 1;
     T.depth_node.assign((size_t)T.dptr[n], 0);
@@ -405,7 +407,10 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             const uint32_t zf_node = (uint32_t)TF.node_op.size(), zb_node = (uint32_t)TB.node_op.size();   // all-zero rows
             std::vector<uint4> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
             bool trie_ok = true;
-            for (int64_t i = 0; i < n_rows; ++i) {
+            // units are emitted in SUFFIX-lexicographic circuit order: consecutive units then gather from the same
+            // region of the (large) backward table H, and the small forward table S stays L2 resident
+            for (int64_t si = 0; si < n_rows; ++si) {
+                const int64_t i = TB.sorted[si];
                 const uint32_t b0 = cptr[i];
                 const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
                 // padded index lists of this circuit's gates (shared by all of its outcome groups)
@@ -681,7 +686,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     int gA = 2 * c->sm_count * 4;                  // even = forward trie, odd = backward trie
-    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch);
+    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 0);
     int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS - 1) / AT_WARPS, 8);
     k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<uint4>(), a->n_units,
                                                                a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(),
@@ -765,10 +770,29 @@ static int compute_w(b200_ctx* c, b200_atom* a, double* W, double* probs) {
     return fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
 }
 
+static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
+    TrieDev t; memset(&t, 0, sizeof t);
+    t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
+    t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
+    t.S = a->t_S.as<double>(); t.ready_f = a->t_ready_f.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
+    const unsigned epoch = ++a->epoch;
+    CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
+    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
+    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 1);
+    int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 15) / 16, (int64_t)c->sm_count * 8));
+    k_probs_trie_d16<<<gp, 256, 0, c->stream>>>(atom_dev(a), model_dev(a), a->t_fend.as<uint32_t>(), a->t_S.as<double>(), d_out, 1);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
 extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     CU(cudaSetDevice(c->device));
+    if (a->has_trie && a->n_rows > 0 && d16_mode() == 2 && (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin)
+        return launch_probs_trie(c, a, d_out);
     return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_out, 1, 0);
 }
 

@@ -56,7 +56,7 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 // dynamic smem: n_ops*256 doubles (backward B fragments) + n_ops*256 doubles (forward fragments)
 //               + TRIE_WARPS*2*16 doubles (forward exchange)
 __global__ void __launch_bounds__(TRIE_WARPS * 32)
-k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
+k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
 {
     extern __shared__ __align__(16) double smt[];
     double* bfrag = smt;
@@ -75,7 +75,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
     }
     __syncthreads();
 
-    const int role = blockIdx.x & 1;      // 0: forward trie, 1: backward trie
+    const int role = fwd_only ? 0 : (blockIdx.x & 1);      // 0: forward trie, 1: backward trie
     if (role == 0) {
         double* fx = fx_all + warp * 32;
         const int half = lane >> 4;
@@ -90,7 +90,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
             uint32_t i0 = 0;
             if (parent < 0) {                       // root chain: first node is the prep itself
                 if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; t.S[(size_t)first * 16 + lane] = v; }
-                __threadfence(); __syncwarp();
+                __syncwarp();
                 if (lane == 0) st_release_u32(t.ready_f + first, epoch);
                 i0 = 1;
             } else {
@@ -113,7 +113,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
                 w += shfl_xor_f64(w, 16);
                 cur ^= 1;
                 if (lane < 16) { fx[cur * 16 + lane] = w; t.S[(size_t)(first + i) * 16 + lane] = w; }
-                __threadfence(); __syncwarp();
+                __syncwarp();
                 if (lane == 0) st_release_u32(t.ready_f + first + i, epoch);
             }
         }
@@ -138,7 +138,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
                     *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
                     *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
                 }
-                __threadfence(); __syncwarp();
+                __syncwarp();
                 if (lane == 0) st_release_u32(t.ready_b + first, epoch);
                 i0 = 1;
             } else {
@@ -165,9 +165,29 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch)
                     *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
                     *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
                 }
-                __threadfence(); __syncwarp();
+                __syncwarp();
                 if (lane == 0) st_release_u32(t.ready_b + first + i, epoch);
             }
+        }
+    }
+}
+
+// probabilities from the forward trie: p_el = E_e . s_L   (one half-warp per outcome)
+__global__ void __launch_bounds__(256)
+k_probs_trie_d16(AtomDev a, ModelDev m, const uint32_t* __restrict__ f_end, const double* __restrict__ S,
+                 double* __restrict__ out, int64_t el_stride)
+{
+    const double* E = m.M + m.off_eff;
+    const int lane = threadIdx.x & 31, sub = lane & 15;
+    const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // half-warp id = (circuit, outcome) slot
+    const int64_t nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    for (int64_t c = hw; c < a.n_circ; c += nhw) {
+        const double sv = S[(size_t)f_end[c] * 16 + sub];
+        for (int q = a.out_ptr[c]; q < a.out_ptr[c + 1]; ++q) {
+            double pr = E[a.out_eff[q] * 16 + sub] * sv;
+#pragma unroll
+            for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
+            if (sub == 0) out[(int64_t)a.out_el[q] * el_stride] = pr;
         }
     }
 }
@@ -234,29 +254,27 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
     // per-gate flag: every lane of every tile can use a 16-byte store (the common, fully parameterised case)
     for (int u = blockIdx.x * AT_WARPS + warp; u < n_units; u += ustride) {
         const uint4 un = __ldg(units + u);
-        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y));       // el[4] by effect
-        const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y) + 1);   // e_base | prep | f_end | b_end
+        const uint4 cg0 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y));       // el[4] by effect
+        const uint4 cg1 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y) + 1);   // e_base | prep | f_end | b_end
         const int g = (int)(un.z & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(un.z >> 16);
-        const unsigned ebase16 = g1.x * 16u;
+        const unsigned ebase16 = cg1.x * 16u;
         double acc[4][8];
 #pragma unroll
         for (int o = 0; o < 4; ++o)
 #pragma unroll
             for (int r = 0; r < 8; ++r) acc[o][r] = 0.0;
-        // two-deep software pipeline: node indices are fetched two groups ahead, table rows one group ahead, so
-        // the L2 gathers of group gi+1 are in flight while the 16 DMMA of group gi issue
-        const uint2* ip = uidx + un.x + q;        // (uidx is padded: two groups past the end are readable)
-        uint2 nd1 = __ldg(ip + 4);
+        const uint2 nd0 = __ldg(uidx + un.x + q);
+        uint2 nd1 = __ldg(uidx + un.x + q + 4);
+        // two-deep software pipeline over the groups: node indices two groups ahead, table rows one group ahead
+        const uint2* ip = uidx + un.x + q + 8;    // (uidx is padded: readable past the end)
         double r[10];
         {
-            const uint2 nd0 = __ldg(ip);
             const double* sp = Sb + nd0.x * 16u;
             const double* hp = Hb + (nd0.y * ne16 + ebase16);
             r[0] = ldk(sp); r[1] = ldk(sp + 8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[2 + k] = ldk(hp + 8 * k);
         }
-        ip += 8;
 #pragma unroll 1
         for (int gi = 0; gi < ngroups; ++gi) {
             const uint2 nd2 = __ldg(ip); ip += 4;
@@ -282,7 +300,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
         int2 cc[4];
 #pragma unroll
         for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
-        const int els[4] = {(int)g0.x, (int)g0.y, (int)g0.z, (int)g0.w};
+        const int els[4] = {(int)cg0.x, (int)cg0.y, (int)cg0.z, (int)cg0.w};
         const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
         if (dbg == 2) { if (acc[0][0] + acc[1][1] + acc[2][2] + acc[3][3] == 1.2345e300) args.J[0] = 1.0; continue; }
         const int gb = gbase_s[g];
@@ -337,11 +355,11 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
         }
         if (g == 0) {
             // SPAM / unmapped columns and probabilities of the group's outcomes
-            const int prep = (int)g1.y;
-            const double* sL = t.S + (size_t)g1.z * 16;
+            const int prep = (int)cg1.y;
+            const double* sL = t.S + (size_t)cg1.z * 16;
             for (int o = 0; o < 4; ++o) {
                 if (els[o] < 0) continue;
-                const int ei = (int)g1.x + o;
+                const int ei = (int)cg1.x + o;
                 double* Jr = args.J + (int64_t)els[o] * args.ld;
                 if (args.probs) {
                     double pr = (lane < 16) ? E[ei * 16 + lane] * sL[lane] : 0.0;
@@ -350,7 +368,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
                     if (lane == 0) args.probs[els[o]] = pr;
                 }
                 const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
-                const double* e0 = t.H + (size_t)g1.w * ne16 + ei * 16;
+                const double* e0 = t.H + (size_t)cg1.w * ne16 + ei * 16;
                 for (int tt = lane; tt < args.n_spam; tt += 32) {
                     const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
                     const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
