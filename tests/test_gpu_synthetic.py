@@ -1,0 +1,118 @@
+"""Edge cases on the GPU against the oracle, with synthetic layouts (no pyGSTi): empty circuits, duplicate circuits,
+cache links, outcome subsets, more than 4 / fewer than 4 effects, more than 8 gates, several preps, every kernel
+family (d = 4, 16, 64, 256), permuted and general derivative maps, every d = 16 code path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(gpu_ctx, t, G, rho, E, D):
+    at = gpu_ctx.upload_atom(t)
+    at.set_model(G, rho, E)
+    at.set_derivs(D)
+    p = np.full(t.n_elements, np.nan)
+    at.fill_probs(p)
+    J = np.full((t.n_elements, D.n_params), np.nan)
+    p2 = np.full(t.n_elements, np.nan)
+    at.fill_dprobs(J, p2)
+    info = at.info()
+    at.free()
+    return p, p2, J, info
+
+
+@pytest.mark.parametrize("dim,n_ops,n_rho,n_eff,depth", [(16, 5, 1, 4, 40), (16, 11, 2, 6, 30), (16, 3, 2, 2, 70),
+                                                        (16, 20, 1, 8, 25), (4, 3, 1, 2, 50), (64, 4, 1, 8, 12)])
+def test_fused_path_edge_cases(gpu_ctx, dim, n_ops, n_rho, n_eff, depth):
+    circs = synth.random_circuits(40 if dim < 64 else 14, depth, n_ops, n_rho, n_eff, seed=dim + n_ops)
+    t = synth.make_tables(dim, n_ops, n_rho, n_eff, circs)
+    G, rho, E = synth.random_model(dim, n_ops, n_rho, n_eff, seed=1)
+    D = synth.full_derivs(t)
+    p, p2, J, info = _run(gpu_ctx, t, G, rho, E, D)
+    po = onp.mapfill_probs(t, G, rho, E)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D)
+    scale = max(1.0, np.max(np.abs(Jo)))
+    assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    assert np.max(np.abs(p2 - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * scale
+    assert info["fused_path"] == 1
+
+
+def test_permuted_and_partial_column_map(gpu_ctx):
+    """unit partial permutation that is NOT contiguous: shuffled columns, some member elements without a parameter,
+    some parameters fed by nothing (must come out exactly zero)."""
+    from pygsti_b200.packing import DerivMap
+    circs = synth.random_circuits(30, 30, 5, 1, 4, seed=3)
+    t = synth.make_tables(16, 5, 1, 4, circs)
+    G, rho, E = synth.random_model(16, 5, 1, 4, seed=2)
+    n_w = 5 * 256 + 16 + 64
+    rng = np.random.default_rng(0)
+    keep = np.sort(rng.choice(n_w, size=n_w - 200, replace=False)).astype(np.int32)
+    n_params = n_w + 37
+    cols = rng.permutation(n_params)[:keep.size].astype(np.int32)
+    D = DerivMap(n_w, n_params, keep, cols, np.ones(keep.size))
+    p, p2, J, info = _run(gpu_ctx, t, G, rho, E, D)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D)
+    assert info["fused_path"] == 1
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    unfed = np.setdiff1d(np.arange(n_params), cols)
+    assert np.all(J[:, unfed] == 0.0)
+
+
+@pytest.mark.parametrize("dim,n_ops,n_eff", [(16, 6, 4), (16, 9, 5), (4, 3, 2), (64, 3, 8)])
+def test_general_derivative_map(gpu_ctx, dim, n_ops, n_eff):
+    circs = synth.random_circuits(24 if dim < 64 else 10, 20 if dim < 64 else 8, n_ops, 2, n_eff, seed=7)
+    t = synth.make_tables(dim, n_ops, 2, n_eff, circs)
+    G, rho, E = synth.random_model(dim, n_ops, 2, n_eff, seed=5)
+    D = synth.random_derivs(t, 57, density=0.03, seed=1)
+    p, p2, J, info = _run(gpu_ctx, t, G, rho, E, D)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D)
+    assert info["fused_path"] == 0
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+
+
+def test_probs_d256(gpu_ctx):
+    circs = synth.random_circuits(10, 6, 3, 1, 16, seed=11, subsets=False)
+    t = synth.make_tables(256, 3, 1, 16, circs)
+    G, rho, E = synth.random_model(256, 3, 1, 16, seed=4)
+    at = gpu_ctx.upload_atom(t); at.set_model(G, rho, E)
+    p = np.full(t.n_elements, np.nan); at.fill_probs(p); at.free()
+    po = onp.mapfill_probs(t, G, rho, E)
+    assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+
+
+@pytest.mark.parametrize("mode", ["fused", "2p", "trie"])
+def test_every_d16_code_path(mode):
+    """The three d = 16 Jacobian implementations (B200_D16_MODE) give the same answers; run in a subprocess because the
+    mode is latched at first use."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from pygsti_b200 import engine
+from oracle import oracle_np as onp
+from tests import synth
+ctx = engine.Context(0)
+for (n_ops, n_rho, n_eff, depth, seed) in [(5, 1, 4, 60, 0), (7, 2, 3, 33, 1)]:
+    circs = synth.random_circuits(50, depth, n_ops, n_rho, n_eff, seed=seed)
+    t = synth.make_tables(16, n_ops, n_rho, n_eff, circs)
+    G, rho, E = synth.random_model(16, n_ops, n_rho, n_eff, seed=seed)
+    D = synth.full_derivs(t)
+    at = ctx.upload_atom(t); at.set_model(G, rho, E); at.set_derivs(D)
+    J = np.full((t.n_elements, D.n_params), np.nan); p = np.full(t.n_elements, np.nan)
+    at.fill_dprobs(J, p)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D); po = onp.mapfill_probs(t, G, rho, E)
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo))), np.max(np.abs(J - Jo))
+    assert np.max(np.abs(p - po)) <= 1e-12
+print("ok")
+''' % REPO
+    env = dict(os.environ, B200_D16_MODE=mode)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
