@@ -72,6 +72,44 @@ def _engine_atom(fwdsim, layout_atom):
     return ctx, ent
 
 
+_REGISTERED = {}
+
+
+def _pin_destination(arr):
+    """Page-lock the caller's destination buffer once (cudaHostRegister, cached by base address) so that results
+    are DMA'd straight into it at PCIe rate.  pyGSTi's objective functions re-use their `probs` / `jac` arrays
+    across optimizer iterations (objectivefns.py:4548, 4609), so the one-time pinning cost is amortised.
+    Small arrays and foreign memory (e.g. MPI shared memory that refuses registration) are left alone."""
+    if os.environ.get("B200_NO_HOST_REGISTER") or arr.nbytes < (1 << 25):
+        return
+    base = arr
+    while isinstance(getattr(base, "base", None), np.ndarray):
+        base = base.base
+    if not isinstance(base, np.ndarray) or not base.flags.c_contiguous:
+        return
+    key = base.ctypes.data
+    if _REGISTERED.get(key, 0) >= base.nbytes:
+        return
+    try:
+        from . import _lib
+        import ctypes as C
+        lib = _lib.load()
+        rc = lib.b200_host_register(C.c_void_p(key), int(base.nbytes))
+        _REGISTERED[key] = base.nbytes if rc == 0 else (1 << 62)     # do not retry a buffer that cannot be pinned
+        if rc == 0:   # un-pin when the owner array is garbage collected (before its pages go back to the allocator)
+            def _unpin(k=key):
+                _REGISTERED.pop(k, None)
+                lib.b200_host_unregister(C.c_void_p(k))
+            weakref.finalize(base, _unpin)
+        if len(_REGISTERED) > 64:                                    # keep the table small: forget the oldest entries
+            for k in list(_REGISTERED)[:16]:
+                if _REGISTERED[k] < (1 << 62):
+                    _lib.load().b200_host_unregister(C.c_void_p(k))
+                del _REGISTERED[k]
+    except Exception:
+        pass
+
+
 def _to_index_array(idx, n):
     if idx is None:
         return None
@@ -212,6 +250,7 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
     if nE == 0 or nP == 0:
         return
     if direct:
+        _pin_destination(array_to_fill)
         fill(array_to_fill[rblk[0]:rblk[1], cblk[0]:cblk[1]])
     else:
         tmp = np.empty((nE, nP))

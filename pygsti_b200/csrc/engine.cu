@@ -7,6 +7,7 @@
 #include "kernels_d16.cuh"
 #include "kernels_d16_2p.cuh"
 #include "kernels_d16_trie.cuh"
+#include "kernels_level.cuh"
 #include <cstdlib>
 
 #include <algorithm>
@@ -61,6 +62,7 @@ struct b200_ctx {
     DevBuf w_buf;        // W matrix of the general path
     DevBuf scratch;      // forward-state scratch of the generic kernels
     DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
+    DevBuf lvl_states;   // ping-pong state buffers of the level-batched dense path
     DevBuf fd_models, fd_gt, fd_probs;
     void* pinned = nullptr; size_t pinned_cap = 0;   // pinned staging for pageable destinations
 };
@@ -75,6 +77,10 @@ struct b200_atom {
     DevBuf circ_ptr, circ_ops, circ_prep, out_ptr, out_eff, out_el;
     DevBuf srow, bperm, bcnt;          // two-phase d16 path: scratch row offsets, per-circuit gate buckets
     int64_t scratch_rows = 0;
+    // level-batched dense path (d >= 64)
+    bool has_levels = false;
+    DevBuf lvl_circ, lvl_tiles;
+    std::vector<uint32_t> lvl_tile_ptr;     // [max_depth+1] tile offsets per level (host)
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
     DevBuf tf_parent, tf_first, tf_len, tf_op, tb_parent, tb_first, tb_len, tb_op, t_fn, t_bn, t_fend, t_bend;
@@ -155,7 +161,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (!c) return B200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release();
+    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release(); c->lvl_states.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -385,6 +391,33 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
         (rc = upload_vec(a->bcnt, bcnt, ctx->stream))) {
         b200_atom_free(ctx, a); return rc;
     }
+    // level-batched dense path (d >= 64): per depth level, circuits grouped by the gate of that level, in tiles of 32
+    if (dim >= 64 && n_rows > 0 && n_ops <= 65535) {
+        std::vector<uint32_t> lc; lc.reserve(cops.size());
+        std::vector<LevelTile> tiles;
+        a->lvl_tile_ptr.assign((size_t)max_depth + 1, 0);
+        std::vector<std::vector<uint32_t>> by_gate((size_t)n_ops);
+        // circuits are stored longest first: those with depth > k are a prefix [0, n_k)
+        int64_t n_k = n_rows;
+        for (int k = 0; k < max_depth; ++k) {
+            while (n_k > 0 && (int)(cptr[n_k] - cptr[n_k - 1]) <= k) --n_k;
+            for (auto& v : by_gate) v.clear();
+            for (int64_t i = 0; i < n_k; ++i) by_gate[cops[cptr[i] + k]].push_back((uint32_t)i);
+            a->lvl_tile_ptr[k] = (uint32_t)tiles.size();
+            for (int g = 0; g < n_ops; ++g) {
+                const auto& v = by_gate[g];
+                for (size_t o = 0; o < v.size(); o += 32) {
+                    LevelTile tl; tl.first = (uint32_t)lc.size() + (uint32_t)o; tl.count = (uint16_t)std::min<size_t>(32, v.size() - o);
+                    tl.gate = (uint16_t)g; tiles.push_back(tl);
+                }
+                lc.insert(lc.end(), v.begin(), v.end());
+            }
+        }
+        a->lvl_tile_ptr[max_depth] = (uint32_t)tiles.size();
+        if ((rc = upload_vec(a->lvl_circ, lc, ctx->stream)) || (rc = upload_vec(a->lvl_tiles, tiles, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
+        CU(cudaStreamSynchronize(ctx->stream));
+        a->has_levels = true;
+    }
     // trie path tables (d = 16, <= 8 effects, <= 255 ops): prefix trie of (prep, ops), suffix trie of reversed ops
     if (dim == 16 && n_eff <= 8 && n_ops <= 255 && n_ops >= 1 && scratch_rows > 0 && xptr[n_rows] < ((uint64_t)1 << 31)) {
         TrieHost TF, TB;
@@ -479,7 +512,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
-                      &a->srow, &a->bperm, &a->bcnt, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
+                      &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
                       &a->tb_first, &a->tb_len, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
                       &a->t_ready_f, &a->t_ready_b, &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
@@ -770,6 +803,30 @@ static int compute_w(b200_ctx* c, b200_atom* a, double* W, double* probs) {
     return fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
 }
 
+template <int D>
+static int launch_probs_level(b200_ctx* c, b200_atom* a, double* d_out) {
+    const size_t nS = (size_t)a->n_rows * D;
+    CU(c->lvl_states.ensure(2 * nS * sizeof(double)));
+    double* S0 = c->lvl_states.as<double>(); double* S1 = S0 + nS;
+    const double* M = a->M.as<double>();
+    int g0 = (int)std::min<int64_t>((int64_t)(nS + 127) / 128, (int64_t)c->sm_count * 8);
+    k_level_init<D><<<g0, 128, 0, c->stream>>>(atom_dev(a), M + a->off_rho, S0);
+    const size_t smem = (size_t)32 * (D + 4) * sizeof(double);
+    CU(cudaFuncSetAttribute(k_level_gemm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int k = 0; k < a->max_depth; ++k) {
+        const uint32_t t0 = a->lvl_tile_ptr[k], t1 = a->lvl_tile_ptr[k + 1];
+        if (t1 == t0) continue;
+        k_level_gemm<D><<<t1 - t0, 128, smem, c->stream>>>(M, a->lvl_tiles.as<LevelTile>() + t0, a->lvl_circ.as<uint32_t>(),
+                                                           (k & 1) ? S1 : S0, (k & 1) ? S0 : S1);
+        c->launches++;
+    }
+    int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 3) / 4, (int64_t)c->sm_count * 8));
+    k_level_probs<D><<<gp, 128, 0, c->stream>>>(atom_dev(a), M + a->off_eff, S0, S1, d_out, 1);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
 static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     TrieDev t; memset(&t, 0, sizeof t);
     t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
@@ -793,6 +850,10 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     CU(cudaSetDevice(c->device));
     if (a->has_trie && a->n_rows > 0 && d16_mode() == 2 && (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin)
         return launch_probs_trie(c, a, d_out);
+    if (a->has_levels && a->n_rows > 0 && !getenv("B200_NO_LEVELS")) {
+        if (a->dim == 64) return launch_probs_level<64>(c, a, d_out);
+        if (a->dim == 256) return launch_probs_level<256>(c, a, d_out);
+    }
     return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_out, 1, 0);
 }
 
