@@ -714,6 +714,9 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.ready_f = a->t_ready_f.as<unsigned>(); t.ready_b = a->t_ready_b.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
     const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_H.as<double>(), (size_t)a->n_bnodes * a->n_eff * 16);
+    c->launches += 2;
     const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)AT_WARPS * 4 * 256 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
@@ -834,6 +837,8 @@ static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     t.S = a->t_S.as<double>(); t.ready_f = a->t_ready_f.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
     const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
+    c->launches++;
     const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 1);

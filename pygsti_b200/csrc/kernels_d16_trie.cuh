@@ -52,6 +52,17 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 
 #define TRIE_WARPS 4
+// Hand-off between chains without fences or flags: the tables are pre-filled with a NaN payload no computation can
+// produce; a node value is complete when none of its words equals the sentinel (every 8-byte store is atomic, each
+// word is written exactly once per call, readers poll through L2 with ld.cg).  A release/acquire flag per node was
+// measured first: the MEMBAR of every release store put ~1.5 k cycles on each step of the critical path.
+#define TRIE_SENT 0x7FF8DEADBEEF5EEDull
+__device__ __forceinline__ bool is_sent(double v) { return (unsigned long long)__double_as_longlong(v) == TRIE_SENT; }
+
+__global__ void k_fill_sentinel(double* __restrict__ p, size_t n) {
+    const double s = __longlong_as_double((long long)TRIE_SENT);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = s;
+}
 
 // dynamic smem: n_ops*256 doubles (backward B fragments) + n_ops*256 doubles (forward fragments)
 //               + TRIE_WARPS*2*16 doubles (forward exchange)
@@ -89,14 +100,15 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
             double v = 0.0;
             uint32_t i0 = 0;
             if (parent < 0) {                       // root chain: first node is the prep itself
-                if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; t.S[(size_t)first * 16 + lane] = v; }
-                __syncwarp();
-                if (lane == 0) st_release_u32(t.ready_f + first, epoch);
+                if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; __stcg(t.S + (size_t)first * 16 + lane, v); }
                 i0 = 1;
             } else {
-                if (lane == 0) { while (ld_acquire_u32(t.ready_f + parent) != epoch) __nanosleep(20); }
+                if (lane < 16) {
+                    const double* pp = t.S + (size_t)parent * 16 + lane;
+                    v = __ldcg(pp);
+                    while (is_sent(v)) { __nanosleep(40); v = __ldcg(pp); }
+                }
                 __syncwarp();
-                if (lane < 16) v = __ldcg(t.S + (size_t)parent * 16 + lane);
             }
             int cur = 0;
             if (lane < 16) fx[lane] = v;
@@ -112,9 +124,8 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
                 double w = (f0 + f1) + (f2 + f3);
                 w += shfl_xor_f64(w, 16);
                 cur ^= 1;
-                if (lane < 16) { fx[cur * 16 + lane] = w; t.S[(size_t)(first + i) * 16 + lane] = w; }
+                if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
                 __syncwarp();
-                if (lane == 0) st_release_u32(t.ready_f + first + i, epoch);
             }
         }
     } else {
@@ -135,21 +146,22 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
                     const double* Er = E + mrow * 16;
                     a0 = Er[2 * q]; a1 = Er[2 * q + 1]; a2 = Er[8 + 2 * q]; a3 = Er[9 + 2 * q];
                     double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
-                    *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
-                    *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
+                    __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
+                    __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
                 }
-                __syncwarp();
-                if (lane == 0) st_release_u32(t.ready_b + first, epoch);
                 i0 = 1;
             } else {
-                if (lane == 0) { while (ld_acquire_u32(t.ready_b + parent) != epoch) __nanosleep(20); }
-                __syncwarp();
                 if (rowok) {
                     const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
-                    const double2 x = __ldcg(reinterpret_cast<const double2*>(hp));
-                    const double2 y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                    double2 x = __ldcg(reinterpret_cast<const double2*>(hp));
+                    double2 y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                    while (is_sent(x.x) || is_sent(x.y) || is_sent(y.x) || is_sent(y.y)) {
+                        __nanosleep(40);
+                        x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                    }
                     a0 = x.x; a1 = x.y; a2 = y.x; a3 = y.y;
                 }
+                __syncwarp();
             }
             for (uint32_t i = i0; i < len; ++i) {
                 const int g = t.b_op[first + i];
@@ -162,11 +174,9 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
                 a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
                 if (rowok) {
                     double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
-                    *reinterpret_cast<double2*>(hp) = make_double2(a0, a1);
-                    *reinterpret_cast<double2*>(hp + 8) = make_double2(a2, a3);
+                    __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
+                    __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
                 }
-                __syncwarp();
-                if (lane == 0) st_release_u32(t.ready_b + first + i, epoch);
             }
         }
     }
