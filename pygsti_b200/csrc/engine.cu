@@ -436,28 +436,19 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
                 fend[i] = TF.depth_node[TF.dptr[i] + L];
                 bend[i] = TB.depth_node[TB.dptr[i] + L];
             }
-            // phase-B units: (circuit, outcome group of <= 4, gate); padded (fwd node, bwd node) pairs
+            // phase-B units: (circuit, outcome group of <= 4 effects, gate), in suffix-lexicographic circuit order
+            // (consecutive units then gather from the same region of the large backward table H, and the small
+            // forward table S stays L2 resident).  `uidx` is one contiguous stream in unit order of
+            // (S element offset, H element offset incl. the group's effect base); buckets padded to 4 steps with the
+            // offsets of the all-zero rows.
             const uint32_t zf_node = (uint32_t)TF.node_op.size(), zb_node = (uint32_t)TB.node_op.size();   // all-zero rows
-            std::vector<uint4> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
-            bool trie_ok = true;
-            // units are emitted in SUFFIX-lexicographic circuit order: consecutive units then gather from the same
-            // region of the (large) backward table H, and the small forward table S stays L2 resident
+            const uint32_t ne16 = (uint32_t)n_eff * 16u;
+            std::vector<UnitRec> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
+            bool trie_ok = ((uint64_t)(zb_node + 2) * ne16 < ((uint64_t)1 << 32)) && ((uint64_t)(zf_node + 2) * 16 < ((uint64_t)1 << 32));
             for (int64_t si = 0; si < n_rows; ++si) {
                 const int64_t i = TB.sorted[si];
                 const uint32_t b0 = cptr[i];
                 const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
-                // padded index lists of this circuit's gates (shared by all of its outcome groups)
-                std::vector<uint32_t> goff((size_t)n_ops), gng((size_t)n_ops);
-                uint32_t tbase = 0;
-                for (int g = 0; g < n_ops; ++g) {
-                    goff[g] = (uint32_t)uidx.size(); gng[g] = (cn[g] + 3u) / 4u;
-                    for (uint32_t t = 0; t < gng[g] * 4u; ++t) {
-                        uint2 e; e.x = (t < cn[g]) ? fn[b0 + tbase + t] : zf_node; e.y = (t < cn[g]) ? bn[b0 + tbase + t] : zb_node;
-                        uidx.push_back(e);
-                    }
-                    tbase += cn[g];
-                }
-                // outcome groups by effect index block [4k, 4k+4): the H rows of a group are then contiguous
                 for (int eb = 0; eb < n_eff; eb += 4) {
                     CGroup cgp; memset(&cgp, 0, sizeof cgp);
                     bool any = false;
@@ -473,20 +464,33 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
                     cgp.e_base = (uint32_t)eb; cgp.prep = (uint32_t)cprep[i]; cgp.f_end = fend[i]; cgp.b_end = bend[i];
                     const uint32_t cgi = (uint32_t)cgrp.size();
                     cgrp.push_back(cgp);
+                    uint32_t tbase = 0;
                     for (int g = 0; g < n_ops; ++g) {
-                        uint4 un; un.x = goff[g]; un.y = cgi; un.z = (uint32_t)g | (gng[g] << 16); un.w = 0;
+                        UnitRec un; memset(&un, 0, sizeof un);
+                        for (int o = 0; o < 4; ++o) un.el[o] = cgp.el[o];
+                        const uint32_t ng = (cn[g] + 3u) / 4u;
+                        un.off = (uint32_t)uidx.size(); un.g_ng = (uint32_t)g | (ng << 16); un.cgi = cgi;
+                        for (uint32_t t = 0; t < ng * 4u; ++t) {
+                            const bool ok = t < cn[g];
+                            uint2 e;
+                            e.x = (ok ? fn[b0 + tbase + t] : zf_node) * 16u;
+                            e.y = (ok ? bn[b0 + tbase + t] : zb_node) * ne16 + (uint32_t)eb * 16u;
+                            uidx.push_back(e);
+                        }
+                        tbase += cn[g];
                         units.push_back(un);
                     }
                 }
             }
-            for (int pad = 0; pad < 16; ++pad) uidx.push_back(make_uint2(zf_node, zb_node));   // prefetch slack
+            if (uidx.size() >= ((size_t)1 << 32) - 64) trie_ok = false;
+            for (int pad = 0; pad < 16; ++pad) uidx.push_back(make_uint2(zf_node * 16u, zb_node * ne16));   // prefetch slack
             if (uidx.empty()) uidx.push_back(make_uint2(zf_node, zb_node));
             a->n_units = (int)units.size();
             if ((rc = upload_vec(a->t_units, units, ctx->stream)) || (rc = upload_vec(a->t_uidx, uidx, ctx->stream)) ||
                 (rc = upload_vec(a->t_cgrp, cgrp, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
             a->n_fchains = (int)TF.chain_first.size(); a->n_bchains = (int)TB.chain_first.size();
             a->n_fnodes = (uint32_t)TF.node_op.size(); a->n_bnodes = (uint32_t)TB.node_op.size();
-            std::vector<unsigned> zf((size_t)a->n_fnodes, 0u), zb((size_t)a->n_bnodes, 0u), zc(2, 0u);
+            std::vector<unsigned> zf((size_t)a->n_fnodes, 0u), zb((size_t)a->n_bnodes, 0u), zc(4, 0u);
             if ((rc = upload_vec(a->tf_parent, TF.chain_parent, ctx->stream)) || (rc = upload_vec(a->tf_first, TF.chain_first, ctx->stream)) ||
                 (rc = upload_vec(a->tf_len, TF.chain_len, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
                 (rc = upload_vec(a->tb_parent, TB.chain_parent, ctx->stream)) || (rc = upload_vec(a->tb_first, TB.chain_first, ctx->stream)) ||
@@ -713,19 +717,19 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.S = a->t_S.as<double>(); t.H = a->t_H.as<double>();
     t.ready_f = a->t_ready_f.as<unsigned>(); t.ready_b = a->t_ready_b.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
     const unsigned epoch = ++a->epoch;
-    CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
+    CU(cudaMemsetAsync(a->t_counters.p, 0, 4 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_H.as<double>(), (size_t)a->n_bnodes * a->n_eff * 16);
     c->launches += 2;
     const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    const size_t smemB = (size_t)AT_WARPS * 4 * 256 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
+    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     int gA = 2 * c->sm_count * 4;                  // even = forward trie, odd = backward trie
     k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 0);
-    int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS - 1) / AT_WARPS, 8);
-    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<uint4>(), a->n_units,
-                                                               a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(),
+    int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
+    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                               a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2,
                                                                getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0);
     c->launches += 2;
     CU(cudaGetLastError());

@@ -203,17 +203,20 @@ k_probs_trie_d16(AtomDev a, ModelDev m, const uint32_t* __restrict__ f_end, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// phase B: one warp per unit = (circuit, outcome group of <= 4, gate); the group's outcomes are stacked along M:
-//   W_g^{(o)}[i][j] = sum_t e_t^{(o)}[i] s_t[j]  ->  A = [e^{(0)}; e^{(1)}; e^{(2)}; e^{(3)}] (64 x 4 per group of
-//   4 time steps), B = s (4 x 16): 16 DMMA per 4 steps; the s rows and node indices are loaded once for the 4
-//   outcomes and the 4 effect rows of a backward node are contiguous (512 B).
-// All index work is done once on the host (engine.cu): `uidx` holds (forward node, backward node) pairs in
-// gate-bucket order, every bucket padded to a multiple of 4 with the index of an all-zero table row, so the
-// inner loop has no predication: 1 + 2 + 8 eight-byte loads and 16 DMMA per 4 steps.
-// The unit of gate 0 also writes the SPAM / unmapped columns and the probabilities of its outcomes.
+// phase B: one warp per unit = (circuit, outcome group of <= 4 consecutive effects, gate); the group's outcomes are
+// stacked along M:  W_g^{(o)}[i][j] = sum_t e_t^{(o)}[i] s_t[j]  ->  A = [e^{(0)}; ...; e^{(3)}] (64 x 4 per group of
+// 4 time steps), B = s (4 x 16): 16 DMMA per 4 steps; the s rows are loaded once for the 4 outcomes and the 4 effect
+// rows of a backward node are contiguous (512 B).
+// All index work is done once on the host (engine.cu): `uidx` is ONE CONTIGUOUS STREAM, in unit order, of
+// (S element offset, H element offset) pairs, every (unit) bucket padded to a multiple of 4 steps with the offsets of
+// all-zero table rows.  Warps take chunks of consecutive units from an atomic counter and run a software pipeline
+// over the stream that does not stop at unit boundaries (offsets two groups ahead, table rows one group ahead): the
+// only exposed load latency is at the start of a chunk.  No predication in the loop: 1 + 2 + 8 eight-byte loads and
+// 16 DMMA per 4 steps.  The unit of gate 0 also writes the SPAM / unmapped columns and the probabilities.
 // dynamic smem: n_ops*4*32 int2 (column map fragments) + 2*SPAM_MAX ints
 // ------------------------------------------------------------------------------------------------------------
 #define AT_WARPS 8
+#define AT_CHUNK 16
 
 struct CGroup {            // 32 bytes: the outcomes of one circuit whose effect index lies in [e_base, e_base+4)
     int32_t el[4];         // element (Jacobian row) of the outcome with effect e_base + i, -1 = no such outcome
@@ -221,17 +224,22 @@ struct CGroup {            // 32 bytes: the outcomes of one circuit whose effect
     uint32_t prep;
     uint32_t f_end, b_end; // node of s_L, node of e_0
 };
+struct UnitRec {           // 32 bytes
+    int32_t el[4];         // copy of the group's Jacobian rows
+    uint32_t off;          // first stream entry of the unit
+    uint32_t g_ng;         // gate | n_groups << 16
+    uint32_t cgi;          // CGroup index (SPAM / probabilities, gate 0 only)
+    uint32_t pad;
+};
 
 __global__ void __launch_bounds__(AT_WARPS * 32, 2)
-k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __restrict__ units, int n_units,
-                 const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, int dbg)
+k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
+                 const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, unsigned* __restrict__ counter, int dbg)
 {
     extern __shared__ __align__(16) unsigned char smb[];
-    double* stage_all = reinterpret_cast<double*>(smb);                 // [warps][4 outcomes][256] TMA store staging
-    int2* cm_s = reinterpret_cast<int2*>(stage_all + AT_WARPS * 4 * 256);   // [n_ops*4][32]
+    int2* cm_s = reinterpret_cast<int2*>(smb);                          // [n_ops*4][32]
     int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
     int* spamw_s = spamc_s + D16_SPAM_MAX;
-    int* gbase_s = spamw_s + D16_SPAM_MAX;                              // [n_ops] first J column of a fully contiguous gate block, else -1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
         const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
@@ -239,13 +247,6 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
         int2 cc = *reinterpret_cast<const int2*>(args.colmap + g * 256 + i * 16 + jc);
         if (cc.y == cc.x + 1 && cc.x >= 0 && ((cc.x | (int)(args.ld & 1)) & 1) == 0) cc.y = -2;
         cm_s[idx] = cc;
-    }
-    for (int g = threadIdx.x; g < a.n_ops; g += blockDim.x) {
-        // whole 16x16 block maps to 256 consecutive, 16-byte aligned columns -> one 2 KB bulk (TMA) store per outcome
-        const int b0 = args.colmap[g * 256];
-        bool ok = b0 >= 0 && (b0 & 1) == 0 && (args.ld & 1) == 0 && ((reinterpret_cast<size_t>(args.J) & 15) == 0);
-        for (int k = 1; k < 256 && ok; ++k) ok = (args.colmap[g * 256 + k] == b0 + k);
-        gbase_s[g] = ok ? b0 : -1;
     }
     const int n_spam_s = args.n_spam < D16_SPAM_MAX ? args.n_spam : D16_SPAM_MAX;
     for (int tt = threadIdx.x; tt < n_spam_s; tt += blockDim.x) { spamc_s[tt] = args.spam_col[tt]; spamw_s[tt] = args.spam_w[tt]; }
@@ -260,135 +261,124 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const uint4* __
     const double* E = m.M + m.off_eff;
     const double* Sb = t.S + mrow;
     const double* Hb = t.H + mrow;
-    const int ustride = gridDim.x * AT_WARPS;
-    // per-gate flag: every lane of every tile can use a 16-byte store (the common, fully parameterised case)
-    for (int u = blockIdx.x * AT_WARPS + warp; u < n_units; u += ustride) {
-        const uint4 un = __ldg(units + u);
-        const uint4 cg0 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y));       // el[4] by effect
-        const uint4 cg1 = __ldg(reinterpret_cast<const uint4*>(cgrp + un.y) + 1);   // e_base | prep | f_end | b_end
-        const int g = (int)(un.z & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(un.z >> 16);
-        const unsigned ebase16 = cg1.x * 16u;
-        double acc[4][8];
-#pragma unroll
-        for (int o = 0; o < 4; ++o)
-#pragma unroll
-            for (int r = 0; r < 8; ++r) acc[o][r] = 0.0;
-        const uint2 nd0 = __ldg(uidx + un.x + q);
-        uint2 nd1 = __ldg(uidx + un.x + q + 4);
-        // two-deep software pipeline over the groups: node indices two groups ahead, table rows one group ahead
-        const uint2* ip = uidx + un.x + q + 8;    // (uidx is padded: readable past the end)
+
+    for (;;) {
+        int u0 = 0;
+        if (lane == 0) u0 = (int)atomicAdd(counter, 1u) * AT_CHUNK;
+        u0 = __shfl_sync(0xffffffffu, u0, 0);
+        if (u0 >= n_units) break;
+        const int u1 = (u0 + AT_CHUNK < n_units) ? u0 + AT_CHUNK : n_units;
+        // ---- chunk prologue: the only exposed latency ----
+        uint4 ra = __ldg(reinterpret_cast<const uint4*>(units + u0));        // el[4]
+        uint4 rb = __ldg(reinterpret_cast<const uint4*>(units + u0) + 1);    // off, g_ng, cgi
+        const uint2* ip = uidx + rb.x + q;
+        uint2 nd1 = __ldg(ip + 4);
         double r[10];
         {
-            const double* sp = Sb + nd0.x * 16u;
-            const double* hp = Hb + (nd0.y * ne16 + ebase16);
+            const uint2 nd0 = __ldg(ip);
+            const double* sp = Sb + nd0.x;
+            const double* hp = Hb + nd0.y;
             r[0] = ldk(sp); r[1] = ldk(sp + 8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) r[2 + k] = ldk(hp + 8 * k);
         }
-#pragma unroll 1
-        for (int gi = 0; gi < ngroups; ++gi) {
-            const uint2 nd2 = __ldg(ip); ip += 4;
-            const double* sp = Sb + nd1.x * 16u;
-            const double* hp = Hb + (nd1.y * ne16 + ebase16);
-            double n[10];
-            n[0] = ldk(sp); n[1] = ldk(sp + 8);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) n[2 + k] = ldk(hp + 8 * k);
-            dmma884(acc[0][0], acc[0][1], r[2], r[0]); dmma884(acc[0][2], acc[0][3], r[2], r[1]);
-            dmma884(acc[0][4], acc[0][5], r[3], r[0]); dmma884(acc[0][6], acc[0][7], r[3], r[1]);
-            dmma884(acc[1][0], acc[1][1], r[4], r[0]); dmma884(acc[1][2], acc[1][3], r[4], r[1]);
-            dmma884(acc[1][4], acc[1][5], r[5], r[0]); dmma884(acc[1][6], acc[1][7], r[5], r[1]);
-            dmma884(acc[2][0], acc[2][1], r[6], r[0]); dmma884(acc[2][2], acc[2][3], r[6], r[1]);
-            dmma884(acc[2][4], acc[2][5], r[7], r[0]); dmma884(acc[2][6], acc[2][7], r[7], r[1]);
-            dmma884(acc[3][0], acc[3][1], r[8], r[0]); dmma884(acc[3][2], acc[3][3], r[8], r[1]);
-            dmma884(acc[3][4], acc[3][5], r[9], r[0]); dmma884(acc[3][6], acc[3][7], r[9], r[1]);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) r[k] = n[k];
-            nd1 = nd2;
-        }
-        const int2* cm = cm_s + g * 128 + lane;
-        int2 cc[4];
-#pragma unroll
-        for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
-        const int els[4] = {(int)cg0.x, (int)cg0.y, (int)cg0.z, (int)cg0.w};
-        const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
-        if (dbg == 2) { if (acc[0][0] + acc[1][1] + acc[2][2] + acc[3][3] == 1.2345e300) args.J[0] = 1.0; continue; }
-        const int gb = gbase_s[g];
-        if (gb >= 0 && dbg == 4) {   // opt-in (B200_DBG=4): measured equal to the LSU path on B200 (profiles/README.md)
-            // TMA path: fragments -> shared staging (row-major 16x16 per outcome) -> cp.async.bulk to the Jacobian rows.
-            // The bulk engine drains the stores while this warp's LSU goes on gathering the next unit.
-            double* stg = stage_all + warp * (4 * 256);
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // previous unit's bulk stores have read the staging
-            __syncwarp();
+        ip += 8;
+        for (int u = u0; u < u1; ++u) {
+            // next unit's record (needed only after this unit's groups)
+            const int un = (u + 1 < u1) ? u + 1 : u;
+            const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
+            const uint4 rbn = __ldg(reinterpret_cast<const uint4*>(units + un) + 1);
+            const int g = (int)(rb.y & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(rb.y >> 16);
+            double acc[4][8];
 #pragma unroll
             for (int o = 0; o < 4; ++o)
 #pragma unroll
-                for (int tile = 0; tile < 4; ++tile) {
-                    const int i = 8 * (tile >> 1) + (int)mrow, jc = 8 * (tile & 1) + 2 * (int)q;
-                    *reinterpret_cast<double2*>(stg + o * 256 + i * 16 + jc) = make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]);
-                }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane < 4 && els[lane] >= 0) {
-                double* dst = args.J + (int64_t)els[lane] * args.ld + gb;
-                const unsigned src = (unsigned)__cvta_generic_to_shared(stg + lane * 256);
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(dst), "r"(src) : "memory");
+                for (int k = 0; k < 8; ++k) acc[o][k] = 0.0;
+#pragma unroll 1
+            for (int gi = 0; gi < ngroups; ++gi) {
+                const uint2 nd2 = __ldg(ip); ip += 4;
+                const double* sp = Sb + nd1.x;
+                const double* hp = Hb + nd1.y;
+                double n[10];
+                n[0] = ldk(sp); n[1] = ldk(sp + 8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) n[2 + k] = ldk(hp + 8 * k);
+                dmma884(acc[0][0], acc[0][1], r[2], r[0]); dmma884(acc[0][2], acc[0][3], r[2], r[1]);
+                dmma884(acc[0][4], acc[0][5], r[3], r[0]); dmma884(acc[0][6], acc[0][7], r[3], r[1]);
+                dmma884(acc[1][0], acc[1][1], r[4], r[0]); dmma884(acc[1][2], acc[1][3], r[4], r[1]);
+                dmma884(acc[1][4], acc[1][5], r[5], r[0]); dmma884(acc[1][6], acc[1][7], r[5], r[1]);
+                dmma884(acc[2][0], acc[2][1], r[6], r[0]); dmma884(acc[2][2], acc[2][3], r[6], r[1]);
+                dmma884(acc[2][4], acc[2][5], r[7], r[0]); dmma884(acc[2][6], acc[2][7], r[7], r[1]);
+                dmma884(acc[3][0], acc[3][1], r[8], r[0]); dmma884(acc[3][2], acc[3][3], r[8], r[1]);
+                dmma884(acc[3][4], acc[3][5], r[9], r[0]); dmma884(acc[3][6], acc[3][7], r[9], r[1]);
+#pragma unroll
+                for (int k = 0; k < 10; ++k) r[k] = n[k];
+                nd1 = nd2;
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        } else if (fast) {
+            if (dbg == 2) { if (acc[0][0] + acc[1][1] + acc[2][2] + acc[3][3] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
+            // ---------------- epilogue: the finished 16x16 blocks are Jacobian entries ----------------
+            const int2* cm = cm_s + g * 128 + lane;
+            int2 cc[4];
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (els[o] >= 0) {
-                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+            for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
+            const int els[4] = {(int)ra.x, (int)ra.y, (int)ra.z, (int)ra.w};
+            const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+            if (fast) {
 #pragma unroll
-                    for (int tile = 0; tile < 4; ++tile)
-                        __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                for (int o = 0; o < 4; ++o) {
+                    if (els[o] >= 0) {
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                        for (int tile = 0; tile < 4; ++tile)
+                            __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                    }
                 }
-            }
-        } else {
+            } else {
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (els[o] >= 0) {
-                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+                for (int o = 0; o < 4; ++o) {
+                    if (els[o] >= 0) {
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
 #pragma unroll
-                    for (int tile = 0; tile < 4; ++tile) {
-                        const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
-                        if (cc[tile].y == -2) {
-                            *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
-                        } else {
-                            if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
-                            if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                        for (int tile = 0; tile < 4; ++tile) {
+                            const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
+                            if (cc[tile].y == -2) {
+                                *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
+                            } else {
+                                if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
+                                if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                            }
                         }
                     }
                 }
             }
-        }
-        if (g == 0) {
-            // SPAM / unmapped columns and probabilities of the group's outcomes
-            const int prep = (int)cg1.y;
-            const double* sL = t.S + (size_t)cg1.z * 16;
-            for (int o = 0; o < 4; ++o) {
-                if (els[o] < 0) continue;
-                const int ei = (int)cg1.x + o;
-                double* Jr = args.J + (int64_t)els[o] * args.ld;
-                if (args.probs) {
-                    double pr = (lane < 16) ? E[ei * 16 + lane] * sL[lane] : 0.0;
+            if (g == 0) {
+                // SPAM / unmapped columns and probabilities of the group's outcomes
+                const uint4 cg1 = __ldg(reinterpret_cast<const uint4*>(cgrp + rb.z) + 1);   // e_base | prep | f_end | b_end
+                const int prep = (int)cg1.y;
+                const double* sL = t.S + (size_t)cg1.z * 16;
+                for (int o = 0; o < 4; ++o) {
+                    if (els[o] < 0) continue;
+                    const int ei = (int)cg1.x + o;
+                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+                    if (args.probs) {
+                        double pr = (lane < 16) ? E[ei * 16 + lane] * sL[lane] : 0.0;
 #pragma unroll
-                    for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
-                    if (lane == 0) args.probs[els[o]] = pr;
-                }
-                const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
-                const double* e0 = t.H + (size_t)cg1.w * ne16 + ei * 16;
-                for (int tt = lane; tt < args.n_spam; tt += 32) {
-                    const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
-                    const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
-                    double val = 0.0;
-                    if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0];
-                    else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0];
-                    Jr[col] = val;
+                        for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
+                        if (lane == 0) args.probs[els[o]] = pr;
+                    }
+                    const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
+                    const double* e0 = t.H + (size_t)cg1.w * ne16 + ei * 16;
+                    for (int tt = lane; tt < args.n_spam; tt += 32) {
+                        const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
+                        const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
+                        double val = 0.0;
+                        if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0];
+                        else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0];
+                        Jr[col] = val;
+                    }
                 }
             }
+            ra = ran; rb = rbn;
         }
     }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
