@@ -42,7 +42,7 @@ WORKLOAD = "c2_full_layout"
 WORKLOAD_DESC = ("smq2Q_XYCNOT full model (d=16, Np=1360), GST design maxL=128 lite=False: 68335 circuits, "
                  "273340 outcomes; bulk_fill_dprobs + probs")
 METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
-NCU_TRAFFIC_BYTES = 3.351e9   # dram__bytes_read.sum + dram__bytes_write.sum of one step (both kernels), see profiles/
+NCU_TRAFFIC_BYTES = 3.32e9   # dram__bytes_read.sum + dram__bytes_write.sum of one step (all kernels of the step), see profiles/
 
 
 def _peaks():
@@ -295,13 +295,14 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full, profiles/r01_ncu_full_trie_kernels_raw.csv: k_accum_trie_d16 "
-                                           "dram read 0.376 GB + write 2.923 GB, k_trie_chains read 0.003 + write 0.049 GB",
+                         "traffic_source": "ncu --set full, profiles/r01_ncu_full_final_kernels_raw.csv: k_accum_trie_d16 "
+                                           "dram read 0.245 GB + write 2.921 GB, k_trie_chains read 0.005 + write 0.048 GB, "
+                                           "k_fill_sentinel write 0.10 GB",
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": ms_per_step,
                          "note": "conservative: duration of the WHOLE step (k_trie_chains + k_accum_trie_d16, CUDA events "
-                                 "on the launching stream); the dominant kernel k_accum_trie_d16 alone is ~77% of it "
-                                 "(profiles/)"},
+                                 "on the launching stream: 2 x k_fill_sentinel + k_trie_chains + k_accum_trie_d16); the "
+                                 "dominant kernel k_accum_trie_d16 alone is 83% of it (profiles/README.md)"},
             "clocks": clocks,
             "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
         }
