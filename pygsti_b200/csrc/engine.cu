@@ -52,8 +52,6 @@ struct b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int sm_count = 148;
     size_t smem_optin = 0;
     int64_t launches = 0;
@@ -64,7 +62,6 @@ struct b200_ctx {
     DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
     DevBuf lvl_states;   // ping-pong state buffers of the level-batched dense path
     DevBuf fd_models, fd_gt, fd_probs;
-    void* pinned = nullptr; size_t pinned_cap = 0;   // pinned staging for pageable destinations
 };
 
 struct b200_atom {
@@ -84,8 +81,8 @@ struct b200_atom {
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
     DevBuf tf_parent, tf_first, tf_len, tf_op, tb_parent, tb_first, tb_len, tb_op, t_fn, t_bn, t_fend, t_bend;
-    DevBuf t_S, t_H, t_ready_f, t_ready_b, t_counters, t_units, t_uidx, t_cgrp;
-    int n_units = 0;
+    DevBuf t_S, t_H, t_counters, t_units, t_uidx, t_cgrp;
+    int n_units = 0, unit_outcomes = 4;
     int n_fchains = 0, n_bchains = 0; uint32_t n_fnodes = 0, n_bnodes = 0;
     unsigned epoch = 0;
     // model
@@ -146,9 +143,6 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
     c->device = device;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
@@ -163,10 +157,6 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release(); c->lvl_states.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
-    if (c->pinned) cudaFreeHost(c->pinned);
-    if (c->ev_a) cudaEventDestroy(c->ev_a);
-    if (c->ev_b) cudaEventDestroy(c->ev_b);
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B200_OK;
@@ -443,19 +433,21 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             // offsets of the all-zero rows.
             const uint32_t zf_node = (uint32_t)TF.node_op.size(), zb_node = (uint32_t)TB.node_op.size();   // all-zero rows
             const uint32_t ne16 = (uint32_t)n_eff * 16u;
+            const int gsz = (getenv("B200_UNIT_OUTCOMES") && atoi(getenv("B200_UNIT_OUTCOMES")) == 2) ? 2 : 4;   // outcomes per phase-B unit
+            a->unit_outcomes = gsz;
             std::vector<UnitRec> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
             bool trie_ok = ((uint64_t)(zb_node + 2) * ne16 < ((uint64_t)1 << 32)) && ((uint64_t)(zf_node + 2) * 16 < ((uint64_t)1 << 32));
             for (int64_t si = 0; si < n_rows; ++si) {
                 const int64_t i = TB.sorted[si];
                 const uint32_t b0 = cptr[i];
                 const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
-                for (int eb = 0; eb < n_eff; eb += 4) {
+                for (int eb = 0; eb < n_eff; eb += gsz) {
                     CGroup cgp; memset(&cgp, 0, sizeof cgp);
                     bool any = false;
                     for (int o = 0; o < 4; ++o) cgp.el[o] = -1;
                     for (int32_t oq = coptr[i]; oq < coptr[i + 1]; ++oq) {
                         const int e = coeff[oq];
-                        if (e >= eb && e < eb + 4) {
+                        if (e >= eb && e < eb + gsz) {
                             if (cgp.el[e - eb] >= 0) trie_ok = false;      // same effect twice in one circuit: not representable
                             cgp.el[e - eb] = coel[oq]; any = true;
                         }
@@ -490,14 +482,13 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
                 (rc = upload_vec(a->t_cgrp, cgrp, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
             a->n_fchains = (int)TF.chain_first.size(); a->n_bchains = (int)TB.chain_first.size();
             a->n_fnodes = (uint32_t)TF.node_op.size(); a->n_bnodes = (uint32_t)TB.node_op.size();
-            std::vector<unsigned> zf((size_t)a->n_fnodes, 0u), zb((size_t)a->n_bnodes, 0u), zc(4, 0u);
+            std::vector<unsigned> zc(4, 0u);
             if ((rc = upload_vec(a->tf_parent, TF.chain_parent, ctx->stream)) || (rc = upload_vec(a->tf_first, TF.chain_first, ctx->stream)) ||
                 (rc = upload_vec(a->tf_len, TF.chain_len, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
                 (rc = upload_vec(a->tb_parent, TB.chain_parent, ctx->stream)) || (rc = upload_vec(a->tb_first, TB.chain_first, ctx->stream)) ||
                 (rc = upload_vec(a->tb_len, TB.chain_len, ctx->stream)) || (rc = upload_vec(a->tb_op, TB.node_op, ctx->stream)) ||
                 (rc = upload_vec(a->t_fn, fn, ctx->stream)) || (rc = upload_vec(a->t_bn, bn, ctx->stream)) ||
                 (rc = upload_vec(a->t_fend, fend, ctx->stream)) || (rc = upload_vec(a->t_bend, bend, ctx->stream)) ||
-                (rc = upload_vec(a->t_ready_f, zf, ctx->stream)) || (rc = upload_vec(a->t_ready_b, zb, ctx->stream)) ||
                 (rc = upload_vec(a->t_counters, zc, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
             cudaError_t e1 = a->t_S.ensure(((size_t)a->n_fnodes + 1) * 128), e2 = a->t_H.ensure(((size_t)a->n_bnodes + 2) * n_eff * 128);
             if (e1 != cudaSuccess || e2 != cudaSuccess) { b200_atom_free(ctx, a); return fail(B200_E_NOMEM, "trie tables: out of device memory"); }
@@ -518,7 +509,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
                       &a->tb_first, &a->tb_len, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
-                      &a->t_ready_f, &a->t_ready_b, &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
+                      &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
     for (DevBuf* b : bufs) b->release();
@@ -715,7 +706,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.fn_b = a->t_fn.as<uint32_t>(); t.bn_b = a->t_bn.as<uint32_t>(); t.f_end = a->t_fend.as<uint32_t>(); t.b_end = a->t_bend.as<uint32_t>();
     t.bcnt = a->bcnt.as<uint16_t>();
     t.S = a->t_S.as<double>(); t.H = a->t_H.as<double>();
-    t.ready_f = a->t_ready_f.as<unsigned>(); t.ready_b = a->t_ready_b.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
+    t.counters = a->t_counters.as<unsigned>();
     const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 4 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
@@ -724,13 +715,20 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    CU(cudaFuncSetAttribute(k_accum_trie_d16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     int gA = 2 * c->sm_count * 4;                  // even = forward trie, odd = backward trie
     k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 0);
     int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
-    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                               a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2,
-                                                               getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0);
+    const int dbg = getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0;
+    if (a->unit_outcomes == 2) {
+        CU(cudaFuncSetAttribute(k_accum_trie_d16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 3);
+        k_accum_trie_d16<2><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
+    } else {
+        k_accum_trie_d16<4><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
+    }
     c->launches += 2;
     CU(cudaGetLastError());
     return B200_OK;
@@ -838,7 +836,7 @@ static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     TrieDev t; memset(&t, 0, sizeof t);
     t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
-    t.S = a->t_S.as<double>(); t.ready_f = a->t_ready_f.as<unsigned>(); t.counters = a->t_counters.as<unsigned>();
+    t.S = a->t_S.as<double>(); t.counters = a->t_counters.as<unsigned>();
     const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
@@ -898,20 +896,12 @@ extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, in
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
-static bool is_pinned(const void* p) {
-    cudaPointerAttributes at;
-    cudaError_t e = cudaPointerGetAttributes(&at, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
-
 // device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles
 static int copy_out_2d(b200_ctx* c, const double* d_src, int64_t width, int64_t n_rows, double* h_dst, int64_t hstride) {
     if (n_rows == 0 || width == 0) return B200_OK;
     CU(cudaMemcpy2DAsync(h_dst, (size_t)hstride * 8, d_src, (size_t)width * 8, (size_t)width * 8, (size_t)n_rows,
                          cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    (void)is_pinned;
     return B200_OK;
 }
 
@@ -965,8 +955,7 @@ extern "C" int b200_fill_dprobs_fd(b200_ctx* c, b200_atom* a, double eps, double
     for (int p0 = 0; p0 < Np; p0 += B) {
         const int nb = std::min(B, Np - p0);
         dim3 g1((unsigned)std::min<int64_t>((a->n_w + 255) / 256, 256), nb);
-        k_perturb_models<<<g1, 256, 0, c->stream>>>(a->M.as<double>(), a->n_w, nb, p0, eps, a->cptr.as<int32_t>(),
-                                                    a->crow.as<int32_t>(), a->cval.as<double>(), c->fd_models.as<double>());
+        k_perturb_models<<<g1, 256, 0, c->stream>>>(a->M.as<double>(), a->n_w, c->fd_models.as<double>());
         dim3 g2(4, nb);
         k_perturb_apply<<<g2, 128, 0, c->stream>>>(a->n_w, p0, eps, a->cptr.as<int32_t>(), a->crow.as<int32_t>(),
                                                    a->cval.as<double>(), c->fd_models.as<double>());

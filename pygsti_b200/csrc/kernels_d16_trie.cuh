@@ -8,16 +8,15 @@
 // chain steps).  Both tries are built once per layout atom on the host (engine.cu: build_trie).
 //
 //   phase A  k_trie_chains : each trie is cut into chains (maximal runs of nodes created together); warps pull
-//            chains in creation order from an atomic counter, wait (acquire) for the parent node published by an
-//            earlier chain, then walk their chain: forward chains s = G s (DFMA), backward chains
-//            E^T[8x16] <- E^T . G for all effects at once (DMMA, rows = effects).  Every node value is written to
-//            the tables S[n_fnodes][16], H[n_bnodes][n_eff][16] and published (release) for dependent chains.
-//            Critical path = deepest circuit, ~340 k mat-vecs in total at BASELINE size: tens of microseconds.
-//   phase B  k_accum_trie_d16 : one warp per (circuit, outcome), gate by gate:
+//            chains, ordered by start depth, from an atomic counter, wait for the parent node written by an
+//            earlier chain (fence-free sentinel hand-off, see TRIE_SENT), then walk their chain: forward chains
+//            s = G s (DFMA), backward chains E^T[8x16] <- E^T . G for all effects at once (DMMA, rows = effects).
+//            Node values go to the tables S[n_fnodes][16], H[n_bnodes][n_eff][16].
+//            Critical path = deepest circuit, ~340 k mat-vecs in total at BASELINE size: ~0.1 ms.
+//   phase B  k_accum_trie_d16 : one warp per (circuit, outcome group, gate) unit:
 //            W_g[i][j] = sum_{t: g_t = g} e_t[i] s_t[j]  as DMMA with K = 4 time steps; the rows are gathered from
-//            the (L2-resident, ~100 MB) tables through per-step node indices stored in gate-bucket order; only one
-//            gate's 16x16 accumulator is live at a time and it is stored to the Jacobian row as soon as the gate
-//            is finished.  This kernel is the whole HBM-write-bound cost.
+//            the (~100 MB) tables through a host-built offset stream; a finished 16x16 block is a set of Jacobian
+//            entries and is stored at once.  This kernel is the whole HBM-write-bound cost.
 #pragma once
 #include "common.cuh"
 #include "kernels_d16.cuh"   // dmma884, D16Args, D16_SPAM_MAX
@@ -40,16 +39,8 @@ struct TrieDev {
     // value tables + synchronisation
     double* S;                 // [n_fnodes][16]
     double* H;                 // [n_bnodes][n_eff][16]
-    unsigned* ready_f; unsigned* ready_b;   // [n_nodes] epoch stamps
-    unsigned* counters;        // [2] chain work counters (zeroed before launch)
+    unsigned* counters;        // [4] work counters: forward chains, backward chains, accumulate chunks (zeroed before launch)
 };
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 #define TRIE_WARPS 4
 // Hand-off between chains without fences or flags: the tables are pre-filled with a NaN payload no computation can
@@ -232,7 +223,8 @@ struct UnitRec {           // 32 bytes
     uint32_t pad;
 };
 
-__global__ void __launch_bounds__(AT_WARPS * 32, 2)
+template <int NO>          // outcomes (consecutive effects) per unit: 4 (126 registers, 16 warps/SM) or 2 (<= 80 registers, 24 warps/SM)
+__global__ void __launch_bounds__(AT_WARPS * 32, (NO == 4 ? 2 : 3))
 k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
                  const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, unsigned* __restrict__ counter, int dbg)
 {
@@ -273,14 +265,14 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
         uint4 rb = __ldg(reinterpret_cast<const uint4*>(units + u0) + 1);    // off, g_ng, cgi
         const uint2* ip = uidx + rb.x + q;
         uint2 nd1 = __ldg(ip + 4);
-        double r[10];
+        double r[2 + 2 * NO];
         {
             const uint2 nd0 = __ldg(ip);
             const double* sp = Sb + nd0.x;
             const double* hp = Hb + nd0.y;
             r[0] = ldk(sp); r[1] = ldk(sp + 8);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) r[2 + k] = ldk(hp + 8 * k);
+            for (int k = 0; k < 2 * NO; ++k) r[2 + k] = ldk(hp + 8 * k);
         }
         ip += 8;
         for (int u = u0; u < u1; ++u) {
@@ -289,9 +281,9 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
             const uint4 rbn = __ldg(reinterpret_cast<const uint4*>(units + un) + 1);
             const int g = (int)(rb.y & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(rb.y >> 16);
-            double acc[4][8];
+            double acc[NO][8];
 #pragma unroll
-            for (int o = 0; o < 4; ++o)
+            for (int o = 0; o < NO; ++o)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) acc[o][k] = 0.0;
 #pragma unroll 1
@@ -299,23 +291,20 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 const uint2 nd2 = __ldg(ip); ip += 4;
                 const double* sp = Sb + nd1.x;
                 const double* hp = Hb + nd1.y;
-                double n[10];
+                double n[2 + 2 * NO];
                 n[0] = ldk(sp); n[1] = ldk(sp + 8);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) n[2 + k] = ldk(hp + 8 * k);
-                dmma884(acc[0][0], acc[0][1], r[2], r[0]); dmma884(acc[0][2], acc[0][3], r[2], r[1]);
-                dmma884(acc[0][4], acc[0][5], r[3], r[0]); dmma884(acc[0][6], acc[0][7], r[3], r[1]);
-                dmma884(acc[1][0], acc[1][1], r[4], r[0]); dmma884(acc[1][2], acc[1][3], r[4], r[1]);
-                dmma884(acc[1][4], acc[1][5], r[5], r[0]); dmma884(acc[1][6], acc[1][7], r[5], r[1]);
-                dmma884(acc[2][0], acc[2][1], r[6], r[0]); dmma884(acc[2][2], acc[2][3], r[6], r[1]);
-                dmma884(acc[2][4], acc[2][5], r[7], r[0]); dmma884(acc[2][6], acc[2][7], r[7], r[1]);
-                dmma884(acc[3][0], acc[3][1], r[8], r[0]); dmma884(acc[3][2], acc[3][3], r[8], r[1]);
-                dmma884(acc[3][4], acc[3][5], r[9], r[0]); dmma884(acc[3][6], acc[3][7], r[9], r[1]);
+                for (int k = 0; k < 2 * NO; ++k) n[2 + k] = ldk(hp + 8 * k);
 #pragma unroll
-                for (int k = 0; k < 10; ++k) r[k] = n[k];
+                for (int o = 0; o < NO; ++o) {
+                    dmma884(acc[o][0], acc[o][1], r[2 + 2 * o], r[0]); dmma884(acc[o][2], acc[o][3], r[2 + 2 * o], r[1]);
+                    dmma884(acc[o][4], acc[o][5], r[3 + 2 * o], r[0]); dmma884(acc[o][6], acc[o][7], r[3 + 2 * o], r[1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 2 + 2 * NO; ++k) r[k] = n[k];
                 nd1 = nd2;
             }
-            if (dbg == 2) { if (acc[0][0] + acc[1][1] + acc[2][2] + acc[3][3] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
+            if (dbg == 2) { if (acc[0][0] + acc[NO - 1][1] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
             // ---------------- epilogue: the finished 16x16 blocks are Jacobian entries ----------------
             const int2* cm = cm_s + g * 128 + lane;
             int2 cc[4];
@@ -325,7 +314,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
             if (fast) {
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
+                for (int o = 0; o < NO; ++o) {
                     if (els[o] >= 0) {
                         double* Jr = args.J + (int64_t)els[o] * args.ld;
 #pragma unroll
@@ -335,7 +324,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 }
             } else {
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
+                for (int o = 0; o < NO; ++o) {
                     if (els[o] >= 0) {
                         double* Jr = args.J + (int64_t)els[o] * args.ld;
 #pragma unroll
@@ -356,7 +345,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 const uint4 cg1 = __ldg(reinterpret_cast<const uint4*>(cgrp + rb.z) + 1);   // e_base | prep | f_end | b_end
                 const int prep = (int)cg1.y;
                 const double* sL = t.S + (size_t)cg1.z * 16;
-                for (int o = 0; o < 4; ++o) {
+                for (int o = 0; o < NO; ++o) {
                     if (els[o] < 0) continue;
                     const int ei = (int)cg1.x + o;
                     double* Jr = args.J + (int64_t)els[o] * args.ld;

@@ -294,16 +294,13 @@ k_contract_csc(const double* __restrict__ W, int64_t ldw, int64_t n_el, int n_pa
 // ---------------------------------------------------------------------------------------------
 // forward-difference helpers (reference semantics, pyx:349-378)
 // ---------------------------------------------------------------------------------------------
-// build perturbed models: Mb[b] = M + eps * D[:, p0+b]  (and their transposed gates)
-__global__ void k_perturb_models(const double* __restrict__ M, int64_t n_w, int nb, int p0, double eps,
-                                 const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
-                                 const double* __restrict__ cval, double* __restrict__ Mb)
+// perturbed models, step 1: Mb[b] = M   (step 2, k_perturb_apply, adds eps * D[:, p0+b]; then the gates are transposed)
+__global__ void k_perturb_models(const double* __restrict__ M, int64_t n_w, double* __restrict__ Mb)
 {
     const int b = blockIdx.y;
     double* dst = Mb + (int64_t)b * n_w;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_w; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = M[i];
-    (void)nb; (void)p0; (void)eps; (void)cptr; (void)crow; (void)cval;
 }
 __global__ void k_perturb_apply(int64_t n_w, int p0, double eps,
                                 const int32_t* __restrict__ cptr, const int32_t* __restrict__ crow,
