@@ -123,6 +123,23 @@ int b200_fill_hprobs_linear(b200_ctx* ctx, b200_atom* atom, int32_t n1, const in
 int b200_fill_probs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out);
 int b200_fill_dprobs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out, int64_t ld, double* d_probs);
 
+/* ---- "next" row: the objective-function Jacobian fill, fused ------------------------------
+ * b200_fill_dprobs_scaled  = b200_fill_dprobs followed by the row scaling the objective functions apply to it,
+ *     out[el, p] = row_scale[el] * d p_el / d theta_p
+ * replacing `dprobs *= dg_probs[:, None]` of TimeIndependentMDCObjectiveFunction.dterms and
+ * `jac *= p5over_lsvec[:, None]` of dlsvec (pygsti/objectivefns/objectivefns.py:4609-4616, 4644-4649): the scaling
+ * is applied in the kernel epilogue instead of a second pass over a (2.97 GB at BASELINE size) host array.
+ * row_scale: host vector [n_elements] (the caller computes it from the probabilities and the data, as the reference
+ * does); NULL = no scaling.
+ * b200_jtj  keeps the scaled Jacobian J on the device and returns only  JTJ = J^T J  [n_params x n_params, row-major,
+ * full symmetric] and, if f != NULL,  JTf = J^T f  [n_params]: what the Levenberg-Marquardt step consumes
+ * (DistributableCOPALayout.fill_jtj / fill_jtf, pygsti/layouts/distlayout.py:1220-1359;
+ * pygsti/optimize/simplerlm.py:677-678).  jtf_out may be NULL. */
+int b200_fill_dprobs_scaled(b200_ctx* ctx, b200_atom* atom, const double* row_scale, double* out, int64_t row_stride,
+                            double* probs_out, int64_t probs_stride);
+int b200_jtj(b200_ctx* ctx, b200_atom* atom, const double* row_scale, const double* f,
+             double* jtj_out, double* jtf_out);
+
 /* ---- pinned host memory for zero-staging transfers --------------------------------------------- */
 int b200_host_alloc(void** out, int64_t bytes);     /* cudaHostAlloc */
 int b200_host_free(void* p);

@@ -222,9 +222,10 @@ def _deriv_map(fwdsim, layout_atom, ent, param_indices):
 
 
 def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices, layout_atom, param_indices,
-                        resource_alloc, eps):
+                        resource_alloc, eps, row_scale=None):
     """array_to_fill[dest_indices, dest_param_indices] = d(probabilities)/d(params[param_indices])
-    (replaces pyx:290-383).  ``eps`` is used only in 'fd' mode."""
+    (replaces pyx:290-383).  ``eps`` is used only in 'fd' mode.  ``row_scale`` (extension, length = number of
+    elements of the atom): every Jacobian row is multiplied by its entry on the device (objective-function fill)."""
     shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
@@ -237,7 +238,12 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
     nE = layout_atom.num_elements
     nP = int(pidx.size)
     mode = getattr(fwdsim, "derivative_mode", "analytic")
-    fill = (lambda out: atom.fill_dprobs_fd(out, eps=eps)) if mode == "fd" else atom.fill_dprobs
+    if mode == "fd":
+        if row_scale is not None:
+            raise ValueError("row_scale is only supported with derivative_mode='analytic'")
+        fill = (lambda out: atom.fill_dprobs_fd(out, eps=eps))
+    else:
+        fill = (lambda out: atom.fill_dprobs(out, row_scale=row_scale))
 
     rblk = _contiguous_block(dest_indices, array_to_fill.shape[0])
     if dest_param_indices is None:
@@ -258,6 +264,16 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
         r = _to_index_array(dest_indices, array_to_fill.shape[0])
         c = np.arange(nP) if dest_param_indices is None else _to_index_array(dest_param_indices, array_to_fill.shape[1])
         array_to_fill[np.ix_(r, c)] = tmp
+
+
+def atom_jtj(fwdsim, layout_atom, row_scale=None, f=None):
+    """(J^T J, J^T f) of one atom with J = diag(row_scale) . dprobs kept on the device."""
+    model = fwdsim.model
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
+    _deriv_map(fwdsim, layout_atom, ent, None)
+    return atom.jtj(row_scale, f)
 
 
 # The reference calclib also exports six time-dependent functions (pyx:400-586).  They are OUT OF SCOPE for

@@ -9,6 +9,7 @@
 #include "kernels_d16_trie.cuh"
 #include "kernels_level.cuh"
 #include <cstdlib>
+#include <cublas_v2.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -61,6 +62,8 @@ struct b200_ctx {
     DevBuf scratch;      // forward-state scratch of the generic kernels
     DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
     DevBuf lvl_states;   // ping-pong state buffers of the level-batched dense path
+    DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
+    cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
 };
 
@@ -156,6 +159,8 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release(); c->lvl_states.release();
+    c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
+    if (c->cublas) cublasDestroy(c->cublas);
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -795,7 +800,7 @@ static int compute_w(b200_ctx* c, b200_atom* a, double* W, double* probs) {
         D16Args args;
         args.colmap = a->id_colmap.as<int32_t>(); args.spam_col = a->id_spam_col.as<int32_t>();
         args.spam_w = a->id_spam_w.as<int32_t>(); args.n_spam = a->id_n_spam;
-        args.J = W; args.ld = a->n_w; args.probs = probs;
+        args.J = W; args.ld = a->n_w; args.probs = probs; args.row_scale = nullptr;
         return launch_d16(c, a, args);
     }
     CU(cudaMemsetAsync(W, 0, (size_t)a->n_elements * a->n_w * sizeof(double), c->stream));
@@ -864,14 +869,15 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_out, 1, 0);
 }
 
-extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs) {
+// Jacobian into a device buffer; d_scale (device, [n_elements]) or nullptr
+static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
     if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (ld < a->n_params) return fail(B200_E_INVALID, "ld=%lld < n_params=%d", (long long)ld, a->n_params);
     CU(cudaSetDevice(c->device));
     if (a->n_elements == 0 || a->n_params == 0) {
-        if (d_probs && a->n_elements) return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_probs, 1, 0);
+        if (d_probs && a->n_elements) return b200_fill_probs_dev(c, a, d_probs);
         return B200_OK;
     }
     if (a->unit_perm && d16_ok(c, a)) {
@@ -879,7 +885,16 @@ extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, in
         args.colmap = a->colmap.as<int32_t>(); args.spam_col = a->spam_col.as<int32_t>();
         args.spam_w = a->spam_w.as<int32_t>(); args.n_spam = a->n_spam;
         args.J = d_out; args.ld = ld; args.probs = d_probs;
-        return launch_d16(c, a, args);
+        const bool fused_scale = (d16_mode() == 2 && a->has_trie && d16_2p_ok(c, a));   // trie epilogue applies the scale itself
+        args.row_scale = fused_scale ? d_scale : nullptr;
+        int rc = launch_d16(c, a, args);
+        if (rc) return rc;
+        if (d_scale && !fused_scale) {
+            k_scale_rows<<<(unsigned)std::min<int64_t>(a->n_elements, 65535 * 4), 256, 0, c->stream>>>(d_out, ld, a->n_elements, a->n_params, d_scale);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        return B200_OK;
     }
     // general path: W then J = W . D
     CU(c->w_buf.ensure((size_t)a->n_elements * a->n_w * sizeof(double)));
@@ -887,10 +902,14 @@ extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, in
     if (rc) return rc;
     dim3 grid((a->n_params + 127) / 128, (unsigned)std::min<int64_t>(a->n_elements, 65535));
     k_contract_csc<<<grid, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, a->n_elements, a->n_params,
-                                                 a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(), d_out, ld);
+                                                 a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(), d_out, ld, d_scale);
     c->launches++;
     CU(cudaGetLastError());
     return B200_OK;
+}
+
+extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs) {
+    return fill_dprobs_device(c, a, d_out, ld, d_probs, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -930,6 +949,87 @@ extern "C" int b200_fill_dprobs(b200_ctx* c, b200_atom* a, double* out, int64_t 
     rc = copy_out_2d(c, c->out_buf.as<double>(), a->n_params, a->n_elements, out, row_stride);
     if (rc) return rc;
     if (probs_out) return copy_out_2d(c, d_probs, 1, a->n_elements, probs_out, probs_stride);
+    return B200_OK;
+}
+
+static int upload_scale(b200_ctx* c, b200_atom* a, const double* row_scale, const double** d_scale) {
+    *d_scale = nullptr;
+    if (!row_scale || a->n_elements == 0) return B200_OK;
+    CU(c->scale_buf.ensure((size_t)a->n_elements * 8));
+    CU(cudaMemcpyAsync(c->scale_buf.p, row_scale, (size_t)a->n_elements * 8, cudaMemcpyHostToDevice, c->stream));
+    *d_scale = c->scale_buf.as<double>();
+    return B200_OK;
+}
+
+extern "C" int b200_fill_dprobs_scaled(b200_ctx* c, b200_atom* a, const double* row_scale, double* out, int64_t row_stride,
+                                       double* probs_out, int64_t probs_stride) {
+    if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (row_stride < a->n_params) return fail(B200_E_INVALID, "row_stride < n_params");
+    if (probs_out && probs_stride < 1) return fail(B200_E_INVALID, "probs_stride must be >= 1");
+    CU(cudaSetDevice(c->device));
+    CU(c->out_buf.ensure(std::max<size_t>((size_t)a->n_elements * a->n_params * 8, 16)));
+    double* d_probs = nullptr;
+    if (probs_out) { CU(c->probs_buf.ensure(std::max<size_t>((size_t)a->n_elements * 8, 16))); d_probs = c->probs_buf.as<double>(); }
+    const double* d_scale = nullptr;
+    int rc = upload_scale(c, a, row_scale, &d_scale);
+    if (rc) return rc;
+    rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), a->n_params, d_probs, d_scale);
+    if (rc) return rc;
+    rc = copy_out_2d(c, c->out_buf.as<double>(), a->n_params, a->n_elements, out, row_stride);
+    if (rc) return rc;
+    if (probs_out) return copy_out_2d(c, d_probs, 1, a->n_elements, probs_out, probs_stride);
+    return B200_OK;
+}
+
+#define CB(x) do { cublasStatus_t s_ = (x); if (s_ != CUBLAS_STATUS_SUCCESS) \
+    return fail(B200_E_CUDA, "%s failed: cublas status %d (%s:%d)", #x, (int)s_, __FILE__, __LINE__); } while (0)
+
+extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, const double* f, double* jtj_out, double* jtf_out) {
+    if (!c || !a || !jtj_out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (jtf_out && !f) return fail(B200_E_INVALID, "jtf_out requires f");
+    CU(cudaSetDevice(c->device));
+    const int Np = a->n_params; const int64_t nE = a->n_elements;
+    if (Np == 0) return B200_OK;
+    if (nE >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "too many elements for the BLAS call");
+    CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * Np * 8, 16)));
+    CU(c->jtj_buf.ensure((size_t)Np * Np * 8));
+    const double* d_scale = nullptr;
+    int rc = upload_scale(c, a, row_scale, &d_scale);
+    if (rc) return rc;
+    rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), Np, nullptr, d_scale);
+    if (rc) return rc;
+    if (!c->cublas) { CB(cublasCreate(&c->cublas)); }
+    CB(cublasSetStream(c->cublas, c->stream));
+    // J is row-major [nE x Np] = column-major A [Np x nE] (lda = Np):  J^T J = A A^T  (plain library SYRK)
+    const double one = 1.0, zero = 0.0;
+    if (nE > 0) {
+        CB(cublasDsyrk(c->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, &zero,
+                       c->jtj_buf.as<double>(), Np));
+        dim3 blk(16, 16), grd((Np + 15) / 16, (Np + 15) / 16);
+        // column-major lower triangle == row-major upper triangle: mirror it
+        k_symmetrize<<<grd, blk, 0, c->stream>>>(c->jtj_buf.as<double>(), Np);
+        c->launches += 2;
+    } else {
+        CU(cudaMemsetAsync(c->jtj_buf.p, 0, (size_t)Np * Np * 8, c->stream));
+    }
+    if (jtf_out) {
+        CU(c->f_buf.ensure(std::max<size_t>((size_t)nE * 8, 16)));
+        CU(c->jtf_buf.ensure((size_t)Np * 8));
+        if (nE > 0) {
+            CU(cudaMemcpyAsync(c->f_buf.p, f, (size_t)nE * 8, cudaMemcpyHostToDevice, c->stream));
+            CB(cublasDgemv(c->cublas, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, c->f_buf.as<double>(), 1, &zero,
+                           c->jtf_buf.as<double>(), 1));
+            c->launches++;
+        } else {
+            CU(cudaMemsetAsync(c->jtf_buf.p, 0, (size_t)Np * 8, c->stream));
+        }
+        CU(cudaMemcpyAsync(jtf_out, c->jtf_buf.p, (size_t)Np * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(jtj_out, c->jtj_buf.p, (size_t)Np * Np * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
 }
 

@@ -59,6 +59,8 @@ struct D16Args {
     double* J;                // [n_elements][ld]
     int64_t ld;
     double* probs;            // [n_elements] or nullptr
+    const double* row_scale;  // [n_elements] or nullptr: J row el is multiplied by row_scale[el] (trie path: fused in the
+                              // epilogue; other d = 16 kernels: applied by k_scale_rows afterwards)
 };
 
 __host__ __device__ inline int d16_lpad(int max_depth) { return (max_depth + 2 * D16_C) & ~(D16_C - 1); }

@@ -312,6 +312,14 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
             const int els[4] = {(int)ra.x, (int)ra.y, (int)ra.z, (int)ra.w};
             const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+            if (args.row_scale) {          // objective-function row scaling fused into the epilogue
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    const double sc = (els[o] >= 0) ? __ldg(args.row_scale + els[o]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
+                }
+            }
             if (fast) {
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -357,12 +365,13 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                     }
                     const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
                     const double* e0 = t.H + (size_t)cg1.w * ne16 + ei * 16;
+                    const double sc = args.row_scale ? __ldg(args.row_scale + els[o]) : 1.0;
                     for (int tt = lane; tt < args.n_spam; tt += 32) {
                         const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
                         const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
                         double val = 0.0;
-                        if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0];
-                        else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0];
+                        if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0] * sc;
+                        else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0] * sc;
                         Jr[col] = val;
                     }
                 }

@@ -141,11 +141,27 @@ class Atom:
             raise ValueError("unsupported row stride")
         return (a.strides[0] // 8) if a.shape[0] > 1 else max(a.shape[1], 1)
 
-    def fill_dprobs(self, out, probs_out=None):
+    def fill_dprobs(self, out, probs_out=None, row_scale=None):
+        """Jacobian into `out`; with `row_scale` (length n_elements) row el is multiplied by row_scale[el] on the
+        device (the objective functions' `dprobs *= dg[:, None]`, objectivefns.py:4609-4616, fused)."""
         rs = self._mat_stride(out)
         ps = self._vec_stride(probs_out, self.n_elements) if probs_out is not None else 1
-        _lib.check(self._lib.b200_fill_dprobs(self.ctx._h, self._h, _ptr(out), rs, _ptr(probs_out), ps))
+        if row_scale is None:
+            _lib.check(self._lib.b200_fill_dprobs(self.ctx._h, self._h, _ptr(out), rs, _ptr(probs_out), ps))
+        else:
+            sc = _f64(row_scale).reshape(self.n_elements)
+            _lib.check(self._lib.b200_fill_dprobs_scaled(self.ctx._h, self._h, _ptr(sc), _ptr(out), rs, _ptr(probs_out), ps))
         return out
+
+    def jtj(self, row_scale=None, f=None):
+        """(J^T J, J^T f) with J = diag(row_scale) . dprobs kept on the device (distlayout.py:1220-1359 fill_jtj/fill_jtf)."""
+        n = self.n_params
+        sc = _f64(row_scale).reshape(self.n_elements) if row_scale is not None else None
+        fv = _f64(f).reshape(self.n_elements) if f is not None else None
+        JTJ = np.empty((n, n))
+        JTf = np.empty(n) if fv is not None else None
+        _lib.check(self._lib.b200_jtj(self.ctx._h, self._h, _ptr(sc), _ptr(fv), _ptr(JTJ), _ptr(JTf)))
+        return JTJ, JTf
 
     def fill_dprobs_fd(self, out, eps=1e-7, probs_out=None):
         rs = self._mat_stride(out)

@@ -105,6 +105,34 @@ class B200ForwardSimulator(_MapForwardSimulator):
             super()._bulk_fill_hprobs_atom(array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
                                            param_slice1, param_slice2, resource_alloc)
 
+    # ---- extensions for the objective-function Jacobian fill --------------------
+    def bulk_fill_dprobs_scaled(self, array_to_fill, layout, row_scale, pr_array_to_fill=None):
+        """``bulk_fill_dprobs`` with every row multiplied by ``row_scale[el]`` on the device: the
+        `dprobs *= dg_probs[:, None]` / `jac *= p5over_lsvec[:, None]` passes of the objective functions
+        (objectivefns.py:4609-4616, 4644-4649) fused into the kernel epilogue."""
+        if pr_array_to_fill is not None:
+            self.bulk_fill_probs(pr_array_to_fill, layout)
+        ralloc = layout.resource_alloc('param-processing')
+        for atom in layout.atoms:
+            sl = atom.element_slice
+            _b200_calclib.mapfill_dprobs_atom(self, array_to_fill[sl, :], slice(0, atom.num_elements), None, atom,
+                                              layout.global_param_slice, ralloc, self.derivative_eps,
+                                              row_scale=_np.ascontiguousarray(row_scale[sl]))
+        return array_to_fill
+
+    def bulk_jtj(self, layout, row_scale=None, f=None):
+        """(J^T J, J^T f) for J = diag(row_scale) . dprobs without the Jacobian leaving the device (what
+        `fill_jtj` / `fill_jtf` hand the Levenberg-Marquardt step, distlayout.py:1220-1359)."""
+        JTJ, JTf = None, None
+        for atom in layout.atoms:
+            sl = atom.element_slice
+            a, b = _b200_calclib.atom_jtj(self, atom, None if row_scale is None else row_scale[sl],
+                                          None if f is None else f[sl])
+            JTJ = a if JTJ is None else JTJ + a
+            if b is not None:
+                JTf = b if JTf is None else JTf + b
+        return JTJ, JTf
+
     def __getstate__(self):
         state = super().__getstate__()
         state.pop('calclib', None)

@@ -1,0 +1,73 @@
+"""
+Fused objective-function Jacobian fill (the "next" row of SURVEY.md section 8f, rank 1).
+
+``TimeIndependentMDCObjectiveFunction.dterms`` / ``dlsvec`` (pygsti/objectivefns/objectivefns.py:4595-4653) fill the
+Jacobian with ``bulk_fill_dprobs`` and then make one or two more passes over the (nE x Np) host array to scale its
+rows (``dprobs *= dg_probs[:, None]``; ``jac *= p5over_lsvec[:, None]``).  The functions below compute exactly the
+same arrays but hand the row scale to the engine, which applies it in the kernel epilogue; ``fused_jtj`` goes one
+step further and returns only ``J^T J`` and ``J^T f`` (``fill_jtj`` / ``fill_jtf``, distlayout.py:1220-1359,
+simplerlm.py:677-678), so that the Jacobian never leaves the device.
+
+They apply to objective functions without omitted-outcome corrections (``firsts is None``) and without penalty rows;
+anything else is delegated to the objective function's own (reference) method, which still runs on the GPU simulator.
+"""
+import numpy as np
+
+
+def _plain(objfn):
+    return getattr(objfn, "firsts", None) is None and not getattr(objfn, "_process_penalties", False) \
+        and hasattr(objfn.model.sim, "bulk_fill_dprobs_scaled") and objfn.local_ex == 0
+
+
+def _row_scale_terms(objfn):
+    """probs (clipped) -> dg_probs, following dterms (objectivefns.py:4609-4616)."""
+    objfn.model.sim.bulk_fill_probs(objfn.probs, objfn.layout)
+    objfn._clip_probs()
+    return objfn.raw_objfn.dterms(objfn.probs, objfn.counts, objfn.total_counts, objfn.freqs)
+
+
+def fused_dterms(objfn, paramvec=None):
+    """== objfn.dterms(paramvec)"""
+    if not _plain(objfn):
+        return objfn.dterms(paramvec)
+    if paramvec is not None:
+        objfn.model.from_vector(paramvec)
+    dg = _row_scale_terms(objfn)
+    jac = objfn.jac[0:objfn.nelements, :]
+    objfn.model.sim.bulk_fill_dprobs_scaled(jac, objfn.layout, dg)
+    objfn._reweight_jac(jac)
+    return objfn.jac
+
+
+def _lsvec_scale(objfn, paramvec):
+    """dg_probs * 0.5 / lsvec  and lsvec, following dlsvec (objectivefns.py:4633-4653)."""
+    dg = _row_scale_terms(objfn)
+    lsvec = objfn.lsvec(paramvec).copy()
+    with np.errstate(divide='ignore', invalid='ignore'):
+        p5 = 0.5 / lsvec
+    p5[np.abs(lsvec) < 1e-100] = 0.0
+    return dg * p5[:objfn.nelements], lsvec
+
+
+def fused_dlsvec(objfn, paramvec=None):
+    """== objfn.dlsvec(paramvec)"""
+    if not _plain(objfn):
+        return objfn.dlsvec(paramvec)
+    if paramvec is not None:
+        objfn.model.from_vector(paramvec)
+    scale, _ = _lsvec_scale(objfn, paramvec)
+    jac = objfn.jac[0:objfn.nelements, :]
+    objfn.model.sim.bulk_fill_dprobs_scaled(jac, objfn.layout, scale)
+    objfn._reweight_jac(jac)
+    return objfn.jac
+
+
+def fused_jtj(objfn, paramvec=None):
+    """(J^T J, J^T f) with J = objfn.dlsvec(paramvec), f = objfn.lsvec(paramvec), J never materialised on the host."""
+    if paramvec is not None:
+        objfn.model.from_vector(paramvec)
+    if not _plain(objfn):
+        J = objfn.dlsvec(paramvec); f = objfn.lsvec(paramvec)
+        return J.T @ J, J.T @ f
+    scale, lsvec = _lsvec_scale(objfn, paramvec)
+    return objfn.model.sim.bulk_jtj(objfn.layout, scale, lsvec[:objfn.nelements])

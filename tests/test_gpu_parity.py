@@ -138,3 +138,25 @@ def test_hprobs_linear_vs_reference_matrix(gpu_ctx, load_case, name):
     at.fill_hprobs_linear(p1, p2, Hb)
     assert np.max(np.abs(Hb - c["hprobs_matrix"][:, p1][:, :, p2])) <= 1e-10
     at.free()
+
+
+@pytest.mark.parametrize("name", ["c2_2q_full_sub", "c4_2q_cptplnd_sub", "c1_1q_tp", "c3_3q_localnoise_sub"])
+def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name):
+    """b200_fill_dprobs_scaled / b200_jtj (fused objective Jacobian fill) on every kernel path: fused d=16 (trie
+    epilogue), general d=16 (W + contraction), d=4 and d=64 generic."""
+    c = load_case(name)
+    a = c.atoms[0]
+    at = _atom(gpu_ctx, a)
+    rng = np.random.default_rng(3)
+    w = rng.uniform(-2.0, 2.0, size=c.n_elements)
+    f = rng.standard_normal(c.n_elements)
+    Jref = c["dprobs_matrix"] * w[:, None]
+    J = np.full((c.n_elements, c.num_params), np.nan)
+    at.fill_dprobs(J, row_scale=w)
+    assert np.max(np.abs(J - Jref)) <= 1e-10 * max(1.0, np.max(np.abs(Jref)))
+    JTJ, JTf = at.jtj(w, f)
+    R = Jref.T @ Jref
+    assert np.max(np.abs(JTJ - R)) <= 1e-10 * max(1.0, np.max(np.abs(R)))
+    assert np.max(np.abs(JTJ - JTJ.T)) == 0.0
+    assert np.max(np.abs(JTf - Jref.T @ f)) <= 1e-10 * max(1.0, np.max(np.abs(Jref.T @ f)))
+    at.free()

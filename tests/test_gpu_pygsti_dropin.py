@@ -174,3 +174,92 @@ def test_gst_fit_reaches_reference_quality():
     mdl = results.estimates["testGST"].models['stdgaugeopt']
     assert isinstance(results.estimates["testGST"].models['final iteration estimate'].sim, B200ForwardSimulator)
     assert two_delta_logl(mdl, ds) <= 0.05
+
+
+def _random_circuits(model, n, max_depth, line_labels, seed=0):
+    rng = np.random.default_rng(seed)
+    prim = list(model.primitive_op_labels)
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(1, max_depth + 1))
+        out.append(pygsti.circuits.Circuit([prim[int(rng.integers(len(prim)))] for _ in range(L)], line_labels=line_labels))
+    return out
+
+
+def test_three_qubit_local_noise_model_d64():
+    """BASELINE config 3 model family: 3-qubit crosstalk-free model (embedded / composed layer ops, tensor-product
+    SPAM -> densified through to_dense at the boundary), d = 64.  probs vs the reference Cython Map simulator; the
+    Jacobian of this model family is pinned against the reference's Matrix simulator by the committed golden
+    fixture c3_3q_localnoise_sub (tests/test_gpu_parity.py)."""
+    from pygsti.processors import QubitProcessorSpec
+    from pygsti.models import modelconstruction as mc
+    pspec = QubitProcessorSpec(3, ['Gxpi2', 'Gypi2', 'Gcnot'], geometry='line')
+    model = mc.create_crosstalk_free_model(pspec, ideal_gate_type='full TP', ideal_spam_type='full TP')
+    v = model.to_vector(); rng = np.random.default_rng(0)
+    model.from_vector(v + 0.01 * rng.standard_normal(v.size))
+    circuits = _random_circuits(model, 40, 40, (0, 1, 2), seed=5)
+    pmap, _ = _bulk_arrays(model, MapForwardSimulator(), circuits, want_jac=False)
+    pb, jb = _bulk_arrays(model, B200ForwardSimulator(), circuits)
+    assert np.max(np.abs(pmap - pb)) <= 1e-10
+    # FD check of the analytic device Jacobian against the reference Map simulator's own finite differences
+    _, jmap = _bulk_arrays(model, MapForwardSimulator(), circuits[:6])
+    n = jmap.shape[0]
+    assert np.max(np.abs(jmap - jb[:n])) <= 2e-5
+
+
+def test_four_qubit_cloud_crosstalk_model_d256():
+    """BASELINE config 5 model family: 4-qubit cloud-crosstalk model, d = 256, NON-dense reference reps
+    (OpCRep_Embedded / Composed / ExpErrorgen, computational POVM; evotype.py:97 prefer_dense_reps = False for
+    dim > 64).  The engine sees them as dense superoperators (to_dense) and must reproduce the reference."""
+    from pygsti.processors import QubitProcessorSpec
+    from pygsti.models import modelconstruction as mc
+    pspec = QubitProcessorSpec(4, ['Gxpi2', 'Gypi2', 'Gcnot'], geometry='line')
+    errs = {('Gxpi2', 0): {('H', 'X'): 0.01, ('S', 'Z'): 0.005}, ('Gypi2', 1): {('H', 'Y'): 0.02, ('S', 'Z'): 0.004},
+            ('Gcnot', 1, 2): {('H', 'ZZ'): 0.01, ('S', 'XX'): 0.003}}
+    model = mc.create_cloud_crosstalk_model(pspec, lindblad_error_coeffs=errs)
+    circuits = _random_circuits(model, 12, 12, (0, 1, 2, 3), seed=7)
+    pmap, _ = _bulk_arrays(model, MapForwardSimulator(), circuits, want_jac=False)
+    pb, _ = _bulk_arrays(model, B200ForwardSimulator(), circuits, want_jac=False)
+    assert pmap.shape == pb.shape and pmap.size == 12 * 16
+    assert np.max(np.abs(pmap - pb)) <= 1e-10
+
+
+@pytest.mark.parametrize("objname", ["chi2", "logl"])
+def test_fused_objective_jacobian_and_jtj(objname):
+    """'next' row 8f-1: dterms / dlsvec with the row scaling fused into the kernel epilogue, and J^T J / J^T f without
+    the Jacobian leaving the device, against the reference objective function evaluated with the reference Map and
+    Matrix simulators."""
+    from pygsti.data import simulate_data
+    from pygsti.objectivefns import objectivefns as _objfns
+    from pygsti_b200 import objective as fused
+    target = smq1Q_XYI.target_model("full TP")
+    # (noise levels chosen so that no lsvec entry sits at 0, where dlsvec = dterms * 0.5 / lsvec is discontinuous:
+    #  there even the reference's own Map and Matrix simulators disagree by O(1e3) in J^T J)
+    datagen = target.depolarize(op_noise=0.1, spam_noise=0.05)
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    ds = simulate_data(datagen, circuits, 1000, seed=1234)
+    start = target.depolarize(op_noise=0.06, spam_noise=0.03)
+    cls = _objfns.Chi2Function if objname == "chi2" else _objfns.PoissonPicDeltaLogLFunction
+
+    def make(sim):
+        m = start.copy(); m.sim = sim
+        return cls.create_from(m, ds, circuits, method_names=('lsvec', 'dlsvec', 'dterms'))
+
+    ref = make(MatrixForwardSimulator())      # independent simulator AND independent layout (element order differs)
+    ours = make(B200ForwardSimulator())
+    same = make(B200ForwardSimulator())       # reference objective-function code path on top of the GPU simulator
+    v = start.to_vector()
+    Jref = ref.dlsvec(v).copy(); fref = ref.lsvec(v).copy()
+    Jsame = same.dlsvec(v).copy(); Dsame = same.dterms(v).copy()
+    Jf = fused.fused_dlsvec(ours, v).copy()
+    Df = fused.fused_dterms(ours, v).copy()
+    # (1) fused row scaling == the reference's host-side `jac *= ...` passes, element by element
+    assert np.max(np.abs(Jf - Jsame)) <= 1e-11 * max(1.0, np.max(np.abs(Jsame)))
+    assert np.max(np.abs(Df - Dsame)) <= 1e-11 * max(1.0, np.max(np.abs(Dsame)))
+    # (2) against the reference objective on the reference's analytic Matrix simulator, through quantities that do not
+    #     depend on the element order of the layout: J^T J and J^T f (what the LM step consumes)
+    JTJ, JTf = fused.fused_jtj(ours, v)
+    R = Jref.T @ Jref
+    assert np.max(np.abs(JTJ - R)) <= 1e-7 * np.max(np.abs(R))
+    assert np.max(np.abs(JTf - Jref.T @ fref)) <= 1e-7 * max(1.0, np.max(np.abs(Jref.T @ fref)))
+    assert np.max(np.abs(Jf.T @ Jf - JTJ)) <= 1e-10 * np.max(np.abs(R))
