@@ -41,3 +41,13 @@ Jp = np.empty((nE, Np))
 for r in range(2):
     t0 = time.time(); at.fill_dprobs(Jp, ph); t1 = time.time()
     print("e2e pageable host dprobs: %.1f ms" % ((t1 - t0) * 1e3))
+# fused objective pieces (8f-1): scaled Jacobian into pinned host memory, and J^T J / J^T f only
+w = np.random.default_rng(0).uniform(0.5, 1.5, nE); f = np.random.default_rng(1).standard_normal(nE)
+for r in range(2):
+    t0 = time.time(); at.fill_dprobs(Jh, row_scale=w); t1 = time.time()
+    print("e2e scaled dprobs (pinned): %.1f ms" % ((t1 - t0) * 1e3))
+for r in range(3):
+    t0 = time.time(); JTJ, JTf = at.jtj(w, f); t1 = time.time()
+    print("e2e J^T J + J^T f (Jacobian stays on the device): %.1f ms" % ((t1 - t0) * 1e3))
+chk = Jh[:, :5].T @ Jh
+print("   max |JTJ[:5] - host| rel = %.2e" % (np.max(np.abs(JTJ[:5] - chk)) / np.max(np.abs(chk))))

@@ -52,3 +52,21 @@ print("C5 sample:", at.info())
 print("  GPU probs  %.2f ms  (%.3e outcomes/s)" % (tp * 1e3, t.n_elements / tp))
 t0 = time.time(); po = orc.mapfill_probs(t, G, rho, E); tc = time.time() - t0
 print("  CPU oracle probs %.1f ms (1 core); max|p-po| = %.2e" % (tc * 1e3, np.max(np.abs(p - po))))
+
+# ---- C5 at BASELINE size: 5000 circuits, depth U{1..128}: FP64 tensor (DMMA) throughput of the level-batched path ----
+import torch
+circs = [(0, [int(x) for x in rng.integers(0, 14, size=int(rng.integers(1, 129)))], list(range(16))) for _ in range(5000)]
+t = synth.make_tables(256, 14, 1, 16, circs, use_cache=False)
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+ctx2 = engine.Context(0, stream=stream.cuda_stream)
+at = ctx2.upload_atom(t); at.set_model(G, rho, E)
+P = torch.empty(t.n_elements, dtype=torch.float64, device="cuda")
+ts = []
+for _ in range(5):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream); at.fill_probs_dev(P.data_ptr()); e1.record(stream); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+info = at.info(); flops = 2.0 * 256 * 256 * info["n_prop_expanded"]
+print("C5 full size:", info)
+print("  GPU probs (device) %.2f ms -> %.2f TFLOP/s FP64 (%.3e outcomes/s); launches/level ~%d levels" % (min(ts), flops / (min(ts) * 1e-3) / 1e12, t.n_elements / (min(ts) * 1e-3), info["max_depth"]))
+po = orc.mapfill_probs(synth.make_tables(256, 14, 1, 16, circs[:40], use_cache=False), G, rho, E)
+print("  max|p - oracle| (first 40 circuits) = %.2e" % np.max(np.abs(P[:po.size].cpu().numpy() - po)))
