@@ -139,6 +139,13 @@ int b200_fill_dprobs_scaled(b200_ctx* ctx, b200_atom* atom, const double* row_sc
                             double* probs_out, int64_t probs_stride);
 int b200_jtj(b200_ctx* ctx, b200_atom* atom, const double* row_scale, const double* f,
              double* jtj_out, double* jtf_out);
+/* Device-buffer variant (asynchronous on the ctx stream; d_row_scale / d_f / d_jtf may be NULL): with one process per
+ * GPU each rank reduces its own element shard and the [n_params x n_params] partial sums are added with ONE
+ * all-reduce (NCCL) -- the analogue of the reference summing per-rank `fill_jtj` blocks through its shared-memory /
+ * MPI reduction (pygsti/layouts/distlayout.py:1220-1359, resourceallocation.py:331-376 allreduce_sum).
+ * See pygsti_b200/dist.py: allreduce_jtj. */
+int b200_jtj_dev(b200_ctx* ctx, b200_atom* atom, const double* d_row_scale, const double* d_f,
+                 double* d_jtj, double* d_jtf);
 
 /* ---- pinned host memory for zero-staging transfers --------------------------------------------- */
 int b200_host_alloc(void** out, int64_t bytes);     /* cudaHostAlloc */

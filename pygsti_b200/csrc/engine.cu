@@ -8,6 +8,7 @@
 #include "kernels_d16_2p.cuh"
 #include "kernels_d16_trie.cuh"
 #include "kernels_level.cuh"
+#include "kernels_levelj.cuh"
 #include <cstdlib>
 #include <cublas_v2.h>
 
@@ -62,6 +63,8 @@ struct b200_ctx {
     DevBuf scratch;      // forward-state scratch of the generic kernels
     DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
     DevBuf lvl_states;   // ping-pong state buffers of the level-batched dense path
+    DevBuf lj_fs, lj_bh; // level-batched Jacobian path: state table / adjoint table (all levels kept)
+    cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
@@ -81,6 +84,12 @@ struct b200_atom {
     bool has_levels = false;
     DevBuf lvl_circ, lvl_tiles;
     std::vector<uint32_t> lvl_tile_ptr;     // [max_depth+1] tile offsets per level (host)
+    // level-batched Jacobian path (d >= 64): row maps of the state / adjoint tables, backward-sweep tiles, D tile plan
+    bool has_lj = false;
+    DevBuf lj_fbase, lj_bbase, lj_frow, lj_brow, lj_btiles, lj_ti_ptr, lj_items;
+    std::vector<uint32_t> lj_btile_ptr;     // [max_depth+1]
+    uint64_t lj_rows_f = 0, lj_rows_b = 0;
+    int lj_no_max = 0, lj_n_tiles = 0;
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
     DevBuf tf_parent, tf_first, tf_len, tf_op, tb_parent, tb_first, tb_len, tb_op, t_fn, t_bn, t_fend, t_bend;
@@ -159,6 +168,10 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release(); c->lvl_states.release();
+    c->lj_fs.release(); c->lj_bh.release();
+    if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     if (c->cublas) cublasDestroy(c->cublas);
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
@@ -350,7 +363,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
     // two-phase d16 tables: scratch rows per circuit = (L+1)*(1+n_out); steps of each circuit sorted by gate
     std::vector<uint32_t> srow; std::vector<uint16_t> bperm, bcnt;
     int64_t scratch_rows = 0;
-    if (dim == 16 && max_depth < 65535) {
+    if ((dim == 16 || dim >= 64) && max_depth < 65535) {
         srow.resize((size_t)n_rows + 1); bperm.resize(cops.size()); bcnt.assign((size_t)n_rows * std::max(n_ops, 1), 0);
         uint64_t acc_rows = 0;
         std::vector<uint32_t> off((size_t)std::max(n_ops, 1) + 1);
@@ -365,7 +378,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             for (uint32_t k = 0; k < L; ++k) bperm[b0 + off[cops[b0 + k]]++] = (uint16_t)k;
         }
         srow[n_rows] = (uint32_t)acc_rows;
-        scratch_rows = (acc_rows < ((uint64_t)1 << 32)) ? (int64_t)acc_rows : 0;   // 0 disables the two-phase path
+        scratch_rows = (dim == 16 && acc_rows < ((uint64_t)1 << 32)) ? (int64_t)acc_rows : 0;   // 0 disables the two-phase path
     }
 
     b200_atom* a = new b200_atom();
@@ -412,6 +425,58 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
         if ((rc = upload_vec(a->lvl_circ, lc, ctx->stream)) || (rc = upload_vec(a->lvl_tiles, tiles, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
         CU(cudaStreamSynchronize(ctx->stream));
         a->has_levels = true;
+        // Jacobian tables: every level is kept.  FS rows fbase[i] + k (k = 0..L), BH rows bbase[i] + o (L+1) + k.
+        uint64_t rows_f = 0, rows_b = 0; int no_max = 0;
+        std::vector<uint32_t> fbase((size_t)n_rows), bbase((size_t)n_rows);
+        for (int64_t i = 0; i < n_rows; ++i) {
+            const uint64_t L = cptr[i + 1] - cptr[i], no = (uint64_t)(coptr[i + 1] - coptr[i]);
+            fbase[i] = (uint32_t)rows_f; bbase[i] = (uint32_t)rows_b;
+            rows_f += L + 1; rows_b += no * (L + 1);
+            no_max = std::max(no_max, (int)no);
+        }
+        if (rows_f < ((uint64_t)1 << 32) - 64 && rows_b < ((uint64_t)1 << 32) - 64 && !bperm.empty() && no_max >= 1) {
+            // forward sweep reuses the level tiles; frow[e] = FS row of the state entering level k for lvl_circ[e]
+            std::vector<uint32_t> frow(lc.size());
+            {
+                size_t e = 0; int64_t nk = n_rows;
+                for (int k = 0; k < max_depth; ++k) {
+                    while (nk > 0 && (int)(cptr[nk] - cptr[nk - 1]) <= k) --nk;
+                    for (int64_t j = 0; j < nk; ++j, ++e) frow[e] = fbase[lc[e]] + (uint32_t)k;
+                }
+            }
+            // backward sweep: level m handles step k = L-1-m of every circuit with L > m; rows are (circuit, outcome)
+            std::vector<uint32_t> brow; brow.reserve((size_t)std::min<uint64_t>(rows_b, (uint64_t)1 << 31));
+            std::vector<LevelTile> btiles;
+            a->lj_btile_ptr.assign((size_t)max_depth + 1, 0);
+            std::vector<std::vector<uint32_t>> rows_by_gate((size_t)n_ops);
+            int64_t nm = n_rows;
+            for (int mlev = 0; mlev < max_depth; ++mlev) {
+                while (nm > 0 && (int)(cptr[nm] - cptr[nm - 1]) <= mlev) --nm;
+                for (auto& v : rows_by_gate) v.clear();
+                for (int64_t i = 0; i < nm; ++i) {
+                    const uint32_t L = cptr[i + 1] - cptr[i];
+                    const int g = cops[cptr[i] + (L - 1 - (uint32_t)mlev)];
+                    const uint32_t no = (uint32_t)(coptr[i + 1] - coptr[i]);
+                    for (uint32_t o = 0; o < no; ++o) rows_by_gate[g].push_back(bbase[i] + o * (L + 1) + (L - (uint32_t)mlev));
+                }
+                a->lj_btile_ptr[mlev] = (uint32_t)btiles.size();
+                for (int g = 0; g < n_ops; ++g) {
+                    const auto& v = rows_by_gate[g];
+                    for (size_t o = 0; o < v.size(); o += 32) {
+                        LevelTile tl; tl.first = (uint32_t)(brow.size() + o); tl.count = (uint16_t)std::min<size_t>(32, v.size() - o);
+                        tl.gate = (uint16_t)g; btiles.push_back(tl);
+                    }
+                    brow.insert(brow.end(), v.begin(), v.end());
+                }
+            }
+            a->lj_btile_ptr[max_depth] = (uint32_t)btiles.size();
+            if ((rc = upload_vec(a->lj_fbase, fbase, ctx->stream)) || (rc = upload_vec(a->lj_bbase, bbase, ctx->stream)) ||
+                (rc = upload_vec(a->lj_frow, frow, ctx->stream)) || (rc = upload_vec(a->lj_brow, brow, ctx->stream)) ||
+                (rc = upload_vec(a->lj_btiles, btiles, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
+            CU(cudaStreamSynchronize(ctx->stream));
+            a->lj_rows_f = rows_f; a->lj_rows_b = rows_b; a->lj_no_max = no_max;
+            a->has_lj = brow.size() < ((size_t)1 << 32);
+        }
     }
     // trie path tables (d = 16, <= 8 effects, <= 255 ops): prefix trie of (prep, ops), suffix trie of reversed ops
     if (dim == 16 && n_eff <= 8 && n_ops <= 255 && n_ops >= 1 && scratch_rows > 0 && xptr[n_rows] < ((uint64_t)1 << 31)) {
@@ -512,7 +577,8 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
-                      &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
+                      &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
+                      &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
                       &a->tb_first, &a->tb_len, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
                       &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
@@ -610,6 +676,37 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
         a->n_spam = (int)spam_col.size();
         if ((rc = upload_vec(a->colmap, colmap, ctx->stream)) || (rc = upload_vec(a->spam_col, spam_col, ctx->stream)) ||
             (rc = upload_vec(a->spam_w, spam_w, ctx->stream))) return rc;
+    }
+    if (a->has_lj) {
+        // tile plan of the level-batched Jacobian path: per (tile of LJ_PT parameters, W-space block) the columns that
+        // have non-zeros in that block, as (p_local, lo, hi) ranges of the CSC arrays (rows are sorted within a column)
+        const int nb = a->n_ops + 1;                       // gate blocks + one block for the prep / effect rows
+        const int n_tiles = std::max(1, (n_params + LJ_PT - 1) / LJ_PT);
+        const int64_t dd = (int64_t)a->dim * a->dim;
+        std::vector<std::vector<uint4>> lists((size_t)n_tiles * nb);
+        for (int p = 0; p < n_params; ++p) {
+            int t = cptr[p];
+            while (t < cptr[p + 1]) {
+                const int b = (crow[t] < a->off_rho) ? (int)(crow[t] / dd) : a->n_ops;
+                int t1 = t + 1;
+                while (t1 < cptr[p + 1] && ((crow[t1] < a->off_rho) ? (int)(crow[t1] / dd) : a->n_ops) == b) ++t1;
+                lists[(size_t)(p / LJ_PT) * nb + b].push_back(make_uint4((unsigned)(p % LJ_PT), (unsigned)t, (unsigned)t1, 0u));
+                t = t1;
+            }
+        }
+        std::vector<uint32_t> ti_ptr((size_t)n_tiles * (nb + 1));
+        std::vector<uint4> items;
+        for (int tl = 0; tl < n_tiles; ++tl) {
+            for (int b = 0; b < nb; ++b) {
+                ti_ptr[(size_t)tl * (nb + 1) + b] = (uint32_t)items.size();
+                const auto& v = lists[(size_t)tl * nb + b];
+                items.insert(items.end(), v.begin(), v.end());
+            }
+            ti_ptr[(size_t)tl * (nb + 1) + nb] = (uint32_t)items.size();
+        }
+        if (items.empty()) items.push_back(make_uint4(0, 0, 0, 0));
+        a->lj_n_tiles = n_tiles;
+        if ((rc = upload_vec(a->lj_ti_ptr, ti_ptr, ctx->stream)) || (rc = upload_vec(a->lj_items, items, ctx->stream))) return rc;
     }
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_derivs = true;
@@ -717,11 +814,13 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_H.as<double>(), (size_t)a->n_bnodes * a->n_eff * 16);
     c->launches += 2;
-    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
+    const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     CU(cudaFuncSetAttribute(k_accum_trie_d16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-    int gA = 2 * c->sm_count * 4;                  // even = forward trie, odd = backward trie
+    static int chain_ctas = -1;                    // CTAs per SM and role (dev knob B200_CHAIN_CTAS)
+    if (chain_ctas < 0) { const char* e = getenv("B200_CHAIN_CTAS"); chain_ctas = (e && atoi(e) > 0) ? atoi(e) : 4; }
+    int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
     k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 0);
     int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
     const int dbg = getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0;
@@ -826,7 +925,7 @@ static int launch_probs_level(b200_ctx* c, b200_atom* a, double* d_out) {
     for (int k = 0; k < a->max_depth; ++k) {
         const uint32_t t0 = a->lvl_tile_ptr[k], t1 = a->lvl_tile_ptr[k + 1];
         if (t1 == t0) continue;
-        k_level_gemm<D><<<t1 - t0, 128, smem, c->stream>>>(M, a->lvl_tiles.as<LevelTile>() + t0, a->lvl_circ.as<uint32_t>(),
+        k_level_gemm<D><<<dim3(t1 - t0, D / 64), 128, smem, c->stream>>>(M, a->lvl_tiles.as<LevelTile>() + t0, a->lvl_circ.as<uint32_t>(),
                                                            (k & 1) ? S1 : S0, (k & 1) ? S0 : S1);
         c->launches++;
     }
@@ -846,7 +945,7 @@ static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
     c->launches++;
-    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)TRIE_WARPS * 32 * 8;
+    const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 1);
     int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 15) / 16, (int64_t)c->sm_count * 8));
@@ -867,6 +966,74 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
         if (a->dim == 256) return launch_probs_level<256>(c, a, d_out);
     }
     return launch_probs(c, a, a->M.as<double>(), a->Gt.as<double>(), 1, d_out, 1, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// level-batched Jacobian (d >= 64): forward sweep || backward sweep (two streams), then the sparse contraction
+// ------------------------------------------------------------------------------------------------
+static int levelj_ts(b200_ctx* c, b200_atom* a, size_t* smem_out) {
+    const size_t acc = (size_t)a->lj_no_max * LJ_PT * 8;
+    const size_t per_ts = (size_t)(1 + a->lj_no_max) * a->dim * 8;
+    int ts = 8;
+    while (ts > 1 && acc + ts * per_ts + (size_t)a->lj_no_max * 8 > (size_t)64 * 1024) --ts;
+    const size_t smem = acc + ts * per_ts + (size_t)a->lj_no_max * 8 + 16;
+    if (smem_out) *smem_out = smem;
+    return (smem + 1024 <= c->smem_optin) ? ts : 0;
+}
+static bool levelj_ok(b200_ctx* c, b200_atom* a) {
+    return a->has_lj && a->has_levels && (a->dim == 64 || a->dim == 256) && !getenv("B200_NO_LEVELJ") &&
+           (int64_t)a->n_rows * std::max(a->lj_n_tiles, 1) < ((int64_t)1 << 31) && levelj_ts(c, a, nullptr) > 0;
+}
+template <int D>
+static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
+    if (a->n_rows == 0) return B200_OK;
+    CU(c->lj_fs.ensure((size_t)a->lj_rows_f * D * 8));
+    CU(c->lj_bh.ensure((size_t)a->lj_rows_b * D * 8));
+    if (!c->aux) {
+        CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    LevelJDev lj;
+    lj.fbase = a->lj_fbase.as<uint32_t>(); lj.bbase = a->lj_bbase.as<uint32_t>();
+    lj.bperm = a->bperm.as<uint16_t>(); lj.bcnt = a->bcnt.as<uint16_t>();
+    lj.ti_ptr = a->lj_ti_ptr.as<uint32_t>(); lj.items = a->lj_items.as<uint4>();
+    lj.crow = a->crow.as<int32_t>(); lj.cval = a->cval.as<double>();
+    lj.FS = c->lj_fs.as<double>(); lj.BH = c->lj_bh.as<double>();
+    lj.n_tiles = a->lj_n_tiles; lj.n_params = a->n_params; lj.no_max = a->lj_no_max;
+    size_t smemC = 0;
+    lj.ts = levelj_ts(c, a, &smemC);
+    const AtomDev ad = atom_dev(a); const ModelDev md = model_dev(a);
+    int gi = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 3) / 4, (int64_t)c->sm_count * 8));
+    k_levelj_init<D><<<gi, 128, 0, c->stream>>>(ad, md, lj);
+    c->launches++;
+    const size_t smem = (size_t)32 * (D + 4) * sizeof(double);
+    CU(cudaFuncSetAttribute(k_level_gemm_rows<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool serial = getenv("B200_LJ_SERIAL") != nullptr;
+    cudaStream_t sb = serial ? c->stream : c->aux;
+    if (!serial) { CU(cudaEventRecord(c->ev_fork, c->stream)); CU(cudaStreamWaitEvent(sb, c->ev_fork, 0)); }
+    for (int k = 0; k < a->max_depth; ++k) {          // forward sweep: FS[row + 1] = G FS[row]
+        const uint32_t t0 = a->lvl_tile_ptr[k], t1 = a->lvl_tile_ptr[k + 1];
+        if (t1 > t0) {
+            k_level_gemm_rows<D><<<dim3(t1 - t0, D / 64), 128, smem, c->stream>>>(md.M, a->lvl_tiles.as<LevelTile>() + t0, a->lj_frow.as<uint32_t>(), lj.FS, +1);
+            c->launches++;
+        }
+        const uint32_t b0 = a->lj_btile_ptr[k], b1 = a->lj_btile_ptr[k + 1];
+        if (b1 > b0) {                                 // backward sweep (other stream): BH[row - 1] = G^T BH[row]
+            k_level_gemm_rows<D><<<dim3(b1 - b0, D / 64), 128, smem, sb>>>(md.Gt, a->lj_btiles.as<LevelTile>() + b0, a->lj_brow.as<uint32_t>(), lj.BH, -1);
+            c->launches++;
+        }
+    }
+    if (!serial) { CU(cudaEventRecord(c->ev_join, sb)); CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); }
+    if (d_probs) {
+        k_levelj_probs<D><<<gi, 128, 0, c->stream>>>(ad, md, lj, d_probs);
+        c->launches++;
+    }
+    CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    k_level_accum<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC, c->stream>>>(ad, md, lj, d_out, ld, d_scale);
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
 }
 
 // Jacobian into a device buffer; d_scale (device, [n_elements]) or nullptr
@@ -896,6 +1063,8 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
         }
         return B200_OK;
     }
+    if (levelj_ok(c, a))
+        return a->dim == 64 ? launch_levelj<64>(c, a, d_out, ld, d_probs, d_scale) : launch_levelj<256>(c, a, d_out, ld, d_probs, d_scale);
     // general path: W then J = W . D
     CU(c->w_buf.ensure((size_t)a->n_elements * a->n_w * sizeof(double)));
     int rc = compute_w(c, a, c->w_buf.as<double>(), d_probs);
@@ -985,20 +1154,13 @@ extern "C" int b200_fill_dprobs_scaled(b200_ctx* c, b200_atom* a, const double* 
 #define CB(x) do { cublasStatus_t s_ = (x); if (s_ != CUBLAS_STATUS_SUCCESS) \
     return fail(B200_E_CUDA, "%s failed: cublas status %d (%s:%d)", #x, (int)s_, __FILE__, __LINE__); } while (0)
 
-extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, const double* f, double* jtj_out, double* jtf_out) {
-    if (!c || !a || !jtj_out) return fail(B200_E_INVALID, "NULL argument");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
-    if (jtf_out && !f) return fail(B200_E_INVALID, "jtf_out requires f");
-    CU(cudaSetDevice(c->device));
+// J^T J (full symmetric, row-major) and J^T f into DEVICE buffers; everything asynchronous on the ctx stream
+static int jtj_device(b200_ctx* c, b200_atom* a, const double* d_scale, const double* d_f, double* d_jtj, double* d_jtf) {
     const int Np = a->n_params; const int64_t nE = a->n_elements;
     if (Np == 0) return B200_OK;
     if (nE >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "too many elements for the BLAS call");
     CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * Np * 8, 16)));
-    CU(c->jtj_buf.ensure((size_t)Np * Np * 8));
-    const double* d_scale = nullptr;
-    int rc = upload_scale(c, a, row_scale, &d_scale);
-    if (rc) return rc;
-    rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), Np, nullptr, d_scale);
+    int rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), Np, nullptr, d_scale);
     if (rc) return rc;
     if (!c->cublas) { CB(cublasCreate(&c->cublas)); }
     CB(cublasSetStream(c->cublas, c->stream));
@@ -1006,31 +1168,59 @@ extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, cons
     const double one = 1.0, zero = 0.0;
     if (nE > 0) {
         CB(cublasDsyrk(c->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, &zero,
-                       c->jtj_buf.as<double>(), Np));
+                       d_jtj, Np));
         dim3 blk(16, 16), grd((Np + 15) / 16, (Np + 15) / 16);
         // column-major lower triangle == row-major upper triangle: mirror it
-        k_symmetrize<<<grd, blk, 0, c->stream>>>(c->jtj_buf.as<double>(), Np);
+        k_symmetrize<<<grd, blk, 0, c->stream>>>(d_jtj, Np);
         c->launches += 2;
     } else {
-        CU(cudaMemsetAsync(c->jtj_buf.p, 0, (size_t)Np * Np * 8, c->stream));
+        CU(cudaMemsetAsync(d_jtj, 0, (size_t)Np * Np * 8, c->stream));
     }
+    if (d_jtf) {
+        if (nE > 0) {
+            CB(cublasDgemv(c->cublas, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, d_f, 1, &zero, d_jtf, 1));
+            c->launches++;
+        } else {
+            CU(cudaMemsetAsync(d_jtf, 0, (size_t)Np * 8, c->stream));
+        }
+    }
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, const double* f, double* jtj_out, double* jtf_out) {
+    if (!c || !a || !jtj_out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (jtf_out && !f) return fail(B200_E_INVALID, "jtf_out requires f");
+    CU(cudaSetDevice(c->device));
+    const int Np = a->n_params; const int64_t nE = a->n_elements;
+    if (Np == 0) return B200_OK;
+    CU(c->jtj_buf.ensure((size_t)Np * Np * 8));
+    const double* d_scale = nullptr;
+    int rc = upload_scale(c, a, row_scale, &d_scale);
+    if (rc) return rc;
+    double* d_f = nullptr; double* d_jtf = nullptr;
     if (jtf_out) {
         CU(c->f_buf.ensure(std::max<size_t>((size_t)nE * 8, 16)));
         CU(c->jtf_buf.ensure((size_t)Np * 8));
-        if (nE > 0) {
-            CU(cudaMemcpyAsync(c->f_buf.p, f, (size_t)nE * 8, cudaMemcpyHostToDevice, c->stream));
-            CB(cublasDgemv(c->cublas, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, c->f_buf.as<double>(), 1, &zero,
-                           c->jtf_buf.as<double>(), 1));
-            c->launches++;
-        } else {
-            CU(cudaMemsetAsync(c->jtf_buf.p, 0, (size_t)Np * 8, c->stream));
-        }
-        CU(cudaMemcpyAsync(jtf_out, c->jtf_buf.p, (size_t)Np * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (nE > 0) CU(cudaMemcpyAsync(c->f_buf.p, f, (size_t)nE * 8, cudaMemcpyHostToDevice, c->stream));
+        d_f = c->f_buf.as<double>(); d_jtf = c->jtf_buf.as<double>();
     }
-    CU(cudaGetLastError());
+    rc = jtj_device(c, a, d_scale, d_f, c->jtj_buf.as<double>(), d_jtf);
+    if (rc) return rc;
+    if (jtf_out) CU(cudaMemcpyAsync(jtf_out, c->jtf_buf.p, (size_t)Np * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(jtj_out, c->jtj_buf.p, (size_t)Np * Np * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
+}
+
+extern "C" int b200_jtj_dev(b200_ctx* c, b200_atom* a, const double* d_row_scale, const double* d_f, double* d_jtj, double* d_jtf) {
+    if (!c || !a || !d_jtj) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (d_jtf && !d_f) return fail(B200_E_INVALID, "d_jtf requires d_f");
+    CU(cudaSetDevice(c->device));
+    return jtj_device(c, a, d_row_scale, d_f, d_jtj, d_jtf);
 }
 
 extern "C" int b200_fill_dprobs_fd(b200_ctx* c, b200_atom* a, double eps, double* out, int64_t row_stride,

@@ -55,39 +55,67 @@ __global__ void k_fill_sentinel(double* __restrict__ p, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = s;
 }
 
-// dynamic smem: n_ops*256 doubles (backward B fragments) + n_ops*256 doubles (forward fragments)
+// Work hand-out with a two-deep software pipeline: a warp always holds the index of its next chain (`n1`, metadata
+// already loaded) and has the atomicAdd for the one after (`n2`) in flight while it walks the current chain -- with
+// ~2.5 nodes per chain on GST layouts the atomic + metadata round trips (~2 us) were most of the per-chain time.
+// Deadlock freedom is unchanged: a warp processes the chains it holds in increasing index order and a chain only waits
+// for a chain with a smaller index.
+struct ChainMeta { int parent; uint32_t first, len; };
+__device__ __forceinline__ ChainMeta chain_meta(const int32_t* par, const uint32_t* fst, const uint32_t* ln, int ci, int n) {
+    ChainMeta mt; mt.parent = 0; mt.first = 0; mt.len = 0;
+    if (ci < n) { mt.parent = __ldg(par + ci); mt.first = __ldg(fst + ci); mt.len = __ldg(ln + ci); }
+    return mt;
+}
+
+// dynamic smem: n_ops*256 doubles (the CTA's role: backward B fragments or forward fragments)
 //               + TRIE_WARPS*2*16 doubles (forward exchange)
 __global__ void __launch_bounds__(TRIE_WARPS * 32)
 k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
 {
     extern __shared__ __align__(16) double smt[];
-    double* bfrag = smt;
-    double* ffrag = bfrag + a.n_ops * 256;
-    double* fx_all = ffrag + a.n_ops * 256;
+    double* frag = smt;
+    double* fx_all = frag + a.n_ops * 256;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const double* G = m.M;
     const double* rho = m.M + m.off_rho;
     const double* E = m.M + m.off_eff;
+    const int role = fwd_only ? 0 : (blockIdx.x & 1);      // 0: forward trie, 1: backward trie
     for (int idx = threadIdx.x; idx < a.n_ops * 256; idx += blockDim.x) {
         const int g = idx >> 8, r = (idx >> 5) & 7, l = idx & 31;
-        const int tt = r >> 1, u = r & 1, mr = l >> 2, q = l & 3;
-        const int kk = (tt >> 1) * 8 + 2 * q + (tt & 1);
-        bfrag[idx] = G[g * 256 + kk * 16 + 8 * u + mr];
-        ffrag[idx] = G[g * 256 + (l & 15) * 16 + (l >> 4) * 8 + r];
+        if (role) {
+            const int tt = r >> 1, u = r & 1, mr = l >> 2, q = l & 3;
+            const int kk = (tt >> 1) * 8 + 2 * q + (tt & 1);
+            frag[idx] = G[g * 256 + kk * 16 + 8 * u + mr];
+        } else {
+            frag[idx] = G[g * 256 + (l & 15) * 16 + (l >> 4) * 8 + r];
+        }
     }
     __syncthreads();
 
-    const int role = fwd_only ? 0 : (blockIdx.x & 1);      // 0: forward trie, 1: backward trie
+    unsigned* ctr = t.counters + role;
+    const int n_chains = role ? t.n_bchains : t.n_fchains;
+    const int32_t* c_par = role ? t.b_parent : t.f_parent;
+    const uint32_t* c_first = role ? t.b_first : t.f_first;
+    const uint32_t* c_len = role ? t.b_len : t.f_len;
+    // pipeline prologue (lane 0 owns the raw atomic results; they are broadcast one iteration later)
+    int n1 = 0, n2raw = 0;
+    if (lane == 0) n1 = (int)atomicAdd(ctr, 1u);
+    n1 = __shfl_sync(0xffffffffu, n1, 0);
+    if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
+    ChainMeta m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
+
     if (role == 0) {
+        const double* ffrag = frag;
         double* fx = fx_all + warp * 32;
         const int half = lane >> 4;
         for (;;) {
-            int ci = 0;
-            if (lane == 0) ci = (int)atomicAdd(t.counters + 0, 1u);
-            ci = __shfl_sync(0xffffffffu, ci, 0);
-            if (ci >= t.n_fchains) break;
-            const int parent = t.f_parent[ci];
-            const uint32_t first = t.f_first[ci], len = t.f_len[ci];
+            const int ci = n1;
+            if (ci >= n_chains) break;
+            const int parent = m1.parent;
+            const uint32_t first = m1.first, len = m1.len;
+            n1 = __shfl_sync(0xffffffffu, n2raw, 0);
+            if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
+            m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
             double v = 0.0;
             uint32_t i0 = 0;
             if (parent < 0) {                       // root chain: first node is the prep itself
@@ -120,16 +148,18 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
             }
         }
     } else {
+        const double* bfrag = frag;
         const int mrow = lane >> 2, q = lane & 3;
         const int ne = a.n_eff;
         const bool rowok = mrow < ne;
         for (;;) {
-            int ci = 0;
-            if (lane == 0) ci = (int)atomicAdd(t.counters + 1, 1u);
-            ci = __shfl_sync(0xffffffffu, ci, 0);
-            if (ci >= t.n_bchains) break;
-            const int parent = t.b_parent[ci];
-            const uint32_t first = t.b_first[ci], len = t.b_len[ci];
+            const int ci = n1;
+            if (ci >= n_chains) break;
+            const int parent = m1.parent;
+            const uint32_t first = m1.first, len = m1.len;
+            n1 = __shfl_sync(0xffffffffu, n2raw, 0);
+            if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
+            m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             uint32_t i0 = 0;
             if (parent < 0) {                       // root: E itself

@@ -38,7 +38,7 @@ k_level_gemm(const double* __restrict__ G, const LevelTile* __restrict__ tiles, 
              const double* __restrict__ Sin, double* __restrict__ Sout)
 {
     constexpr int LDS_ = D + 4;                 // row stride (doubles): (D+4) mod 16 = 4 -> conflict-free fragment loads
-    constexpr int NT = D / 32;                  // n-tiles (of 8 outputs) per warp
+    constexpr int NT = 2;                       // n-tiles (of 8 outputs) per warp: a CTA owns 64 outputs (blockIdx.y)
     extern __shared__ __align__(16) double st[];   // [32][LDS_]
     const LevelTile tl = tiles[blockIdx.x];
     const uint32_t* circ = lvl_circ + tl.first;
@@ -54,7 +54,7 @@ k_level_gemm(const double* __restrict__ G, const LevelTile* __restrict__ tiles, 
     }
     __syncthreads();
     const int mrow = lane >> 2, q = lane & 3;
-    const int n0 = warp * (D / 4);              // this warp's output components [n0, n0 + D/4)
+    const int n0 = blockIdx.y * 64 + warp * 16; // this warp's output components [n0, n0 + 16)
     double acc[4][NT][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)

@@ -1,0 +1,236 @@
+// kernels_levelj.cuh -- analytic Jacobian for large superoperators (d = 64, 256): level-batched forward AND backward
+// sweeps on the FP64 tensor cores, then a sparse contraction with the member-derivative map.  This is the dprobs
+// path of BASELINE configs 3 (3 qubits, d = 64, 50 k random circuits) and 5 (4 qubits, d = 256).
+//
+// Same mathematics as the d = 16 kernels (== MatrixForwardSimulator._dprobs_from_rho_e,
+// pygsti/forwardsims/matrixforwardsim.py:1059-1139):
+//     s_0 = rho, s_{k+1} = G_{ops[k]} s_k;      e^(L) = E_j, e^(k) = G_{ops[k]}^T e^(k+1)
+//     J[el, p] = sum_k sum_{(i,j) in nz(dG_{ops[k]}/dp)} v e^(k+1)[i] s_k[j]  + sum_i dRho_i/dp e^(0)[i] + sum_i dE_i/dp s_L[i]
+// but organised for matrices that do not fit in shared memory:
+//   phase F  k_level_gemm_rows<D> (forward):  one launch per depth level; the circuits whose layer at that level is
+//            gate g form a dense product (tiles of 32 rows) exactly as in kernels_level.cuh, except that EVERY level is
+//            kept: state table FS[fbase[c] + k][D].
+//   phase B  the same kernel on the transposed gates: rows are (circuit, outcome) pairs, level m handles step
+//            k = L-1-m of every circuit with L > m: table BH[bbase[c] + o (L+1) + k][D].
+//   phase C  k_level_accum<D>: one CTA per (circuit, tile of PT parameters).  Gate by gate, the circuit's steps that
+//            apply that gate are staged in shared memory (s_k and e^(k+1) of every outcome); each thread owns a
+//            (parameter, outcome) pair and walks the non-zeros of that parameter's column of D inside the gate's block.
+//            Parameters shared by several gates (e.g. one `Gxpi2` on three qubits) accumulate in shared memory, so every
+//            Jacobian entry is written exactly once, in a fixed order (deterministic), coalesced along p, with the
+//            objective-function row scale applied in the same store.
+// The W matrix (n_elements x n_ops d^2) of the correctness-first generic path is never formed.
+#pragma once
+#include "common.cuh"
+#include "kernels_level.cuh"
+
+#define LJ_PT 256          // parameters per accumulate tile
+#define LJ_THREADS 128
+
+struct LevelJDev {
+    const uint32_t* fbase;     // [n_circ] first FS row of the circuit (rows fbase + 0..L)
+    const uint32_t* bbase;     // [n_circ] first BH row (rows bbase + o*(L+1) + 0..L)
+    const uint16_t* bperm;     // [n_prop] per circuit: step indices sorted by gate
+    const uint16_t* bcnt;      // [n_circ][n_ops] bucket sizes
+    const uint32_t* ti_ptr;    // [n_tiles][n_ops + 2] item ranges per (tile, gate); slot n_ops = SPAM rows
+    const uint4* items;        // (p_local, nz lo, nz hi, 0) into crow / cval
+    const int32_t* crow;       // CSC rows of D (W-space index)
+    const double* cval;
+    double* FS; double* BH;
+    int n_tiles, n_params, no_max, ts;
+};
+
+// FS[fbase[c]] = rho[prep_c];  BH[bbase[c] + o (L+1) + L] = E[eff_o]
+template <int D>
+__global__ void __launch_bounds__(128)
+k_levelj_init(AtomDev a, ModelDev m, LevelJDev lj)
+{
+    const double* rho = m.M + m.off_rho;
+    const double* E = m.M + m.off_eff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * 4 + warp; c < a.n_circ; c += gridDim.x * 4) {
+        const uint32_t L = a.circ_ptr[c + 1] - a.circ_ptr[c];
+        double* f = lj.FS + (size_t)lj.fbase[c] * D;
+        const double* r = rho + (size_t)a.circ_prep[c] * D;
+        for (int i = lane; i < D; i += 32) f[i] = r[i];
+        const int q0 = a.out_ptr[c], nout = a.out_ptr[c + 1] - q0;
+        for (int o = 0; o < nout; ++o) {
+            double* h = lj.BH + ((size_t)lj.bbase[c] + (size_t)o * (L + 1) + L) * D;
+            const double* e = E + (size_t)a.out_eff[q0 + o] * D;
+            for (int i = lane; i < D; i += 32) h[i] = e[i];
+        }
+    }
+}
+
+// One level of a sweep: T[rows[e] + delta] = Gm_g . T[rows[e]]  for the 32 rows of a tile (Gm = G forward, G^T backward).
+// dynamic smem: 32 * (D + 4) doubles
+template <int D>
+__global__ void __launch_bounds__(128)
+k_level_gemm_rows(const double* __restrict__ Gm, const LevelTile* __restrict__ tiles, const uint32_t* __restrict__ rows,
+                  double* __restrict__ T, int delta)
+{
+    constexpr int LDS_ = D + 4;
+    constexpr int NT = 2;                       // a CTA owns 64 output components (blockIdx.y selects which)
+    extern __shared__ __align__(16) double st[];
+    const LevelTile tl = tiles[blockIdx.x];
+    const uint32_t* rw = rows + tl.first;
+    const int cnt = tl.count;
+    const double* Gg = Gm + (size_t)tl.gate * D * D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int idx = threadIdx.x; idx < 32 * (D / 2); idx += blockDim.x) {
+        const int r = idx / (D / 2), j2 = idx - r * (D / 2);
+        double2 v = make_double2(0.0, 0.0);
+        if (r < cnt) v = *reinterpret_cast<const double2*>(T + (size_t)rw[r] * D + 2 * j2);
+        *reinterpret_cast<double2*>(st + r * LDS_ + 2 * j2) = v;
+    }
+    __syncthreads();
+    const int mrow = lane >> 2, q = lane & 3;
+    const int n0 = blockIdx.y * 64 + warp * 16;
+    double acc[4][NT][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+    const double* bp = Gg + (size_t)(n0 + mrow) * D + q;
+    const double* ap = st + mrow * LDS_ + q;
+#pragma unroll 2
+    for (int k0 = 0; k0 < D; k0 += 4) {
+        double af[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + k0];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double b = __ldg(bp + (size_t)nt * 8 * D + k0);
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], b);
+        }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const int r = mt * 8 + mrow;
+        if (r < cnt) {
+            double* op = T + (size_t)((int64_t)rw[r] + delta) * D + n0 + 2 * q;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                *reinterpret_cast<double2*>(op + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        }
+    }
+}
+
+// probabilities from the state table: p_el = E_e . s_L  (one warp per circuit)
+template <int D>
+__global__ void __launch_bounds__(128)
+k_levelj_probs(AtomDev a, ModelDev m, LevelJDev lj, double* __restrict__ out)
+{
+    const double* E = m.M + m.off_eff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * 4 + warp; c < a.n_circ; c += gridDim.x * 4) {
+        const uint32_t L = a.circ_ptr[c + 1] - a.circ_ptr[c];
+        const double* s = lj.FS + ((size_t)lj.fbase[c] + L) * D;
+        for (int qo = a.out_ptr[c]; qo < a.out_ptr[c + 1]; ++qo) {
+            const double* e = E + (size_t)a.out_eff[qo] * D;
+            double part = 0.0;
+#pragma unroll
+            for (int i = lane; i < D; i += 32) part += e[i] * s[i];
+#pragma unroll
+            for (int mk = 16; mk > 0; mk >>= 1) part += shfl_xor_f64(part, mk);
+            if (lane == 0) out[a.out_el[qo]] = part;
+        }
+    }
+}
+
+// phase C.  dynamic smem (doubles): no_max * LJ_PT  (accumulators)  +  ts * D  (states)  +  no_max * (ts * D + 1)  (adjoints)
+template <int D>
+__global__ void __launch_bounds__(LJ_THREADS)
+k_level_accum(AtomDev a, ModelDev m, LevelJDev lj, double* __restrict__ J, int64_t ld, const double* __restrict__ row_scale)
+{
+    extern __shared__ __align__(16) double sml[];
+    const int TS = lj.ts;
+    const int ES = TS * D + 1;                       // outcome stride of the adjoint stage (odd: consecutive outcomes -> different banks)
+    double* Jacc = sml;                              // [no_max][LJ_PT]
+    double* s_st = Jacc + (size_t)lj.no_max * LJ_PT; // [TS][D]
+    double* e_st = s_st + (size_t)TS * D;            // [no_max][ES]
+    const int c = blockIdx.x / lj.n_tiles, tile = blockIdx.x - c * lj.n_tiles;
+    const int tid = threadIdx.x;
+    const int q0 = a.out_ptr[c], nout = a.out_ptr[c + 1] - q0;
+    const uint32_t p0 = a.circ_ptr[c], Lc = a.circ_ptr[c + 1] - p0;
+    const size_t fb = lj.fbase[c], bb = lj.bbase[c];
+    const int tile_p0 = tile * LJ_PT;
+    const int tile_np = (lj.n_params - tile_p0 < LJ_PT) ? lj.n_params - tile_p0 : LJ_PT;
+    const uint32_t* tp = lj.ti_ptr + (size_t)tile * (a.n_ops + 2);
+    const uint16_t* cn = lj.bcnt + (size_t)c * a.n_ops;
+    const uint16_t* perm = lj.bperm + p0;
+
+    for (int idx = tid; idx < nout * LJ_PT; idx += LJ_THREADS) Jacc[idx] = 0.0;
+    uint32_t tb = 0;
+    for (int g = 0; g < a.n_ops; ++g) {
+        const int cnt = cn[g];
+        const uint32_t it0 = tp[g], it1 = tp[g + 1];
+        if (cnt > 0 && it1 > it0) {
+            const int gbase = g * D * D;
+            const int nwork = (int)(it1 - it0) * nout;
+            for (int s0 = 0; s0 < cnt; s0 += TS) {
+                const int ns = (cnt - s0 < TS) ? cnt - s0 : TS;
+                __syncthreads();                                  // consumers of the previous stage are done
+                for (int idx = tid; idx < (1 + nout) * ns * D; idx += LJ_THREADS) {
+                    const int row = idx / D, col = idx - row * D;
+                    if (row < ns) {
+                        const uint32_t k = perm[tb + s0 + row];
+                        s_st[row * D + col] = lj.FS[(fb + k) * D + col];
+                    } else {
+                        const int r2 = row - ns, o = r2 / ns, ts = r2 - o * ns;
+                        const uint32_t k = perm[tb + s0 + ts];
+                        e_st[o * ES + ts * D + col] = lj.BH[(bb + (size_t)o * (Lc + 1) + k + 1) * D + col];
+                    }
+                }
+                __syncthreads();
+                for (int w = tid; w < nwork; w += LJ_THREADS) {
+                    const int it = w / nout, o = w - it * nout;
+                    const uint4 item = __ldg(lj.items + it0 + it);
+                    const double* eo = e_st + o * ES;
+                    double acc = 0.0;
+                    for (uint32_t t = item.y; t < item.z; ++t) {
+                        const int wl = __ldg(lj.crow + t) - gbase;
+                        const int i = wl / D, j = wl - i * D;
+                        double tacc = 0.0;
+                        for (int ts = 0; ts < ns; ++ts) tacc = fma(eo[ts * D + i], s_st[ts * D + j], tacc);
+                        acc = fma(__ldg(lj.cval + t), tacc, acc);
+                    }
+                    Jacc[o * LJ_PT + item.x] += acc;
+                }
+            }
+        }
+        tb += cnt;
+    }
+    __syncthreads();
+    {   // state-preparation and effect rows of D
+        const uint32_t it0 = tp[a.n_ops], it1 = tp[a.n_ops + 1];
+        const int nwork = (int)(it1 - it0) * nout;
+        const int prep = a.circ_prep[c];
+        const double* sL = lj.FS + (fb + Lc) * D;
+        for (int w = tid; w < nwork; w += LJ_THREADS) {
+            const int it = w / nout, o = w - it * nout;
+            const uint4 item = __ldg(lj.items + it0 + it);
+            const int eff = a.out_eff[q0 + o];
+            const double* e0 = lj.BH + (bb + (size_t)o * (Lc + 1)) * D;
+            double acc = 0.0;
+            for (uint32_t t = item.y; t < item.z; ++t) {
+                const int64_t wl = __ldg(lj.crow + t);
+                if (wl < m.off_eff) {
+                    const int r = (int)((wl - m.off_rho) / D), i = (int)((wl - m.off_rho) - (int64_t)r * D);
+                    if (r == prep) acc = fma(__ldg(lj.cval + t), e0[i], acc);
+                } else {
+                    const int r = (int)((wl - m.off_eff) / D), i = (int)((wl - m.off_eff) - (int64_t)r * D);
+                    if (r == eff) acc = fma(__ldg(lj.cval + t), sL[i], acc);
+                }
+            }
+            Jacc[o * LJ_PT + item.x] += acc;
+        }
+    }
+    __syncthreads();
+    for (int o = 0; o < nout; ++o) {
+        const int64_t el = a.out_el[q0 + o];
+        const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
+        double* Jr = J + el * ld + tile_p0;
+        for (int p = tid; p < tile_np; p += LJ_THREADS) __stcs(Jr + p, Jacc[o * LJ_PT + p] * sc);
+    }
+}

@@ -163,6 +163,12 @@ class Atom:
         _lib.check(self._lib.b200_jtj(self.ctx._h, self._h, _ptr(sc), _ptr(fv), _ptr(JTJ), _ptr(JTf)))
         return JTJ, JTf
 
+    def jtj_dev(self, d_jtj, d_row_scale=0, d_f=0, d_jtf=0):
+        """Device-pointer variant of :meth:`jtj` (asynchronous on the ctx stream): partial J^T J [n_params^2] / J^T f of
+        this atom's element shard, ready for an all-reduce over ranks (``pygsti_b200.dist.allreduce_jtj``)."""
+        _lib.check(self._lib.b200_jtj_dev(self.ctx._h, self._h, C.c_void_p(d_row_scale or None), C.c_void_p(d_f or None),
+                                          C.c_void_p(d_jtj), C.c_void_p(d_jtf or None)))
+
     def fill_dprobs_fd(self, out, eps=1e-7, probs_out=None):
         rs = self._mat_stride(out)
         ps = self._vec_stride(probs_out, self.n_elements) if probs_out is not None else 1

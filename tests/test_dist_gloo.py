@@ -65,3 +65,44 @@ def test_shards_cover_every_element_once_full_layout():
     assert max(loads) <= 1.1 * (sum(loads) / 8)
     local, glob = bd.shard_tables(t, 3, 8, rows=rows[3])
     assert local.n_elements == glob.shape[0] and len(np.unique(glob)) == glob.shape[0]
+
+
+def _worker_jtj(rank, world, port, name, q):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pygsti_b200.fixtures import Case
+    from pygsti_b200 import dist as bd
+    from oracle import oracle_np as onp
+    c = Case(name)
+    a = c.atoms[0]
+    local, glob = bd.shard_tables(a["tables"], rank, world)
+    rs = np.random.default_rng(0).uniform(0.5, 1.5, c.n_elements)      # same on every rank
+    f = np.random.default_rng(1).standard_normal(c.n_elements)
+    J = onp.dprobs_analytic(local, a["G"], a["rho"], a["E"], a["D"]) * rs[glob][:, None]
+    jtj = torch.from_numpy(J.T @ J)
+    jtf = torch.from_numpy(J.T @ f[glob])
+    bd.allreduce_jtj(jtj, jtf)
+    Jfull = c["dprobs_matrix"] * rs[:, None]
+    e1 = float(np.max(np.abs(jtj.numpy() - Jfull.T @ Jfull)) / np.max(np.abs(Jfull.T @ Jfull)))
+    e2 = float(np.max(np.abs(jtf.numpy() - Jfull.T @ f)) / np.max(np.abs(Jfull.T @ f)))
+    q.put((rank, e1, e2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_jtj_allreduce():
+    """Sharded J^T J / J^T f: each rank reduces its element shard, one all-reduce adds the partial sums."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker_jtj, args=(r, 2, port, "c1_1q_full", q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, e1, e2 in res:
+        assert e1 <= 1e-12 and e2 <= 1e-12, res

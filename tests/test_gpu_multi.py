@@ -38,7 +38,18 @@ def _worker(rank, world, port, name, q):
     e1 = float(np.max(np.abs(Pf.cpu().numpy()[::st] - c["probs_map_sample"])))
     rows = torch.as_tensor(c["dprobs_matrix_sample_elements"], device="cuda")
     e2 = float(np.max(np.abs(Jf[rows].cpu().numpy() - c["dprobs_matrix_sample_rows"])))
-    q.put((rank, e1, e2))
+    # sharded J^T J / J^T f: per-rank b200_jtj_dev on the element shard + ONE NCCL all-reduce
+    rs = np.random.default_rng(0).uniform(0.5, 1.5, c.n_elements); fv = np.random.default_rng(1).standard_normal(c.n_elements)
+    d_rs = torch.from_numpy(rs[glob]).cuda(); d_f = torch.from_numpy(fv[glob]).cuda()
+    jtj = torch.empty((Np, Np), dtype=torch.float64, device="cuda"); jtf = torch.empty(Np, dtype=torch.float64, device="cuda")
+    at.jtj_dev(jtj.data_ptr(), d_rs.data_ptr(), d_f.data_ptr(), jtf.data_ptr())
+    bd.allreduce_jtj(jtj, jtf)
+    torch.cuda.synchronize()
+    Js = Jf * torch.from_numpy(rs).cuda()[:, None]
+    ref_jtj = Js.T @ Js; ref_jtf = Js.T @ torch.from_numpy(fv).cuda()
+    e3 = float((jtj - ref_jtj).abs().max() / ref_jtj.abs().max())
+    e4 = float((jtf - ref_jtf).abs().max() / ref_jtf.abs().max())
+    q.put((rank, e1, e2, e3, e4))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,5 +69,5 @@ def test_two_gpu_shard_fill_allgather():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, e1, e2 in res:
-        assert e1 <= 1e-12 and e2 <= 1e-10, res
+    for rank, e1, e2, e3, e4 in res:
+        assert e1 <= 1e-12 and e2 <= 1e-10 and e3 <= 1e-10 and e4 <= 1e-10, res

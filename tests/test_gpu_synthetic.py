@@ -116,3 +116,88 @@ print("ok")
     env = dict(os.environ, B200_D16_MODE=mode)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def _shared_param_derivs(t, n_params, seed=0):
+    """Derivative map in the style of a crosstalk-free model: every parameter touches the SAME (i, j) positions of
+    several gates (one 1-qubit gate embedded on different qubits), plus TP-POVM-like rows (one parameter feeding two
+    effects with opposite signs) and a state-preparation block."""
+    from pygsti_b200.packing import DerivMap
+    d = t.dim
+    rng = np.random.default_rng(seed)
+    rows, cols, vals = [], [], []
+    for p in range(n_params - 2 * d):
+        gates = rng.choice(t.n_ops, size=min(t.n_ops, 1 + p % 3), replace=False)
+        ij = rng.integers(0, d * d, size=int(rng.integers(1, 9)))
+        for g in gates:
+            for w in ij:
+                rows.append(g * d * d + int(w)); cols.append(p); vals.append(float(rng.standard_normal()))
+    off_rho = t.n_ops * d * d
+    off_eff = off_rho + t.n_rho * d
+    for i in range(d):                                   # prep parameters (all preps share them)
+        p = n_params - 2 * d + i
+        for r in range(t.n_rho):
+            rows.append(off_rho + r * d + i); cols.append(p); vals.append(1.0 + r)
+    for i in range(d):                                   # effect parameters: +1 on effect 0, -1 on the last effect
+        p = n_params - d + i
+        rows.append(off_eff + i); cols.append(p); vals.append(1.0)
+        rows.append(off_eff + (t.n_eff - 1) * d + i); cols.append(p); vals.append(-1.0)
+    return DerivMap(off_eff + t.n_eff * d, n_params, np.asarray(rows, np.int32), np.asarray(cols, np.int32), np.asarray(vals))
+
+
+@pytest.mark.parametrize("dim,n_ops,n_rho,n_eff,n_circ,depth,n_params", [(64, 6, 2, 8, 30, 70, 700), (64, 3, 1, 5, 12, 150, 300),
+                                                                         (256, 3, 1, 16, 6, 9, 600)])
+def test_level_batched_jacobian(gpu_ctx, dim, n_ops, n_rho, n_eff, n_circ, depth, n_params):
+    """d = 64 / 256 Jacobian path (level-batched sweeps + sparse contraction): parameters shared between gates, several
+    parameter tiles, gate buckets longer than one shared-memory stage, outcome subsets, row scaling, J^T J."""
+    circs = synth.random_circuits(n_circ, depth, n_ops, n_rho, n_eff, seed=dim + depth)
+    t = synth.make_tables(dim, n_ops, n_rho, n_eff, circs)
+    G, rho, E = synth.random_model(dim, n_ops, n_rho, n_eff, seed=9)
+    D = _shared_param_derivs(t, n_params, seed=2)
+    p, p2, J, info = _run(gpu_ctx, t, G, rho, E, D)
+    po = onp.mapfill_probs(t, G, rho, E)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D)
+    sc = max(1.0, np.max(np.abs(Jo)))
+    assert info["fused_path"] == 0
+    assert np.max(np.abs(p2 - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * sc
+    # fused row scaling and J^T J / J^T f on the same path
+    at = gpu_ctx.upload_atom(t); at.set_model(G, rho, E); at.set_derivs(D)
+    rs = np.random.default_rng(1).standard_normal(t.n_elements)
+    Js = np.full_like(J, np.nan)
+    at.fill_dprobs(Js, row_scale=rs)
+    assert np.max(np.abs(Js - Jo * rs[:, None])) <= 1e-11 * sc * max(1.0, np.max(np.abs(rs)))
+    f = np.random.default_rng(2).standard_normal(t.n_elements)
+    jtj, jtf = at.jtj(rs, f)
+    Jr = Jo * rs[:, None]
+    assert np.max(np.abs(jtj - Jr.T @ Jr)) <= 1e-9 * max(1.0, np.max(np.abs(Jr.T @ Jr)))
+    assert np.max(np.abs(jtf - Jr.T @ f)) <= 1e-9 * max(1.0, np.max(np.abs(Jr.T @ f)))
+    at.free()
+
+
+def test_level_batched_matches_generic_path():
+    """The level-batched d = 64 Jacobian and the correctness-first W-matrix path agree (subprocess: env latch)."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from pygsti_b200 import engine
+from tests import synth
+ctx = engine.Context(0)
+circs = synth.random_circuits(16, 20, 4, 1, 8, seed=5)
+t = synth.make_tables(64, 4, 1, 8, circs)
+G, rho, E = synth.random_model(64, 4, 1, 8, seed=3)
+D = synth.random_derivs(t, 90, density=0.01, seed=4)
+at = ctx.upload_atom(t); at.set_model(G, rho, E); at.set_derivs(D)
+J = np.full((t.n_elements, D.n_params), np.nan); at.fill_dprobs(J)
+np.save(sys.argv[1], J); print("ok", ctx.launch_count)
+''' % REPO
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for tag, extra in (("lj", {}), ("gen", {"B200_NO_LEVELJ": "1"})):
+            f = os.path.join(td, tag + ".npy")
+            r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+            outs.append(np.load(f))
+    assert np.all(np.isfinite(outs[0]))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))
