@@ -118,6 +118,16 @@ int b200_fill_dprobs_fd(b200_ctx* ctx, b200_atom* atom, double eps, double* out,
  * p1/p2 index columns of the uploaded derivative map. */
 int b200_fill_hprobs_linear(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t* p1,
                             int32_t n2, const int32_t* p2, double* out);
+/* Hessian block for ARBITRARY members, fully analytic: the linear-member expression above plus the second-derivative
+ * term  sum_w (d p_el / d M_w) * d2 M_w / d theta_{p1[a]} d theta_{p2[b]},  with the members' second derivatives given
+ * as COO entries (h_rows[t] = w, h_a[t] = a, h_b[t] = b, h_vals[t]) taken from member.hessian_wrt_params() -- the same
+ * quantity MatrixForwardSimulator reads in `_hoperation` and `_hprobs_from_rho_e` (matrixforwardsim.py:172-218,
+ * 1141-1287).  Replaces the reference Map simulator's finite differences of finite differences
+ * (mapforwardsim.py:394-438, (B1+1)(B2+1) table passes per block) for CPTPLND / H+S / ... models.  nnz2 = 0 is
+ * b200_fill_hprobs_linear. */
+int b200_fill_hprobs(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
+                     int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
+                     double* out);
 
 /* ---- the hot path, DEVICE buffers (no copies; asynchronous on the ctx stream) ------------------ */
 int b200_fill_probs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out);

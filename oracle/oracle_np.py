@@ -207,3 +207,18 @@ def hprobs_linear(t, G, rho, E, D):
             Hel += np.einsum('ip,iq->pq', de, drho[r])     # J_q += e_0 . drho[:,q]
             H[el] = Hel
     return H
+
+
+def hprobs_general(t, G, rho, E, D, H2=None, p1=None, p2=None):
+    """Hessian rectangle for arbitrary members:  H[el, a, b] = (linear-member part)[el, p1[a], p2[b]]
+    + sum_w W[el, w] d2M_w/dp1[a]dp2[b]   (== MatrixForwardSimulator._hprobs_from_rho_e, matrixforwardsim.py:1141-1287,
+    where the second term is the `_hoperation` / SPAM-hessian contribution).  H2: (rows, a, b, vals) COO or None."""
+    Np = D.n_params
+    p1 = np.arange(Np) if p1 is None else np.asarray(p1)
+    p2 = np.arange(Np) if p2 is None else np.asarray(p2)
+    H = hprobs_linear(t, G, rho, E, D)[:, p1][:, :, p2]
+    if H2 is not None and len(H2[0]):
+        W = w_matrix(t, G, rho, E)
+        rows, a, b, vals = H2
+        np.add.at(H, (slice(None), a, b), W[:, rows] * vals[None, :])
+    return H

@@ -204,6 +204,37 @@ def mapfill_hprobs_atom_linear(fwdsim, array_to_fill, dest_param_indices1, dest_
     array_to_fill[np.ix_(np.arange(nE), d1, d2)] = tmp
 
 
+def mapfill_hprobs_atom_analytic(fwdsim, array_to_fill, dest_param_indices1, dest_param_indices2, layout_atom,
+                                 param_indices1, param_indices2, resource_alloc):
+    """Fully analytic Hessian rectangle for arbitrary members (CPTPLND, H+S, ...): the members' own
+    ``hessian_wrt_params`` supply the second-derivative term (as in MatrixForwardSimulator._hprobs_from_rho_e,
+    matrixforwardsim.py:1141-1287).  Returns False -- nothing written -- when a member cannot provide it, so that the
+    caller can fall back to the reference's finite-difference driver (mapforwardsim.py:394-438)."""
+    model = fwdsim.model
+    p1 = packing.param_slice_to_array(param_indices1, model.num_params)
+    p2 = packing.param_slice_to_array(param_indices2, model.num_params)
+    try:
+        hess = packing.pack_hessians(model, layout_atom, model.dim, p1, p2)
+    except (NotImplementedError, ValueError, AssertionError):
+        return False
+    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
+    _deriv_map(fwdsim, layout_atom, ent, None)
+    if not shared_mem_leader:
+        return True
+    nE = layout_atom.num_elements
+    if nE == 0 or p1.size == 0 or p2.size == 0:
+        return True
+    tmp = np.empty((nE, p1.size, p2.size))
+    atom.fill_hprobs(p1, p2, tmp, hess)
+    d1 = np.arange(p1.size) if dest_param_indices1 is None else _to_index_array(dest_param_indices1, array_to_fill.shape[1])
+    d2 = np.arange(p2.size) if dest_param_indices2 is None else _to_index_array(dest_param_indices2, array_to_fill.shape[2])
+    array_to_fill[np.ix_(np.arange(nE), d1, d2)] = tmp
+    return True
+
+
 def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     """Upload the derivative map for this parameter block (cached when every member is linear in its
     parameters, in which case D does not depend on the current parameter vector)."""

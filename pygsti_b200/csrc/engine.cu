@@ -92,11 +92,10 @@ struct b200_atom {
     int lj_no_max = 0, lj_n_tiles = 0;
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
-    DevBuf tf_parent, tf_first, tf_len, tf_op, tb_parent, tb_first, tb_len, tb_op, t_fn, t_bn, t_fend, t_bend;
+    DevBuf tf_meta, tf_op, tb_meta, tb_op, t_fn, t_bn, t_fend, t_bend;
     DevBuf t_S, t_H, t_counters, t_units, t_uidx, t_cgrp;
     int n_units = 0, unit_outcomes = 4;
     int n_fchains = 0, n_bchains = 0; uint32_t n_fnodes = 0, n_bnodes = 0;
-    unsigned epoch = 0;
     // model
     bool has_model = false;
     DevBuf M, Gt;
@@ -553,10 +552,14 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             a->n_fchains = (int)TF.chain_first.size(); a->n_bchains = (int)TB.chain_first.size();
             a->n_fnodes = (uint32_t)TF.node_op.size(); a->n_bnodes = (uint32_t)TB.node_op.size();
             std::vector<unsigned> zc(4, 0u);
-            if ((rc = upload_vec(a->tf_parent, TF.chain_parent, ctx->stream)) || (rc = upload_vec(a->tf_first, TF.chain_first, ctx->stream)) ||
-                (rc = upload_vec(a->tf_len, TF.chain_len, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
-                (rc = upload_vec(a->tb_parent, TB.chain_parent, ctx->stream)) || (rc = upload_vec(a->tb_first, TB.chain_first, ctx->stream)) ||
-                (rc = upload_vec(a->tb_len, TB.chain_len, ctx->stream)) || (rc = upload_vec(a->tb_op, TB.node_op, ctx->stream)) ||
+            auto pack_meta = [](const TrieHost& T) {
+                std::vector<int4> mt(T.chain_first.size());
+                for (size_t i = 0; i < mt.size(); ++i) mt[i] = make_int4(T.chain_parent[i], (int)T.chain_first[i], (int)T.chain_len[i], 0);
+                return mt; };
+            const std::vector<int4> fmeta = pack_meta(TF), bmeta = pack_meta(TB);
+            TF.node_op.resize(TF.node_op.size() + 32, 0); TB.node_op.resize(TB.node_op.size() + 32, 0);   // 32-wide op fetches
+            if ((rc = upload_vec(a->tf_meta, fmeta, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
+                (rc = upload_vec(a->tb_meta, bmeta, ctx->stream)) || (rc = upload_vec(a->tb_op, TB.node_op, ctx->stream)) ||
                 (rc = upload_vec(a->t_fn, fn, ctx->stream)) || (rc = upload_vec(a->t_bn, bn, ctx->stream)) ||
                 (rc = upload_vec(a->t_fend, fend, ctx->stream)) || (rc = upload_vec(a->t_bend, bend, ctx->stream)) ||
                 (rc = upload_vec(a->t_counters, zc, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
@@ -578,8 +581,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
-                      &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items, &a->tf_parent, &a->tf_first, &a->tf_len, &a->tf_op, &a->tb_parent,
-                      &a->tb_first, &a->tb_len, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
+                      &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
                       &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
@@ -801,15 +803,14 @@ static int d16_mode() {   // 0 = fused kernel, 1 = two-phase per-circuit chains,
 static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (a->n_rows == 0) return B200_OK;
     TrieDev t;
-    t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
+    t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
-    t.b_parent = a->tb_parent.as<int32_t>(); t.b_first = a->tb_first.as<uint32_t>(); t.b_len = a->tb_len.as<uint32_t>();
+    t.b_meta = a->tb_meta.as<int4>();
     t.b_op = a->tb_op.as<uint8_t>(); t.n_bchains = a->n_bchains; t.n_bnodes = a->n_bnodes;
     t.fn_b = a->t_fn.as<uint32_t>(); t.bn_b = a->t_bn.as<uint32_t>(); t.f_end = a->t_fend.as<uint32_t>(); t.b_end = a->t_bend.as<uint32_t>();
     t.bcnt = a->bcnt.as<uint16_t>();
     t.S = a->t_S.as<double>(); t.H = a->t_H.as<double>();
     t.counters = a->t_counters.as<unsigned>();
-    const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 4 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_H.as<double>(), (size_t)a->n_bnodes * a->n_eff * 16);
@@ -817,22 +818,25 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    CU(cudaFuncSetAttribute(k_accum_trie_d16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-    static int chain_ctas = -1;                    // CTAs per SM and role (dev knob B200_CHAIN_CTAS)
+    static int chain_ctas = -1, chain_k = -1, st256 = -1;   // dev knobs: chain CTAs per SM and role, chains per atomic grab, 256-bit stores
     if (chain_ctas < 0) { const char* e = getenv("B200_CHAIN_CTAS"); chain_ctas = (e && atoi(e) > 0) ? atoi(e) : 4; }
+    if (chain_k < 0) { const char* e = getenv("B200_CHAIN_K"); chain_k = (e && atoi(e) > 0) ? atoi(e) : 2; }
+    if (st256 < 0) { const char* e = getenv("B200_ACC_ST256"); st256 = e ? atoi(e) : 1; }
     int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
-    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 0);
-    int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
+    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, chain_k, 0);
     const int dbg = getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0;
-    if (a->unit_outcomes == 2) {
-        CU(cudaFuncSetAttribute(k_accum_trie_d16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 3);
-        k_accum_trie_d16<2><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
-    } else {
-        k_accum_trie_d16<4><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
-    }
+    const bool w256 = st256 && (((uintptr_t)args.J & 31) == 0);        // 32-byte stores need 32-byte aligned rows
+    auto launchB = [&](auto kern, int per_sm) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), per_sm);
+        kern<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
+        return B200_OK;
+    };
+    int rcB;
+    if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
+    else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
+    if (rcB) return rcB;
     c->launches += 2;
     CU(cudaGetLastError());
     return B200_OK;
@@ -938,16 +942,15 @@ static int launch_probs_level(b200_ctx* c, b200_atom* a, double* d_out) {
 
 static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     TrieDev t; memset(&t, 0, sizeof t);
-    t.f_parent = a->tf_parent.as<int32_t>(); t.f_first = a->tf_first.as<uint32_t>(); t.f_len = a->tf_len.as<uint32_t>();
+    t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
     t.S = a->t_S.as<double>(); t.counters = a->t_counters.as<unsigned>();
-    const unsigned epoch = ++a->epoch;
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
     k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
     c->launches++;
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, epoch, 1);
+    k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, 2, 1);
     int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 15) / 16, (int64_t)c->sm_count * 8));
     k_probs_trie_d16<<<gp, 256, 0, c->stream>>>(atom_dev(a), model_dev(a), a->t_fend.as<uint32_t>(), a->t_S.as<double>(), d_out, 1);
     c->launches += 2;
@@ -1285,8 +1288,25 @@ static int launch_w_tangent(b200_ctx* c, b200_atom* a, int nb, const double* dMb
     return B200_OK;
 }
 
+static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
+                           int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
+                           double* out);
+
 extern "C" int b200_fill_hprobs_linear(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1,
                                        int32_t n2, const int32_t* p2, double* out) {
+    return fill_hprobs_impl(c, a, n1, p1, n2, p2, 0, nullptr, nullptr, nullptr, nullptr, out);
+}
+
+extern "C" int b200_fill_hprobs(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
+                                int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b,
+                                const double* h_vals, double* out) {
+    if (nnz2 < 0 || (nnz2 > 0 && (!h_rows || !h_a || !h_b || !h_vals))) return fail(B200_E_INVALID, "bad second-derivative map");
+    return fill_hprobs_impl(c, a, n1, p1, n2, p2, nnz2, h_rows, h_a, h_b, h_vals, out);
+}
+
+static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
+                           int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
+                           double* out) {
     if (!c || !a || !out || (n1 > 0 && !p1) || (n2 > 0 && !p2)) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
@@ -1300,8 +1320,46 @@ extern "C" int b200_fill_hprobs_linear(b200_ctx* c, b200_atom* a, int32_t n1, co
     int rc;
     if ((rc = upload_vec(d_p1, v1, c->stream)) || (rc = upload_vec(d_p2, v2, c->stream))) return rc;
     CU(d_out.ensure((size_t)nE * n1 * n2 * 8));
-    // batch of tangent directions bounded by ~1 GB of W scratch
     const int64_t per = nE * a->n_w * 8;
+    int accumulate = 0;
+    if (nnz2 > 0) {
+        // second-derivative term first: out = sum_w W[el, w] d2M_w/dp1 dp2, entries grouped by (a, b)
+        if (nnz2 >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "second-derivative map too large");
+        for (int64_t t = 0; t < nnz2; ++t) {
+            if (h_rows[t] < 0 || h_rows[t] >= a->n_w) return fail(B200_E_INVALID, "D2 row %d out of range", h_rows[t]);
+            if (h_a[t] < 0 || h_a[t] >= n1 || h_b[t] < 0 || h_b[t] >= n2) return fail(B200_E_INVALID, "D2 index out of range");
+        }
+        std::vector<int64_t> idx((size_t)nnz2);
+        std::iota(idx.begin(), idx.end(), 0);
+        auto keyof = [&](int64_t t) { return (int64_t)h_a[t] * n2 + h_b[t]; };
+        std::sort(idx.begin(), idx.end(), [&](int64_t x, int64_t y) {
+            const int64_t kx = keyof(x), ky = keyof(y);
+            return kx != ky ? kx < ky : h_rows[x] < h_rows[y]; });
+        std::vector<int64_t> ukey; std::vector<int32_t> kptr, krow((size_t)nnz2); std::vector<double> kval((size_t)nnz2);
+        for (int64_t t = 0; t < nnz2; ++t) {
+            const int64_t i = idx[t];
+            if (ukey.empty() || ukey.back() != keyof(i)) { ukey.push_back(keyof(i)); kptr.push_back((int32_t)t); }
+            krow[t] = h_rows[i]; kval[t] = h_vals[i];
+        }
+        kptr.push_back((int32_t)nnz2);
+        DevBuf d_ukey, d_kptr, d_krow, d_kval;
+        if ((rc = upload_vec(d_ukey, ukey, c->stream)) || (rc = upload_vec(d_kptr, kptr, c->stream)) ||
+            (rc = upload_vec(d_krow, krow, c->stream)) || (rc = upload_vec(d_kval, kval, c->stream))) return rc;
+        CU(c->w_buf.ensure((size_t)per));
+        CU(cudaMemsetAsync(d_out.p, 0, (size_t)nE * n1 * n2 * 8, c->stream));
+        rc = compute_w(c, a, c->w_buf.as<double>(), nullptr);
+        if (rc) return rc;
+        const int nk = (int)ukey.size();
+        dim3 gk((nk + 127) / 128, (unsigned)std::min<int64_t>(nE, 65535));
+        k_hess_d2<<<gk, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, n1, n2, nk, d_ukey.as<int64_t>(), d_kptr.as<int32_t>(),
+                                            d_krow.as<int32_t>(), d_kval.as<double>(), d_out.as<double>());
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        d_ukey.release(); d_kptr.release(); d_krow.release(); d_kval.release();
+        accumulate = 1;
+    }
+    // batch of tangent directions bounded by ~1 GB of W scratch
     const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n1, ((int64_t)1 << 30) / std::max<int64_t>(per, 1)));
     CU(c->w_buf.ensure((size_t)B * per));
     CU(c->fd_models.ensure((size_t)B * a->n_w * 8));
@@ -1331,7 +1389,7 @@ extern "C" int b200_fill_hprobs_linear(b200_ctx* c, b200_atom* a, int32_t n1, co
         dim3 g4((n2 + 127) / 128, (unsigned)std::min<int64_t>(nE * nb, 65535));
         k_contract_hess<<<g4, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, nb, a0, n1, n2, d_p2.as<int32_t>(),
                                                    a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
-                                                   d_out.as<double>());
+                                                   d_out.as<double>(), accumulate);
         c->launches++;
         CU(cudaGetLastError());
     }

@@ -23,13 +23,12 @@
 
 struct TrieDev {
     // forward trie (node value = state after the prefix; depth 0 = the prep itself)
-    const int32_t* f_parent;   // [n_fchains] parent node id, or -(1+prep) for a root chain
-    const uint32_t* f_first;   // [n_fchains] first node id (nodes of a chain are consecutive)
-    const uint32_t* f_len;     // [n_fchains]
+    const int4* f_meta;        // [n_fchains] (parent node id or -(1+prep) for a root chain, first node id, length, 0):
+                               //             the nodes of a chain are consecutive
     const uint8_t* f_op;       // [n_fnodes]  op applied to reach the node (255 = root copy)
     int n_fchains; uint32_t n_fnodes;
     // backward trie (node value = (suffix product)^T E_e for every effect e; depth 0 = E itself)
-    const int32_t* b_parent; const uint32_t* b_first; const uint32_t* b_len; const uint8_t* b_op;
+    const int4* b_meta; const uint8_t* b_op;
     int n_bchains; uint32_t n_bnodes;
     // per circuit step, in gate-bucket order (same order as TwoPhaseDev.bperm): node of s_k and node of e_k
     const uint32_t* fn_b; const uint32_t* bn_b;
@@ -55,22 +54,15 @@ __global__ void k_fill_sentinel(double* __restrict__ p, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = s;
 }
 
-// Work hand-out with a two-deep software pipeline: a warp always holds the index of its next chain (`n1`, metadata
-// already loaded) and has the atomicAdd for the one after (`n2`) in flight while it walks the current chain -- with
-// ~2.5 nodes per chain on GST layouts the atomic + metadata round trips (~2 us) were most of the per-chain time.
-// Deadlock freedom is unchanged: a warp processes the chains it holds in increasing index order and a chain only waits
-// for a chain with a smaller index.
-struct ChainMeta { int parent; uint32_t first, len; };
-__device__ __forceinline__ ChainMeta chain_meta(const int32_t* par, const uint32_t* fst, const uint32_t* ln, int ci, int n) {
-    ChainMeta mt; mt.parent = 0; mt.first = 0; mt.len = 0;
-    if (ci < n) { mt.parent = __ldg(par + ci); mt.first = __ldg(fst + ci); mt.len = __ldg(ln + ci); }
-    return mt;
-}
-
+// Work hand-out: a warp takes `kgrab` consecutive chains per atomicAdd (same-address L2 atomics serialise: ~136 k of them
+// per Jacobian were a measurable part of the kernel) and reads one 16-byte record per chain; the ops of a chain are
+// consecutive bytes and are fetched 32 at a time (one coalesced load, then a shuffle per step) so that no global load
+// sits on the per-step critical path.  A warp processes the chains it holds in increasing index order and a chain only
+// waits for a chain with a smaller index, handed out earlier: the spin-waits cannot deadlock.
 // dynamic smem: n_ops*256 doubles (the CTA's role: backward B fragments or forward fragments)
 //               + TRIE_WARPS*2*16 doubles (forward exchange)
 __global__ void __launch_bounds__(TRIE_WARPS * 32)
-k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
+k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
 {
     extern __shared__ __align__(16) double smt[];
     double* frag = smt;
@@ -94,57 +86,56 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
 
     unsigned* ctr = t.counters + role;
     const int n_chains = role ? t.n_bchains : t.n_fchains;
-    const int32_t* c_par = role ? t.b_parent : t.f_parent;
-    const uint32_t* c_first = role ? t.b_first : t.f_first;
-    const uint32_t* c_len = role ? t.b_len : t.f_len;
-    // pipeline prologue (lane 0 owns the raw atomic results; they are broadcast one iteration later)
-    int n1 = 0, n2raw = 0;
-    if (lane == 0) n1 = (int)atomicAdd(ctr, 1u);
-    n1 = __shfl_sync(0xffffffffu, n1, 0);
-    if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
-    ChainMeta m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
+    const int4* meta = role ? t.b_meta : t.f_meta;
+    const uint8_t* ops = role ? t.b_op : t.f_op;
 
     if (role == 0) {
         const double* ffrag = frag;
         double* fx = fx_all + warp * 32;
         const int half = lane >> 4;
         for (;;) {
-            const int ci = n1;
-            if (ci >= n_chains) break;
-            const int parent = m1.parent;
-            const uint32_t first = m1.first, len = m1.len;
-            n1 = __shfl_sync(0xffffffffu, n2raw, 0);
-            if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
-            m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
-            double v = 0.0;
-            uint32_t i0 = 0;
-            if (parent < 0) {                       // root chain: first node is the prep itself
-                if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; __stcg(t.S + (size_t)first * 16 + lane, v); }
-                i0 = 1;
-            } else {
-                if (lane < 16) {
-                    const double* pp = t.S + (size_t)parent * 16 + lane;
-                    v = __ldcg(pp);
-                    while (is_sent(v)) { __nanosleep(40); v = __ldcg(pp); }
+            int c0 = 0;
+            if (lane == 0) c0 = (int)atomicAdd(ctr, (unsigned)kgrab);
+            c0 = __shfl_sync(0xffffffffu, c0, 0);
+            if (c0 >= n_chains) break;
+            const int c1 = (c0 + kgrab < n_chains) ? c0 + kgrab : n_chains;
+            int4 mt = __ldg(meta + c0);
+            for (int ci = c0; ci < c1; ++ci) {
+                const int parent = mt.x;
+                const uint32_t first = (uint32_t)mt.y, len = (uint32_t)mt.z;
+                if (ci + 1 < c1) mt = __ldg(meta + ci + 1);
+                int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
+                double v = 0.0;
+                uint32_t i0 = 0;
+                if (parent < 0) {                       // root chain: first node is the prep itself
+                    if (lane < 16) { v = rho[(-1 - parent) * 16 + lane]; __stcg(t.S + (size_t)first * 16 + lane, v); }
+                    i0 = 1;
+                } else {
+                    if (lane < 16) {
+                        const double* pp = t.S + (size_t)parent * 16 + lane;
+                        v = __ldcg(pp);
+                        while (is_sent(v)) { __nanosleep(40); v = __ldcg(pp); }
+                    }
+                    __syncwarp();
                 }
+                int cur = 0;
+                if (lane < 16) fx[lane] = v;
                 __syncwarp();
-            }
-            int cur = 0;
-            if (lane < 16) fx[lane] = v;
-            __syncwarp();
-            for (uint32_t i = i0; i < len; ++i) {
-                const int g = t.f_op[first + i];
-                const double2* s2 = reinterpret_cast<const double2*>(fx + cur * 16 + half * 8);
-                const double2 s0 = s2[0], s1 = s2[1], s2v = s2[2], s3 = s2[3];
-                const double* fp = ffrag + g * 256 + lane;
-                double f0 = fp[0] * s0.x, f1 = fp[32] * s0.y, f2 = fp[64] * s1.x, f3 = fp[96] * s1.y;
-                f0 = fma(fp[128], s2v.x, f0); f1 = fma(fp[160], s2v.y, f1);
-                f2 = fma(fp[192], s3.x, f2); f3 = fma(fp[224], s3.y, f3);
-                double w = (f0 + f1) + (f2 + f3);
-                w += shfl_xor_f64(w, 16);
-                cur ^= 1;
-                if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
-                __syncwarp();
+                for (uint32_t i = i0; i < len; ++i) {
+                    if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
+                    const int g = __shfl_sync(0xffffffffu, opv, (int)(i & 31u));
+                    const double2* s2 = reinterpret_cast<const double2*>(fx + cur * 16 + half * 8);
+                    const double2 s0 = s2[0], s1 = s2[1], s2v = s2[2], s3 = s2[3];
+                    const double* fp = ffrag + g * 256 + lane;
+                    double f0 = fp[0] * s0.x, f1 = fp[32] * s0.y, f2 = fp[64] * s1.x, f3 = fp[96] * s1.y;
+                    f0 = fma(fp[128], s2v.x, f0); f1 = fma(fp[160], s2v.y, f1);
+                    f2 = fma(fp[192], s3.x, f2); f3 = fma(fp[224], s3.y, f3);
+                    double w = (f0 + f1) + (f2 + f3);
+                    w += shfl_xor_f64(w, 16);
+                    cur ^= 1;
+                    if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
+                    __syncwarp();
+                }
             }
         }
     } else {
@@ -153,50 +144,56 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, unsigned epoch, int fwd_only)
         const int ne = a.n_eff;
         const bool rowok = mrow < ne;
         for (;;) {
-            const int ci = n1;
-            if (ci >= n_chains) break;
-            const int parent = m1.parent;
-            const uint32_t first = m1.first, len = m1.len;
-            n1 = __shfl_sync(0xffffffffu, n2raw, 0);
-            if (lane == 0) n2raw = (n1 < n_chains) ? (int)atomicAdd(ctr, 1u) : n_chains;
-            m1 = chain_meta(c_par, c_first, c_len, n1, n_chains);
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            uint32_t i0 = 0;
-            if (parent < 0) {                       // root: E itself
-                if (rowok) {
-                    const double* Er = E + mrow * 16;
-                    a0 = Er[2 * q]; a1 = Er[2 * q + 1]; a2 = Er[8 + 2 * q]; a3 = Er[9 + 2 * q];
-                    double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
-                    __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
-                    __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
-                }
-                i0 = 1;
-            } else {
-                if (rowok) {
-                    const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
-                    double2 x = __ldcg(reinterpret_cast<const double2*>(hp));
-                    double2 y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
-                    while (is_sent(x.x) || is_sent(x.y) || is_sent(y.x) || is_sent(y.y)) {
-                        __nanosleep(40);
-                        x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+            int c0 = 0;
+            if (lane == 0) c0 = (int)atomicAdd(ctr, (unsigned)kgrab);
+            c0 = __shfl_sync(0xffffffffu, c0, 0);
+            if (c0 >= n_chains) break;
+            const int c1 = (c0 + kgrab < n_chains) ? c0 + kgrab : n_chains;
+            int4 mt = __ldg(meta + c0);
+            for (int ci = c0; ci < c1; ++ci) {
+                const int parent = mt.x;
+                const uint32_t first = (uint32_t)mt.y, len = (uint32_t)mt.z;
+                if (ci + 1 < c1) mt = __ldg(meta + ci + 1);
+                int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                uint32_t i0 = 0;
+                if (parent < 0) {                       // root: E itself
+                    if (rowok) {
+                        const double* Er = E + mrow * 16;
+                        a0 = Er[2 * q]; a1 = Er[2 * q + 1]; a2 = Er[8 + 2 * q]; a3 = Er[9 + 2 * q];
+                        double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
+                        __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
+                        __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
                     }
-                    a0 = x.x; a1 = x.y; a2 = y.x; a3 = y.y;
+                    i0 = 1;
+                } else {
+                    if (rowok) {
+                        const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
+                        double2 x = __ldcg(reinterpret_cast<const double2*>(hp));
+                        double2 y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                        while (is_sent(x.x) || is_sent(x.y) || is_sent(y.x) || is_sent(y.y)) {
+                            __nanosleep(40);
+                            x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                        }
+                        a0 = x.x; a1 = x.y; a2 = y.x; a3 = y.y;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
-            for (uint32_t i = i0; i < len; ++i) {
-                const int g = t.b_op[first + i];
-                const double* bp = bfrag + g * 256 + lane;
-                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
-                dmma884(d00, d01, a0, bp[0]);   dmma884(d10, d11, a0, bp[32]);
-                dmma884(x00, x01, a1, bp[64]);  dmma884(x10, x11, a1, bp[96]);
-                dmma884(d00, d01, a2, bp[128]); dmma884(d10, d11, a2, bp[160]);
-                dmma884(x00, x01, a3, bp[192]); dmma884(x10, x11, a3, bp[224]);
-                a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
-                if (rowok) {
-                    double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
-                    __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
-                    __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
+                for (uint32_t i = i0; i < len; ++i) {
+                    if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
+                    const int g = __shfl_sync(0xffffffffu, opv, (int)(i & 31u));
+                    const double* bp = bfrag + g * 256 + lane;
+                    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+                    dmma884(d00, d01, a0, bp[0]);   dmma884(d10, d11, a0, bp[32]);
+                    dmma884(x00, x01, a1, bp[64]);  dmma884(x10, x11, a1, bp[96]);
+                    dmma884(d00, d01, a2, bp[128]); dmma884(d10, d11, a2, bp[160]);
+                    dmma884(x00, x01, a3, bp[192]); dmma884(x10, x11, a3, bp[224]);
+                    a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
+                    if (rowok) {
+                        double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
+                        __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
+                        __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
+                    }
                 }
             }
         }
@@ -253,7 +250,15 @@ struct UnitRec {           // 32 bytes
     uint32_t pad;
 };
 
-template <int NO>          // outcomes (consecutive effects) per unit: 4 (126 registers, 16 warps/SM) or 2 (<= 80 registers, 24 warps/SM)
+// 256-bit Jacobian stores (W256): the s-vector components are fed to the B fragments in the order
+// jmap = {0,1,4,5,8,9,12,13 | 2,3,6,7,10,11,14,15}, so that a lane's four accumulators of one block row are the four
+// CONSECUTIVE columns 4q..4q+3; one st.global.v4.f64 per lane then writes 8 full 128-byte lines per warp instruction
+// (SASS STG.E.256) instead of two instructions that each touch half of 8 lines.
+__device__ __forceinline__ void st256_cs(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <int NO, bool W256>   // outcomes (consecutive effects) per unit: 4 (16 warps/SM) or 2 (24 warps/SM)
 __global__ void __launch_bounds__(AT_WARPS * 32, (NO == 4 ? 2 : 3))
 k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
                  const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, unsigned* __restrict__ counter, int dbg)
@@ -265,6 +270,16 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
         const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
+        if (W256) {
+            // tile = 2*h + z: z = 0 -> .x = first of the 4 consecutive columns of row 8h + mrow (or -1), .y unused
+            const int i = 8 * (tile >> 1) + (l >> 2), j0 = 4 * (l & 3);
+            const int* cp = args.colmap + g * 256 + i * 16 + j0;
+            int2 cc = make_int2(-1, -1);
+            if ((tile & 1) == 0 && cp[0] >= 0 && (cp[0] & 3) == 0 && (args.ld & 3) == 0 && cp[1] == cp[0] + 1 && cp[2] == cp[0] + 2 &&
+                cp[3] == cp[0] + 3) cc.x = cp[0];
+            cm_s[idx] = cc;
+            continue;
+        }
         const int i = 8 * (tile >> 1) + (l >> 2), jc = 8 * (tile & 1) + 2 * (l & 3);
         int2 cc = *reinterpret_cast<const int2*>(args.colmap + g * 256 + i * 16 + jc);
         if (cc.y == cc.x + 1 && cc.x >= 0 && ((cc.x | (int)(args.ld & 1)) & 1) == 0) cc.y = -2;
@@ -281,7 +296,8 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     const unsigned mrow = lane >> 2, q = lane & 3;
     const unsigned ne16 = (unsigned)a.n_eff * 16u;
     const double* E = m.M + m.off_eff;
-    const double* Sb = t.S + mrow;
+    const double* Sb = t.S + (W256 ? (4 * (mrow >> 1) + (mrow & 1)) : mrow);   // B-fragment column mrow <-> s component jmap0(mrow)
+    constexpr int SB1 = W256 ? 2 : 8;                                         // second fragment: jmap1 = jmap0 + 2  |  mrow + 8
     const double* Hb = t.H + mrow;
 
     for (;;) {
@@ -300,7 +316,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             const uint2 nd0 = __ldg(ip);
             const double* sp = Sb + nd0.x;
             const double* hp = Hb + nd0.y;
-            r[0] = ldk(sp); r[1] = ldk(sp + 8);
+            r[0] = ldk(sp); r[1] = ldk(sp + SB1);
 #pragma unroll
             for (int k = 0; k < 2 * NO; ++k) r[2 + k] = ldk(hp + 8 * k);
         }
@@ -322,7 +338,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 const double* sp = Sb + nd1.x;
                 const double* hp = Hb + nd1.y;
                 double n[2 + 2 * NO];
-                n[0] = ldk(sp); n[1] = ldk(sp + 8);
+                n[0] = ldk(sp); n[1] = ldk(sp + SB1);
 #pragma unroll
                 for (int k = 0; k < 2 * NO; ++k) n[2 + k] = ldk(hp + 8 * k);
 #pragma unroll
@@ -341,7 +357,8 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
             const int els[4] = {(int)ra.x, (int)ra.y, (int)ra.z, (int)ra.w};
-            const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+            const bool fast = W256 ? __all_sync(0xffffffffu, (cc[0].x >= 0) & (cc[2].x >= 0))
+                                   : __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
             if (args.row_scale) {          // objective-function row scaling fused into the epilogue
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -350,7 +367,29 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                     for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
                 }
             }
-            if (fast) {
+            if (W256) {
+                if (fast) {
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] >= 0) {
+                            double* Jr = args.J + (int64_t)els[o] * args.ld;
+                            st256_cs(Jr + cc[0].x, acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+                            st256_cs(Jr + cc[2].x, acc[o][4], acc[o][5], acc[o][6], acc[o][7]);
+                        }
+                    }
+                } else {                       // arbitrary column map: scalar stores through the map itself
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] < 0) continue;
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int* cp = args.colmap + g * 256 + (8 * h + (int)mrow) * 16 + 4 * (int)q;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const int col = __ldg(cp + k); if (col >= 0) Jr[col] = acc[o][4 * h + k]; }
+                        }
+                    }
+                }
+            } else if (fast) {
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
                     if (els[o] >= 0) {

@@ -256,7 +256,7 @@ __global__ void k_tangent_models(int64_t n_w, const int32_t* __restrict__ cols, 
 __global__ void __launch_bounds__(128)
 k_contract_hess(const double* __restrict__ Wb, int64_t ldw, int64_t n_el, int nb, int a0, int n1, int n2,
                 const int32_t* __restrict__ cols2, const int32_t* __restrict__ cptr,
-                const int32_t* __restrict__ crow, const double* __restrict__ cval, double* __restrict__ out)
+                const int32_t* __restrict__ crow, const double* __restrict__ cval, double* __restrict__ out, int accumulate)
 {
     const int c = blockIdx.x * 128 + threadIdx.x;
     if (c >= n2) return;
@@ -267,7 +267,29 @@ k_contract_hess(const double* __restrict__ Wb, int64_t ldw, int64_t n_el, int nb
         const double* Wr = Wb + ((int64_t)b * n_el + el) * ldw;
         double acc = 0.0;
         for (int t = tb; t < te; ++t) acc += cval[t] * Wr[crow[t]];
-        out[(el * n1 + a0 + b) * n2 + c] = acc;
+        double* o = out + (el * n1 + a0 + b) * n2 + c;
+        *o = accumulate ? *o + acc : acc;
+    }
+}
+
+// Second-derivative term of the Hessian for members NOT linear in their parameters:
+//   out[(el * n1 + a) * n2 + b] = sum_t kval[t] * W[el][krow[t]]   over the entries t of key (a, b) = ukey[k]
+// (d2M_w / dtheta_a dtheta_b from member.hessian_wrt_params; == the `_hoperation` / SPAM-hessian terms of
+// MatrixForwardSimulator._hprobs_from_rho_e, matrixforwardsim.py:1196-1237).  One thread per key, grid.y over elements.
+__global__ void __launch_bounds__(128)
+k_hess_d2(const double* __restrict__ W, int64_t ldw, int64_t n_el, int n1, int n2, int nk,
+          const int64_t* __restrict__ ukey, const int32_t* __restrict__ kptr, const int32_t* __restrict__ krow,
+          const double* __restrict__ kval, double* __restrict__ out)
+{
+    const int k = blockIdx.x * 128 + threadIdx.x;
+    if (k >= nk) return;
+    const int64_t key = ukey[k];
+    const int tb = kptr[k], te = kptr[k + 1];
+    for (int64_t el = blockIdx.y; el < n_el; el += gridDim.y) {
+        const double* Wr = W + el * ldw;
+        double acc = 0.0;
+        for (int t = tb; t < te; ++t) acc += kval[t] * Wr[krow[t]];
+        out[el * (int64_t)n1 * n2 + key] = acc;
     }
 }
 

@@ -185,6 +185,22 @@ class Atom:
                                                      p2.shape[0], _ptr(p2), _ptr(out)))
         return out
 
+    def fill_hprobs(self, p1, p2, out, hess=None):
+        """Analytic Hessian rectangle for arbitrary members; ``hess`` is a ``packing.HessMap`` with the members' second
+        derivatives for this rectangle (None / empty: members linear in their parameters)."""
+        if hess is None or hess.nnz == 0:
+            return self.fill_hprobs_linear(p1, p2, out)
+        p1, p2 = _i32(p1), _i32(p2)
+        if out.dtype != np.float64 or not out.flags.c_contiguous or \
+                out.shape != (self.n_elements, p1.shape[0], p2.shape[0]):
+            raise ValueError("expected C-contiguous float64 array (n_elements, n1, n2)")
+        if hess.n1 != p1.shape[0] or hess.n2 != p2.shape[0] or hess.n_w != self.n_w:
+            raise ValueError("second-derivative map does not match the rectangle")
+        _lib.check(self._lib.b200_fill_hprobs(self.ctx._h, self._h, p1.shape[0], _ptr(p1), p2.shape[0], _ptr(p2),
+                                              hess.nnz, _ptr(hess.rows), _ptr(hess.a), _ptr(hess.b), _ptr(hess.vals),
+                                              _ptr(out)))
+        return out
+
     # ---- device-buffer fills (raw device pointers, e.g. torch.Tensor.data_ptr()) -----------------
     def fill_probs_dev(self, d_out_ptr):
         _lib.check(self._lib.b200_fill_probs_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr))))

@@ -33,6 +33,14 @@ class Case:
             self.atoms.append(dict(tables=t, G=z[pre + "G"], rho=z[pre + "rho"], E=z[pre + "E"], D=D,
                                    element_slice=slice(int(es[0]), int(es[1]))))
 
+    def hess_map(self, tag="H2", atom=0):
+        """Second-derivative map stored by make_golden.py (`a<atom>_<tag>_*`): full Hessian ("H2") or rectangle i
+        ("H2r<i>")."""
+        from .packing import HessMap
+        z, pre = self.z, "a%d_%s_" % (atom, tag)
+        sh = z[pre + "shape"]
+        return HessMap(int(sh[0]), int(sh[1]), int(sh[2]), z[pre + "rows"], z[pre + "a"], z[pre + "b"], z[pre + "vals"])
+
     def __getitem__(self, k):
         return self.z[k]
 

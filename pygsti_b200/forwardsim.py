@@ -34,13 +34,19 @@ class B200ForwardSimulator(_MapForwardSimulator):
         ``num_atoms > 1`` and no MPI communicator, atoms are spread round-robin over ``devices``.
     devices : sequence of int or None
         GPUs to spread a single process's atoms over (default: just ``device``).
+    analytic_hessian : bool
+        True (default): `bulk_fill_hprobs` is fully analytic on the device for every member that provides
+        `hessian_wrt_params`.  False: members not linear in their parameters go through the reference's own
+        finite-difference driver (mapforwardsim.py:394-438) on top of the analytic device Jacobian.
     """
 
     def __init__(self, model=None, max_cache_size=None, num_atoms=None, processor_grid=None, param_blk_sizes=None,
-                 derivative_eps=1e-7, hessian_eps=1e-5, derivative_mode='analytic', device=None, devices=None):
+                 derivative_eps=1e-7, hessian_eps=1e-5, derivative_mode='analytic', device=None, devices=None,
+                 analytic_hessian=True):
         if derivative_mode not in ('analytic', 'fd'):
             raise ValueError("derivative_mode must be 'analytic' or 'fd'")
         self.derivative_mode = derivative_mode
+        self.analytic_hessian = bool(analytic_hessian)   # False: non-linear members use the reference's FD driver
         self._b200_device = device
         self._b200_devices = tuple(devices) if devices is not None else None
         super().__init__(model, max_cache_size, num_atoms, processor_grid, param_blk_sizes,
@@ -61,7 +67,8 @@ class B200ForwardSimulator(_MapForwardSimulator):
 
     def _to_nice_serialization(self):
         state = super()._to_nice_serialization()
-        state.update({'derivative_mode': self.derivative_mode, 'device': self._b200_device})
+        state.update({'derivative_mode': self.derivative_mode, 'device': self._b200_device,
+                      'analytic_hessian': self.analytic_hessian})
         return state
 
     @classmethod
@@ -70,14 +77,14 @@ class B200ForwardSimulator(_MapForwardSimulator):
                    derivative_eps=state.get('derivative_epsilon', 1e-7),
                    hessian_eps=state.get('hessian_epsilon', 1e-5),
                    derivative_mode=state.get('derivative_mode', 'analytic'),
-                   device=state.get('device', None))
+                   device=state.get('device', None), analytic_hessian=state.get('analytic_hessian', True))
 
     def copy(self, keep_model_attached=True):
         # MapForwardSimulator.copy hard-codes its own class (mapforwardsim.py:190-204) -> must override,
         # otherwise `model.copy()` / a "stolen" simulator silently degrades to the CPU simulator.
         out = B200ForwardSimulator(self.model, self._max_cache_size, self._num_atoms, self._processor_grid,
                                    self._pblk_sizes, self.derivative_eps, self.hessian_eps,
-                                   self.derivative_mode, self._b200_device, self._b200_devices)
+                                   self.derivative_mode, self._b200_device, self._b200_devices, self.analytic_hessian)
         if not keep_model_attached:
             out.model = None
         return out
@@ -95,15 +102,21 @@ class B200ForwardSimulator(_MapForwardSimulator):
     def _bulk_fill_hprobs_atom(self, array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
                                param_slice1, param_slice2, resource_alloc):
         """Replaces mapforwardsim.py:384-391.  Members linear in their parameters (full / TP / static):
-        fully analytic second order on the device (== MatrixForwardSimulator to ~1e-13).  Otherwise the
-        reference's own driver `_mapfill_hprobs_atom` (mapforwardsim.py:394-438: finite differences along the
-        first parameter axis, `hessian_eps`) runs on top of the ANALYTIC device Jacobian."""
+        fully analytic second order on the device (== MatrixForwardSimulator to ~1e-13).  Other members (CPTPLND,
+        H+S, ...): the same plus the members' own `hessian_wrt_params` second-derivative term, also on the device
+        (`b200_fill_hprobs`).  Only if a member cannot provide that (parameter interposer, no analytic Hessian) does
+        the reference's own driver `_mapfill_hprobs_atom` (mapforwardsim.py:394-438: finite differences along the
+        first parameter axis, `hessian_eps`) run on top of the ANALYTIC device Jacobian."""
         if self.derivative_mode == 'analytic' and _b200_calclib.all_members_linear(self, layout_atom):
             _b200_calclib.mapfill_hprobs_atom_linear(self, array_to_fill, dest_param_slice1, dest_param_slice2,
                                                      layout_atom, param_slice1, param_slice2, resource_alloc)
-        else:
-            super()._bulk_fill_hprobs_atom(array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
-                                           param_slice1, param_slice2, resource_alloc)
+            return
+        if self.derivative_mode == 'analytic' and self.analytic_hessian and \
+                _b200_calclib.mapfill_hprobs_atom_analytic(self, array_to_fill, dest_param_slice1, dest_param_slice2,
+                                                           layout_atom, param_slice1, param_slice2, resource_alloc):
+            return
+        super()._bulk_fill_hprobs_atom(array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
+                                       param_slice1, param_slice2, resource_alloc)
 
     # ---- extensions for the objective-function Jacobian fill (SURVEY.md 8f rank 1) --------------------
     def bulk_fill_dprobs_scaled(self, array_to_fill, layout, row_scale, pr_array_to_fill=None):

@@ -219,3 +219,53 @@ def pack_derivs(model, atom, dim, param_indices=None):
     return DerivMap(n_w=n_w, n_params=int(pidx.size),
                     rows=D.row[keep].astype(np.int32), cols=D.col[keep].astype(np.int32),
                     vals=D.data[keep].astype(np.float64))
+
+
+class HessMap:
+    """Sparse second derivatives of the dense member elements for one Hessian rectangle:
+    entries (w, a, b, val) = d2 M_w / d theta_{p1[a]} d theta_{p2[b]}  (zero for members linear in their parameters)."""
+
+    def __init__(self, n_w, n1, n2, rows, a, b, vals):
+        self.n_w, self.n1, self.n2 = int(n_w), int(n1), int(n2)
+        self.rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self.a = np.ascontiguousarray(a, dtype=np.int32)
+        self.b = np.ascontiguousarray(b, dtype=np.int32)
+        self.vals = np.ascontiguousarray(vals, dtype=np.float64)
+
+    @property
+    def nnz(self):
+        return int(self.rows.size)
+
+
+def pack_hessians(model, atom, dim, param_indices1=None, param_indices2=None):
+    """Second derivatives of every member with ``has_nonzero_hessian()`` through its own ``hessian_wrt_params`` -- the
+    quantity MatrixForwardSimulator._hoperation / _hprobs_from_rho_e read (matrixforwardsim.py:172-218, 1196-1237) --
+    restricted to the rectangle (param_indices1 x param_indices2).  Parameter interposers are not supported here
+    (the caller falls back to the reference driver)."""
+    if getattr(model, '_param_interposer', None) is not None:
+        raise NotImplementedError("pack_hessians: parameter interposer")
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    n_w = len(ops) * d * d + len(rhos) * d + len(effs) * d
+    n_model_params = int(model.num_params)
+    p1 = param_slice_to_array(param_indices1, n_model_params)
+    p2 = param_slice_to_array(param_indices2, n_model_params)
+    pos1 = np.full(n_model_params, -1, np.int64); pos1[p1] = np.arange(p1.size)
+    pos2 = np.full(n_model_params, -1, np.int64); pos2[p2] = np.arange(p2.size)
+    rows, aa, bb, vals = [], [], [], []
+    off = 0
+    for group, size in ((ops, d * d), (rhos, d), (effs, d)):
+        for m in group:
+            gp = _gp_array(m.gpindices)
+            if gp.size and m.has_nonzero_hessian():
+                l1 = np.flatnonzero(pos1[gp] >= 0); l2 = np.flatnonzero(pos2[gp] >= 0)
+                if l1.size and l2.size:
+                    H = np.asarray(m.hessian_wrt_params(list(l1), list(l2)))
+                    if np.iscomplexobj(H):
+                        H = H.real
+                    H = H.reshape(size, l1.size, l2.size)
+                    r, i, j = np.nonzero(H)
+                    rows.append(off + r); aa.append(pos1[gp[l1[i]]]); bb.append(pos2[gp[l2[j]]]); vals.append(H[r, i, j])
+            off += size
+    cat = lambda x, dt: np.concatenate(x).astype(dt) if x else np.zeros(0, dt)
+    return HessMap(n_w, p1.size, p2.size, cat(rows, np.int32), cat(aa, np.int32), cat(bb, np.int32), cat(vals, np.float64))

@@ -49,7 +49,11 @@ def _canon_perm(map_layout, other_layout, n_circuits):
 
 
 def build_case(name, model, circuits, num_atoms=None, want_hprobs=False, want_map_fd=True,
-               want_matrix=True, extra=None):
+               want_matrix=True, extra=None, hess_rects=None):
+    """hess_rects = [(slice1, slice2), ...]: store the reference Matrix simulator's Hessian for those parameter
+    rectangles only (`hprobs_matrix_rect<i>`, via the rectangle iterator the MLE Hessian uses, forwardsim.py:787-878)
+    together with the members' second derivatives (packing.pack_hessians: `a0_H2r<i>_*`; `a0_H2_*` for the full
+    Hessian of want_hprobs) so that the GPU tests need no pyGSTi."""
     t0 = time.time()
     d = model.dim
     Np = model.num_params
@@ -72,6 +76,11 @@ def build_case(name, model, circuits, num_atoms=None, want_hprobs=False, want_ma
         out[pre + "D_shape"] = np.array([D.n_w, D.n_params])
         es = atom.element_slice
         out[pre + "element_slice"] = np.array([es.start, es.stop])
+        for tag, (sl1, sl2) in ([("H2", (None, None))] if want_hprobs else []) + \
+                [("H2r%d" % i, r) for i, r in enumerate(hess_rects or [])]:
+            H2 = packing.pack_hessians(mdl, atom, d, sl1, sl2)
+            out[pre + tag + "_rows"] = H2.rows; out[pre + tag + "_a"] = H2.a; out[pre + tag + "_b"] = H2.b
+            out[pre + tag + "_vals"] = H2.vals; out[pre + tag + "_shape"] = np.array([H2.n_w, H2.n1, H2.n2])
 
     probs_map = np.empty(nE); mdl.sim.bulk_fill_probs(probs_map, layout)
     out["probs_map"] = probs_map
@@ -92,6 +101,14 @@ def build_case(name, model, circuits, num_atoms=None, want_hprobs=False, want_ma
         if want_hprobs:
             hp = np.empty((nE, Np, Np)); mm.sim.bulk_fill_hprobs(hp, ml)
             out["hprobs_matrix"] = hp[perm]
+        if hess_rects:
+            ml2 = mm.sim.create_layout(circuits, array_types=('e', 'ep', 'epp'))
+            perm2 = _canon_perm(layout, ml2, len(circuits))
+            for i, rect in enumerate(hess_rects):
+                blocks = list(mm.sim.iter_hprobs_by_rectangle(ml2, [rect], False))
+                assert len(blocks) == 1
+                out["hprobs_matrix_rect%d" % i] = np.array(blocks[0][2])[perm2]
+            out["hess_rects"] = np.array([[r[0].start, r[0].stop, r[1].start, r[1].stop] for r in hess_rects])
     if extra:
         out.update(extra)
     path = os.path.join(HERE, name + ".npz")
@@ -158,6 +175,27 @@ def case_c1_1q_tp_hess():
     m = mp.target_model('full TP').depolarize(op_noise=0.03, spam_noise=0.01)
     circs = _subset(mp.create_gst_experiment_design(4).all_circuits_needing_data, 10, seed=2)
     build_case("c1_1q_tp_hess", m, circs, want_hprobs=True)
+
+
+def case_c1_1q_cptplnd_hess():
+    """1-qubit CPTPLND (every member non-linear in its parameters): full analytic Hessian of the Matrix simulator."""
+    from pygsti.modelpacks import smq1Q_XYI as mp
+    m = mp.target_model('CPTPLND')
+    v = m.to_vector(); rng = np.random.default_rng(0)
+    m.from_vector(v + 1e-2 * rng.standard_normal(v.size))
+    circs = _subset(mp.create_gst_experiment_design(4).all_circuits_needing_data, 12, seed=4)
+    build_case("c1_1q_cptplnd_hess", m, circs, want_hprobs=True, want_map_fd=False)
+
+
+def case_c4_2q_cptplnd_hess():
+    """BASELINE config 4 (2-qubit CPTPLND, Np = 1680; parameters: prep [0,240), POVM [240,480), five gates of 240):
+    Hessian rectangles that overlap inside the prep and POVM blocks, inside two gates, and an off-diagonal one."""
+    from pygsti.modelpacks import smq2Q_XYCNOT as mp
+    m = mp.target_model('CPTPLND')
+    v = m.to_vector(); rng = np.random.default_rng(0)
+    m.from_vector(v + 1e-3 * rng.standard_normal(v.size))
+    circs = _subset(mp.create_gst_experiment_design(2).all_circuits_needing_data, 8, seed=5)
+    build_case("c4_2q_cptplnd_hess", m, circs, want_map_fd=False, hess_rects=[(slice(225, 265), slice(230, 278)), (slice(700, 740), slice(690, 738)), (slice(225, 265), slice(700, 748))])
 
 
 def case_c2_2q_full_sub():
@@ -244,7 +282,7 @@ def case_c2_lite_layout():
 
 
 SMALL = ["c1_1q_full", "c1_1q_full_atoms3", "c1_1q_tp", "c1_1q_cptplnd", "c1_1q_hess", "c1_1q_tp_hess",
-         "c2_2q_full_sub", "c4_2q_cptplnd_sub", "c3_3q_localnoise_sub"]
+         "c2_2q_full_sub", "c4_2q_cptplnd_sub", "c3_3q_localnoise_sub", "c1_1q_cptplnd_hess", "c4_2q_cptplnd_hess"]
 
 if __name__ == "__main__":
     names = sys.argv[1:] or SMALL

@@ -140,6 +140,31 @@ def test_hprobs_linear_vs_reference_matrix(gpu_ctx, load_case, name):
     at.free()
 
 
+def test_hprobs_general_vs_reference_matrix(gpu_ctx, load_case):
+    """Fully analytic Hessian for members NOT linear in their parameters (b200_fill_hprobs with the members' second
+    derivatives) against the reference's MatrixForwardSimulator: 1-qubit CPTPLND full Hessian and a sub-block; BASELINE
+    config 4 (2-qubit CPTPLND, Np = 1680) on three rectangles (inside prep/POVM, inside two gates, off-diagonal)."""
+    c = load_case("c1_1q_cptplnd_hess")
+    at = _atom(gpu_ctx, c.atoms[0])
+    Np = c.num_params
+    h2 = c.hess_map("H2")
+    H = np.full((c.n_elements, Np, Np), np.nan)
+    at.fill_hprobs(np.arange(Np), np.arange(Np), H, h2)
+    assert np.max(np.abs(H - c["hprobs_matrix"])) <= 1e-10
+    Hl = np.full_like(H, np.nan)
+    at.fill_hprobs_linear(np.arange(Np), np.arange(Np), Hl)          # without the second-derivative term: must differ
+    assert np.max(np.abs(Hl - c["hprobs_matrix"])) > 1e-3
+    at.free()
+    c = load_case("c4_2q_cptplnd_hess")
+    at = _atom(gpu_ctx, c.atoms[0])
+    for i, r in enumerate(c["hess_rects"]):
+        p1 = np.arange(r[0], r[1]); p2 = np.arange(r[2], r[3])
+        Hb = np.full((c.n_elements, p1.size, p2.size), np.nan)
+        at.fill_hprobs(p1, p2, Hb, c.hess_map("H2r%d" % i))
+        assert np.max(np.abs(Hb - c["hprobs_matrix_rect%d" % i])) <= 1e-10
+    at.free()
+
+
 @pytest.mark.parametrize("name", ["c2_2q_full_sub", "c4_2q_cptplnd_sub", "c1_1q_tp", "c3_3q_localnoise_sub"])
 def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name):
     """b200_fill_dprobs_scaled / b200_jtj (fused objective Jacobian fill) on every kernel path: fused d=16 (trie

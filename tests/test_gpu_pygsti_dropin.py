@@ -117,11 +117,11 @@ def test_atoms_and_param_blocks_equal_single_atom():
                 assert np.max(np.abs(ref[c][1] - cur[c][1])) <= 1e-12
 
 
-@pytest.mark.parametrize("param,tol", [("full", 1e-10), ("full TP", 1e-10), ("CPTPLND", 3e-3)])
+@pytest.mark.parametrize("param,tol", [("full", 1e-10), ("full TP", 1e-10), ("CPTPLND", 1e-10), ("H+S", 1e-10)])
 def test_hprobs_vs_matrix_sim(param, tol):
-    """full / TP members are linear in their parameters -> fully analytic device Hessian (1e-10 vs the
-    reference's analytic Matrix simulator).  CPTPLND: the reference's FD driver (eps=1e-5) over the ANALYTIC
-    device Jacobian; the reference's own Map simulator (FD of FD) is off by ~3e-3 here."""
+    """Fully analytic device Hessian, 1e-10 vs the reference's analytic Matrix simulator: full / TP members are linear
+    in their parameters; CPTPLND / H+S members add their own `hessian_wrt_params` term (b200_fill_hprobs).  The
+    reference's own Map simulator (FD of FD) is off by ~3e-3 on the CPTPLND case."""
     model = smq1Q_XYI.target_model(param)
     v = model.to_vector(); rng = np.random.default_rng(2)
     model.from_vector(v + 5e-3 * rng.standard_normal(v.size))
@@ -135,6 +135,21 @@ def test_hprobs_vs_matrix_sim(param, tol):
         for k in hm[c]:
             worst = max(worst, np.max(np.abs(hm[c][k] - hb[c][k])))
     assert worst <= tol, worst
+
+
+def test_hprobs_fd_driver_fallback():
+    """analytic_hessian=False keeps the reference's own FD driver (mapforwardsim.py:394-438) over the analytic device
+    Jacobian: limited by that driver's truncation error (hessian_eps = 1e-5)."""
+    model = smq1Q_XYI.target_model("CPTPLND")
+    v = model.to_vector(); rng = np.random.default_rng(2)
+    model.from_vector(v + 5e-3 * rng.standard_normal(v.size))
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data[:10]
+    mm = model.copy(); mm.sim = MatrixForwardSimulator()
+    hm = mm.sim.bulk_hprobs(circuits)
+    mb = model.copy(); mb.sim = B200ForwardSimulator(analytic_hessian=False)
+    hb = mb.sim.bulk_hprobs(circuits)
+    worst = max(np.max(np.abs(hm[c][k] - hb[c][k])) for c in circuits for k in hm[c])
+    assert worst <= 3e-3, worst
 
 
 def test_hprobs_rectangles_match_full_blocks():
