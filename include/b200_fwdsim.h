@@ -129,6 +129,19 @@ int b200_fill_hprobs(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t* 
                      int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
                      double* out);
 
+/* "Next" row: one block of the MLE Hessian, reduced on the device.  Replaces
+ * `_hessian_from_block` (pygsti/objectivefns/objectivefns.py:4914-4990) applied to the rectangles produced by
+ * `_iter_atom_hprobs_by_rectangle` (distforwardsim.py:304-340; loop in `_construct_hessian`, objectivefns.py:1576-1693):
+ *     out[a * n2 + b] = sum_el  w_h[el] * d2 p_el / d theta_{p1[a]} d theta_{p2[b]}
+ *                             + w_d[el] * d p_el / d theta_{p1[a]} * d p_el / d theta_{p2[b]}
+ * with w_h = raw_objfn.dterms(probs, ...) and w_d = raw_objfn.hterms(probs, ...) computed by the caller from the
+ * probabilities and the data, exactly as the reference does.  The (n_elements x n1 x n2) Hessian-of-probabilities block
+ * and the Jacobian never leave the device: only n1*n2 doubles are copied out (host buffer `out`).  Arguments p1..h_vals
+ * as in b200_fill_hprobs. */
+int b200_hessian_block(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
+                       int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
+                       const double* w_h, const double* w_d, double* out);
+
 /* ---- the hot path, DEVICE buffers (no copies; asynchronous on the ctx stream) ------------------ */
 int b200_fill_probs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out);
 int b200_fill_dprobs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out, int64_t ld, double* d_probs);

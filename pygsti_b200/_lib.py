@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200_fill_dprobs_fd": (C.c_int, [vp, vp, C.c_double, vp, C.c_int64, vp, C.c_int64]),
     "b200_fill_hprobs_linear": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
     "b200_fill_hprobs": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp]),
+    "b200_hessian_block": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]),
     "b200_fill_dprobs_scaled": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp, C.c_int64]),
     "b200_jtj": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "b200_jtj_dev": (C.c_int, [vp, vp, vp, vp, vp, vp]),

@@ -235,6 +235,28 @@ def mapfill_hprobs_atom_analytic(fwdsim, array_to_fill, dest_param_indices1, des
     return True
 
 
+def atom_hessian_block(fwdsim, layout_atom, param_indices1, param_indices2, w_h, w_d):
+    """One (n1 x n2) block of the MLE Hessian of this atom's elements, reduced on the device
+    (`_hessian_from_block`, objectivefns.py:4914-4990).  Returns None when a member cannot provide analytic second
+    derivatives (the caller then uses the reference path)."""
+    model = fwdsim.model
+    p1 = packing.param_slice_to_array(param_indices1, model.num_params)
+    p2 = packing.param_slice_to_array(param_indices2, model.num_params)
+    hess = None
+    if not all_members_linear(fwdsim, layout_atom):
+        try:
+            hess = packing.pack_hessians(model, layout_atom, model.dim, p1, p2)
+        except (NotImplementedError, ValueError, AssertionError):
+            return None
+    ctx, ent = _engine_atom(fwdsim, layout_atom)
+    atom = ent["atom"]
+    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
+    _deriv_map(fwdsim, layout_atom, ent, None)
+    if layout_atom.num_elements == 0 or p1.size == 0 or p2.size == 0:
+        return np.zeros((p1.size, p2.size))
+    return atom.hessian_block(p1, p2, w_h, w_d, hess)
+
+
 def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     """Upload the derivative map for this parameter block (cached when every member is linear in its
     parameters, in which case D does not depend on the current parameter vector)."""

@@ -201,6 +201,21 @@ class Atom:
                                               _ptr(out)))
         return out
 
+    def hessian_block(self, p1, p2, w_h, w_d, hess=None):
+        """sum_el w_h[el] hprobs[el, p1, p2] + w_d[el] dprobs[el, p1] dprobs[el, p2]  -> (n1, n2); the per-element arrays
+        stay on the device (`_hessian_from_block`, objectivefns.py:4914-4990)."""
+        p1, p2 = _i32(p1), _i32(p2)
+        wh = _f64(w_h).reshape(self.n_elements); wd = _f64(w_d).reshape(self.n_elements)
+        out = np.zeros((p1.shape[0], p2.shape[0]))
+        if hess is not None and (hess.n1 != p1.shape[0] or hess.n2 != p2.shape[0] or hess.n_w != self.n_w):
+            raise ValueError("second-derivative map does not match the rectangle")
+        nnz = hess.nnz if hess is not None else 0
+        _lib.check(self._lib.b200_hessian_block(
+            self.ctx._h, self._h, p1.shape[0], _ptr(p1), p2.shape[0], _ptr(p2), nnz,
+            _ptr(hess.rows) if nnz else None, _ptr(hess.a) if nnz else None, _ptr(hess.b) if nnz else None,
+            _ptr(hess.vals) if nnz else None, _ptr(wh), _ptr(wd), _ptr(out)))
+        return out
+
     # ---- device-buffer fills (raw device pointers, e.g. torch.Tensor.data_ptr()) -----------------
     def fill_probs_dev(self, d_out_ptr):
         _lib.check(self._lib.b200_fill_probs_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr))))

@@ -146,6 +146,20 @@ class B200ForwardSimulator(_MapForwardSimulator):
                 JTf = b if JTf is None else JTf + b
         return JTJ, JTf
 
+    def bulk_hessian_block(self, layout, param_slice1, param_slice2, w_h, w_d):
+        """sum_el w_h[el] hprobs[el, s1, s2] + w_d[el] dprobs[el, s1] dprobs[el, s2] over all local atoms, each reduced on
+        the device: the per-rectangle work of the MLE Hessian (`_construct_hessian` / `_hessian_from_block`,
+        objectivefns.py:1576-1693, 4914-4990) without moving (nE x B1 x B2) arrays to the host.  Returns None if a member
+        has no analytic second derivative."""
+        total = None
+        for atom in layout.atoms:
+            sl = atom.element_slice
+            blk = _b200_calclib.atom_hessian_block(self, atom, param_slice1, param_slice2, w_h[sl], w_d[sl])
+            if blk is None:
+                return None
+            total = blk if total is None else total + blk
+        return total
+
     def __getstate__(self):
         state = super().__getstate__()
         state.pop('calclib', None)

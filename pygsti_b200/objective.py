@@ -71,3 +71,36 @@ def fused_jtj(objfn, paramvec=None):
         return J.T @ J, J.T @ f
     scale, lsvec = _lsvec_scale(objfn, paramvec)
     return objfn.model.sim.bulk_jtj(objfn.layout, scale, lsvec[:objfn.nelements])
+
+
+def fused_hessian(objfn, paramvec=None, block_size=None):
+    """== objfn.hessian(paramvec) for a TimeIndependentMDCObjectiveFunction without omitted-outcome rows or penalties:
+    the loop of `_construct_hessian` (objectivefns.py:1576-1693) over parameter rectangles, with every rectangle's
+    `_hessian_from_block` (objectivefns.py:4914-4990) evaluated and reduced on the device
+    (`B200ForwardSimulator.bulk_hessian_block` -> b200_hessian_block): only B1 x B2 doubles per rectangle reach the host.
+    Anything else is delegated to the objective function's own method."""
+    if paramvec is not None:
+        objfn.model.from_vector(paramvec)
+    sim = objfn.model.sim
+    if not (_plain(objfn) and hasattr(sim, "bulk_hessian_block")) or objfn.ex != 0:
+        return objfn.hessian(paramvec)
+    layout = objfn.layout
+    nE, Np = objfn.nelements, objfn.model.num_params
+    probs = np.empty(nE)
+    sim.bulk_fill_probs(probs, layout)
+    if objfn.prob_clip_interval is not None:
+        np.clip(probs, objfn.prob_clip_interval[0], objfn.prob_clip_interval[1], out=probs)
+    w_d = objfn.raw_objfn.hterms(probs, objfn.counts, objfn.total_counts, objfn.freqs)   # multiplies dprobs12
+    w_h = objfn.raw_objfn.dterms(probs, objfn.counts, objfn.total_counts, objfn.freqs)   # multiplies hprobs
+    B = int(block_size) if block_size else min(Np, 64)
+    H = np.zeros((Np, Np))
+    for a0 in range(0, Np, B):
+        for b0 in range(a0, Np, B):                      # symmetric: upper block triangle, mirrored
+            s1, s2 = slice(a0, min(a0 + B, Np)), slice(b0, min(b0 + B, Np))
+            blk = sim.bulk_hessian_block(layout, s1, s2, w_h, w_d)
+            if blk is None:
+                return objfn.hessian(paramvec)
+            H[s1, s2] = blk
+            if b0 != a0:
+                H[s2, s1] = blk.T
+    return H

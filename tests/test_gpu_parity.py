@@ -165,6 +165,40 @@ def test_hprobs_general_vs_reference_matrix(gpu_ctx, load_case):
     at.free()
 
 
+def test_hessian_block_reduction(gpu_ctx, load_case):
+    """b200_hessian_block: sum_el w_h hprobs + w_d dprobs dprobs reduced on the device == the same reduction of the
+    reference Matrix simulator's hprobs / dprobs goldens (linear members, CPTPLND 1Q full, CPTPLND 2Q rectangles)."""
+    rng = np.random.default_rng(11)
+    for name, tag in (("c1_1q_tp_hess", None), ("c1_1q_cptplnd_hess", "H2")):
+        c = load_case(name)
+        at = _atom(gpu_ctx, c.atoms[0])
+        wh = rng.standard_normal(c.n_elements); wd = rng.standard_normal(c.n_elements)
+        p1 = np.arange(3, 31); p2 = np.arange(10, c.num_params)
+        Hp = c["hprobs_matrix"][:, p1][:, :, p2]; Jm = c["dprobs_matrix"]
+        ref = np.einsum('e,eab->ab', wh, Hp) + np.einsum('e,ea,eb->ab', wd, Jm[:, p1], Jm[:, p2])
+        hess = None
+        if tag:
+            full = c.hess_map(tag)
+            from pygsti_b200.packing import HessMap
+            pos1 = np.full(c.num_params, -1); pos1[p1] = np.arange(p1.size)
+            pos2 = np.full(c.num_params, -1); pos2[p2] = np.arange(p2.size)
+            keep = (pos1[full.a] >= 0) & (pos2[full.b] >= 0)
+            hess = HessMap(full.n_w, p1.size, p2.size, full.rows[keep], pos1[full.a[keep]], pos2[full.b[keep]], full.vals[keep])
+        out = at.hessian_block(p1, p2, wh, wd, hess)
+        assert np.max(np.abs(out - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), name
+        at.free()
+    c = load_case("c4_2q_cptplnd_hess")
+    at = _atom(gpu_ctx, c.atoms[0])
+    wh = rng.standard_normal(c.n_elements); wd = rng.standard_normal(c.n_elements)
+    Jm = c["dprobs_matrix"]
+    for i, r in enumerate(c["hess_rects"]):
+        p1 = np.arange(r[0], r[1]); p2 = np.arange(r[2], r[3])
+        ref = np.einsum('e,eab->ab', wh, c["hprobs_matrix_rect%d" % i]) + np.einsum('e,ea,eb->ab', wd, Jm[:, p1], Jm[:, p2])
+        out = at.hessian_block(p1, p2, wh, wd, c.hess_map("H2r%d" % i))
+        assert np.max(np.abs(out - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref))), i
+    at.free()
+
+
 @pytest.mark.parametrize("name", ["c2_2q_full_sub", "c4_2q_cptplnd_sub", "c1_1q_tp", "c3_3q_localnoise_sub"])
 def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name):
     """b200_fill_dprobs_scaled / b200_jtj (fused objective Jacobian fill) on every kernel path: fused d=16 (trie

@@ -278,3 +278,32 @@ def test_fused_objective_jacobian_and_jtj(objname):
     assert np.max(np.abs(JTJ - R)) <= 1e-7 * np.max(np.abs(R))
     assert np.max(np.abs(JTf - Jref.T @ fref)) <= 1e-7 * max(1.0, np.max(np.abs(Jref.T @ fref)))
     assert np.max(np.abs(Jf.T @ Jf - JTJ)) <= 1e-10 * np.max(np.abs(R))
+
+
+@pytest.mark.parametrize("param", ["full TP", "CPTPLND"])
+def test_fused_mle_hessian(param):
+    """'next' row 8f-2: the MLE Hessian assembled from rectangles that are evaluated AND reduced on the device
+    (b200_hessian_block) against the reference objective function's own `hessian()` on the reference's analytic Matrix
+    simulator (objectivefns.py:4892-4990, 1576-1693)."""
+    from pygsti.data import simulate_data
+    from pygsti.objectivefns import objectivefns as _objfns
+    from pygsti_b200 import objective as fused
+    target = smq1Q_XYI.target_model(param)
+    datagen = smq1Q_XYI.target_model("full TP").depolarize(op_noise=0.1, spam_noise=0.05)
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data[:40]
+    ds = simulate_data(datagen, circuits, 1000, seed=1234)
+    v = target.to_vector(); rng = np.random.default_rng(5)
+    start = target.copy(); start.from_vector(v + 5e-3 * rng.standard_normal(v.size))
+
+    def make(sim):
+        m = start.copy(); m.sim = sim
+        return _objfns.PoissonPicDeltaLogLFunction.create_from(m, ds, circuits, method_names=('hessian',))
+
+    Href = make(MatrixForwardSimulator()).hessian()
+    ours = make(B200ForwardSimulator())
+    H = fused.fused_hessian(ours, block_size=17)          # ragged blocks on purpose
+    assert H.shape == Href.shape
+    assert np.max(np.abs(H - H.T)) <= 1e-9 * np.max(np.abs(Href))
+    assert np.max(np.abs(H - Href)) <= 1e-8 * np.max(np.abs(Href))
+    Hsame = ours.hessian()                                # reference code path on the GPU simulator (host-side reduction)
+    assert np.max(np.abs(H - Hsame)) <= 1e-8 * np.max(np.abs(Href))
