@@ -87,6 +87,7 @@ struct b200_atom {
     // level-batched Jacobian path (d >= 64): row maps of the state / adjoint tables, backward-sweep tiles, D tile plan
     bool has_lj = false;
     DevBuf lj_fbase, lj_bbase, lj_frow, lj_brow, lj_btiles, lj_ti_ptr, lj_items;
+    DevBuf lj2_ti_ptr, lj2_mask, lj2_items, lj2_ij, lj2_v;       // DMMA accumulate (k_level_accum2): per (tile, gate, sub-block)
     std::vector<uint32_t> lj_btile_ptr;     // [max_depth+1]
     uint64_t lj_rows_f = 0, lj_rows_b = 0;
     int lj_no_max = 0, lj_n_tiles = 0;
@@ -581,7 +582,8 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
-                      &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
+                      &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
+                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
                       &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
@@ -709,6 +711,51 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
         if (items.empty()) items.push_back(make_uint4(0, 0, 0, 0));
         a->lj_n_tiles = n_tiles;
         if ((rc = upload_vec(a->lj_ti_ptr, ti_ptr, ctx->stream)) || (rc = upload_vec(a->lj_items, items, ctx->stream))) return rc;
+        // plan of the DMMA accumulate: gate-block non-zeros regrouped by (parameter tile, gate, 64 x 64 sub-block), with the
+        // 8 x 8 tiles each group touches
+        {
+            const int d = a->dim, sbd = d / 64, nsb = sbd * sbd;
+            struct Rec { uint64_t key; uint32_t p_local; uint16_t ij; double v; };
+            std::vector<Rec> recs;
+            for (int p = 0; p < n_params; ++p)
+                for (int t = cptr[p]; t < cptr[p + 1]; ++t) {
+                    if (crow[t] >= a->off_rho) break;                      // rows are sorted: the rest is prep / effect rows
+                    const int g = (int)(crow[t] / dd); const int wl = (int)(crow[t] - (int64_t)g * dd);
+                    const int i = wl / d, j = wl - i * d;
+                    const int sb = (i / 64) * sbd + (j / 64);
+                    Rec r; r.key = ((uint64_t)(p / LJ_PT) * a->n_ops + g) * nsb + sb; r.p_local = (uint32_t)(p % LJ_PT);
+                    r.ij = (uint16_t)(((i & 63) << 8) | (j & 63)); r.v = cval[t];
+                    recs.push_back(r);
+                }
+            std::stable_sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) {
+                return x.key != y.key ? x.key < y.key : x.p_local < y.p_local; });
+            const size_t n_keys = (size_t)n_tiles * a->n_ops * nsb;
+            std::vector<uint32_t> tp2((size_t)n_tiles * a->n_ops * (nsb + 1), 0);
+            std::vector<uint64_t> mask2(std::max<size_t>(n_keys, 1), 0);
+            std::vector<uint4> items2; std::vector<uint16_t> nz_ij(recs.size()); std::vector<double> nz_v(recs.size());
+            size_t r = 0;
+            for (size_t key = 0; key < n_keys; ++key) {
+                const size_t tg = key / nsb, sb = key % nsb;               // tg = tile * n_ops + g
+                tp2[tg * (nsb + 1) + sb] = (uint32_t)items2.size();
+                while (r < recs.size() && recs[r].key == key) {
+                    uint4 it = make_uint4(recs[r].p_local, (unsigned)r, (unsigned)r, 0u);
+                    while (r < recs.size() && recs[r].key == key && recs[r].p_local == it.x) {
+                        nz_ij[r] = recs[r].ij; nz_v[r] = recs[r].v;
+                        mask2[key] |= (uint64_t)1 << (8 * ((recs[r].ij >> 8) / 8) + (recs[r].ij & 0xff) / 8);
+                        ++r;
+                    }
+                    it.z = (unsigned)r;
+                    items2.push_back(it);
+                }
+                if (sb == (size_t)nsb - 1) tp2[tg * (nsb + 1) + nsb] = (uint32_t)items2.size();
+            }
+            if (items2.empty()) items2.push_back(make_uint4(0, 0, 0, 0));
+            if (nz_ij.empty()) { nz_ij.push_back(0); nz_v.push_back(0.0); }
+            if ((rc = upload_vec(a->lj2_ti_ptr, tp2, ctx->stream)) || (rc = upload_vec(a->lj2_mask, mask2, ctx->stream)) ||
+                (rc = upload_vec(a->lj2_items, items2, ctx->stream)) || (rc = upload_vec(a->lj2_ij, nz_ij, ctx->stream)) ||
+                (rc = upload_vec(a->lj2_v, nz_v, ctx->stream))) return rc;
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_derivs = true;
@@ -823,7 +870,21 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (chain_k < 0) { const char* e = getenv("B200_CHAIN_K"); chain_k = (e && atoi(e) > 0) ? atoi(e) : 2; }
     if (st256 < 0) { const char* e = getenv("B200_ACC_ST256"); st256 = e ? atoi(e) : 0; }   // measured: 0.914 ms with, 0.891 ms without
     int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
+    static const bool chain_prof = getenv("B200_CHAIN_PROF") != nullptr;
+    t.prof = nullptr;
+    if (chain_prof) {
+        CU(c->f_buf.ensure(std::max<size_t>(c->f_buf.cap, 128)));
+        t.prof = c->f_buf.as<unsigned long long>(); CU(cudaMemsetAsync(t.prof, 0, 128, c->stream));
+    }
     k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, chain_k, 0);
+    if (t.prof) {
+        unsigned long long h[8];
+        CU(cudaMemcpyAsync(h, t.prof, 64, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+        const double nw = (double)gA / 2 * TRIE_WARPS;
+        for (int r = 0; r < 2; ++r)
+            fprintf(stderr, "[chain prof] role %d (%d chains): per-warp mean cycles: hand-out %.0f, parent wait %.0f, steps %.0f, total %.0f\n",
+                    r, r ? a->n_bchains : a->n_fchains, h[r * 4] / nw, h[r * 4 + 1] / nw, h[r * 4 + 2] / nw, h[r * 4 + 3] / nw);
+    }
     const int dbg = getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0;
     const bool w256 = st256 && (((uintptr_t)args.J & 31) == 0);        // 32-byte stores need 32-byte aligned rows
     auto launchB = [&](auto kern, int per_sm) -> int {
@@ -837,6 +898,13 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
     else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
     if (rcB) return rcB;
+    if (t.prof) {
+        unsigned long long h[4];
+        CU(cudaMemcpyAsync(h, t.prof + 8, 32, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
+        const double nw = (double)grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), a->unit_outcomes == 2 ? 3 : 2) * AT_WARPS;
+        fprintf(stderr, "[accum prof] %d units: per-warp mean cycles: chunk prologue %.0f, group loop %.0f, epilogue %.0f, total %.0f\n",
+                a->n_units, h[0] / nw, h[1] / nw, h[2] / nw, h[3] / nw);
+    }
     c->launches += 2;
     CU(cudaGetLastError());
     return B200_OK;
@@ -941,7 +1009,7 @@ static int launch_probs_level(b200_ctx* c, b200_atom* a, double* d_out) {
 }
 
 static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
-    TrieDev t; memset(&t, 0, sizeof t);
+    TrieDev t; memset(&t, 0, sizeof t);      // (prof = nullptr)
     t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
     t.S = a->t_S.as<double>(); t.counters = a->t_counters.as<unsigned>();
@@ -990,8 +1058,10 @@ static bool levelj_ok(b200_ctx* c, b200_atom* a) {
 template <int D>
 static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
     if (a->n_rows == 0) return B200_OK;
-    CU(c->lj_fs.ensure((size_t)a->lj_rows_f * D * 8));
-    CU(c->lj_bh.ensure((size_t)a->lj_rows_b * D * 8));
+    CU(c->lj_fs.ensure(((size_t)a->lj_rows_f + 1) * D * 8));      // + one all-zero row each (bucket padding of the DMMA accumulate)
+    CU(c->lj_bh.ensure(((size_t)a->lj_rows_b + 1) * D * 8));
+    CU(cudaMemsetAsync(c->lj_fs.as<double>() + (size_t)a->lj_rows_f * D, 0, (size_t)D * 8, c->stream));
+    CU(cudaMemsetAsync(c->lj_bh.as<double>() + (size_t)a->lj_rows_b * D, 0, (size_t)D * 8, c->stream));
     if (!c->aux) {
         CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
@@ -1032,8 +1102,19 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
         k_levelj_probs<D><<<gi, 128, 0, c->stream>>>(ad, md, lj, d_probs);
         c->launches++;
     }
-    CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-    k_level_accum<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC, c->stream>>>(ad, md, lj, d_out, ld, d_scale);
+    static const bool accum_v1 = getenv("B200_LJ_ACCUM_V1") != nullptr;      // dev knob: scalar shared-memory contraction
+    const size_t smemC2 = ((size_t)a->lj_no_max * LJ_PT + 64 * LJ_LDW) * 8 + LJ_KMAX * 4 + 16;
+    if (accum_v1 || smemC2 + 1024 > c->smem_optin) {
+        CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+        k_level_accum<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC, c->stream>>>(ad, md, lj, d_out, ld, d_scale);
+    } else {
+        LevelJ2Dev l2;
+        l2.ti_ptr2 = a->lj2_ti_ptr.as<uint32_t>(); l2.mask2 = a->lj2_mask.as<uint64_t>(); l2.items2 = a->lj2_items.as<uint4>();
+        l2.nz_ij = a->lj2_ij.as<uint16_t>(); l2.nz_v = a->lj2_v.as<double>();
+        l2.zrow_f = (uint32_t)a->lj_rows_f; l2.zrow_b = (uint32_t)a->lj_rows_b; l2.nsb = (D / 64) * (D / 64);
+        CU(cudaFuncSetAttribute(k_level_accum2<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC2));
+        k_level_accum2<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC2, c->stream>>>(ad, md, lj, l2, d_out, ld, d_scale);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return B200_OK;

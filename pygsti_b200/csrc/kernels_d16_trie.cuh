@@ -39,6 +39,7 @@ struct TrieDev {
     double* S;                 // [n_fnodes][16]
     double* H;                 // [n_bnodes][n_eff][16]
     unsigned* counters;        // [4] work counters: forward chains, backward chains, accumulate chunks (zeroed before launch)
+    unsigned long long* prof;  // dev knob B200_CHAIN_PROF: [2 roles][4] warp-cycles in hand-out, parent wait, steps, total; [8..11] accumulate (or nullptr)
 };
 
 #define TRIE_WARPS 4
@@ -84,6 +85,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
     }
     __syncthreads();
 
+    long long pr_grab = 0, pr_wait = 0, pr_step = 0; const long long pr_t0 = clock64();
     unsigned* ctr = t.counters + role;
     const int n_chains = role ? t.n_bchains : t.n_fchains;
     const int4* meta = role ? t.b_meta : t.f_meta;
@@ -94,6 +96,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
         double* fx = fx_all + warp * 32;
         const int half = lane >> 4;
         for (;;) {
+            const long long tq0 = clock64();
             int c0 = 0;
             if (lane == 0) c0 = (int)atomicAdd(ctr, (unsigned)kgrab);
             c0 = __shfl_sync(0xffffffffu, c0, 0);
@@ -105,6 +108,8 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                 const uint32_t first = (uint32_t)mt.y, len = (uint32_t)mt.z;
                 if (ci + 1 < c1) mt = __ldg(meta + ci + 1);
                 int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
+                const long long tq1 = clock64();
+                if (ci == c0) pr_grab += tq1 - tq0;
                 double v = 0.0;
                 uint32_t i0 = 0;
                 if (parent < 0) {                       // root chain: first node is the prep itself
@@ -118,6 +123,8 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                     }
                     __syncwarp();
                 }
+                const long long tq2 = clock64();
+                pr_wait += tq2 - tq1;
                 int cur = 0;
                 if (lane < 16) fx[lane] = v;
                 __syncwarp();
@@ -136,6 +143,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                     if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
                     __syncwarp();
                 }
+                pr_step += clock64() - tq2;
             }
         }
     } else {
@@ -144,6 +152,7 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
         const int ne = a.n_eff;
         const bool rowok = mrow < ne;
         for (;;) {
+            const long long tq0 = clock64();
             int c0 = 0;
             if (lane == 0) c0 = (int)atomicAdd(ctr, (unsigned)kgrab);
             c0 = __shfl_sync(0xffffffffu, c0, 0);
@@ -155,6 +164,8 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                 const uint32_t first = (uint32_t)mt.y, len = (uint32_t)mt.z;
                 if (ci + 1 < c1) mt = __ldg(meta + ci + 1);
                 int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
+                const long long tq1 = clock64();
+                if (ci == c0) pr_grab += tq1 - tq0;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 uint32_t i0 = 0;
                 if (parent < 0) {                       // root: E itself
@@ -179,6 +190,8 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                     }
                     __syncwarp();
                 }
+                const long long tq2 = clock64();
+                pr_wait += tq2 - tq1;
                 for (uint32_t i = i0; i < len; ++i) {
                     if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
                     const int g = __shfl_sync(0xffffffffu, opv, (int)(i & 31u));
@@ -195,8 +208,13 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int kgrab, int fwd_only)
                         __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
                     }
                 }
+                pr_step += clock64() - tq2;
             }
         }
+    }
+    if (t.prof && lane == 0) {
+        atomicAdd(t.prof + role * 4 + 0, (unsigned long long)pr_grab); atomicAdd(t.prof + role * 4 + 1, (unsigned long long)pr_wait);
+        atomicAdd(t.prof + role * 4 + 2, (unsigned long long)pr_step); atomicAdd(t.prof + role * 4 + 3, (unsigned long long)(clock64() - pr_t0));
     }
 }
 
@@ -300,7 +318,9 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     constexpr int SB1 = W256 ? 2 : 8;                                         // second fragment: jmap1 = jmap0 + 2  |  mrow + 8
     const double* Hb = t.H + mrow;
 
+    long long pr_pro = 0, pr_grp = 0, pr_epi = 0; const long long pr_t0 = clock64();   // dev knob B200_CHAIN_PROF
     for (;;) {
+        const long long tq0 = clock64();
         int u0 = 0;
         if (lane == 0) u0 = (int)atomicAdd(counter, 1u) * AT_CHUNK;
         u0 = __shfl_sync(0xffffffffu, u0, 0);
@@ -321,7 +341,9 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             for (int k = 0; k < 2 * NO; ++k) r[2 + k] = ldk(hp + 8 * k);
         }
         ip += 8;
+        pr_pro += clock64() - tq0;
         for (int u = u0; u < u1; ++u) {
+            const long long tq1 = clock64();
             // next unit's record (needed only after this unit's groups)
             const int un = (u + 1 < u1) ? u + 1 : u;
             const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
@@ -350,6 +372,8 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 for (int k = 0; k < 2 + 2 * NO; ++k) r[k] = n[k];
                 nd1 = nd2;
             }
+            const long long tq2 = clock64();
+            pr_grp += tq2 - tq1;
             if (dbg == 2) { if (acc[0][0] + acc[NO - 1][1] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
             // ---------------- epilogue: the finished 16x16 blocks are Jacobian entries ----------------
             const int2* cm = cm_s + g * 128 + lane;
@@ -446,6 +470,11 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 }
             }
             ra = ran; rb = rbn;
+            pr_epi += clock64() - tq2;
         }
+    }
+    if (t.prof && lane == 0) {
+        atomicAdd(t.prof + 8, (unsigned long long)pr_pro); atomicAdd(t.prof + 9, (unsigned long long)pr_grp);
+        atomicAdd(t.prof + 10, (unsigned long long)pr_epi); atomicAdd(t.prof + 11, (unsigned long long)(clock64() - pr_t0));
     }
 }

@@ -234,3 +234,152 @@ k_level_accum(AtomDev a, ModelDev m, LevelJDev lj, double* __restrict__ J, int64
         for (int p = tid; p < tile_np; p += LJ_THREADS) __stcs(Jr + p, Jacc[o * LJ_PT + p] * sc);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// phase C, version 2 (default): the outer products are formed on the FP64 tensor cores.
+//   W_g^{(o)}[i][j] = sum_{t in bucket(c, g)} e^{(o)}_{t+1}[i] s_t[j]   (M = i, N = j, K = the bucket's steps, DMMA m8n8k4)
+// is accumulated in registers for one 64 x 64 sub-block of the d x d matrix at a time (d = 64: the whole matrix), ONLY for
+// the 8 x 8 tiles that contain a non-zero of dG_g/dtheta for a parameter of this CTA's tile (64-bit tile mask built on
+// the host: an embedded 1-qubit gate needs 8-32 of the 64 tiles, a fully parameterised gate only the rows of its tile),
+// parked in shared memory, and contracted with the sparse derivative map by one thread per parameter.
+// A / B fragments are gathered straight from the adjoint / state tables (8-byte loads through L1: the four warps share
+// the state rows); buckets are padded to a multiple of 4 steps with an all-zero table row.
+// One CTA per (circuit, tile of LJ_PT parameters); per gate, per outcome: DMMA -> smem tile -> sparse contraction.
+// dynamic smem (doubles): no_max * LJ_PT (accumulators) + 64 * LJ_LDW (W tile) + LJ_KMAX ints (bucket step list)
+// ------------------------------------------------------------------------------------------------------------
+#define LJ_LDW 66
+#define LJ_KMAX 256
+
+struct LevelJ2Dev {
+    const uint32_t* ti_ptr2;   // [n_tiles][n_ops][nsb + 1] item ranges per (tile, gate, 64x64 sub-block)
+    const uint64_t* mask2;     // [n_tiles][n_ops][nsb] needed 8x8 tiles of the sub-block (bit 8*mt + nt)
+    const uint4* items2;       // (p_local, nz lo, nz hi, 0) into nz_ij / nz_v
+    const uint16_t* nz_ij;     // (i_local << 8) | j_local inside the sub-block
+    const double* nz_v;
+    uint32_t zrow_f, zrow_b;   // all-zero rows of FS / BH
+    int nsb;                   // sub-blocks per matrix = (D / 64)^2
+};
+
+template <int D>
+__global__ void __launch_bounds__(LJ_THREADS)
+k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __restrict__ J, int64_t ld,
+               const double* __restrict__ row_scale)
+{
+    constexpr int SBD = D / 64;                       // sub-blocks per dimension
+    extern __shared__ __align__(16) double sml[];
+    double* Jacc = sml;                               // [no_max][LJ_PT]
+    double* Wt = Jacc + (size_t)lj.no_max * LJ_PT;    // [64][LJ_LDW]
+    int* kidx = reinterpret_cast<int*>(Wt + 64 * LJ_LDW);   // [LJ_KMAX] step index, or -1 = padding
+    const int c = blockIdx.x / lj.n_tiles, tile = blockIdx.x - c * lj.n_tiles;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mrow = lane >> 2, q = lane & 3;
+    const int q0 = a.out_ptr[c], nout = a.out_ptr[c + 1] - q0;
+    const uint32_t p0 = a.circ_ptr[c], Lc = a.circ_ptr[c + 1] - p0;
+    const size_t fb = lj.fbase[c], bb = lj.bbase[c];
+    const int tile_p0 = tile * LJ_PT;
+    const int tile_np = (lj.n_params - tile_p0 < LJ_PT) ? lj.n_params - tile_p0 : LJ_PT;
+    const uint16_t* cn = lj.bcnt + (size_t)c * a.n_ops;
+    const uint16_t* perm = lj.bperm + p0;
+    const uint32_t* tp2 = l2.ti_ptr2 + (size_t)tile * a.n_ops * (l2.nsb + 1);
+    const uint64_t* mk2 = l2.mask2 + (size_t)tile * a.n_ops * l2.nsb;
+
+    for (int idx = tid; idx < nout * LJ_PT; idx += LJ_THREADS) Jacc[idx] = 0.0;
+    uint32_t tb = 0;
+    for (int g = 0; g < a.n_ops; ++g) {
+        const int cnt = cn[g];
+        const uint32_t* tpg = tp2 + (size_t)g * (l2.nsb + 1);
+        if (cnt > 0 && tpg[l2.nsb] > tpg[0]) {
+            for (int s0 = 0; s0 < cnt; s0 += LJ_KMAX) {           // (buckets longer than LJ_KMAX steps: several passes)
+                const int ns = (cnt - s0 < LJ_KMAX) ? cnt - s0 : LJ_KMAX;
+                const int ns4 = (ns + 3) & ~3;
+                __syncthreads();
+                for (int t = tid; t < ns4; t += LJ_THREADS) kidx[t] = (t < ns) ? (int)perm[tb + s0 + t] : -1;
+                __syncthreads();
+                for (int sb = 0; sb < l2.nsb; ++sb) {
+                    const uint32_t it0 = tpg[sb], it1 = tpg[sb + 1];
+                    if (it1 == it0) continue;
+                    const uint64_t mask = mk2[(size_t)g * l2.nsb + sb];
+                    const unsigned wm = (unsigned)(mask >> (16 * warp)) & 0xffffu;     // this warp: m-tiles 2w, 2w+1
+                    const unsigned need_n = (wm | (wm >> 8)) & 0xffu;
+                    const int ib = (sb / SBD) * 64, jb = (sb % SBD) * 64;
+                    for (int o = 0; o < nout; ++o) {
+                        double acc[2][8][2];
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+                        if (wm) {
+                            const size_t brow0 = bb + (size_t)o * (Lc + 1) + 1;
+                            for (int k0 = 0; k0 < ns4; k0 += 4) {
+                                const int k = kidx[k0 + q];
+                                const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l2.zrow_b) * D + ib + warp * 16 + mrow;
+                                const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l2.zrow_f) * D + jb + mrow;
+                                const double a0 = __ldg(er), a1 = __ldg(er + 8);
+#pragma unroll
+                                for (int nt = 0; nt < 8; ++nt) {
+                                    if (need_n & (1u << nt)) {                 // warp-uniform
+                                        const double b = __ldg(sr + nt * 8);
+                                        if (wm & (1u << nt)) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
+                                        if (wm & (1u << (8 + nt))) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
+                                    }
+                                }
+                            }
+                        }
+                        __syncthreads();                                        // previous contraction has read Wt
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 8; ++nt)
+                                if (wm & (1u << (8 * mt + nt)))
+                                    *reinterpret_cast<double2*>(Wt + (warp * 16 + mt * 8 + mrow) * LJ_LDW + nt * 8 + 2 * q) =
+                                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                        __syncthreads();
+                        for (uint32_t it = it0 + tid; it < it1; it += LJ_THREADS) {
+                            const uint4 item = __ldg(l2.items2 + it);
+                            double s = 0.0;
+                            for (uint32_t t = item.y; t < item.z; ++t) {
+                                const unsigned ij = __ldg(l2.nz_ij + t);
+                                s = fma(__ldg(l2.nz_v + t), Wt[(ij >> 8) * LJ_LDW + (ij & 0xffu)], s);
+                            }
+                            Jacc[o * LJ_PT + item.x] += s;
+                        }
+                    }
+                }
+            }
+        }
+        tb += cnt;
+    }
+    __syncthreads();
+    {   // state-preparation and effect rows of D (same as version 1)
+        const uint32_t* tp = lj.ti_ptr + (size_t)tile * (a.n_ops + 2);
+        const uint32_t it0 = tp[a.n_ops], it1 = tp[a.n_ops + 1];
+        const int nwork = (int)(it1 - it0) * nout;
+        const int prep = a.circ_prep[c];
+        const double* sL = lj.FS + (fb + Lc) * D;
+        for (int w = tid; w < nwork; w += LJ_THREADS) {
+            const int it = w / nout, o = w - it * nout;
+            const uint4 item = __ldg(lj.items + it0 + it);
+            const int eff = a.out_eff[q0 + o];
+            const double* e0 = lj.BH + (bb + (size_t)o * (Lc + 1)) * D;
+            double acc = 0.0;
+            for (uint32_t t = item.y; t < item.z; ++t) {
+                const int64_t wl = __ldg(lj.crow + t);
+                if (wl < m.off_eff) {
+                    const int r = (int)((wl - m.off_rho) / D), i = (int)((wl - m.off_rho) - (int64_t)r * D);
+                    if (r == prep) acc = fma(__ldg(lj.cval + t), e0[i], acc);
+                } else {
+                    const int r = (int)((wl - m.off_eff) / D), i = (int)((wl - m.off_eff) - (int64_t)r * D);
+                    if (r == eff) acc = fma(__ldg(lj.cval + t), sL[i], acc);
+                }
+            }
+            Jacc[o * LJ_PT + item.x] += acc;
+        }
+    }
+    __syncthreads();
+    for (int o = 0; o < nout; ++o) {
+        const int64_t el = a.out_el[q0 + o];
+        const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
+        double* Jr = J + el * ld + tile_p0;
+        for (int p = tid; p < tile_np; p += LJ_THREADS) __stcs(Jr + p, Jacc[o * LJ_PT + p] * sc);
+    }
+}

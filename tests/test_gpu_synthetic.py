@@ -176,7 +176,8 @@ def test_level_batched_jacobian(gpu_ctx, dim, n_ops, n_rho, n_eff, n_circ, depth
 
 
 def test_level_batched_matches_generic_path():
-    """The level-batched d = 64 Jacobian and the correctness-first W-matrix path agree (subprocess: env latch)."""
+    """The level-batched d = 64 Jacobian (DMMA accumulate, and its scalar predecessor) and the correctness-first W-matrix
+    path agree (subprocess: env latch)."""
     code = r'''
 import sys, numpy as np
 sys.path.insert(0, %r)
@@ -194,10 +195,11 @@ np.save(sys.argv[1], J); print("ok", ctx.launch_count)
     import tempfile
     outs = []
     with tempfile.TemporaryDirectory() as td:
-        for tag, extra in (("lj", {}), ("gen", {"B200_NO_LEVELJ": "1"})):
+        for tag, extra in (("lj", {}), ("gen", {"B200_NO_LEVELJ": "1"}), ("lj_v1", {"B200_LJ_ACCUM_V1": "1"})):
             f = os.path.join(td, tag + ".npy")
             r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=600)
             assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
             outs.append(np.load(f))
     assert np.all(np.isfinite(outs[0]))
-    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))
+    assert np.max(np.abs(outs[0] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # DMMA accumulate vs W-matrix path
+    assert np.max(np.abs(outs[2] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # scalar accumulate vs W-matrix path
