@@ -894,9 +894,23 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
                                                       a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
         return B200_OK;
     };
-    int rcB;
-    if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
-    else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
+    static int acc_v6 = -1;                           // dev knob: register-pipelined version 6 instead of the cp.async ring
+    if (acc_v6 < 0) { const char* e = getenv("B200_ACC_V6"); acc_v6 = (e && atoi(e)) ? 1 : 0; }
+    auto launchB7 = [&](auto kern, int no) -> int {
+        const size_t smem7 = (size_t)AT_WARPS * AT_RING * (4 * 20 + 4 * (no * 16 + 4)) * 8 + smemB;
+        if (smem7 + 1024 > c->smem_optin) return 1;                       // does not fit: use version 6
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
+        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
+        kern<<<gB, AT_WARPS * 32, smem7, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                     a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
+        return B200_OK;
+    };
+    int rcB = 1;
+    if (!acc_v6) rcB = (a->unit_outcomes == 2) ? launchB7(k_accum_trie_d16_cp<2>, 2) : launchB7(k_accum_trie_d16_cp<4>, 4);
+    if (rcB == 1) {
+        if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
+        else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
+    }
     if (rcB) return rcB;
     if (t.prof) {
         unsigned long long h[4];

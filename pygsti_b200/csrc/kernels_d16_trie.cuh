@@ -478,3 +478,225 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
         atomicAdd(t.prof + 10, (unsigned long long)pr_epi); atomicAdd(t.prof + 11, (unsigned long long)(clock64() - pr_t0));
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// phase B, version 7 (default): same units, same epilogue, but the table rows travel global -> shared with cp.async
+// (LDGSTS, 16-byte chunks, L2 evict_last) into a per-warp ring of AT_RING groups, so that AT_RING-1 groups of gathers
+// (2.5 KB each) are in flight per warp -- also while the warp is busy storing a finished block.  Version 6 kept one
+// group in registers; its profile (B200_CHAIN_PROF) showed 57 % of the warp cycles in the gather loop at ~1.8 k cycles
+// per group of 4 steps, i.e. one exposed L2 round trip per group: by Little's law ~20 KB in flight per SM was all it
+// could sustain.  Ring slot layout (doubles): S rows at q*20 (+mrow, +8+mrow), H rows at 80 + q*(NO*16+4) + o*16 (+mrow,
+// +8+mrow): both strides are 4 mod 16, which makes the 64-bit fragment loads conflict-free per half-warp.
+// dynamic smem: AT_WARPS * AT_RING * slot doubles, then the column-map fragments and SPAM lists as in version 6.
+// ------------------------------------------------------------------------------------------------------------
+#define AT_RING 4
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, uint64_t pol) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NO>
+__global__ void __launch_bounds__(AT_WARPS * 32, 2)
+k_accum_trie_d16_cp(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
+                    const uint2* __restrict__ uidx, const CGroup* __restrict__ cgrp, unsigned* __restrict__ counter, int dbg)
+{
+    constexpr bool W256 = false;
+    constexpr int SS = 20, HS = NO * 16 + 4, SLOT = 4 * SS + 4 * HS;       // doubles
+    extern __shared__ __align__(16) unsigned char smb[];
+    double* ring_all = reinterpret_cast<double*>(smb);                   // [AT_WARPS][AT_RING][SLOT]
+    int2* cm_s = reinterpret_cast<int2*>(ring_all + AT_WARPS * AT_RING * SLOT);   // [n_ops*4][32]
+    int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
+    int* spamw_s = spamc_s + D16_SPAM_MAX;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ring = ring_all + warp * (AT_RING * SLOT);
+    for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
+        const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
+        const int i = 8 * (tile >> 1) + (l >> 2), jc = 8 * (tile & 1) + 2 * (l & 3);
+        int2 cc = *reinterpret_cast<const int2*>(args.colmap + g * 256 + i * 16 + jc);
+        if (cc.y == cc.x + 1 && cc.x >= 0 && ((cc.x | (int)(args.ld & 1)) & 1) == 0) cc.y = -2;
+        cm_s[idx] = cc;
+    }
+    const int n_spam_s = args.n_spam < D16_SPAM_MAX ? args.n_spam : D16_SPAM_MAX;
+    for (int tt = threadIdx.x; tt < n_spam_s; tt += blockDim.x) { spamc_s[tt] = args.spam_col[tt]; spamw_s[tt] = args.spam_w[tt]; }
+    __syncthreads();
+
+    uint64_t pol_keep;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+    const unsigned mrow = lane >> 2, q = lane & 3;
+    const unsigned ne16 = (unsigned)a.n_eff * 16u;
+    const double* E = m.M + m.off_eff;
+    // copy roles of this lane: S chunk (step lane>>3, 16-byte chunk lane&7); H chunks j = 0..NO-1 (step j' = (lane + 32 j) / (8 NO))
+    const int s_step = lane >> 3, s_chunk = lane & 7;
+    // issue the copies of one group (4 stream entries at ipg) into ring slot `slot`
+    auto issue = [&](const uint2 nd, int slot) {                       // nd: stream entry q of the group (lane q holds entry q)
+        double* sl = ring + slot * SLOT;
+        const unsigned so = __shfl_sync(0xffffffffu, nd.x, s_step);
+        cp_async16(sl + s_step * SS + 2 * s_chunk, t.S + so + 2 * s_chunk, pol_keep);
+#pragma unroll
+        for (int j = 0; j < NO; ++j) {
+            const int id = lane + 32 * j;                                // chunk id in [0, 4 * 8 NO)
+            const int st = id / (8 * NO), ch = id - st * (8 * NO);
+            const unsigned ho = __shfl_sync(0xffffffffu, nd.y, st);
+            cp_async16(sl + 4 * SS + st * HS + 2 * ch, t.H + ho + 2 * ch, pol_keep);
+        }
+        cp_async_commit();
+    };
+
+    long long pr_pro = 0, pr_grp = 0, pr_epi = 0; const long long pr_t0 = clock64();   // dev knob B200_CHAIN_PROF
+    for (;;) {
+        const long long tq0 = clock64();
+        int u0 = 0;
+        if (lane == 0) u0 = (int)atomicAdd(counter, 1u) * AT_CHUNK;
+        u0 = __shfl_sync(0xffffffffu, u0, 0);
+        if (u0 >= n_units) break;
+        const int u1 = (u0 + AT_CHUNK < n_units) ? u0 + AT_CHUNK : n_units;
+        uint4 ra = __ldg(reinterpret_cast<const uint4*>(units + u0));        // el[4]
+        uint4 rb = __ldg(reinterpret_cast<const uint4*>(units + u0) + 1);    // off, g_ng, cgi
+        const uint2* ip = uidx + rb.x + q;                                    // this lane's entry of the next group to ISSUE
+        __syncwarp();                                                         // all lanes are done with the ring of the last chunk
+        uint2 ndq[AT_RING];
+#pragma unroll
+        for (int k = 0; k < AT_RING; ++k) ndq[k] = __ldg(ip + 4 * k);
+#pragma unroll
+        for (int k = 0; k < AT_RING - 1; ++k) issue(ndq[k], k);
+        uint2 nd_next = ndq[AT_RING - 1];                                     // entries of the group issued in the first iteration
+        ip += 4 * AT_RING;
+        int gcur = 0;                                                         // ring slot of the next group to CONSUME
+        pr_pro += clock64() - tq0;
+        for (int u = u0; u < u1; ++u) {
+            const long long tq1 = clock64();
+            const int un = (u + 1 < u1) ? u + 1 : u;
+            const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
+            const uint4 rbn = __ldg(reinterpret_cast<const uint4*>(units + un) + 1);
+            const int g = (int)(rb.y & 0xffffu), ngroups = (dbg == 1) ? 0 : (int)(rb.y >> 16);
+            double acc[NO][8];
+#pragma unroll
+            for (int o = 0; o < NO; ++o)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[o][k] = 0.0;
+#pragma unroll 1
+            for (int gi = 0; gi < ngroups; ++gi) {
+                cp_async_wait<AT_RING - 2>();                                 // the oldest group in flight has landed (this lane's part)
+                __syncwarp();                                                 // ... all lanes' parts; everyone left the slot refilled below
+                issue(nd_next, (gcur + AT_RING - 1) & (AT_RING - 1));
+                nd_next = __ldg(ip); ip += 4;                                 // (used one iteration later)
+                const double* sl = ring + gcur * SLOT;
+                const double b0 = sl[q * SS + mrow], b1 = sl[q * SS + 8 + mrow];
+                const double* hp = sl + 4 * SS + q * HS + mrow;
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    const double a0 = hp[o * 16], a1 = hp[o * 16 + 8];
+                    dmma884(acc[o][0], acc[o][1], a0, b0); dmma884(acc[o][2], acc[o][3], a0, b1);
+                    dmma884(acc[o][4], acc[o][5], a1, b0); dmma884(acc[o][6], acc[o][7], a1, b1);
+                }
+                gcur = (gcur + 1) & (AT_RING - 1);
+            }
+            const long long tq2 = clock64();
+            pr_grp += tq2 - tq1;
+            if (dbg == 2) { if (acc[0][0] + acc[NO - 1][1] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
+            // ---------------- epilogue: the finished 16x16 blocks are Jacobian entries ----------------
+            const int2* cm = cm_s + g * 128 + lane;
+            int2 cc[4];
+#pragma unroll
+            for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
+            const int els[4] = {(int)ra.x, (int)ra.y, (int)ra.z, (int)ra.w};
+            const bool fast = W256 ? __all_sync(0xffffffffu, (cc[0].x >= 0) & (cc[2].x >= 0))
+                                   : __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+            if (args.row_scale) {          // objective-function row scaling fused into the epilogue
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    const double sc = (els[o] >= 0) ? __ldg(args.row_scale + els[o]) : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
+                }
+            }
+            if (W256) {
+                if (fast) {
+#pragma unroll
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] >= 0) {
+                            double* Jr = args.J + (int64_t)els[o] * args.ld;
+                            st256_cs(Jr + cc[0].x, acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
+                            st256_cs(Jr + cc[2].x, acc[o][4], acc[o][5], acc[o][6], acc[o][7]);
+                        }
+                    }
+                } else {                       // arbitrary column map: scalar stores through the map itself
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] < 0) continue;
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int* cp = args.colmap + g * 256 + (8 * h + (int)mrow) * 16 + 4 * (int)q;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) { const int col = __ldg(cp + k); if (col >= 0) Jr[col] = acc[o][4 * h + k]; }
+                        }
+                    }
+                }
+            } else if (fast) {
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    if (els[o] >= 0) {
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                        for (int tile = 0; tile < 4; ++tile)
+                            __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < NO; ++o) {
+                    if (els[o] >= 0) {
+                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+#pragma unroll
+                        for (int tile = 0; tile < 4; ++tile) {
+                            const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
+                            if (cc[tile].y == -2) {
+                                *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
+                            } else {
+                                if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
+                                if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                            }
+                        }
+                    }
+                }
+            }
+            if (g == 0) {
+                // SPAM / unmapped columns and probabilities of the group's outcomes
+                const uint4 cg1 = __ldg(reinterpret_cast<const uint4*>(cgrp + rb.z) + 1);   // e_base | prep | f_end | b_end
+                const int prep = (int)cg1.y;
+                const double* sL = t.S + (size_t)cg1.z * 16;
+                for (int o = 0; o < NO; ++o) {
+                    if (els[o] < 0) continue;
+                    const int ei = (int)cg1.x + o;
+                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+                    if (args.probs) {
+                        double pr = (lane < 16) ? E[ei * 16 + lane] * sL[lane] : 0.0;
+#pragma unroll
+                        for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
+                        if (lane == 0) args.probs[els[o]] = pr;
+                    }
+                    const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
+                    const double* e0 = t.H + (size_t)cg1.w * ne16 + ei * 16;
+                    const double sc = args.row_scale ? __ldg(args.row_scale + els[o]) : 1.0;
+                    for (int tt = lane; tt < args.n_spam; tt += 32) {
+                        const int w = tt < D16_SPAM_MAX ? spamw_s[tt] : args.spam_w[tt];
+                        const int col = tt < D16_SPAM_MAX ? spamc_s[tt] : args.spam_col[tt];
+                        double val = 0.0;
+                        if (w >= w_rho0 && w < w_rho0 + 16) val = e0[w - w_rho0] * sc;
+                        else if (w >= w_eff0 && w < w_eff0 + 16) val = sL[w - w_eff0] * sc;
+                        Jr[col] = val;
+                    }
+                }
+            }
+            ra = ran; rb = rbn;
+            pr_epi += clock64() - tq2;
+        }
+        cp_async_wait<0>();                                                   // drain the look-ahead copies before the ring is reused
+    }
+    if (t.prof && lane == 0) {
+        atomicAdd(t.prof + 8, (unsigned long long)pr_pro); atomicAdd(t.prof + 9, (unsigned long long)pr_grp);
+        atomicAdd(t.prof + 10, (unsigned long long)pr_epi); atomicAdd(t.prof + 11, (unsigned long long)(clock64() - pr_t0));
+    }
+}

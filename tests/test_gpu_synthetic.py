@@ -89,10 +89,12 @@ def test_probs_d256(gpu_ctx):
     assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
 
 
-@pytest.mark.parametrize("mode", ["fused", "2p", "trie"])
+@pytest.mark.parametrize("mode", ["fused", "2p", "trie", "trie:B200_ACC_V6=1", "trie:B200_UNIT_OUTCOMES=2",
+                                  "trie:B200_ACC_V6=1,B200_UNIT_OUTCOMES=2", "trie:B200_ACC_V6=1,B200_ACC_ST256=1"])
 def test_every_d16_code_path(mode):
-    """The three d = 16 Jacobian implementations (B200_D16_MODE) give the same answers; run in a subprocess because the
-    mode is latched at first use."""
+    """The d = 16 Jacobian implementations (B200_D16_MODE; for the trie path also the accumulate-kernel variants:
+    cp.async ring (default) / register pipeline, 4 / 2 outcomes per unit, 256-bit stores) give the same answers; run in
+    a subprocess because the knobs are latched at first use."""
     code = r'''
 import sys, numpy as np
 sys.path.insert(0, %r)
@@ -113,7 +115,10 @@ for (n_ops, n_rho, n_eff, depth, seed) in [(5, 1, 4, 60, 0), (7, 2, 3, 33, 1)]:
     assert np.max(np.abs(p - po)) <= 1e-12
 print("ok")
 ''' % REPO
+    mode, _, knobs = mode.partition(":")
     env = dict(os.environ, B200_D16_MODE=mode)
+    for kv in filter(None, knobs.split(",")):
+        k, v = kv.split("="); env[k] = v
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
