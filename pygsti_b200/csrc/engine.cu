@@ -894,8 +894,11 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
                                                       a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
         return B200_OK;
     };
-    static int acc_v6 = -1;                           // dev knob: register-pipelined version 6 instead of the cp.async ring
-    if (acc_v6 < 0) { const char* e = getenv("B200_ACC_V6"); acc_v6 = (e && atoi(e)) ? 1 : 0; }
+    // version 6 (register pipeline) is the default: the cp.async ring (B200_ACC_CPASYNC=1) was measured SLOWER (1.015 vs
+    // 0.894 ms per Jacobian): three groups of gathers in flight did not shorten the gather/DMMA loop (727 k vs 777 k warp
+    // cycles) -- it is not latency-bound -- and the 90 KB of ring per CTA slowed the store epilogue (profiles/README.md)
+    static int acc_v6 = -1;
+    if (acc_v6 < 0) { const char* e = getenv("B200_ACC_CPASYNC"); acc_v6 = (e && atoi(e)) ? 0 : 1; }
     auto launchB7 = [&](auto kern, int no) -> int {
         const size_t smem7 = (size_t)AT_WARPS * AT_RING * (4 * 20 + 4 * (no * 16 + 4)) * 8 + smemB;
         if (smem7 + 1024 > c->smem_optin) return 1;                       // does not fit: use version 6

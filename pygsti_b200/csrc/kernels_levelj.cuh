@@ -309,20 +309,28 @@ k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __res
 #pragma unroll
                             for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
                         if (wm) {
+                            // fragments of the next 4 steps are fetched while the current ones are multiplied
                             const size_t brow0 = bb + (size_t)o * (Lc + 1) + 1;
-                            for (int k0 = 0; k0 < ns4; k0 += 4) {
+                            double a0, a1, b[8], na0, na1, nb[8];
+                            auto fetch = [&](int k0, double& fa0, double& fa1, double (&fb_)[8]) {
                                 const int k = kidx[k0 + q];
                                 const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l2.zrow_b) * D + ib + warp * 16 + mrow;
                                 const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l2.zrow_f) * D + jb + mrow;
-                                const double a0 = __ldg(er), a1 = __ldg(er + 8);
+                                fa0 = __ldg(er); fa1 = __ldg(er + 8);
+#pragma unroll
+                                for (int nt = 0; nt < 8; ++nt) fb_[nt] = (need_n & (1u << nt)) ? __ldg(sr + nt * 8) : 0.0;
+                            };
+                            fetch(0, a0, a1, b);
+                            for (int k0 = 0; k0 < ns4; k0 += 4) {
+                                if (k0 + 4 < ns4) fetch(k0 + 4, na0, na1, nb);
 #pragma unroll
                                 for (int nt = 0; nt < 8; ++nt) {
-                                    if (need_n & (1u << nt)) {                 // warp-uniform
-                                        const double b = __ldg(sr + nt * 8);
-                                        if (wm & (1u << nt)) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
-                                        if (wm & (1u << (8 + nt))) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
-                                    }
+                                    if (wm & (1u << nt)) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);          // warp-uniform
+                                    if (wm & (1u << (8 + nt))) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
                                 }
+                                a0 = na0; a1 = na1;
+#pragma unroll
+                                for (int nt = 0; nt < 8; ++nt) b[nt] = nb[nt];
                             }
                         }
                         __syncthreads();                                        // previous contraction has read Wt
@@ -334,14 +342,21 @@ k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __res
                                     *reinterpret_cast<double2*>(Wt + (warp * 16 + mt * 8 + mrow) * LJ_LDW + nt * 8 + 2 * q) =
                                         make_double2(acc[mt][nt][0], acc[mt][nt][1]);
                         __syncthreads();
-                        for (uint32_t it = it0 + tid; it < it1; it += LJ_THREADS) {
-                            const uint4 item = __ldg(l2.items2 + it);
-                            double s = 0.0;
-                            for (uint32_t t = item.y; t < item.z; ++t) {
-                                const unsigned ij = __ldg(l2.nz_ij + t);
-                                s = fma(__ldg(l2.nz_v + t), Wt[(ij >> 8) * LJ_LDW + (ij & 0xffu)], s);
+                        // four adjacent lanes share one parameter (non-zeros lo + sub, lo + sub + 4, ...); a warp takes 8 per round
+                        const uint32_t n_it = it1 - it0;
+                        for (uint32_t base = warp * 8; base < n_it; base += (LJ_THREADS / 32) * 8) {     // warp-uniform trip count
+                            const bool ok = base + (lane >> 2) < n_it;
+                            double s = 0.0; uint32_t pl = 0;
+                            if (ok) {
+                                const uint4 item = __ldg(l2.items2 + it0 + base + (lane >> 2));
+                                pl = item.x;
+                                for (uint32_t t = item.y + (lane & 3); t < item.z; t += 4) {
+                                    const unsigned ij = __ldg(l2.nz_ij + t);
+                                    s = fma(__ldg(l2.nz_v + t), Wt[(ij >> 8) * LJ_LDW + (ij & 0xffu)], s);
+                                }
                             }
-                            Jacc[o * LJ_PT + item.x] += s;
+                            s += shfl_xor_f64(s, 1); s += shfl_xor_f64(s, 2);
+                            if (ok && (lane & 3) == 0) Jacc[o * LJ_PT + pl] += s;
                         }
                     }
                 }
