@@ -68,6 +68,8 @@ struct b200_ctx {
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
+    long long l2_persist_max = -1, l2_window_max = -1, l2_persist_cur = 0;   // device limits (queried on first use), current set-aside
+    const void* l2_window_atom = nullptr;                // atom whose trie tables hold the stream's persisting L2 window
 };
 
 struct b200_atom {
@@ -94,7 +96,10 @@ struct b200_atom {
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
     DevBuf tf_meta, tf_op, tb_meta, tb_op, t_fn, t_bn, t_fend, t_bend;
-    DevBuf t_S, t_H, t_counters, t_units, t_uidx, t_cgrp;
+    DevBuf t_SH, t_counters, t_units, t_uidx;      // t_SH: both value tables in ONE allocation, [H | S] (one L2 persisting window)
+    size_t t_S_bytes = 0, t_H_bytes = 0;
+    double* tH() { return t_SH.as<double>(); }
+    double* tS() { return reinterpret_cast<double*>(reinterpret_cast<char*>(t_SH.p) + t_H_bytes); }
     int n_units = 0, unit_outcomes = 4;
     int n_fchains = 0, n_bchains = 0; uint32_t n_fnodes = 0, n_bnodes = 0;
     // model
@@ -204,74 +209,7 @@ static int upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
     return B200_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// trie of circuits (prefix sharing) -- host side, once per atom.  Sequences are (root id, symbols...);
-// nodes are created chain by chain while scanning the circuits in lexicographic order, so a chain's parent
-// node always has a smaller id and belongs to an earlier chain (kernels_d16_trie.cuh relies on this).
-// ------------------------------------------------------------------------------------------------
-struct TrieHost {
-    std::vector<int32_t> chain_parent; std::vector<uint32_t> chain_first, chain_len, chain_depth;
-    std::vector<uint8_t> node_op;
-    std::vector<uint32_t> depth_node;   // per circuit c, depth d in [0, L_c]: node id, at offset dptr[c] + d
-    std::vector<uint64_t> dptr;
-    std::vector<int64_t> sorted;        // circuits in lexicographic key order
-};
-static void build_trie(int64_t n, const std::vector<int32_t>& root, const std::vector<uint32_t>& ptr,
-                       const std::vector<int32_t>& sym, bool reversed, TrieHost& T) {
-    auto at = [&](int64_t c, uint32_t d) -> int32_t {      // d-th symbol of circuit c's key
-        const uint32_t L = ptr[c + 1] - ptr[c];
-        return reversed ? sym[ptr[c] + (L - 1 - d)] : sym[ptr[c] + d];
-    };
-    std::vector<int64_t> order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
-        if (root[x] != root[y]) return root[x] < root[y];
-        const uint32_t lx = ptr[x + 1] - ptr[x], ly = ptr[y + 1] - ptr[y];
-        const uint32_t l = std::min(lx, ly);
-        for (uint32_t d = 0; d < l; ++d) { const int32_t a = at(x, d), b = at(y, d); if (a != b) return a < b; }
-        return lx < ly; });
-    T.sorted = order;
-    T.dptr.assign((size_t)n + 1, 0);
-    for (int64_t c = 0; c < n; ++c) T.dptr[c + 1] = T.dptr[c] + (ptr[c + 1] - ptr[c]) + 1;
-    T.depth_node.assign((size_t)T.dptr[n], 0);
-    std::vector<uint32_t> path;
-    int64_t prev = -1;
-    for (int64_t oi = 0; oi < n; ++oi) {
-        const int64_t c = order[oi];
-        const uint32_t L = ptr[c + 1] - ptr[c];
-        uint32_t lcp = 0;
-        if (prev < 0 || root[prev] != root[c]) {
-            const uint32_t id = (uint32_t)T.node_op.size();
-            T.chain_parent.push_back(-(1 + root[c])); T.chain_first.push_back(id); T.chain_len.push_back(1);
-            T.chain_depth.push_back(0);
-            T.node_op.push_back(255);
-            path.assign(1, id);
-        } else {
-            const uint32_t Lp = ptr[prev + 1] - ptr[prev];
-            const uint32_t l = std::min(L, Lp);
-            while (lcp < l && at(prev, lcp) == at(c, lcp)) ++lcp;
-            path.resize((size_t)lcp + 1);
-        }
-        if (L > lcp) {
-            const uint32_t id0 = (uint32_t)T.node_op.size();
-            T.chain_parent.push_back((int32_t)path[lcp]); T.chain_first.push_back(id0); T.chain_len.push_back(L - lcp);
-            T.chain_depth.push_back(lcp + 1);
-            for (uint32_t d = lcp; d < L; ++d) { T.node_op.push_back((uint8_t)at(c, d)); path.push_back(id0 + (d - lcp)); }
-        }
-        for (uint32_t d = 0; d <= L; ++d) T.depth_node[T.dptr[c] + d] = path[d];
-        prev = c;
-    }
-    // work order of the chains: by start depth (a chain's parent chain starts at a smaller depth => is handed out
-    // earlier: the spin-waits in k_trie_chains cannot deadlock), long chains first within a depth
-    std::vector<uint32_t> ord(T.chain_first.size());
-    std::iota(ord.begin(), ord.end(), 0u);
-    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) {
-        if (T.chain_depth[x] != T.chain_depth[y]) return T.chain_depth[x] < T.chain_depth[y];
-        return T.chain_len[x] > T.chain_len[y]; });
-    std::vector<int32_t> cp(ord.size()); std::vector<uint32_t> cf(ord.size()), cl(ord.size());
-    for (size_t i = 0; i < ord.size(); ++i) { cp[i] = T.chain_parent[ord[i]]; cf[i] = T.chain_first[ord[i]]; cl[i] = T.chain_len[ord[i]]; }
-    T.chain_parent.swap(cp); T.chain_first.swap(cf); T.chain_len.swap(cl);
-}
+#include "trie_host.h"   // TrieHost, build_trie: prefix / suffix tries cut into chains (heavy-path decomposition)
 
 extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, int n_eff,
                                 int64_t n_rows, const int32_t* row_ptr, const int32_t* row_ops,
@@ -505,33 +443,33 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             const uint32_t ne16 = (uint32_t)n_eff * 16u;
             const int gsz = (getenv("B200_UNIT_OUTCOMES") && atoi(getenv("B200_UNIT_OUTCOMES")) == 2) ? 2 : 4;   // outcomes per phase-B unit
             a->unit_outcomes = gsz;
-            std::vector<UnitRec> units; std::vector<uint2> uidx; std::vector<CGroup> cgrp;
+            std::vector<UnitRec> units; std::vector<uint2> uidx;
             bool trie_ok = ((uint64_t)(zb_node + 2) * ne16 < ((uint64_t)1 << 32)) && ((uint64_t)(zf_node + 2) * 16 < ((uint64_t)1 << 32));
             for (int64_t si = 0; si < n_rows; ++si) {
                 const int64_t i = TB.sorted[si];
                 const uint32_t b0 = cptr[i];
                 const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
                 for (int eb = 0; eb < n_eff; eb += gsz) {
-                    CGroup cgp; memset(&cgp, 0, sizeof cgp);
+                    int32_t gel[4] = {-1, -1, -1, -1};
                     bool any = false;
-                    for (int o = 0; o < 4; ++o) cgp.el[o] = -1;
                     for (int32_t oq = coptr[i]; oq < coptr[i + 1]; ++oq) {
                         const int e = coeff[oq];
                         if (e >= eb && e < eb + gsz) {
-                            if (cgp.el[e - eb] >= 0) trie_ok = false;      // same effect twice in one circuit: not representable
-                            cgp.el[e - eb] = coel[oq]; any = true;
+                            if (gel[e - eb] >= 0) trie_ok = false;         // same effect twice in one circuit: not representable
+                            gel[e - eb] = coel[oq]; any = true;
                         }
                     }
                     if (!any) continue;
-                    cgp.e_base = (uint32_t)eb; cgp.prep = (uint32_t)cprep[i]; cgp.f_end = fend[i]; cgp.b_end = bend[i];
-                    const uint32_t cgi = (uint32_t)cgrp.size();
-                    cgrp.push_back(cgp);
+                    if ((uint32_t)cprep[i] > UNIT_MAX_PREP || eb > 7) trie_ok = false;      // (packed into the unit record)
                     uint32_t tbase = 0;
                     for (int g = 0; g < n_ops; ++g) {
                         UnitRec un; memset(&un, 0, sizeof un);
-                        for (int o = 0; o < 4; ++o) un.el[o] = cgp.el[o];
+                        for (int o = 0; o < 4; ++o) un.el[o] = gel[o];
                         const uint32_t ng = (cn[g] + 3u) / 4u;
-                        un.off = (uint32_t)uidx.size(); un.g_ng = (uint32_t)g | (ng << 16); un.cgi = cgi;
+                        if (ng > UNIT_MAX_GROUPS) trie_ok = false;
+                        un.off = (uint32_t)uidx.size();
+                        un.g_ng = (uint32_t)g | ((ng & UNIT_MAX_GROUPS) << 8) | ((uint32_t)(eb & 7) << 22) | (((uint32_t)cprep[i] & UNIT_MAX_PREP) << 25);
+                        un.f_end = fend[i]; un.b_end = bend[i];
                         for (uint32_t t = 0; t < ng * 4u; ++t) {
                             const bool ok = t < cn[g];
                             uint2 e;
@@ -548,8 +486,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             for (int pad = 0; pad < 16; ++pad) uidx.push_back(make_uint2(zf_node * 16u, zb_node * ne16));   // prefetch slack
             if (uidx.empty()) uidx.push_back(make_uint2(zf_node, zb_node));
             a->n_units = (int)units.size();
-            if ((rc = upload_vec(a->t_units, units, ctx->stream)) || (rc = upload_vec(a->t_uidx, uidx, ctx->stream)) ||
-                (rc = upload_vec(a->t_cgrp, cgrp, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
+            if ((rc = upload_vec(a->t_units, units, ctx->stream)) || (rc = upload_vec(a->t_uidx, uidx, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
             a->n_fchains = (int)TF.chain_first.size(); a->n_bchains = (int)TB.chain_first.size();
             a->n_fnodes = (uint32_t)TF.node_op.size(); a->n_bnodes = (uint32_t)TB.node_op.size();
             std::vector<unsigned> zc(4, 0u);
@@ -564,10 +501,10 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
                 (rc = upload_vec(a->t_fn, fn, ctx->stream)) || (rc = upload_vec(a->t_bn, bn, ctx->stream)) ||
                 (rc = upload_vec(a->t_fend, fend, ctx->stream)) || (rc = upload_vec(a->t_bend, bend, ctx->stream)) ||
                 (rc = upload_vec(a->t_counters, zc, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
-            cudaError_t e1 = a->t_S.ensure(((size_t)a->n_fnodes + 1) * 128), e2 = a->t_H.ensure(((size_t)a->n_bnodes + 2) * n_eff * 128);
-            if (e1 != cudaSuccess || e2 != cudaSuccess) { b200_atom_free(ctx, a); return fail(B200_E_NOMEM, "trie tables: out of device memory"); }
-            CU(cudaMemsetAsync(a->t_S.p, 0, ((size_t)a->n_fnodes + 1) * 128, ctx->stream));            // incl. the zero rows
-            CU(cudaMemsetAsync(a->t_H.p, 0, ((size_t)a->n_bnodes + 2) * n_eff * 128, ctx->stream));
+            a->t_S_bytes = ((size_t)a->n_fnodes + 1) * 128;                                              // incl. the zero rows
+            a->t_H_bytes = (((size_t)a->n_bnodes + 2) * n_eff * 128 + 255) & ~(size_t)255;
+            if (a->t_SH.ensure(a->t_S_bytes + a->t_H_bytes) != cudaSuccess) { b200_atom_free(ctx, a); return fail(B200_E_NOMEM, "trie tables: out of device memory"); }
+            CU(cudaMemsetAsync(a->t_SH.p, 0, a->t_S_bytes + a->t_H_bytes, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             a->has_trie = trie_ok;
         }
@@ -580,11 +517,17 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
 extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx && ctx->l2_window_atom == a) {       // drop the stream's persisting-L2 window over this atom's tables
+        cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaCtxResetPersistingL2Cache();
+        ctx->l2_window_atom = nullptr;
+    }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
                       &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
-                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_S, &a->t_H,
-                      &a->t_counters, &a->t_units, &a->t_uidx, &a->t_cgrp,
+                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_SH,
+                      &a->t_counters, &a->t_units, &a->t_uidx,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
     for (DevBuf* b : bufs) b->release();
@@ -847,6 +790,62 @@ static int d16_mode() {   // 0 = fused kernel, 1 = two-phase per-circuit chains,
     }
     return mode;
 }
+// Optional L2 set-aside for the trie value tables (dev knob B200_L2_PERSIST_MB=<n>, default off).  MEASURED HARMFUL on the
+// BASELINE layout: a persisting carve-out (cudaLimitPersistingL2CacheSize) of 79 MB slowed the Jacobian from 0.86 to
+// 1.44 ms, and the stores alone from ~0.55 to ~1.1 ms -- the 3 GB write stream needs the L2 capacity as its write-back
+// buffer more than the gathers need the tables resident.  Kept for experiments only.
+static int trie_l2_window(b200_ctx* c, b200_atom* a) {
+    const char* ef = getenv("B200_L2_PERSIST_MB");
+    const long long want = (ef && atoi(ef) > 0) ? (long long)atoi(ef) << 20 : 0;
+    if (want == 0 && c->l2_persist_cur <= 0) return B200_OK;               // never enabled: nothing to do
+    if (c->l2_persist_max < 0) {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, c->device));
+        c->l2_persist_max = (long long)prop.persistingL2CacheMaxSize;
+        c->l2_window_max = (long long)prop.accessPolicyMaxWindowSize;
+    }
+    const long long lim = std::min(want, c->l2_persist_max);
+    if (lim != c->l2_persist_cur || c->l2_window_atom != a) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+        CU(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        CU(cudaCtxResetPersistingL2Cache());
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)std::max<long long>(lim, 0)));
+        c->l2_persist_cur = lim; c->l2_window_atom = nullptr;
+        if (lim <= 0) return B200_OK;
+        // the allocation is [H | S]: S is gathered from during the whole accumulate kernel, H is consumed front to back
+        // (its node ids follow the suffix order of the units): the window is the last `lim` bytes, all of them persisting
+        const size_t total = a->t_S_bytes + a->t_H_bytes;
+        const size_t bytes = std::min(std::min<size_t>(total, (size_t)c->l2_window_max), (size_t)lim) & ~(size_t)4095;
+        if (bytes == 0) return B200_OK;
+        attr.accessPolicyWindow.base_ptr = reinterpret_cast<char*>(a->t_SH.p) + (total - bytes);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        CU(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        c->l2_window_atom = a;
+        if (getenv("B200_VERBOSE")) fprintf(stderr, "[b200] L2 persisting window %.1f MB of %.1f MB tables (device set-aside max %.1f MB)\n", bytes / 1048576.0, total / 1048576.0, c->l2_persist_max / 1048576.0);
+    }
+    return B200_OK;
+}
+
+// phase A of the trie path: KG = chains per atomic grab (template: the per-batch loop is fully unrolled)
+static int launch_trie_chains(b200_ctx* c, b200_atom* a, const TrieDev& t, int grid, size_t smem, int kg, int fwd_only) {
+    const char* es = getenv("B200_CHAIN_SLEEP");
+    const unsigned sleep_ns = (es && atoi(es) > 0) ? (unsigned)atoi(es) : 40u;      // dev knob: poll interval of a waiting chain
+    auto go = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TRIE_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), t, fwd_only, sleep_ns);
+        return B200_OK;
+    };
+    const char* ee = getenv("B200_CHAIN_EARLY");
+    const bool early = !(ee && *ee == '0');                 // dev knob: issue the next atomic before a short last chain is walked
+    if (t.prof) return kg >= 2 ? go(k_trie_chains<2, true, true>) : go(k_trie_chains<1, true, true>);
+    if (kg >= 3) return early ? go(k_trie_chains<3, true, false>) : go(k_trie_chains<3, false, false>);
+    if (kg >= 2) return early ? go(k_trie_chains<2, true, false>) : go(k_trie_chains<2, false, false>);
+    return early ? go(k_trie_chains<1, true, false>) : go(k_trie_chains<1, false, false>);
+}
 static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (a->n_rows == 0) return B200_OK;
     TrieDev t;
@@ -856,27 +855,28 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.b_op = a->tb_op.as<uint8_t>(); t.n_bchains = a->n_bchains; t.n_bnodes = a->n_bnodes;
     t.fn_b = a->t_fn.as<uint32_t>(); t.bn_b = a->t_bn.as<uint32_t>(); t.f_end = a->t_fend.as<uint32_t>(); t.b_end = a->t_bend.as<uint32_t>();
     t.bcnt = a->bcnt.as<uint16_t>();
-    t.S = a->t_S.as<double>(); t.H = a->t_H.as<double>();
+    t.S = a->tS(); t.H = a->tH();
     t.counters = a->t_counters.as<unsigned>();
     CU(cudaMemsetAsync(a->t_counters.p, 0, 4 * sizeof(unsigned), c->stream));
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_H.as<double>(), (size_t)a->n_bnodes * a->n_eff * 16);
+    { int rcW = trie_l2_window(c, a); if (rcW) return rcW; }
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), (size_t)a->n_fnodes * 16);
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tH(), (size_t)a->n_bnodes * a->n_eff * 16);
     c->launches += 2;
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
-    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    static int chain_ctas = -1, chain_k = -1, st256 = -1;   // dev knobs: chain CTAs per SM and role, chains per atomic grab, 256-bit stores
-    if (chain_ctas < 0) { const char* e = getenv("B200_CHAIN_CTAS"); chain_ctas = (e && atoi(e) > 0) ? atoi(e) : 4; }
-    if (chain_k < 0) { const char* e = getenv("B200_CHAIN_K"); chain_k = (e && atoi(e) > 0) ? atoi(e) : 2; }
-    if (st256 < 0) { const char* e = getenv("B200_ACC_ST256"); st256 = e ? atoi(e) : 0; }   // measured: 0.914 ms with, 0.891 ms without
+    // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
+    // grab (2/4/8), 256-bit stores (measured: 0.914 ms with, 0.891 ms without)
+    auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
+    const int chain_ctas = std::max(1, knob("B200_CHAIN_CTAS", 4)), chain_k = std::max(1, knob("B200_CHAIN_K", 1));
+    const int st256 = knob("B200_ACC_ST256", 0);
     int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
-    static const bool chain_prof = getenv("B200_CHAIN_PROF") != nullptr;
+    const bool chain_prof = knob("B200_CHAIN_PROF", 0) != 0;
     t.prof = nullptr;
     if (chain_prof) {
         CU(c->f_buf.ensure(std::max<size_t>(c->f_buf.cap, 128)));
         t.prof = c->f_buf.as<unsigned long long>(); CU(cudaMemsetAsync(t.prof, 0, 128, c->stream));
     }
-    k_trie_chains<<<gA, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, chain_k, 0);
+    { int rcA = launch_trie_chains(c, a, t, gA, smemA, chain_k, 0); if (rcA) return rcA; }
     if (t.prof) {
         unsigned long long h[8];
         CU(cudaMemcpyAsync(h, t.prof, 64, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
@@ -885,33 +885,28 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
             fprintf(stderr, "[chain prof] role %d (%d chains): per-warp mean cycles: hand-out %.0f, parent wait %.0f, steps %.0f, total %.0f\n",
                     r, r ? a->n_bchains : a->n_fchains, h[r * 4] / nw, h[r * 4 + 1] / nw, h[r * 4 + 2] / nw, h[r * 4 + 3] / nw);
     }
-    const int dbg = getenv("B200_DBG") ? atoi(getenv("B200_DBG")) : 0;
+    const int dbg = knob("B200_DBG", 0);
     const bool w256 = st256 && (((uintptr_t)args.J & 31) == 0);        // 32-byte stores need 32-byte aligned rows
+    // phase-B hand-out (see next_chunk in k_accum_trie_d16): chunk = units per warp grab, rsub = sub-chunks per CTA range
+    // (0 = every warp grabs from the global counter).  Dev knobs B200_ACC_CHUNK / B200_ACC_RSUB.
+    const int units_per_circ = std::max(1, a->n_ops);
+    int acc_rsub = std::max(0, knob("B200_ACC_RSUB", 0));
+    int acc_chunk = knob("B200_ACC_CHUNK", acc_rsub > 0 ? 2 * units_per_circ : AT_CHUNK);
+    if (acc_chunk < 1) acc_chunk = AT_CHUNK;
     auto launchB = [&](auto kern, int per_sm) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), per_sm);
+        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * acc_chunk - 1) / (AT_WARPS * acc_chunk), per_sm);
         kern<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                      a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
+                                                      a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, dbg,
+                                                      acc_chunk, acc_rsub);
         return B200_OK;
     };
-    // version 6 (register pipeline) is the default: the cp.async ring (B200_ACC_CPASYNC=1) was measured SLOWER (1.015 vs
-    // 0.894 ms per Jacobian): three groups of gathers in flight did not shorten the gather/DMMA loop (727 k vs 777 k warp
-    // cycles) -- it is not latency-bound -- and the 90 KB of ring per CTA slowed the store epilogue (profiles/README.md)
-    static int acc_v6 = -1;
-    if (acc_v6 < 0) { const char* e = getenv("B200_ACC_CPASYNC"); acc_v6 = (e && atoi(e)) ? 0 : 1; }
-    auto launchB7 = [&](auto kern, int no) -> int {
-        const size_t smem7 = (size_t)AT_WARPS * AT_RING * (4 * 20 + 4 * (no * 16 + 4)) * 8 + smemB;
-        if (smem7 + 1024 > c->smem_optin) return 1;                       // does not fit: use version 6
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7));
-        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
-        kern<<<gB, AT_WARPS * 32, smem7, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                     a->t_uidx.as<uint2>(), a->t_cgrp.as<CGroup>(), a->t_counters.as<unsigned>() + 2, dbg);
-        return B200_OK;
-    };
+    // (a cp.async ring variant with three groups of gathers in flight per warp was measured SLOWER, 1.015 vs 0.894 ms per
+    // Jacobian, and removed: the loop is not bound by the latency of the table gathers -- profiles/README.md)
     int rcB = 1;
-    if (!acc_v6) rcB = (a->unit_outcomes == 2) ? launchB7(k_accum_trie_d16_cp<2>, 2) : launchB7(k_accum_trie_d16_cp<4>, 4);
-    if (rcB == 1) {
-        if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
+    {
+        if (t.prof && a->unit_outcomes != 2 && !w256) rcB = launchB(k_accum_trie_d16<4, false, true>, 2);      // phase profiler (dev)
+        else if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
         else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
     }
     if (rcB) return rcB;
@@ -1029,15 +1024,14 @@ static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     TrieDev t; memset(&t, 0, sizeof t);      // (prof = nullptr)
     t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
-    t.S = a->t_S.as<double>(); t.counters = a->t_counters.as<unsigned>();
+    t.S = a->tS(); t.counters = a->t_counters.as<unsigned>();
     CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->t_S.as<double>(), (size_t)a->n_fnodes * 16);
+    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), (size_t)a->n_fnodes * 16);
     c->launches++;
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, 2, 1);
+    { int rcA = launch_trie_chains(c, a, t, c->sm_count * 4, smemA, std::max(1, getenv("B200_CHAIN_K") ? atoi(getenv("B200_CHAIN_K")) : 1), 1); if (rcA) return rcA; }
     int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 15) / 16, (int64_t)c->sm_count * 8));
-    k_probs_trie_d16<<<gp, 256, 0, c->stream>>>(atom_dev(a), model_dev(a), a->t_fend.as<uint32_t>(), a->t_S.as<double>(), d_out, 1);
+    k_probs_trie_d16<<<gp, 256, 0, c->stream>>>(atom_dev(a), model_dev(a), a->t_fend.as<uint32_t>(), a->tS(), d_out, 1);
     c->launches += 2;
     CU(cudaGetLastError());
     return B200_OK;
