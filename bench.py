@@ -42,7 +42,9 @@ WORKLOAD = "c2_full_layout"
 WORKLOAD_DESC = ("smq2Q_XYCNOT full model (d=16, Np=1360), GST design maxL=128 lite=False: 68335 circuits, "
                  "273340 outcomes; bulk_fill_dprobs + probs")
 METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
-NCU_TRAFFIC_BYTES = 3.32e9   # dram__bytes_read.sum + dram__bytes_write.sum of one step (all kernels of the step), see profiles/
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel k_accum_trie_d16 (ncu --set full,
+# profiles/r01_ncu_full_accum_final_raw.csv): 0.241 GB read + 2.920 GB written
+NCU_TRAFFIC_BYTES = 3.161e9
 
 
 def _peaks():
@@ -241,6 +243,17 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * nE / (ms_per_step * 1e-3)
 
+    # ---------------- dominant kernel alone (roofline.achieved): CUDA events around the phases, on the launching stream ----
+    ctx.phase_timing(True)
+    for _ in range(max(5, min(args.steps, 20))):
+        atom.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
+    (ms_prep, ms_chains, ms_accum), n_ph = ctx.phase_ms()
+    ctx.phase_timing(False)
+    ph = torch.tensor([ms_prep / max(n_ph, 1), ms_chains / max(n_ph, 1), ms_accum / max(n_ph, 1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    ms_prep, ms_chains, ms_accum = (float(x) for x in ph.tolist())
+
     # quick on-device sanity of what was just timed (not part of the timed region)
     st = int(case["probs_map_stride"])
     p_host = P.cpu().numpy()
@@ -277,15 +290,16 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         alg_bytes = nE * (Np + 1) * 8
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        achieved = alg_bytes / (ms_accum * 1e-3) / 1e9          # dominant kernel alone
+        achieved_step = alg_bytes / (ms_per_step * 1e-3) / 1e9  # whole step (prepare + chains + accumulate)
         line = {
             "metric": METRIC, "value": value, "unit": "circuit-outcomes/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (reference-generated GST layout + depolarized target model; no dataset needed)",
             "config": {"workload": WORKLOAD_DESC, "derivative": "analytic adjoint (== reference MatrixForwardSimulator)",
-                       "kernel": ("k_trie_chains (prefix/suffix-trie chains) + k_accum_trie_d16 (DMMA gather-accumulate, "
-                                  "fused Jacobian store)") if info["fused_path"] else "general W.D path",
+                       "kernel": ("k_trie_prepare + k_trie_chains (prefix/suffix-trie chains, heavy-path decomposition) + "
+                                  "k_accum_trie_d16 (DMMA gather-accumulate, fused Jacobian store)") if info["fused_path"] else "general W.D path",
                        "parallelism": "dp%d: one replica of the layout per GPU, no data-path collective" % world,
                        "l2": "each step writes a 2.97 GB Jacobian (>> 126 MB L2); no explicit flush needed",
                        "dprobs_elements_per_s": value * Np},
@@ -295,14 +309,16 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full, profiles/r01_ncu_full_final_kernels_raw.csv: k_accum_trie_d16 "
-                                           "dram read 0.245 GB + write 2.921 GB, k_trie_chains read 0.005 + write 0.048 GB, "
-                                           "k_fill_sentinel write 0.10 GB",
+                         "kernel": "k_accum_trie_d16", "kernel_ms": ms_accum,
                          "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": ms_per_step,
-                         "note": "conservative: duration of the WHOLE step (k_trie_chains + k_accum_trie_d16, CUDA events "
-                                 "on the launching stream: 2 x k_fill_sentinel + k_trie_chains + k_accum_trie_d16); the "
-                                 "dominant kernel k_accum_trie_d16 alone is 83% of it (profiles/README.md)"},
+                         "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 (profiles/README.md): dram read "
+                                           "0.241 GB + write 2.920 GB = 1.06 x the algorithmic bytes",
+                         "step": {"ms": ms_per_step, "achieved": achieved_step, "frac": achieved_step / peak,
+                                  "phases_ms": {"k_trie_prepare": ms_prep, "k_trie_chains": ms_chains,
+                                                "k_accum_trie_d16": ms_accum}},
+                         "note": "achieved = 8*nE*(Np+1) bytes / average duration of the dominant kernel, CUDA events on the "
+                                 "launching stream (b200_ctx_phase_timing, a separate loop after the timed region); 'step' "
+                                 "is the same quantity over the whole timed step (all three kernels), i.e. value * 10888 B"},
             "clocks": clocks,
             "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
         }

@@ -56,6 +56,12 @@ int b200_ctx_destroy(b200_ctx* ctx);
 int b200_ctx_sync(b200_ctx* ctx);
 /* kernels launched by this ctx since creation (the "gpu_launches" bench counter) */
 int b200_ctx_launch_count(b200_ctx* ctx, int64_t* n_out);
+/* Measurement aid (bench.py "roofline"): with phase timing on, the d = 16 Jacobian path brackets its three phases --
+ * table preparation, trie chains, accumulate (the dominant, HBM-write-bound kernel) -- with CUDA events on the launching
+ * stream.  b200_ctx_phase_ms synchronises the stream, returns the summed elapsed milliseconds of each phase over the calls
+ * made since timing was switched on (or since the last read) and their number, and clears the record. */
+int b200_ctx_phase_timing(b200_ctx* ctx, int on);
+int b200_ctx_phase_ms(b200_ctx* ctx, double ms_out[3], int64_t* n_calls_out);
 
 /* ---- layout atom (one-time per layout) ---------------------------------------------------------
  * Replaces convert_maplayout / convert_dict_of_intlists / create_rhocache (pyx:55-101), which the

@@ -69,6 +69,8 @@ struct b200_ctx {
     cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
     long long l2_persist_max = -1, l2_window_max = -1, l2_persist_cur = 0;   // device limits (queried on first use), current set-aside
+    bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
+    std::vector<cudaEvent_t> phase_events;               // 4 per call: start, after prepare, after chains, after accumulate
     const void* l2_window_atom = nullptr;                // atom whose trie tables hold the stream's persisting L2 window
 };
 
@@ -95,7 +97,8 @@ struct b200_atom {
     int lj_no_max = 0, lj_n_tiles = 0;
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
-    DevBuf tf_meta, tf_op, tb_meta, tb_op, t_fn, t_bn, t_fend, t_bend;
+    DevBuf tf_meta, tf_op, tb_meta, tb_op, t_fn, t_bn, t_fend, t_bend, tf_par, tb_par;   // (t*_par: nodes some chain waits for)
+    uint32_t n_fpar = 0, n_bpar = 0;
     DevBuf t_SH, t_counters, t_units, t_uidx;      // t_SH: both value tables in ONE allocation, [H | S] (one L2 persisting window)
     size_t t_S_bytes = 0, t_H_bytes = 0;
     double* tH() { return t_SH.as<double>(); }
@@ -168,6 +171,7 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
     return B200_OK;
 }
 
+static void phase_clear(b200_ctx* c);
 extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (!c) return B200_OK;
     cudaSetDevice(c->device);
@@ -177,6 +181,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    phase_clear(c);
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     if (c->cublas) cublasDestroy(c->cublas);
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
@@ -189,6 +194,43 @@ extern "C" int b200_ctx_sync(b200_ctx* c) {
     if (!c) return fail(B200_E_INVALID, "ctx is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    return B200_OK;
+}
+
+static int phase_mark(b200_ctx* c) {          // record one phase boundary on the launching stream (timing mode only)
+    if (!c->phase_timing) return B200_OK;
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    c->phase_events.push_back(e);
+    CU(cudaEventRecord(e, c->stream));
+    return B200_OK;
+}
+static void phase_clear(b200_ctx* c) {
+    for (cudaEvent_t e : c->phase_events) cudaEventDestroy(e);
+    c->phase_events.clear();
+}
+extern "C" int b200_ctx_phase_timing(b200_ctx* c, int on) {
+    if (!c) return fail(B200_E_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    phase_clear(c);
+    c->phase_timing = on != 0;
+    return B200_OK;
+}
+extern "C" int b200_ctx_phase_ms(b200_ctx* c, double ms_out[3], int64_t* n_calls_out) {
+    if (!c || !ms_out || !n_calls_out) return fail(B200_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+    const size_t n = c->phase_events.size() / 4;
+    for (size_t k = 0; k < n; ++k)
+        for (int ph = 0; ph < 3; ++ph) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->phase_events[4 * k + ph], c->phase_events[4 * k + ph + 1]));
+            ms_out[ph] += ms;
+        }
+    *n_calls_out = (int64_t)n;
+    phase_clear(c);
     return B200_OK;
 }
 
@@ -495,6 +537,14 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
                 for (size_t i = 0; i < mt.size(); ++i) mt[i] = make_int4(T.chain_parent[i], (int)T.chain_first[i], (int)T.chain_len[i], 0);
                 return mt; };
             const std::vector<int4> fmeta = pack_meta(TF), bmeta = pack_meta(TB);
+            auto parents = [](const TrieHost& T) {                          // distinct parent nodes of the chain heads
+                std::vector<uint32_t> v;
+                for (int32_t pnode : T.chain_parent) if (pnode >= 0) v.push_back((uint32_t)pnode);
+                std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end());
+                return v; };
+            const std::vector<uint32_t> fpar = parents(TF), bpar = parents(TB);
+            a->n_fpar = (uint32_t)fpar.size(); a->n_bpar = (uint32_t)bpar.size();
+            if ((rc = upload_vec(a->tf_par, fpar, ctx->stream)) || (rc = upload_vec(a->tb_par, bpar, ctx->stream))) { b200_atom_free(ctx, a); return rc; }
             TF.node_op.resize(TF.node_op.size() + 32, 0); TB.node_op.resize(TB.node_op.size() + 32, 0);   // 32-wide op fetches
             if ((rc = upload_vec(a->tf_meta, fmeta, ctx->stream)) || (rc = upload_vec(a->tf_op, TF.node_op, ctx->stream)) ||
                 (rc = upload_vec(a->tb_meta, bmeta, ctx->stream)) || (rc = upload_vec(a->tb_op, TB.node_op, ctx->stream)) ||
@@ -526,7 +576,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
                       &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
-                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->t_SH,
+                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
                       &a->t_counters, &a->t_units, &a->t_uidx,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
@@ -857,11 +907,12 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.bcnt = a->bcnt.as<uint16_t>();
     t.S = a->tS(); t.H = a->tH();
     t.counters = a->t_counters.as<unsigned>();
-    CU(cudaMemsetAsync(a->t_counters.p, 0, 4 * sizeof(unsigned), c->stream));
     { int rcW = trie_l2_window(c, a); if (rcW) return rcW; }
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), (size_t)a->n_fnodes * 16);
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tH(), (size_t)a->n_bnodes * a->n_eff * 16);
-    c->launches += 2;
+    { int rcP = phase_mark(c); if (rcP) return rcP; }
+    k_trie_prepare<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), a->tf_par.as<uint32_t>(), a->n_fpar, a->tH(), a->tb_par.as<uint32_t>(), a->n_bpar,
+                                                         (uint32_t)a->n_eff * 16u, a->t_counters.as<unsigned>());
+    c->launches += 1;
+    { int rcP = phase_mark(c); if (rcP) return rcP; }
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
     // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
@@ -877,6 +928,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
         t.prof = c->f_buf.as<unsigned long long>(); CU(cudaMemsetAsync(t.prof, 0, 128, c->stream));
     }
     { int rcA = launch_trie_chains(c, a, t, gA, smemA, chain_k, 0); if (rcA) return rcA; }
+    { int rcP = phase_mark(c); if (rcP) return rcP; }
     if (t.prof) {
         unsigned long long h[8];
         CU(cudaMemcpyAsync(h, t.prof, 64, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
@@ -910,6 +962,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
         else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
     }
     if (rcB) return rcB;
+    { int rcP = phase_mark(c); if (rcP) return rcP; }
     if (t.prof) {
         unsigned long long h[4];
         CU(cudaMemcpyAsync(h, t.prof + 8, 32, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
@@ -1025,8 +1078,7 @@ static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
     t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
     t.S = a->tS(); t.counters = a->t_counters.as<unsigned>();
-    CU(cudaMemsetAsync(a->t_counters.p, 0, 2 * sizeof(unsigned), c->stream));
-    k_fill_sentinel<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), (size_t)a->n_fnodes * 16);
+    k_trie_prepare<<<c->sm_count * 4, 256, 0, c->stream>>>(a->tS(), a->tf_par.as<uint32_t>(), a->n_fpar, nullptr, nullptr, 0u, 0u, a->t_counters.as<unsigned>());
     c->launches++;
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
     { int rcA = launch_trie_chains(c, a, t, c->sm_count * 4, smemA, std::max(1, getenv("B200_CHAIN_K") ? atoi(getenv("B200_CHAIN_K")) : 1), 1); if (rcA) return rcA; }

@@ -61,6 +61,17 @@ class Context:
         _lib.check(self._lib.b200_ctx_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def phase_timing(self, on=True):
+        """Bracket the phases of the d = 16 Jacobian path with CUDA events on the launching stream (bench.py roofline)."""
+        _lib.check(self._lib.b200_ctx_phase_timing(self._h, 1 if on else 0))
+
+    def phase_ms(self):
+        """(prepare_ms, chains_ms, accumulate_ms) summed over the calls since the last read, and the number of calls."""
+        ms = (C.c_double * 3)()
+        n = C.c_int64(0)
+        _lib.check(self._lib.b200_ctx_phase_ms(self._h, ms, C.byref(n)))
+        return (ms[0], ms[1], ms[2]), n.value
+
     def upload_atom(self, t: AtomTables):
         return Atom(self, t)
 

@@ -208,3 +208,32 @@ np.save(sys.argv[1], J); print("ok", ctx.launch_count)
     assert np.all(np.isfinite(outs[0]))
     assert np.max(np.abs(outs[0] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # DMMA accumulate vs W-matrix path
     assert np.max(np.abs(outs[2] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # scalar accumulate vs W-matrix path
+
+
+def test_repeated_calls_with_changing_models(gpu_ctx):
+    """The trie path resets only the table rows a chain waits for (k_trie_prepare): successive calls on one atom with
+    DIFFERENT models, and a model repeated, must each match the oracle; the phase-timing events must not change results."""
+    circs = synth.random_circuits(60, 45, 5, 2, 4, seed=11)
+    t = synth.make_tables(16, 5, 2, 4, circs)
+    D = synth.full_derivs(t)
+    at = gpu_ctx.upload_atom(t)
+    at.set_derivs(D)
+    models = [synth.random_model(16, 5, 2, 4, seed=s) for s in (21, 22, 21, 23)]
+    gpu_ctx.phase_timing(True)
+    for k, (G, rho, E) in enumerate(models):
+        at.set_model(G, rho, E)
+        J = np.full((t.n_elements, D.n_params), np.nan)
+        p = np.full(t.n_elements, np.nan)
+        at.fill_dprobs(J, p)
+        if k % 2 == 0:
+            p1 = np.full(t.n_elements, np.nan)
+            at.fill_probs(p1)
+            assert np.max(np.abs(p1 - p)) <= 1e-13
+        po = onp.mapfill_probs(t, G, rho, E)
+        Jo = onp.dprobs_analytic(t, G, rho, E, D)
+        assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+        assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    ms, n = gpu_ctx.phase_ms()
+    gpu_ctx.phase_timing(False)
+    assert n == len(models) and all(x > 0.0 for x in ms)
+    at.free()
