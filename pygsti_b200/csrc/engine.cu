@@ -69,6 +69,7 @@ struct b200_ctx {
     cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
     long long l2_persist_max = -1, l2_window_max = -1, l2_persist_cur = 0;   // device limits (queried on first use), current set-aside
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_copy = nullptr;   // split device->host copies
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
     std::vector<cudaEvent_t> phase_events;               // 4 per call: start, after prepare, after chains, after accumulate
     const void* l2_window_atom = nullptr;                // atom whose trie tables hold the stream's persisting L2 window
@@ -94,7 +95,7 @@ struct b200_atom {
     DevBuf lj2_ti_ptr, lj2_mask, lj2_items, lj2_ij, lj2_v;       // DMMA accumulate (k_level_accum2): per (tile, gate, sub-block)
     std::vector<uint32_t> lj_btile_ptr;     // [max_depth+1]
     uint64_t lj_rows_f = 0, lj_rows_b = 0;
-    int lj_no_max = 0, lj_n_tiles = 0;
+    int lj_no_max = 0, lj_n_tiles = 0, lj_pt = LJ_PT_MIN;   // lj_pt: parameters per accumulate tile (chosen in set_derivs)
     // trie path (prefix + suffix sharing)
     bool has_trie = false;
     DevBuf tf_meta, tf_op, tb_meta, tb_op, t_fn, t_bn, t_fend, t_bend, tf_par, tb_par;   // (t*_par: nodes some chain waits for)
@@ -182,6 +183,8 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     phase_clear(c);
+    for (cudaStream_t& st : c->copy_streams) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
+    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     if (c->cublas) cublasDestroy(c->cublas);
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
@@ -678,6 +681,13 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
         // tile plan of the level-batched Jacobian path: per (tile of LJ_PT parameters, W-space block) the columns that
         // have non-zeros in that block, as (p_local, lo, hi) ranges of the CSC arrays (rows are sorted within a column)
         const int nb = a->n_ops + 1;                       // gate blocks + one block for the prep / effect rows
+        // Parameters per tile (dev knob B200_LJ_PT).  Wider tiles were measured SLOWER on BASELINE config 3 (Np = 775: one
+        // 1024-wide tile per circuit 95 ms, four 256-wide tiles 85 ms): the accumulate kernel is bound by the latency of its
+        // serial (gate, outcome) phases, and narrow tiles spread a circuit's gates over more concurrent CTAs.
+        int pt = LJ_PT_MIN;
+        { const char* e = getenv("B200_LJ_PT"); if (e && atoi(e) >= 32) pt = std::min(LJ_PT_MAX, (atoi(e) + 31) & ~31); }
+        a->lj_pt = pt;
+        const int LJ_PT = pt;
         const int n_tiles = std::max(1, (n_params + LJ_PT - 1) / LJ_PT);
         const int64_t dd = (int64_t)a->dim * a->dim;
         std::vector<std::vector<uint4>> lists((size_t)n_tiles * nb);
@@ -1106,10 +1116,10 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
 // level-batched Jacobian (d >= 64): forward sweep || backward sweep (two streams), then the sparse contraction
 // ------------------------------------------------------------------------------------------------
 static int levelj_ts(b200_ctx* c, b200_atom* a, size_t* smem_out) {
-    const size_t acc = (size_t)a->lj_no_max * LJ_PT * 8;
+    const size_t acc = (size_t)a->lj_no_max * a->lj_pt * 8;
     const size_t per_ts = (size_t)(1 + a->lj_no_max) * a->dim * 8;
     int ts = 8;
-    while (ts > 1 && acc + ts * per_ts + (size_t)a->lj_no_max * 8 > (size_t)64 * 1024) --ts;
+    while (ts > 1 && acc + ts * per_ts + (size_t)a->lj_no_max * 8 > std::max<size_t>((size_t)64 * 1024, acc + per_ts + (size_t)a->lj_no_max * 8)) --ts;
     const size_t smem = acc + ts * per_ts + (size_t)a->lj_no_max * 8 + 16;
     if (smem_out) *smem_out = smem;
     return (smem + 1024 <= c->smem_optin) ? ts : 0;
@@ -1136,7 +1146,7 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
     lj.ti_ptr = a->lj_ti_ptr.as<uint32_t>(); lj.items = a->lj_items.as<uint4>();
     lj.crow = a->crow.as<int32_t>(); lj.cval = a->cval.as<double>();
     lj.FS = c->lj_fs.as<double>(); lj.BH = c->lj_bh.as<double>();
-    lj.n_tiles = a->lj_n_tiles; lj.n_params = a->n_params; lj.no_max = a->lj_no_max;
+    lj.n_tiles = a->lj_n_tiles; lj.n_params = a->n_params; lj.no_max = a->lj_no_max; lj.pt = a->lj_pt;
     size_t smemC = 0;
     lj.ts = levelj_ts(c, a, &smemC);
     const AtomDev ad = atom_dev(a); const ModelDev md = model_dev(a);
@@ -1166,7 +1176,7 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
         c->launches++;
     }
     static const bool accum_v1 = getenv("B200_LJ_ACCUM_V1") != nullptr;      // dev knob: scalar shared-memory contraction
-    const size_t smemC2 = ((size_t)a->lj_no_max * LJ_PT + 64 * LJ_LDW) * 8 + LJ_KMAX * 4 + 16;
+    const size_t smemC2 = ((size_t)a->lj_no_max * a->lj_pt + 64 * LJ_LDW) * 8 + LJ_KMAX * 4 + 16;
     if (accum_v1 || smemC2 + 1024 > c->smem_optin) {
         CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         k_level_accum<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC, c->stream>>>(ad, md, lj, d_out, ld, d_scale);
@@ -1231,11 +1241,36 @@ extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, in
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
-// device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles
+// device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles.  Large results are split into row blocks
+// that travel on separate streams (one DMA engine does not saturate the PCIe link on its own); a contiguous destination is
+// copied with plain 1-D copies.
 static int copy_out_2d(b200_ctx* c, const double* d_src, int64_t width, int64_t n_rows, double* h_dst, int64_t hstride) {
     if (n_rows == 0 || width == 0) return B200_OK;
-    CU(cudaMemcpy2DAsync(h_dst, (size_t)hstride * 8, d_src, (size_t)width * 8, (size_t)width * 8, (size_t)n_rows,
-                         cudaMemcpyDeviceToHost, c->stream));
+    const size_t bytes = (size_t)n_rows * (size_t)width * 8;
+    const char* es = getenv("B200_D2H_SPLIT");
+    int nsplit = (es && atoi(es) > 0) ? atoi(es) : 1;   // measured: 1..4 streams all land at 53-56 GB/s (PCIe-bound), so one copy is the default
+    if (nsplit > 4) nsplit = 4;
+    if (bytes < ((size_t)64 << 20) || n_rows < nsplit) nsplit = 1;
+    auto copy_rows = [&](int64_t r0, int64_t r1, cudaStream_t st) -> int {
+        const double* src = d_src + (size_t)r0 * width; double* dst = h_dst + (size_t)r0 * hstride;
+        if (hstride == width) { CU(cudaMemcpyAsync(dst, src, (size_t)(r1 - r0) * width * 8, cudaMemcpyDeviceToHost, st)); }
+        else CU(cudaMemcpy2DAsync(dst, (size_t)hstride * 8, src, (size_t)width * 8, (size_t)width * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
+        return B200_OK;
+    };
+    if (nsplit == 1) {
+        int rc = copy_rows(0, n_rows, c->stream); if (rc) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+        return B200_OK;
+    }
+    if (!c->ev_copy) CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    CU(cudaEventRecord(c->ev_copy, c->stream));                        // the result is complete on the main stream
+    for (int k = 1; k < nsplit; ++k) {
+        if (!c->copy_streams[k - 1]) CU(cudaStreamCreateWithFlags(&c->copy_streams[k - 1], cudaStreamNonBlocking));
+        CU(cudaStreamWaitEvent(c->copy_streams[k - 1], c->ev_copy, 0));
+        int rc = copy_rows(n_rows * k / nsplit, n_rows * (k + 1) / nsplit, c->copy_streams[k - 1]); if (rc) return rc;
+    }
+    { int rc = copy_rows(0, n_rows / nsplit, c->stream); if (rc) return rc; }
+    for (int k = 1; k < nsplit; ++k) CU(cudaStreamSynchronize(c->copy_streams[k - 1]));
     CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
 }

@@ -20,6 +20,44 @@
 
 struct LevelTile { uint32_t first; uint16_t count; uint16_t gate; };   // entries [first, first+count) of lvl_circ
 
+// Inner product loop shared by k_level_gemm and k_level_gemm_rows (kernels_levelj.cuh): acc[mt][nt] += A[32 x D] . B[D x 8 NT].
+// A fragments come from shared memory (row stride D + 4), B fragments (rows of G, 32 bytes per row and K step) from L2.  The B
+// loads of the NEXT 16 K (the four sectors of one 128-byte line of each row) are issued before the 4 x 8 DMMA of the current
+// 16 K: the first version loaded B inside the step that used it (unroll 2) and left the FP64 tensor pipe waiting on L2.
+template <int D, int NT>
+__device__ __forceinline__ void level_gemm_core(const double* __restrict__ ap, const double* __restrict__ bp, double (&acc)[4][NT][2])
+{
+    constexpr int LDS_ = D + 4;
+    double bb[4][NT];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bb[s4][nt] = __ldg(bp + (size_t)nt * 8 * D + 4 * s4);
+#pragma unroll 1
+    for (int k0 = 0; k0 < D; k0 += 16) {
+        double bn[4][NT];
+        const int kn = (k0 + 16 < D) ? k0 + 16 : k0;          // (last block: reload the current one, unused)
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bn[s4][nt] = __ldg(bp + (size_t)nt * 8 * D + kn + 4 * s4);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            double af[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + k0 + 4 * s4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bb[s4][nt]);
+        }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bb[s4][nt] = bn[s4][nt];
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(128)
 k_level_init(AtomDev a, const double* __restrict__ rho, double* __restrict__ S0)
@@ -63,18 +101,7 @@ k_level_gemm(const double* __restrict__ G, const LevelTile* __restrict__ tiles, 
     // S_next[c][i] = sum_j S[c][j] G[i][j] : A[m=c][k=j] from smem, B[k=j][n=i] = G[i][j] (row i contiguous in j)
     const double* bp = Gg + (size_t)(n0 + mrow) * D + q;      // + nt*8*D + k0
     const double* ap = st + mrow * LDS_ + q;                  // + mt*8*LDS_ + k0
-#pragma unroll 2
-    for (int k0 = 0; k0 < D; k0 += 4) {
-        double af[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + k0];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const double b = __ldg(bp + (size_t)nt * 8 * D + k0);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], b);
-        }
-    }
+    level_gemm_core<D, NT>(ap, bp, acc);
     // D fragment: row m = circuit, cols 2q, 2q+1 of the n-tile
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {

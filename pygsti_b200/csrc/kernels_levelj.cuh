@@ -23,7 +23,8 @@
 #include "common.cuh"
 #include "kernels_level.cuh"
 
-#define LJ_PT 256          // parameters per accumulate tile
+#define LJ_PT_MIN 256      // parameters per accumulate tile: chosen per atom (engine.cu, set_derivs), a power of two in [MIN, MAX]
+#define LJ_PT_MAX 2048
 #define LJ_THREADS 128
 
 struct LevelJDev {
@@ -36,7 +37,7 @@ struct LevelJDev {
     const int32_t* crow;       // CSC rows of D (W-space index)
     const double* cval;
     double* FS; double* BH;
-    int n_tiles, n_params, no_max, ts;
+    int n_tiles, n_params, no_max, ts, pt;   // pt: parameters per accumulate tile
 };
 
 // FS[fbase[c]] = rho[prep_c];  BH[bbase[c] + o (L+1) + L] = E[eff_o]
@@ -92,18 +93,7 @@ k_level_gemm_rows(const double* __restrict__ Gm, const LevelTile* __restrict__ t
         for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
     const double* bp = Gg + (size_t)(n0 + mrow) * D + q;
     const double* ap = st + mrow * LDS_ + q;
-#pragma unroll 2
-    for (int k0 = 0; k0 < D; k0 += 4) {
-        double af[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + k0];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const double b = __ldg(bp + (size_t)nt * 8 * D + k0);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], b);
-        }
-    }
+    level_gemm_core<D, NT>(ap, bp, acc);
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
         const int r = mt * 8 + mrow;
@@ -145,6 +135,7 @@ k_level_accum(AtomDev a, ModelDev m, LevelJDev lj, double* __restrict__ J, int64
 {
     extern __shared__ __align__(16) double sml[];
     const int TS = lj.ts;
+    const int LJ_PT = lj.pt;
     const int ES = TS * D + 1;                       // outcome stride of the adjoint stage (odd: consecutive outcomes -> different banks)
     double* Jacc = sml;                              // [no_max][LJ_PT]
     double* s_st = Jacc + (size_t)lj.no_max * LJ_PT; // [TS][D]
@@ -266,6 +257,7 @@ k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __res
                const double* __restrict__ row_scale)
 {
     constexpr int SBD = D / 64;                       // sub-blocks per dimension
+    const int LJ_PT = lj.pt;
     extern __shared__ __align__(16) double sml[];
     double* Jacc = sml;                               // [no_max][LJ_PT]
     double* Wt = Jacc + (size_t)lj.no_max * LJ_PT;    // [64][LJ_LDW]
