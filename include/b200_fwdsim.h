@@ -100,6 +100,20 @@ int b200_atom_set_model(b200_ctx* ctx, b200_atom* atom,
 int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* atom, int64_t n_w, int32_t n_params,
                          int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals);
 
+/* ---- on-device model update for members AFFINE in their parameters (first part) ----------
+ * FullArbitraryOp / FullTPOp / FullState / TPState / static members and (un)constrained POVM effects are affine in the
+ * parameter vector:  M(theta) = M_const + D theta,  D = the derivative map of b200_atom_set_derivs over ALL parameters.
+ * b200_atom_bind_params fixes M_const = M - D theta0 from the model tensors currently on the device (b200_atom_set_model)
+ * and the parameter vector theta0 they were computed from.  b200_atom_set_params[_dev] then replaces, per optimizer
+ * iteration, OpModel.from_vector (pygsti/models/model.py:1163-1196) + the members' to_dense + the upload by one kernel
+ * (rows of D summed in a fixed order: deterministic; exact for `full` members, whose rows have a single unit entry).
+ * b200_atom_get_model copies M = [G | rho | E] back (n_w doubles) -- used by the parity tests.
+ * Errors: B200_E_STATE if no model / derivative map is set, or the map was uploaded for a parameter sub-block. */
+int b200_atom_bind_params(b200_ctx* ctx, b200_atom* atom, int32_t n_params, const double* theta0);
+int b200_atom_set_params(b200_ctx* ctx, b200_atom* atom, int32_t n_params, const double* theta);
+int b200_atom_set_params_dev(b200_ctx* ctx, b200_atom* atom, int32_t n_params, const double* d_theta);
+int b200_atom_get_model(b200_ctx* ctx, b200_atom* atom, int64_t n_w, double* M_out);
+
 /* ---- the hot path, HOST buffers (copies inside the call) ---------------------------------------
  * b200_fill_probs   replaces mapfill_probs_atom + dm_mapfill_probs (pyx:149-287):
  *     out[el * out_stride] = E . G_L ... G_1 rho        for every element of the atom.

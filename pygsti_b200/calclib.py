@@ -161,8 +161,7 @@ def mapfill_probs_atom(fwdsim, array_to_fill, dest_indices, layout_atom, resourc
         return  # same guard as pyx:158,183: only the host leader writes shared memory
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    mt = packing.pack_model(fwdsim.model, layout_atom, fwdsim.model.dim)
-    atom.set_model(mt)
+    _upload_model(fwdsim, layout_atom, ent)
     nE = layout_atom.num_elements
     blk = _contiguous_block(dest_indices, array_to_fill.shape[0])
     if blk is not None and blk[1] - blk[0] == nE and array_to_fill.dtype == np.float64:
@@ -171,6 +170,38 @@ def mapfill_probs_atom(fwdsim, array_to_fill, dest_indices, layout_atom, resourc
         tmp = np.empty(nE)
         atom.fill_probs(tmp)
         array_to_fill[_to_index_array(dest_indices, array_to_fill.shape[0])] = tmp
+
+
+def _bound_to(ent, model):
+    ref = ent.get("bound")
+    return bool(ref) and ref() is model
+
+
+def _upload_model(fwdsim, layout_atom, ent):
+    """Bring the device copy of the model tensors up to date with ``fwdsim.model``.
+    Default: pack the members' dense matrices on the host and upload them (replaces the rep lookups of pyx:164-167).
+    With ``device_model_update`` and a parameter binding (all members affine, full derivative map resident): upload only
+    the parameter vector; the engine evaluates M = M_const + D theta on the device."""
+    model = fwdsim.model
+    atom = ent["atom"]
+    if getattr(fwdsim, "device_model_update", False) and _bound_to(ent, model):
+        atom.set_params(model.to_vector())
+        return
+    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
+
+
+def _maybe_bind(fwdsim, layout_atom, ent, pidx):
+    """After a host upload of the model AND of the full derivative map: bind the parameter vector so that later fills can
+    update the model on the device."""
+    model = fwdsim.model
+    if not getattr(fwdsim, "device_model_update", False) or _bound_to(ent, model):
+        return
+    if pidx.size != model.num_params or not np.array_equal(pidx, np.arange(model.num_params)):
+        return
+    if not all_members_linear(fwdsim, layout_atom):
+        return
+    ent["atom"].bind_params(model.to_vector())
+    ent["bound"] = weakref.ref(model)       # M_const belongs to THIS model object (its static members, its structure)
 
 
 def all_members_linear(fwdsim, layout_atom):
@@ -188,8 +219,8 @@ def mapfill_hprobs_atom_linear(fwdsim, array_to_fill, dest_param_indices1, dest_
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
-    _deriv_map(fwdsim, layout_atom, ent, None)          # full derivative map; blocks select its columns
+    _upload_model(fwdsim, layout_atom, ent)
+    _maybe_bind(fwdsim, layout_atom, ent, _deriv_map(fwdsim, layout_atom, ent, None))          # full derivative map; blocks select its columns
     if not shared_mem_leader:
         return
     p1 = packing.param_slice_to_array(param_indices1, model.num_params)
@@ -220,8 +251,8 @@ def mapfill_hprobs_atom_analytic(fwdsim, array_to_fill, dest_param_indices1, des
     shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
-    _deriv_map(fwdsim, layout_atom, ent, None)
+    _upload_model(fwdsim, layout_atom, ent)
+    _maybe_bind(fwdsim, layout_atom, ent, _deriv_map(fwdsim, layout_atom, ent, None))
     if not shared_mem_leader:
         return True
     nE = layout_atom.num_elements
@@ -250,8 +281,8 @@ def atom_hessian_block(fwdsim, layout_atom, param_indices1, param_indices2, w_h,
             return None
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
-    _deriv_map(fwdsim, layout_atom, ent, None)
+    _upload_model(fwdsim, layout_atom, ent)
+    _maybe_bind(fwdsim, layout_atom, ent, _deriv_map(fwdsim, layout_atom, ent, None))
     if layout_atom.num_elements == 0 or p1.size == 0 or p2.size == 0:
         return np.zeros((p1.size, p2.size))
     return atom.hessian_block(p1, p2, w_h, w_d, hess)
@@ -271,6 +302,7 @@ def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     D = packing.pack_derivs(model, layout_atom, model.dim, pidx)
     ent["atom"].set_derivs(D)
     ent["deriv_key"] = key
+    ent["bound"] = None             # a parameter binding refers to the map it was made with
     return pidx
 
 
@@ -283,9 +315,9 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    mt = packing.pack_model(model, layout_atom, model.dim)
-    atom.set_model(mt)
+    _upload_model(fwdsim, layout_atom, ent)
     pidx = _deriv_map(fwdsim, layout_atom, ent, param_indices)
+    _maybe_bind(fwdsim, layout_atom, ent, pidx)
     if not shared_mem_leader:
         return
     nE = layout_atom.num_elements
@@ -324,8 +356,8 @@ def atom_jtj(fwdsim, layout_atom, row_scale=None, f=None):
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    atom.set_model(packing.pack_model(model, layout_atom, model.dim))
-    _deriv_map(fwdsim, layout_atom, ent, None)
+    _upload_model(fwdsim, layout_atom, ent)
+    _maybe_bind(fwdsim, layout_atom, ent, _deriv_map(fwdsim, layout_atom, ent, None))
     return atom.jtj(row_scale, f)
 
 

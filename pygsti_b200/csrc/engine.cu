@@ -119,6 +119,9 @@ struct b200_atom {
     DevBuf id_colmap, id_spam_col, id_spam_w;  // identity maps: d16 kernel writing W for the general path
     int id_n_spam = 0;
     std::vector<int32_t> h_cptr, h_crow; std::vector<double> h_cval;  // host copy (hessian / fd)
+    // affine model update (b200_atom_bind_params): CSR of D by W-space row, M_const, parameter staging
+    bool has_bind = false; int32_t bind_n_params = 0;
+    DevBuf aff_rptr, aff_rcol, aff_rval, aff_const, aff_theta;
 };
 
 static AtomDev atom_dev(b200_atom* a) {
@@ -582,6 +585,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
                       &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
                       &a->t_counters, &a->t_units, &a->t_uidx,
                       &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
+                      &a->aff_rptr, &a->aff_rcol, &a->aff_rval, &a->aff_const, &a->aff_theta,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
     for (DevBuf* b : bufs) b->release();
     delete a;
@@ -620,12 +624,100 @@ extern "C" int b200_atom_set_model(b200_ctx* ctx, b200_atom* a, const double* G,
     return B200_OK;
 }
 
+// M[w] = M_const[w] + sum_t rval[t] * theta[rcol[t]]   (one thread per W-space element, rows summed in CSR order)
+__global__ void k_model_affine(int64_t n_w, const int32_t* __restrict__ rptr, const int32_t* __restrict__ rcol,
+                               const double* __restrict__ rval, const double* __restrict__ Mconst,
+                               const double* __restrict__ theta, double* __restrict__ M)
+{
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n_w; w += (int64_t)gridDim.x * blockDim.x) {
+        double acc = Mconst[w];
+        for (int32_t t = rptr[w]; t < rptr[w + 1]; ++t) acc = fma(rval[t], theta[rcol[t]], acc);
+        M[w] = acc;
+    }
+}
+
+extern "C" int b200_atom_get_model(b200_ctx* ctx, b200_atom* a, int64_t n_w, double* M_out) {
+    if (!ctx || !a || !M_out) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (n_w != a->n_w) return fail(B200_E_INVALID, "n_w=%lld does not match the atom's W space (%lld)", (long long)n_w, (long long)a->n_w);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(M_out, a->M.p, (size_t)a->n_w * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+extern "C" int b200_atom_bind_params(b200_ctx* ctx, b200_atom* a, int32_t n_params, const double* theta0) {
+    if (!ctx || !a || (n_params > 0 && !theta0)) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
+    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (n_params != a->n_params)
+        return fail(B200_E_STATE, "the derivative map on the device has %d columns, not the %d parameters of theta0 "
+                                  "(upload it for ALL parameters before binding)", a->n_params, n_params);
+    CU(cudaSetDevice(ctx->device));
+    const int64_t n_w = a->n_w;
+    // CSC (by parameter) -> CSR (by W-space row); entries of a row in increasing parameter order
+    std::vector<int32_t> rptr((size_t)n_w + 1, 0);
+    for (int32_t r : a->h_crow) rptr[(size_t)r + 1]++;
+    for (int64_t w = 0; w < n_w; ++w) rptr[w + 1] += rptr[w];
+    std::vector<int32_t> rcol(a->h_crow.size()); std::vector<double> rval(a->h_crow.size());
+    { std::vector<int32_t> pos(rptr.begin(), rptr.end() - 1);
+      for (int32_t p = 0; p < n_params; ++p)
+          for (int32_t t = a->h_cptr[p]; t < a->h_cptr[p + 1]; ++t) { const int32_t q = pos[a->h_crow[t]]++; rcol[q] = p; rval[q] = a->h_cval[t]; } }
+    // M_const = M - D theta0 (same summation order as the kernel)
+    std::vector<double> Mh((size_t)n_w);
+    CU(cudaMemcpyAsync(Mh.data(), a->M.p, (size_t)n_w * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int64_t w = 0; w < n_w; ++w) {
+        double lin = 0.0;
+        for (int32_t t = rptr[w]; t < rptr[w + 1]; ++t) lin = fma(rval[t], theta0[rcol[t]], lin);
+        Mh[w] -= lin;
+    }
+    int rc;
+    if ((rc = upload_vec(a->aff_rptr, rptr, ctx->stream)) || (rc = upload_vec(a->aff_rcol, rcol, ctx->stream)) ||
+        (rc = upload_vec(a->aff_rval, rval, ctx->stream)) || (rc = upload_vec(a->aff_const, Mh, ctx->stream))) return rc;
+    CU(a->aff_theta.ensure(std::max<size_t>((size_t)n_params * 8, 16)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    a->has_bind = true; a->bind_n_params = n_params;
+    return B200_OK;
+}
+
+extern "C" int b200_atom_set_params_dev(b200_ctx* ctx, b200_atom* a, int32_t n_params, const double* d_theta) {
+    if (!ctx || !a || (n_params > 0 && !d_theta)) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_bind) return fail(B200_E_STATE, "b200_atom_bind_params has not been called");
+    if (n_params != a->bind_n_params) return fail(B200_E_INVALID, "n_params=%d, bound with %d", n_params, a->bind_n_params);
+    CU(cudaSetDevice(ctx->device));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_w + 255) / 256, (int64_t)ctx->sm_count * 8));
+    k_model_affine<<<grid, 256, 0, ctx->stream>>>(a->n_w, a->aff_rptr.as<int32_t>(), a->aff_rcol.as<int32_t>(), a->aff_rval.as<double>(),
+                                                  a->aff_const.as<double>(), d_theta, a->M.as<double>());
+    ctx->launches++;
+    if (a->n_ops) {
+        dim3 gt((unsigned)std::min<int64_t>((a->off_rho + 255) / 256, 1024), 1);
+        k_transpose_gates<<<gt, 256, 0, ctx->stream>>>(a->M.as<double>(), a->n_w, a->n_ops, a->dim, a->Gt.as<double>());
+        ctx->launches++;
+    }
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
+extern "C" int b200_atom_set_params(b200_ctx* ctx, b200_atom* a, int32_t n_params, const double* theta) {
+    if (!ctx || !a || (n_params > 0 && !theta)) return fail(B200_E_INVALID, "NULL argument");
+    if (!a->has_bind) return fail(B200_E_STATE, "b200_atom_bind_params has not been called");
+    if (n_params != a->bind_n_params) return fail(B200_E_INVALID, "n_params=%d, bound with %d", n_params, a->bind_n_params);
+    CU(cudaSetDevice(ctx->device));
+    if (n_params > 0) CU(cudaMemcpyAsync(a->aff_theta.p, theta, (size_t)n_params * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = b200_atom_set_params_dev(ctx, a, n_params, a->aff_theta.as<double>());
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));   // caller may modify theta on return
+    return B200_OK;
+}
+
 extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, int32_t n_params,
                                     int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals)
 {
     if (!ctx || !a) return fail(B200_E_INVALID, "NULL argument");
     if (n_w != a->n_w) return fail(B200_E_INVALID, "n_w=%lld does not match the atom's W space (%lld)", (long long)n_w, (long long)a->n_w);
     if (n_params < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(B200_E_INVALID, "bad derivative map");
+    a->has_bind = false;                      // a parameter binding refers to the map it was made with
     if (nnz >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "derivative map too large");
     CU(cudaSetDevice(ctx->device));
     // COO -> CSC with duplicates summed

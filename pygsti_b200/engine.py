@@ -128,6 +128,28 @@ class Atom:
                                                   int(rows.shape[0]), _ptr(rows), _ptr(cols), _ptr(vals)))
         self.n_params = int(D.n_params)
 
+    # ---- on-device model update for members affine in their parameters -------
+    def bind_params(self, theta0):
+        """Fix M_const = M - D theta0 from the model tensors on the device and the parameter vector they came from
+        (needs ``set_model`` and ``set_derivs`` over ALL parameters)."""
+        th = _f64(theta0).ravel()
+        _lib.check(self._lib.b200_atom_bind_params(self.ctx._h, self._h, int(th.shape[0]), _ptr(th)))
+
+    def set_params(self, theta):
+        """M = M_const + D theta on the device: replaces model.from_vector + to_dense + set_model for affine members."""
+        th = _f64(theta).ravel()
+        _lib.check(self._lib.b200_atom_set_params(self.ctx._h, self._h, int(th.shape[0]), _ptr(th)))
+
+    def set_params_dev(self, d_theta_ptr, n_params):
+        _lib.check(self._lib.b200_atom_set_params_dev(self.ctx._h, self._h, int(n_params), C.c_void_p(int(d_theta_ptr))))
+
+    def get_model(self):
+        """The W-space vector M = [G | rho | E] currently on the device."""
+        n_w = self.n_ops * self.dim * self.dim + (self.n_rho + self.n_eff) * self.dim
+        out = np.empty(n_w)
+        _lib.check(self._lib.b200_atom_get_model(self.ctx._h, self._h, int(n_w), _ptr(out)))
+        return out
+
     # ---- host-buffer fills ---------------------------------------------------------------------
     @staticmethod
     def _vec_stride(a, n):

@@ -307,3 +307,52 @@ def test_fused_mle_hessian(param):
     assert np.max(np.abs(H - Href)) <= 1e-8 * np.max(np.abs(Href))
     Hsame = ours.hessian()                                # reference code path on the GPU simulator (host-side reduction)
     assert np.max(np.abs(H - Hsame)) <= 1e-8 * np.max(np.abs(Href))
+
+
+def _as_index_list(ix, n):
+    return list(range(*ix.indices(n))) if isinstance(ix, slice) else [int(i) for i in ix]
+
+
+@pytest.mark.parametrize("param", ["full", "full TP"])
+def test_device_model_update_follows_from_vector(param):
+    """SURVEY 8f rank 3 (first part): with ``device_model_update=True`` only the parameter vector is uploaded once the
+    parameters are bound; probabilities, Jacobian and the device copy of the model tensors must follow
+    ``model.from_vector`` exactly as the host-packed path does, and a GST-style sequence of parameter updates on ONE
+    layout must agree with the reference's Matrix simulator at every step."""
+    from pygsti_b200 import calclib, packing
+    model = smq2Q_XYCNOT.target_model(param).depolarize(op_noise=0.01, spam_noise=0.01)
+    circuits = smq2Q_XYCNOT.create_gst_experiment_design(2).all_circuits_needing_data[:200]
+    model.sim = B200ForwardSimulator(device_model_update=True)
+    layout = model.sim.create_layout(circuits, array_types=('e', 'ep'))
+    ref = model.copy(); ref.sim = MatrixForwardSimulator()
+    rlayout = ref.sim.create_layout(circuits, array_types=('e', 'ep'))
+    nE, Np = layout.num_elements, model.num_params
+    # element correspondence between the two layouts (Map and Matrix layouts order their elements differently)
+    ib, ir = [], []
+    for c in circuits:
+        eb = dict(zip(layout.outcomes(c), _as_index_list(layout.indices(c), nE)))
+        er = dict(zip(rlayout.outcomes(c), _as_index_list(rlayout.indices(c), nE)))
+        assert set(eb) == set(er)
+        for o in eb:
+            ib.append(eb[o]); ir.append(er[o])
+    ib, ir = np.array(ib), np.array(ir)
+    assert ib.size == nE
+    rng = np.random.default_rng(5)
+    v0 = model.to_vector()
+    for step in range(4):
+        v = v0 + (0.0 if step == 0 else 0.02) * rng.standard_normal(Np)
+        model.from_vector(v); ref.from_vector(v)
+        J = np.empty((nE, Np)); p = np.empty(nE); Jr = np.empty((nE, Np)); pr = np.empty(nE)
+        model.sim.bulk_fill_dprobs(J, layout, pr_array_to_fill=p)
+        ref.sim.bulk_fill_dprobs(Jr, rlayout, pr_array_to_fill=pr)
+        assert np.max(np.abs(p[ib] - pr[ir])) <= 1e-12
+        assert np.max(np.abs(J[ib] - Jr[ir])) <= 1e-10
+        p2 = np.empty(nE)
+        model.sim.bulk_fill_probs(p2, layout)                 # probs-only fill after the binding: parameter upload only
+        assert np.max(np.abs(p2[ib] - pr[ir])) <= 1e-12
+        atom = layout.atoms[0]
+        ent = calclib._ATOM_CACHE[atom][calclib.get_context(calclib._device_for(model.sim, atom)).device]
+        assert step == 0 or calclib._bound_to(ent, model)      # bound after the first full-Jacobian fill
+        mt = packing.pack_model(model, atom, model.dim)
+        M_host = np.concatenate([np.ravel(mt.G), np.ravel(mt.rho), np.ravel(mt.E)])
+        assert np.max(np.abs(ent["atom"].get_model() - M_host)) <= 1e-15

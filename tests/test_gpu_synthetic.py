@@ -237,3 +237,43 @@ def test_repeated_calls_with_changing_models(gpu_ctx):
     gpu_ctx.phase_timing(False)
     assert n == len(models) and all(x > 0.0 for x in ms)
     at.free()
+
+
+def test_affine_model_update_on_device(gpu_ctx):
+    """b200_atom_bind_params / set_params: M = M_const + D theta on the device for a general affine map (several
+    parameters per element, elements without parameters), against numpy; the Jacobian of the updated model against the
+    oracle; binding is refused for a derivative map over a parameter sub-block that does not match theta."""
+    from pygsti_b200.packing import DerivMap
+    circs = synth.random_circuits(20, 25, 4, 1, 4, seed=4)
+    t = synth.make_tables(16, 4, 1, 4, circs)
+    n_w = 4 * 256 + 16 + 64
+    rng = np.random.default_rng(3)
+    n_params = 300
+    nnz = 2000
+    rows = rng.integers(0, n_w, size=nnz).astype(np.int32); cols = rng.integers(0, n_params, size=nnz).astype(np.int32)
+    keep = np.unique(rows.astype(np.int64) * n_params + cols, return_index=True)[1]
+    rows, cols = rows[keep], cols[keep]
+    vals = rng.standard_normal(rows.size)
+    D = DerivMap(n_w, n_params, rows, cols, vals)
+    Dd = np.zeros((n_w, n_params)); Dd[rows, cols] = vals
+    Mc = 0.1 * rng.standard_normal(n_w)
+    th0 = 0.05 * rng.standard_normal(n_params)
+    M0 = Mc + Dd @ th0
+    split = lambda M: (M[:1024].reshape(4, 16, 16), M[1024:1040].reshape(1, 16), M[1040:].reshape(4, 16))
+    at = gpu_ctx.upload_atom(t)
+    at.set_model(*split(M0)); at.set_derivs(D)
+    with pytest.raises(Exception):
+        at.bind_params(th0[:-1])                      # wrong length: refused
+    at.bind_params(th0)
+    for k in range(3):
+        th = 0.05 * rng.standard_normal(n_params)
+        at.set_params(th)
+        M = Mc + Dd @ th
+        assert np.max(np.abs(at.get_model() - M)) <= 1e-14
+        J = np.full((t.n_elements, n_params), np.nan); p = np.full(t.n_elements, np.nan)
+        at.fill_dprobs(J, p)
+        G, rho, E = split(M)
+        assert np.max(np.abs(p - onp.mapfill_probs(t, G, rho, E))) <= 1e-12
+        Jo = onp.dprobs_analytic(t, G, rho, E, D)
+        assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    at.free()
