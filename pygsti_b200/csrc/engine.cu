@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <numeric>
+#include <climits>
 #include <string>
 #include <vector>
 
@@ -493,8 +494,16 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             a->unit_outcomes = gsz;
             std::vector<UnitRec> units; std::vector<uint2> uidx;
             bool trie_ok = ((uint64_t)(zb_node + 2) * ne16 < ((uint64_t)1 << 32)) && ((uint64_t)(zf_node + 2) * 16 < ((uint64_t)1 << 32));
+            // unit order: suffix-lexicographic (default) or, dev knob B200_UNIT_ORDER=el, by Jacobian row (sequential stores)
+            std::vector<int64_t> uorder(TB.sorted);
+            if (getenv("B200_UNIT_ORDER") && !strcmp(getenv("B200_UNIT_ORDER"), "el")) {
+                std::vector<int32_t> first_el((size_t)n_rows, INT32_MAX);
+                for (int64_t i = 0; i < n_rows; ++i)
+                    for (int32_t oq = coptr[i]; oq < coptr[i + 1]; ++oq) first_el[i] = std::min(first_el[i], coel[oq]);
+                std::stable_sort(uorder.begin(), uorder.end(), [&](int64_t x, int64_t y) { return first_el[x] < first_el[y]; });
+            }
             for (int64_t si = 0; si < n_rows; ++si) {
-                const int64_t i = TB.sorted[si];
+                const int64_t i = uorder[si];
                 const uint32_t b0 = cptr[i];
                 const uint16_t* cn = bcnt.data() + (size_t)i * n_ops;
                 for (int eb = 0; eb < n_eff; eb += gsz) {
@@ -1016,7 +1025,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     c->launches += 1;
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
+    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
     // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
     // grab (2/4/8), 256-bit stores (measured: 0.914 ms with, 0.891 ms without)
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
@@ -1059,6 +1068,17 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     // Jacobian, and removed: the loop is not bound by the latency of the table gathers -- profiles/README.md)
     int rcB = 1;
     {
+        const bool tma = knob("B200_ACC_TMA", 0) != 0 && a->unit_outcomes != 2 && !w256;   // bulk-store epilogue (dev knob)
+        if (tma) {
+            auto kern = k_accum_trie_d16<4, false, false, true>;
+            const size_t smemT = smemB + (size_t)AT_WARPS * 4 * 256 * 8;
+            if (smemT + 1024 > c->smem_optin) return fail(B200_E_UNSUPPORTED, "TMA epilogue: shared memory");
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT));
+            const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * acc_chunk - 1) / (AT_WARPS * acc_chunk), 2);
+            kern<<<gB, AT_WARPS * 32, smemT, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                          a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, dbg, acc_chunk, acc_rsub);
+            rcB = B200_OK;
+        } else
         if (t.prof && a->unit_outcomes != 2 && !w256) rcB = launchB(k_accum_trie_d16<4, false, true>, 2);      // phase profiler (dev)
         else if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
         else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
