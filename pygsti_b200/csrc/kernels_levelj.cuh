@@ -251,6 +251,7 @@ struct LevelJ2Dev {
     int nsb;                   // sub-blocks per matrix = (D / 64)^2
 };
 
+// (forcing 128 registers / 4 CTAs per SM was measured slower, 88.6 vs 84.9 ms at BASELINE config 3: the spills cost more than the warps gain)
 template <int D>
 __global__ void __launch_bounds__(LJ_THREADS)
 k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __restrict__ J, int64_t ld,

@@ -47,6 +47,28 @@ def test_layout_is_the_reference_layout_and_no_jacobian_table(model):
     assert not hasattr(layout.atoms[0], "jac_table")     # trap 3: the generic calclib would build it
 
 
+def test_layouts_skip_the_host_prefix_cache_plan_by_default(model):
+    """The engine rebuilds prefix + suffix sharing itself: layouts are created without pyGSTi's cache plan unless asked;
+    the packed tables of both variants describe the same circuits (same oracle probabilities)."""
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    outs = []
+    for kw, want_cache in (({}, False), ({"host_prefix_cache": True}, True), ({"max_cache_size": 5}, True)):
+        m = model.copy()
+        m.sim = B200ForwardSimulator(**kw)
+        layout = m.sim.create_layout(circuits, array_types=('e', 'ep'))
+        atom = layout.atoms[0]
+        assert (atom.cache_size > 0) == want_cache
+        s = m.sim.copy()
+        assert s._max_cache_size == m.sim._max_cache_size and s.host_prefix_cache == m.sim.host_prefix_cache
+        t = packing.pack_atom(atom, m.dim)
+        mt = packing.pack_model(m, atom, m.dim)
+        p = np.empty(layout.num_elements)
+        p[:] = onp.mapfill_probs(t, mt.G, mt.rho, mt.E)
+        outs.append({c: p[layout.indices(c)] for c in circuits})
+    for c in circuits:
+        assert np.max(np.abs(outs[0][c] - outs[1][c])) <= 1e-15 and np.max(np.abs(outs[0][c] - outs[2][c])) <= 1e-15
+
+
 def test_packing_reproduces_reference_probs_through_the_oracle(model):
     m = model.copy()
     circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
