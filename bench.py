@@ -188,6 +188,12 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # the contract is ONE JSON line on stdout: libraries that print there from C (NCCL prints its version line on the first
+    # collective when NCCL_DEBUG=VERSION is set in the image) are sent to stderr; the JSON goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from pygsti_b200 import engine
@@ -324,7 +330,8 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_sample(case, os.cpu_count() or 1, core_seconds=20.0)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
