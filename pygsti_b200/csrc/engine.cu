@@ -1025,7 +1025,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     c->launches += 1;
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
+    const size_t smemB = (size_t)AT_WARPS * 5 * 16 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
     // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
     // grab (2/4/8), 256-bit stores (measured: 0.914 ms with, 0.891 ms without)
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };

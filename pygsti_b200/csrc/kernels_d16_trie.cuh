@@ -327,6 +327,10 @@ struct UnitRec {           // 32 bytes
 //   * a lane's four accumulators of block row i are the four CONSECUTIVE columns 4q..4q+3 (j = 4q + 2c + z): one
 //     st.global.v4.f64 per lane writes 8 full 128-byte lines per warp instruction (SASS STG.E.256) instead of two
 //     instructions that each touch half of 8 lines.
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void st256_cs(double* p, double a, double b, double c, double d) {
     asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
@@ -338,7 +342,8 @@ __device__ __forceinline__ void st256_cs(double* p, double a, double b, double c
 // MEASURED (C2 layout): 0.852 ms per Jacobian against 0.810 ms with plain st.cs stores, and 0.685 against 0.670 ms with the
 // gathers switched off -- taking the stores off the LSU does not help, so the loop's long-scoreboard stalls are not gathers
 // queueing behind stalled stores.  (A first version with 8-way conflicted staging had also measured "no gain".)
-// dynamic smem with TMA: AT_WARPS * NO * 256 doubles of staging in front of the column-map fragments.
+// dynamic smem: AT_WARPS * (1 + NO) * 16 doubles (SPAM slots) [+ with TMA: AT_WARPS * NO * 256 doubles of staging], then the
+// column-map fragments, SPAM lists and gate bases.
 template <int NO, bool W256, bool PROF = false, bool TMA = false>   // outcomes (consecutive effects) per unit: 4 (16 warps/SM) or 2 (24 warps/SM)
 __global__ void __launch_bounds__(AT_WARPS * 32, (NO == 4 ? 2 : 3))
 k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
@@ -352,8 +357,10 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     // rows of the backward table H, and those gathers then hit in L1 instead of going to L2 once per circuit.
     __shared__ unsigned long long s_pack;                               // (first sub-chunk of the range) << 32 | next sub-chunk
     extern __shared__ __align__(128) unsigned char smb[];
-    double* stage_all = reinterpret_cast<double*>(smb);                 // [AT_WARPS][NO][256] (TMA only)
-    int2* cm_s = reinterpret_cast<int2*>(smb + (TMA ? (size_t)AT_WARPS * NO * 256 * 8 : 0));   // [n_ops*4][32]
+    constexpr int SPS = (1 + NO) * 16;                                  // per-warp slot: s_L row + the e_0 rows of the unit's outcomes
+    double* spam_stage = reinterpret_cast<double*>(smb);                // [AT_WARPS][SPS]
+    double* stage_all = spam_stage + AT_WARPS * SPS;                    // [AT_WARPS][NO][256] (TMA only)
+    int2* cm_s = reinterpret_cast<int2*>(stage_all + (TMA ? AT_WARPS * NO * 256 : 0));   // [n_ops*4][32]
     int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
     int* spamw_s = spamc_s + D16_SPAM_MAX;
     int* gbase_s = spamw_s + D16_SPAM_MAX;                              // [n_ops] first column of a gate's block if the 256 columns are
@@ -467,6 +474,16 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
             const uint4 rbn = __ldg(reinterpret_cast<const uint4*>(units + un) + 1);
             const int g = (int)(rb.y & 0xffu), ngroups = (dbg == 1) ? 0 : (int)((rb.y >> 8) & 0x3fffu);
+            if (g == 0) {
+                // gate-0 unit: it also writes the SPAM columns / probabilities, from s_L and the e_0 rows.  They are copied to a
+                // shared slot NOW (cp.async, no registers) so that their latency hides behind the group loop.
+                __syncwarp();
+                double* slot = spam_stage + warp * SPS;
+                const double* e0 = t.H + (size_t)rb.w * ne16 + ((rb.y >> 22) & 7u) * 16u;      // NO consecutive effect rows
+                if (lane < NO * 8) cp_async16(slot + 16 + 2 * lane, e0 + 2 * lane);
+                if (lane < 8) cp_async16(slot + 2 * lane, t.S + (size_t)rb.z * 16 + 2 * lane);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             double acc[NO][8];
 #pragma unroll
             for (int o = 0; o < NO; ++o)
@@ -591,13 +608,13 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 // shuffles (the first version chased circuit-group record -> row -> element: 12 dependent round trips per
                 // gate-0 unit, 20 % of the kernel's stall samples).
                 const int l16 = lane & 15;
-                const double sLv = t.S[(size_t)rb.z * 16 + l16];
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                const double* slot = spam_stage + warp * SPS;
+                const double sLv = slot[l16];
                 double e0v[NO];
-                {
-                    const double* e0 = t.H + (size_t)rb.w * ne16 + ((rb.y >> 22) & 7u) * 16u + l16;
 #pragma unroll
-                    for (int o = 0; o < NO; ++o) e0v[o] = e0[o * 16];
-                }
+                for (int o = 0; o < NO; ++o) e0v[o] = slot[16 + o * 16 + l16];
                 const int prep = (int)(rb.y >> 25), e_base = (int)((rb.y >> 22) & 7u);
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -630,6 +647,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             if (PROF) pr_epi += clock64() - tq2;
         }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this thread are complete
     if (PROF && t.prof && lane == 0) {
         atomicAdd(t.prof + 8, (unsigned long long)pr_pro); atomicAdd(t.prof + 9, (unsigned long long)pr_grp);
