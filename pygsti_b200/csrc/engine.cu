@@ -994,7 +994,7 @@ static int trie_l2_window(b200_ctx* c, b200_atom* a) {
 // phase A of the trie path: KG = chains per atomic grab (template: the per-batch loop is fully unrolled)
 static int launch_trie_chains(b200_ctx* c, b200_atom* a, const TrieDev& t, int grid, size_t smem, int kg, int fwd_only) {
     const char* es = getenv("B200_CHAIN_SLEEP");
-    const unsigned sleep_ns = (es && atoi(es) > 0) ? (unsigned)atoi(es) : 40u;      // dev knob: poll interval of a waiting chain
+    const unsigned sleep_ns = (es && atoi(es) > 0) ? (unsigned)atoi(es) : 100u;      // dev knob: poll interval of a waiting chain
     auto go = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, TRIE_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), t, fwd_only, sleep_ns);
@@ -1029,7 +1029,7 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
     // grab (2/4/8), 256-bit stores (measured: 0.914 ms with, 0.891 ms without)
     auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
-    const int chain_ctas = std::max(1, knob("B200_CHAIN_CTAS", 4)), chain_k = std::max(1, knob("B200_CHAIN_K", 1));
+    const int chain_ctas = std::max(1, knob("B200_CHAIN_CTAS", 3)), chain_k = std::max(1, knob("B200_CHAIN_K", 1));
     const int st256 = knob("B200_ACC_ST256", 0);
     int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
     const bool chain_prof = knob("B200_CHAIN_PROF", 0) != 0;

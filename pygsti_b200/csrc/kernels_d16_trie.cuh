@@ -308,7 +308,7 @@ k_probs_trie_d16(AtomDev a, ModelDev m, const uint32_t* __restrict__ f_end, cons
 // dynamic smem: n_ops*4*32 int2 (column map fragments) + 2*SPAM_MAX ints
 // ------------------------------------------------------------------------------------------------------------
 #define AT_WARPS 8
-#define AT_CHUNK 16
+#define AT_CHUNK 8      // units per atomic grab (measured on C2: 2: 0.843, 4: 0.773, 8: 0.771, 12: 0.788, 16: 0.801, 24: 0.843 ms)
 
 struct UnitRec {           // 32 bytes
     int32_t el[4];         // Jacobian rows (elements) of the outcomes with effect e_base + i, -1 = no such outcome
