@@ -43,8 +43,8 @@ WORKLOAD_DESC = ("smq2Q_XYCNOT full model (d=16, Np=1360), GST design maxL=128 l
                  "273340 outcomes; bulk_fill_dprobs + probs")
 METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel k_accum_trie_d16 (ncu --set full,
-# profiles/r01_accum_final_ncu_raw.csv): 0.229 GB read + 2.930 GB written
-NCU_TRAFFIC_BYTES = 3.158e9
+# profiles/r01_accum_final_ncu_raw.csv): 0.165 GB read + 2.929 GB written
+NCU_TRAFFIC_BYTES = 3.094e9
 
 
 def _peaks():
@@ -318,7 +318,7 @@ def main():
                          "kernel": "k_accum_trie_d16", "kernel_ms": ms_accum,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 (profiles/r01_accum_final_ncu_raw.csv): dram "
-                                           "read 0.229 GB + write 2.930 GB = 1.06 x the algorithmic bytes",
+                                           "read 0.165 GB + write 2.929 GB = 1.04 x the algorithmic bytes",
                          "step": {"ms": ms_per_step, "achieved": achieved_step, "frac": achieved_step / peak,
                                   "phases_ms": {"k_trie_prepare": ms_prep, "k_trie_chains": ms_chains,
                                                 "k_accum_trie_d16": ms_accum}},
