@@ -1,4 +1,7 @@
 #!/bin/bash
+# The round-end check that was run under gpurun (one B200): full GPU test suite, both bench arms, the ncu launch list of the
+# bench command and one ncu --set full capture of the dominant kernel.  Outputs go to gpurun_out/ (scratch); the summaries
+# that are meant to be judged were copied to profiles/.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 > gpurun_out/pytest_final.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err
