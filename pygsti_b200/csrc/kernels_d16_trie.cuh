@@ -5,18 +5,18 @@
 // propagations on the BASELINE layout).  The analytic Jacobian additionally needs the backward vectors
 // e_k = (G_{L-1} ... G_{k+1})^T E, which depend only on the circuit SUFFIX and the effect -- so they share
 // exactly the same way through a trie of reversed circuits (151 802 nodes x 4 effects instead of 12.6 M
-// chain steps).  Both tries are built once per layout atom on the host (engine.cu: build_trie).
+// chain steps).  Both tries are built once per layout atom on the host (trie_host.h: build_trie).
 //
-//   phase A  k_trie_chains : each trie is cut into chains (maximal runs of nodes created together); warps pull
-//            chains, ordered by start depth, from an atomic counter, wait for the parent node written by an
-//            earlier chain (fence-free sentinel hand-off, see TRIE_SENT), then walk their chain: forward chains
+//   phase A  k_trie_prepare, k_trie_chains : each trie is cut into chains by a heavy-path decomposition (trie_host.h); warps
+//            pull chains, ordered by start depth, one at a time from an atomic counter, wait for the parent node written by
+//            an earlier chain (fence-free sentinel hand-off, see TRIE_SENT), then walk their chain: forward chains
 //            s = G s (DFMA), backward chains E^T[8x16] <- E^T . G for all effects at once (DMMA, rows = effects).
 //            Node values go to the tables S[n_fnodes][16], H[n_bnodes][n_eff][16].
-//            Critical path = deepest circuit, ~340 k mat-vecs in total at BASELINE size: ~0.1 ms.
+//            ~340 k mat-vecs in total at BASELINE size: 0.074 ms.
 //   phase B  k_accum_trie_d16 : one warp per (circuit, outcome group, gate) unit:
 //            W_g[i][j] = sum_{t: g_t = g} e_t[i] s_t[j]  as DMMA with K = 4 time steps; the rows are gathered from
 //            the (~100 MB) tables through a host-built offset stream; a finished 16x16 block is a set of Jacobian
-//            entries and is stored at once.  This kernel is the whole HBM-write-bound cost.
+//            entries and is stored at once.  This kernel is the whole HBM-write-bound cost (0.68 ms, 0.67 of HBM peak).
 #pragma once
 #include "common.cuh"
 #include "kernels_d16.cuh"   // dmma884, D16Args, D16_SPAM_MAX
@@ -46,8 +46,8 @@ struct TrieDev {
 #ifndef TRIE_MIN_CTAS
 #define TRIE_MIN_CTAS 8
 #endif
-// Hand-off between chains without fences or flags: the tables are pre-filled with a NaN payload no computation can
-// produce; a node value is complete when none of its words equals the sentinel (every 8-byte store is atomic, each
+// Hand-off between chains without fences or flags: the rows a chain can wait for are pre-filled with a NaN payload no
+// computation can produce; a node value is complete when none of its words equals the sentinel (every 8-byte store is atomic, each
 // word is written exactly once per call, readers poll through L2 with ld.cg).  A release/acquire flag per node was
 // measured first: the MEMBAR of every release store put ~1.5 k cycles on each step of the critical path.
 #define TRIE_SENT 0x7FF8DEADBEEF5EEDull
