@@ -1,0 +1,54 @@
+"""The bench.py JSON contract, checked on the committed round results (profiles/): every key the driver and the judge read is
+present and internally consistent.  (bench.py itself needs a GPU; this keeps the contract from regressing on the CPU box.)"""
+import json
+import os
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PROF = os.path.join(REPO, "profiles")
+
+
+def _load(name):
+    with open(os.path.join(PROF, name)) as f:
+        lines = [l for l in f if l.lstrip().startswith("{")]
+    assert len(lines) == 1, "exactly ONE JSON line"
+    return json.loads(lines[0])
+
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+@pytest.mark.parametrize("name", ["r01_bench_n1_final.json", "r01_bench_n2.json"])
+def test_b200_arm_line(name):
+    d = _load(name)
+    assert BASE_KEYS <= set(d) and {"roofline", "clocks"} <= set(d)
+    assert d["unit"] == "circuit-outcomes/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["dtype"] == "f64" and d["vs_baseline"] is None and "workload" in d["config"] and "model" not in d["config"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+    # value = whole-job outcomes / device time
+    assert abs(d["value"] - d["n_gpus"] * 273340 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e)
+    assert e["d2h_bytes_per_step"] == 273340 * 1361 * 8 and e["h2d_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) <= 1e-12 and 0.0 < r["frac"] < 1.0
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms"] * 1e-3) / 1e9) <= 1e-6 * r["achieved"]
+    assert r["traffic"] >= 0.95 * r["algorithmic_bytes_per_launch"]          # measured DRAM traffic cannot be below the compulsory bytes
+    c = d["clocks"]
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(c)
+    assert not (set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+    if d["n_gpus"] == 1:
+        cb = d["cpu_baseline"]
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] in ("reference", "port") and cb["cores"] >= 1
+
+
+def test_reference_arm_line():
+    d = _load("r01_bench_reference_arm.json")
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["gpu_launches"] == 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("reference", "port")
+    b = _load("r01_bench_n1_final.json")
+    assert d["metric"] == b["metric"] and d["unit"] == b["unit"] and d["config"]["workload"] == b["config"]["workload"]
