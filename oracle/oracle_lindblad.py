@@ -75,3 +75,17 @@ def lindblad_inputs(errorgen):
         col += J.shape[1]
     assert row == c.size and col == n_par
     return B, c, dc
+
+
+def composed_state(c, dc, B, rho0):
+    """`ComposedState` (static state followed by exp(L)): rho = E rho0, d rho / d theta = dE rho0  -> ([d], [d, n_params])
+    (pygsti/modelmembers/states/composedstate.py: to_dense, deriv_wrt_params)."""
+    E, dE = expm_and_frechet(errorgen_from_coefficients(c, B), errorgen_derivs(dc, B))
+    return E @ rho0, np.einsum('pij,j->ip', dE, rho0)
+
+
+def composed_effect(c, dc, B, e0):
+    """`ComposedPOVMEffect` (exp(L) acts on the state before the static effect): e = E^T e0, de/dtheta = dE^T e0
+    (pygsti/modelmembers/povms/composedeffect.py:117-160, 284-311)."""
+    E, dE = expm_and_frechet(errorgen_from_coefficients(c, B), errorgen_derivs(dc, B))
+    return E.T @ e0, np.einsum('pji,j->ip', dE, e0)
