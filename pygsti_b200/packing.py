@@ -269,3 +269,102 @@ def pack_hessians(model, atom, dim, param_indices1=None, param_indices2=None):
             off += size
     cat = lambda x, dt: np.concatenate(x).astype(dt) if x else np.zeros(0, dt)
     return HessMap(n_w, p1.size, p2.size, cat(rows, np.int32), cat(aa, np.int32), cat(bb, np.int32), cat(vals, np.float64))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Lindblad-parameterised members (second part -- host side of the planned on-device model update).
+# A `CPTPLND` / `H+S` / `GLND` member is  exp(L(theta))  composed with a static object, L = Re sum_i c_i(theta) B_i.
+# What stays on the host is cheap and parameterisation-specific (c, dc/dtheta: LindbladCoefficientBlock.from_vector /
+# deriv_wrt_params, lindbladcoefficients.py:897-926); what the device will take over is the dense algebra that dominates an
+# update today (the 240-term contractions, expm, its Frechet derivative: csrc/lindblad_core.h).  This packer extracts exactly
+# the inputs of that algebra; tests/test_plugin_cpu.py assembles M and D from them with the oracle and compares with
+# pack_model / pack_derivs.
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class LindbladMember:
+    kind: str            # 'op' | 'rho' | 'eff'
+    w_offset: int        # first W-space index of the member (d*d entries for an op, d for a state / effect)
+    static: np.ndarray   # op: static target matrix [d, d] (G = exp(L) target); rho: static state [d]; eff: static effect [d]
+    errgen: int          # index into LindbladInputs.errgens (effects of one POVM share theirs)
+    gpindices: np.ndarray  # int64 [n_p]: model parameter of each errorgen parameter
+
+
+@dataclass
+class LindbladErrgen:
+    B_re: np.ndarray     # [n_coeff, d, d]   constant term superoperators (real / imaginary parts)
+    B_im: np.ndarray
+    c: np.ndarray        # complex [n_coeff]          coefficients at the current parameters
+    dc: np.ndarray       # complex [n_coeff, n_p]     their Jacobian w.r.t. the errorgen's parameters
+
+
+@dataclass
+class LindbladInputs:
+    members: list        # LindbladMember, in W-space order
+    errgens: list        # LindbladErrgen
+    host_members: list   # (kind, w_offset, member) of everything else (packed densely on the host as before)
+
+
+def _errgen_inputs(errorgen):
+    B = np.asarray(errorgen.combined_lindblad_term_superops)
+    c = np.concatenate([np.asarray(blk.block_data).ravel() for blk in errorgen.coefficient_blocks]).astype(complex)
+    n_par = int(errorgen.num_params)
+    dc = np.zeros((c.size, n_par), complex)
+    row = col = 0
+    for blk in errorgen.coefficient_blocks:
+        nb = int(blk.num_params)
+        size = int(np.asarray(blk.block_data).size)
+        if nb:
+            # at the errorgen's own parameter values (a block's to_vector() may return an equivalent but different point)
+            J = np.asarray(blk.deriv_wrt_params(np.asarray(errorgen.paramvals[col:col + nb])))
+            dc[row:row + size, col:col + nb] = J.reshape(size, nb)
+        row += size
+        col += nb
+    return LindbladErrgen(B_re=np.ascontiguousarray(B.real), B_im=np.ascontiguousarray(B.imag), c=c, dc=dc)
+
+
+def pack_lindblad(model, atom, dim):
+    """Split the atom's members into Lindblad members (inputs of the device algebra) and host members."""
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    members, errgens, host = [], [], []
+    seen = {}
+
+    def eg_index(errorgen):
+        key = id(errorgen)
+        if key not in seen:
+            seen[key] = len(errgens)
+            errgens.append(_errgen_inputs(errorgen))
+        return seen[key]
+
+    def dense_rep(errorgen):
+        return getattr(errorgen, "_rep_type", None) == "dense" or hasattr(errorgen, "combined_lindblad_term_superops")
+
+    off = 0
+    for kind, group, size in (("op", ops, d * d), ("rho", rhos, d), ("eff", effs, d)):
+        for m in group:
+            name = type(m).__name__
+            lm = None
+            if kind == "op" and name == "ComposedOp":
+                f = list(m.factorops)
+                if len(f) == 2 and type(f[1]).__name__ == "ExpErrorgenOp" and f[0].num_params == 0 \
+                        and type(f[1].errorgen).__name__ == "LindbladErrorgen" and dense_rep(f[1].errorgen):
+                    lm = LindbladMember(kind, off, np.asarray(f[0].to_dense('HilbertSchmidt'), float).reshape(d, d),
+                                        eg_index(f[1].errorgen), _gp_array(m.gpindices))
+            elif kind == "rho" and name == "ComposedState":
+                em = m.error_map
+                if type(em).__name__ == "ExpErrorgenOp" and m.state_vec.num_params == 0 \
+                        and type(em.errorgen).__name__ == "LindbladErrorgen" and dense_rep(em.errorgen):
+                    lm = LindbladMember(kind, off, np.asarray(m.state_vec.to_dense('HilbertSchmidt'), float).reshape(d),
+                                        eg_index(em.errorgen), _gp_array(m.gpindices))
+            elif kind == "eff" and name == "ComposedPOVMEffect":
+                em = m.error_map
+                if type(em).__name__ == "ExpErrorgenOp" and m.effect_vec.num_params == 0 \
+                        and type(em.errorgen).__name__ == "LindbladErrorgen" and dense_rep(em.errorgen):
+                    lm = LindbladMember(kind, off, np.asarray(m.effect_vec.to_dense('HilbertSchmidt'), float).reshape(d),
+                                        eg_index(em.errorgen), _gp_array(m.gpindices))
+            if lm is not None and lm.gpindices.size == errgens[lm.errgen].dc.shape[1]:
+                members.append(lm)
+            else:
+                host.append((kind, off, m))
+            off += size
+    return LindbladInputs(members=members, errgens=errgens, host_members=host)

@@ -98,3 +98,40 @@ def test_fill_fails_loudly_without_gpu(model):
         m.sim.bulk_probs(circuits)
     with pytest.raises(ValueError):
         B200ForwardSimulator(derivative_mode='nope')
+
+
+@pytest.mark.parametrize("pack,param,n_lind", [("smq1Q_XYI", "CPTPLND", 3 + 1 + 2), ("smq1Q_XYI", "H+S", 6), ("smq2Q_XYCNOT", "CPTPLND", 5 + 1 + 4)])
+def test_lindblad_inputs_reassemble_model_and_derivative_map(pack, param, n_lind):
+    """`packing.pack_lindblad` (host side of the planned on-device update of Lindblad members): the model tensors M and the
+    derivative map D rebuilt from (B, c, dc/dtheta, static part) with the oracle's dense algebra equal pack_model / pack_derivs."""
+    import importlib
+    from oracle import oracle_lindblad as ol
+    mp = importlib.import_module("pygsti.modelpacks." + pack)
+    m = mp.target_model(param)
+    rng = np.random.default_rng(2)
+    m.from_vector(m.to_vector() + 1e-2 * rng.standard_normal(m.num_params))
+    m.sim = B200ForwardSimulator()
+    circuits = mp.create_gst_experiment_design(1).all_circuits_needing_data
+    atom = m.sim.create_layout(circuits, array_types=('e', 'ep')).atoms[0]
+    d = m.dim
+    mt = packing.pack_model(m, atom, d)
+    M_ref = np.concatenate([mt.G.ravel(), mt.rho.ravel(), mt.E.ravel()])
+    D_ref = packing.pack_derivs(m, atom, d)
+    D_dense = np.zeros((D_ref.n_w, D_ref.n_params)); D_dense[D_ref.rows, D_ref.cols] = D_ref.vals
+    li = packing.pack_lindblad(m, atom, d)
+    assert len(li.members) == n_lind and not li.host_members
+    M = np.full(M_ref.size, np.nan); Dd = np.zeros_like(D_dense)
+    for lm in li.members:
+        eg = li.errgens[lm.errgen]
+        B = eg.B_re + 1j * eg.B_im
+        if lm.kind == "op":
+            val, dval = ol.composed_gate(eg.c, eg.dc, B, lm.static)
+            val = val.ravel()
+        elif lm.kind == "rho":
+            val, dval = ol.composed_state(eg.c, eg.dc, B, lm.static)
+        else:
+            val, dval = ol.composed_effect(eg.c, eg.dc, B, lm.static)
+        M[lm.w_offset:lm.w_offset + val.size] = val
+        Dd[lm.w_offset:lm.w_offset + val.size][:, lm.gpindices] += dval
+    assert np.max(np.abs(M - M_ref)) <= 1e-12
+    assert np.max(np.abs(Dd - D_dense)) <= 1e-10
