@@ -114,6 +114,21 @@ int b200_atom_set_params(b200_ctx* ctx, b200_atom* atom, int32_t n_params, const
 int b200_atom_set_params_dev(b200_ctx* ctx, b200_atom* atom, int32_t n_params, const double* d_theta);
 int b200_atom_get_model(b200_ctx* ctx, b200_atom* atom, int64_t n_w, double* M_out);
 
+/* ---- Lindblad-parameterised members on the device (second part) ----------------------------------
+ * For every member  exp(L_e) composed with a static part  (kind 0: op G = exp(L) T; 1: state exp(L) rho0; 2: effect exp(L)^T e0),
+ * L_e = Re sum_i c_i B_i, returns the dense member and its derivative w.r.t. the generator's parameters:
+ * replaces LindbladErrorgen._update_rep / deriv_wrt_params (lindbladerrorgen.py:700-708, 1342-1384), ExpErrorgenOp._update_rep /
+ * deriv_wrt_params (experrorgenop.py:114-125, 213-262: scipy expm + commutator series) and the Composed* to_dense / deriv_wrt_params.
+ * The coefficients c and their Jacobian dc (complex, real / imaginary parts separately) come from the host
+ * (LindbladCoefficientBlock.from_vector / deriv_wrt_params).  All arrays are host arrays, concatenated over generators / members:
+ *   B_*  [sum_e n_coeff_e][d*d],  c_* [sum_e n_coeff_e],  dc_* per generator [n_coeff_e][n_par_e],
+ *   stat: d*d doubles per op, d per state / effect;  val_out: same sizes;  dval_out: per member [size][n_par of its generator]. */
+int b200_lindblad_members(b200_ctx* ctx, int d, int n_eg, const int32_t* eg_ncoeff, const int32_t* eg_npar,
+                          const double* B_re, const double* B_im, const double* c_re, const double* c_im,
+                          const double* dc_re, const double* dc_im,
+                          int n_mem, const int32_t* m_kind, const int32_t* m_eg, const double* stat,
+                          double* val_out, double* dval_out);
+
 /* ---- the hot path, HOST buffers (copies inside the call) ---------------------------------------
  * b200_fill_probs   replaces mapfill_probs_atom + dm_mapfill_probs (pyx:149-287):
  *     out[el * out_stride] = E . G_L ... G_1 rho        for every element of the atom.

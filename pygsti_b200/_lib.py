@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200_atom_set_params": (C.c_int, [vp, vp, C.c_int32, vp]),
     "b200_atom_set_params_dev": (C.c_int, [vp, vp, C.c_int32, vp]),
     "b200_atom_get_model": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "b200_lindblad_members": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]),
     "b200_fill_probs": (C.c_int, [vp, vp, vp, C.c_int64]),
     "b200_fill_dprobs": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int64]),
     "b200_fill_dprobs_fd": (C.c_int, [vp, vp, C.c_double, vp, C.c_int64, vp, C.c_int64]),

@@ -71,6 +71,7 @@ struct b200_ctx {
     DevBuf fd_models, fd_gt, fd_probs;
     long long l2_persist_max = -1, l2_window_max = -1, l2_persist_cur = 0;   // device limits (queried on first use), current set-aside
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_copy = nullptr;   // split device->host copies
+    DevBuf lind[20];                                     // b200_lindblad_members: inputs, intermediates, outputs
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
     std::vector<cudaEvent_t> phase_events;               // 4 per call: start, after prepare, after chains, after accumulate
     const void* l2_window_atom = nullptr;                // atom whose trie tables hold the stream's persisting L2 window
@@ -187,6 +188,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     phase_clear(c);
+    for (DevBuf& b : c->lind) b.release();
     for (cudaStream_t& st : c->copy_streams) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
     if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
@@ -258,6 +260,7 @@ static int upload_vec(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
     return B200_OK;
 }
 
+#include "kernels_lindblad.cuh"
 #include "trie_host.h"   // TrieHost, build_trie: prefix / suffix tries cut into chains (heavy-path decomposition)
 
 extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, int n_eff,
@@ -643,6 +646,94 @@ __global__ void k_model_affine(int64_t n_w, const int32_t* __restrict__ rptr, co
         for (int32_t t = rptr[w]; t < rptr[w + 1]; ++t) acc = fma(rval[t], theta[rcol[t]], acc);
         M[w] = acc;
     }
+}
+
+extern "C" int b200_lindblad_members(b200_ctx* c, int d, int n_eg, const int32_t* eg_ncoeff, const int32_t* eg_npar,
+                                     const double* B_re, const double* B_im, const double* c_re, const double* c_im,
+                                     const double* dc_re, const double* dc_im,
+                                     int n_mem, const int32_t* m_kind, const int32_t* m_eg, const double* stat,
+                                     double* val_out, double* dval_out)
+{
+    if (!c || d <= 0 || n_eg <= 0 || n_mem < 0 || !eg_ncoeff || !eg_npar || !B_re || !B_im || !c_re || !c_im || !dc_re || !dc_im)
+        return fail(B200_E_INVALID, "NULL / non-positive argument");
+    if (n_mem > 0 && (!m_kind || !m_eg || !stat || !val_out || !dval_out)) return fail(B200_E_INVALID, "NULL member argument");
+    CU(cudaSetDevice(c->device));
+    const long long n = (long long)d * d;
+    std::vector<int> ncoeff(n_eg), npar(n_eg);
+    std::vector<long long> boff(n_eg), doff(n_eg), poff((size_t)n_eg + 1, 0);
+    long long nc_tot = 0, dc_tot = 0;
+    for (int e = 0; e < n_eg; ++e) {
+        if (eg_ncoeff[e] < 0 || eg_npar[e] < 0) return fail(B200_E_INVALID, "negative generator size");
+        ncoeff[e] = eg_ncoeff[e]; npar[e] = eg_npar[e];
+        boff[e] = nc_tot; doff[e] = dc_tot;
+        nc_tot += eg_ncoeff[e]; dc_tot += (long long)eg_ncoeff[e] * eg_npar[e];
+        poff[e + 1] = poff[e] + eg_npar[e];
+    }
+    const long long np_tot = poff[n_eg], n_rows = np_tot + n_eg;
+    std::vector<int> kind(n_mem), meg(n_mem);
+    std::vector<long long> soff(n_mem), vptr((size_t)n_mem + 1, 0), dptr((size_t)n_mem + 1, 0);
+    long long s_tot = 0;
+    for (int m = 0; m < n_mem; ++m) {
+        if (m_kind[m] < 0 || m_kind[m] > 2 || m_eg[m] < 0 || m_eg[m] >= n_eg) return fail(B200_E_INVALID, "member %d: bad kind / generator", m);
+        kind[m] = m_kind[m]; meg[m] = m_eg[m];
+        const long long size = m_kind[m] == 0 ? n : d;
+        soff[m] = s_tot; s_tot += size;
+        vptr[m + 1] = vptr[m] + size; dptr[m + 1] = dptr[m] + size * eg_npar[m_eg[m]];
+    }
+    enum { I_NC, I_NP, I_BO, I_DO, I_PO, I_BR, I_BI, I_CR, I_CI, I_DR, I_DI, I_L, I_DL, I_E, I_DE, I_WK, I_MK, I_ME, I_ST, I_OUT };
+    DevBuf* b = c->lind;
+    int rc;
+    if ((rc = upload_vec(b[I_NC], ncoeff, c->stream)) || (rc = upload_vec(b[I_NP], npar, c->stream)) ||
+        (rc = upload_vec(b[I_BO], boff, c->stream)) || (rc = upload_vec(b[I_DO], doff, c->stream)) ||
+        (rc = upload_vec(b[I_PO], poff, c->stream)) || (rc = upload_vec(b[I_MK], kind, c->stream)) ||
+        (rc = upload_vec(b[I_ME], meg, c->stream))) return rc;
+    auto up = [&](DevBuf& buf, const double* src, long long count) -> int {
+        CU(buf.ensure(std::max<size_t>((size_t)count * 8, 16)));
+        if (count > 0) CU(cudaMemcpyAsync(buf.p, src, (size_t)count * 8, cudaMemcpyHostToDevice, c->stream));
+        return B200_OK;
+    };
+    if ((rc = up(b[I_BR], B_re, nc_tot * n)) || (rc = up(b[I_BI], B_im, nc_tot * n)) || (rc = up(b[I_CR], c_re, nc_tot)) ||
+        (rc = up(b[I_CI], c_im, nc_tot)) || (rc = up(b[I_DR], dc_re, dc_tot)) || (rc = up(b[I_DI], dc_im, dc_tot)) ||
+        (rc = up(b[I_ST], stat, s_tot))) return rc;
+    CU(b[I_L].ensure((size_t)n_eg * n * 8)); CU(b[I_E].ensure((size_t)n_eg * n * 8));
+    CU(b[I_DL].ensure(std::max<size_t>((size_t)np_tot * n * 8, 16))); CU(b[I_DE].ensure(std::max<size_t>((size_t)np_tot * n * 8, 16)));
+    CU(b[I_WK].ensure((size_t)n_rows * 7 * n * 8));
+    // outputs + the two prefix arrays of the members in one buffer: [val | dval | vptr | dptr]
+    const long long n_val = vptr[n_mem], n_dval = dptr[n_mem];
+    CU(b[I_OUT].ensure(std::max<size_t>((size_t)(n_val + n_dval) * 8 + (size_t)2 * (n_mem + 1) * 8, 16)));
+    double* d_val = b[I_OUT].as<double>(); double* d_dval = d_val + n_val;
+    long long* d_vptr = reinterpret_cast<long long*>(d_dval + n_dval); long long* d_dptr = d_vptr + (n_mem + 1);
+    CU(cudaMemcpyAsync(d_vptr, vptr.data(), (size_t)(n_mem + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_dptr, dptr.data(), (size_t)(n_mem + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    // soff travels at the tail of the static buffer's sibling: a small separate upload through the generic helper
+    DevBuf soff_buf;
+    if ((rc = upload_vec(soff_buf, soff, c->stream))) { soff_buf.release(); return rc; }
+    LindDev a;
+    a.d = d; a.n_eg = n_eg; a.n_mem = n_mem;
+    a.eg_ncoeff = b[I_NC].as<int>(); a.eg_npar = b[I_NP].as<int>(); a.eg_boff = b[I_BO].as<long long>();
+    a.eg_doff = b[I_DO].as<long long>(); a.eg_poff = b[I_PO].as<long long>();
+    a.B_re = b[I_BR].as<double>(); a.B_im = b[I_BI].as<double>(); a.c_re = b[I_CR].as<double>(); a.c_im = b[I_CI].as<double>();
+    a.dc_re = b[I_DR].as<double>(); a.dc_im = b[I_DI].as<double>();
+    a.L = b[I_L].as<double>(); a.dL = b[I_DL].as<double>(); a.E = b[I_E].as<double>(); a.dE = b[I_DE].as<double>(); a.work = b[I_WK].as<double>();
+    a.m_kind = b[I_MK].as<int>(); a.m_eg = b[I_ME].as<int>(); a.m_soff = soff_buf.as<long long>();
+    a.stat = b[I_ST].as<double>(); a.val = d_val; a.dval = d_dval;
+    const int g1 = (int)std::max<long long>(1, std::min<long long>((n_rows * n + 255) / 256, (long long)c->sm_count * 16));
+    k_lind_errgen<<<g1, 256, 0, c->stream>>>(a, n_rows);
+    k_lind_expm<<<(unsigned)((n_rows + 63) / 64), 64, 0, c->stream>>>(a, n_rows);
+    c->launches += 2;
+    if (n_mem > 0) {
+        const int g3 = (int)std::max<long long>(1, std::min<long long>((n_val + n_dval + 255) / 256, (long long)c->sm_count * 16));
+        k_lind_compose<<<g3, 256, 0, c->stream>>>(a, n_val, n_dval, d_vptr, d_dptr);
+        c->launches++;
+        CU(cudaMemcpyAsync(val_out, d_val, (size_t)n_val * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (n_dval > 0) CU(cudaMemcpyAsync(dval_out, d_dval, (size_t)n_dval * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    cudaError_t e1 = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    soff_buf.release();
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(B200_E_CUDA, "b200_lindblad_members: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    return B200_OK;
 }
 
 extern "C" int b200_atom_get_model(b200_ctx* ctx, b200_atom* a, int64_t n_w, double* M_out) {

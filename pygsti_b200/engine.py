@@ -72,6 +72,36 @@ class Context:
         _lib.check(self._lib.b200_ctx_phase_ms(self._h, ms, C.byref(n)))
         return (ms[0], ms[1], ms[2]), n.value
 
+    def lindblad_members(self, d, errgens, members):
+        """Dense Lindblad members and their parameter derivatives on the device (``b200_lindblad_members``).
+
+        errgens : sequence of objects with ``B_re, B_im`` [n_coeff, d, d], ``c`` complex [n_coeff], ``dc`` complex [n_coeff, n_par]
+        members : sequence of objects with ``kind`` ('op' | 'rho' | 'eff'), ``errgen`` (index) and ``static`` ([d, d] or [d])
+        (``packing.LindbladErrgen`` / ``packing.LindbladMember``).  Returns ``[(value, dvalue [size, n_par]), ...]`` per member."""
+        d = int(d)
+        ncoeff = np.array([e.c.size for e in errgens], np.int32)
+        npar = np.array([e.dc.shape[1] for e in errgens], np.int32)
+        cat = lambda xs: np.ascontiguousarray(np.concatenate([np.ravel(x) for x in xs]) if len(xs) else np.zeros(0), np.float64)
+        B_re, B_im = cat([e.B_re for e in errgens]), cat([e.B_im for e in errgens])
+        c_re, c_im = cat([e.c.real for e in errgens]), cat([e.c.imag for e in errgens])
+        dc_re, dc_im = cat([e.dc.real for e in errgens]), cat([e.dc.imag for e in errgens])
+        kinds = {"op": 0, "rho": 1, "eff": 2}
+        m_kind = np.array([kinds[m.kind] for m in members], np.int32)
+        m_eg = np.array([m.errgen for m in members], np.int32)
+        stat = cat([m.static for m in members])
+        sizes = [d * d if k == 0 else d for k in m_kind]
+        val = np.empty(int(sum(sizes)))
+        dsz = [s * int(npar[g]) for s, g in zip(sizes, m_eg)]
+        dval = np.empty(int(sum(dsz)))
+        _lib.check(self._lib.b200_lindblad_members(self._h, d, len(errgens), _ptr(ncoeff), _ptr(npar), _ptr(B_re), _ptr(B_im),
+                                                   _ptr(c_re), _ptr(c_im), _ptr(dc_re), _ptr(dc_im), len(members),
+                                                   _ptr(m_kind), _ptr(m_eg), _ptr(stat), _ptr(val), _ptr(dval)))
+        out, vo, do = [], 0, 0
+        for s, g, ds in zip(sizes, m_eg, dsz):
+            out.append((val[vo:vo + s].copy(), dval[do:do + ds].reshape(s, int(npar[g])).copy()))
+            vo += s; do += ds
+        return out
+
     def upload_atom(self, t: AtomTables):
         return Atom(self, t)
 

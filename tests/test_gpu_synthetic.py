@@ -277,3 +277,36 @@ def test_affine_model_update_on_device(gpu_ctx):
         Jo = onp.dprobs_analytic(t, G, rho, E, D)
         assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
     at.free()
+
+
+@pytest.mark.parametrize("d", [4, 16])
+def test_lindblad_members_on_device(gpu_ctx, d):
+    """b200_lindblad_members (second part): L = Re sum c_i B_i, exp(L), its Frechet derivatives and the composition
+    with the static parts, for random complex coefficients / term superoperators and two generators shared by several members,
+    against the numpy oracle (oracle/oracle_lindblad.py, itself pinned against the reference's CPTPLND / H+S / GLND members)."""
+    from types import SimpleNamespace as NS
+    from oracle import oracle_lindblad as ol
+    rng = np.random.default_rng(100 + d)
+    errgens = []
+    for n_coeff, n_par, scale in ((12, 9, 0.15), (5, 4, 0.6)):
+        B = (rng.standard_normal((n_coeff, d, d)) + 1j * rng.standard_normal((n_coeff, d, d))) / d
+        c = scale * (rng.standard_normal(n_coeff) + 1j * rng.standard_normal(n_coeff))
+        dc = rng.standard_normal((n_coeff, n_par)) + 1j * rng.standard_normal((n_coeff, n_par))
+        errgens.append(NS(B_re=np.ascontiguousarray(B.real), B_im=np.ascontiguousarray(B.imag), c=c, dc=dc, B=B))
+    members = [NS(kind="op", errgen=0, static=rng.standard_normal((d, d))), NS(kind="rho", errgen=1, static=rng.standard_normal(d)),
+               NS(kind="op", errgen=1, static=rng.standard_normal((d, d))), NS(kind="eff", errgen=0, static=rng.standard_normal(d)),
+               NS(kind="eff", errgen=0, static=rng.standard_normal(d))]
+    out = gpu_ctx.lindblad_members(d, errgens, members)
+    assert len(out) == len(members)
+    for m, (val, dval) in zip(members, out):
+        e = errgens[m.errgen]
+        if m.kind == "op":
+            v_ref, dv_ref = ol.composed_gate(e.c, e.dc, e.B, m.static)
+            v_ref = v_ref.ravel()
+        elif m.kind == "rho":
+            v_ref, dv_ref = ol.composed_state(e.c, e.dc, e.B, m.static)
+        else:
+            v_ref, dv_ref = ol.composed_effect(e.c, e.dc, e.B, m.static)
+        assert val.shape == v_ref.shape and dval.shape == dv_ref.shape
+        assert np.max(np.abs(val - v_ref)) <= 1e-12 * max(1.0, np.max(np.abs(v_ref)))
+        assert np.max(np.abs(dval - dv_ref)) <= 1e-11 * max(1.0, np.max(np.abs(dv_ref)))
