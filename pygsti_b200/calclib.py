@@ -204,6 +204,27 @@ def _maybe_bind(fwdsim, layout_atom, ent, pidx):
     ent["bound"] = weakref.ref(model)       # M_const belongs to THIS model object (its static members, its structure)
 
 
+def _lindblad_model_and_derivs(fwdsim, layout_atom, ent, param_indices, ctx):
+    """``device_lindblad``: for models with Lindblad-parameterised members (CPTPLND, H+S, GLND) the dense algebra of the model
+    update -- error generators, exponentials, Frechet derivatives, composition with the static parts -- runs on the device
+    (``b200_lindblad_members``) instead of in ``to_dense`` / ``deriv_wrt_params`` of every member; coefficients and their Jacobian
+    stay on the host.  Returns False (nothing uploaded) when the atom has no such member or the model has a parameter interposer."""
+    model = fwdsim.model
+    if getattr(model, "_param_interposer", None) is not None:
+        return False
+    li = packing.pack_lindblad(model, layout_atom, model.dim)
+    if not li.members:
+        return False
+    outs = ctx.lindblad_members(model.dim, li.errgens, li.members)
+    mt, D = packing.assemble_lindblad(li, outs, model, layout_atom, model.dim, param_indices)
+    atom = ent["atom"]
+    atom.set_model(mt)
+    atom.set_derivs(D)
+    ent["deriv_key"] = None          # the map depends on the parameters: never cached
+    ent["bound"] = None
+    return True
+
+
 def all_members_linear(fwdsim, layout_atom):
     model = fwdsim.model
     ops, rhos, effs = packing._members(model, layout_atom)
@@ -315,9 +336,12 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
     atom = ent["atom"]
-    _upload_model(fwdsim, layout_atom, ent)
-    pidx = _deriv_map(fwdsim, layout_atom, ent, param_indices)
-    _maybe_bind(fwdsim, layout_atom, ent, pidx)
+    if getattr(fwdsim, "device_lindblad", False) and _lindblad_model_and_derivs(fwdsim, layout_atom, ent, param_indices, ctx):
+        pidx = packing.param_slice_to_array(param_indices, model.num_params)
+    else:
+        _upload_model(fwdsim, layout_atom, ent)
+        pidx = _deriv_map(fwdsim, layout_atom, ent, param_indices)
+        _maybe_bind(fwdsim, layout_atom, ent, pidx)
     if not shared_mem_leader:
         return
     nE = layout_atom.num_elements

@@ -42,13 +42,14 @@ class B200ForwardSimulator(_MapForwardSimulator):
 
     def __init__(self, model=None, max_cache_size=None, num_atoms=None, processor_grid=None, param_blk_sizes=None,
                  derivative_eps=1e-7, hessian_eps=1e-5, derivative_mode='analytic', device=None, devices=None,
-                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False):
+                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False, device_lindblad=False):
         if derivative_mode not in ('analytic', 'fd'):
             raise ValueError("derivative_mode must be 'analytic' or 'fd'")
         self.derivative_mode = derivative_mode
         self.analytic_hessian = bool(analytic_hessian)   # False: non-linear members use the reference's FD driver
         self.device_model_update = bool(device_model_update)
         self.host_prefix_cache = bool(host_prefix_cache)
+        self.device_lindblad = bool(device_lindblad)
         if max_cache_size is None and not self.host_prefix_cache:
             max_cache_size = 0                             # SURVEY 8f rank 4 (layout construction): no host-side cache plan
         self._b200_device = device
@@ -73,7 +74,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
         state = super()._to_nice_serialization()
         state.update({'derivative_mode': self.derivative_mode, 'device': self._b200_device,
                       'analytic_hessian': self.analytic_hessian, 'device_model_update': self.device_model_update,
-                      'host_prefix_cache': self.host_prefix_cache})
+                      'host_prefix_cache': self.host_prefix_cache, 'device_lindblad': self.device_lindblad})
         return state
 
     @classmethod
@@ -84,7 +85,8 @@ class B200ForwardSimulator(_MapForwardSimulator):
                    derivative_mode=state.get('derivative_mode', 'analytic'),
                    device=state.get('device', None), analytic_hessian=state.get('analytic_hessian', True),
                    device_model_update=state.get('device_model_update', False),
-                   host_prefix_cache=state.get('host_prefix_cache', False))
+                   host_prefix_cache=state.get('host_prefix_cache', False),
+                   device_lindblad=state.get('device_lindblad', False))
 
     def copy(self, keep_model_attached=True):
         # MapForwardSimulator.copy hard-codes its own class (mapforwardsim.py:190-204) -> must override,
@@ -92,7 +94,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
         out = B200ForwardSimulator(self.model, self._max_cache_size, self._num_atoms, self._processor_grid,
                                    self._pblk_sizes, self.derivative_eps, self.hessian_eps,
                                    self.derivative_mode, self._b200_device, self._b200_devices, self.analytic_hessian,
-                                   self.device_model_update, self.host_prefix_cache)
+                                   self.device_model_update, self.host_prefix_cache, self.device_lindblad)
         if not keep_model_attached:
             out.model = None
         return out

@@ -368,3 +368,46 @@ def pack_lindblad(model, atom, dim):
                 host.append((kind, off, m))
             off += size
     return LindbladInputs(members=members, errgens=errgens, host_members=host)
+
+
+def assemble_lindblad(li, outs, model, atom, dim, param_indices=None):
+    """(ModelTensors, DerivMap) of the atom from the Lindblad members' dense values / derivatives ``outs`` -- the result of
+    ``engine.Context.lindblad_members(dim, li.errgens, li.members)`` -- plus the remaining members packed on the host as in
+    ``pack_model`` / ``pack_derivs``.  Same output as those two functions (no parameter interposer)."""
+    if getattr(model, '_param_interposer', None) is not None:
+        raise ValueError("assemble_lindblad does not support parameter interposers")
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    n_w = len(ops) * d * d + len(rhos) * d + len(effs) * d
+    n_model_params = int(model.num_params)
+    M = np.empty(n_w, dtype=np.float64)
+    rows, cols, vals = [], [], []
+    for lm, (val, dval) in zip(li.members, outs):
+        size = val.size
+        M[lm.w_offset:lm.w_offset + size] = val
+        r, c = np.nonzero(dval)
+        rows.append(lm.w_offset + r); cols.append(lm.gpindices[c]); vals.append(dval[r, c])
+    for kind, off, m in li.host_members:
+        size = d * d if kind == "op" else d
+        M[off:off + size] = np.asarray(m.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(size)
+        gp = _gp_array(m.gpindices)
+        if gp.size:
+            dM = np.asarray(m.deriv_wrt_params(), dtype=np.float64).reshape(size, gp.size)
+            r, c = np.nonzero(dM)
+            rows.append(off + r); cols.append(gp[c]); vals.append(dM[r, c])
+    no, nr = len(ops) * d * d, len(rhos) * d
+    mt = ModelTensors(G=M[:no].reshape(len(ops), d, d).copy(), rho=M[no:no + nr].reshape(len(rhos), d).copy(),
+                      E=M[no + nr:].reshape(len(effs), d).copy())
+    if rows:
+        rows = np.concatenate(rows); cols = np.concatenate(cols); vals = np.concatenate(vals)
+    else:
+        rows = np.zeros(0, np.int64); cols = np.zeros(0, np.int64); vals = np.zeros(0, np.float64)
+    import scipy.sparse as sps
+    D = sps.coo_matrix((vals, (rows, cols)), shape=(n_w, n_model_params)).tocsr()   # sums duplicates (shared generators)
+    pidx = param_slice_to_array(param_indices, n_model_params)
+    if not (pidx.size == n_model_params and np.array_equal(pidx, np.arange(n_model_params))):
+        D = D[:, pidx]
+    D = D.tocoo()
+    keep = D.data != 0.0
+    return mt, DerivMap(n_w=n_w, n_params=int(pidx.size), rows=D.row[keep].astype(np.int32), cols=D.col[keep].astype(np.int32),
+                        vals=D.data[keep].astype(np.float64))

@@ -356,3 +356,19 @@ def test_device_model_update_follows_from_vector(param):
         mt = packing.pack_model(model, atom, model.dim)
         M_host = np.concatenate([np.ravel(mt.G), np.ravel(mt.rho), np.ravel(mt.E)])
         assert np.max(np.abs(ent["atom"].get_model() - M_host)) <= 1e-15
+
+
+def test_device_lindblad_members_match_host_path():
+    """SURVEY 8f rank 3, second part: with ``device_lindblad=True`` the dense matrices and parameter derivatives of CPTPLND
+    members come from the device (b200_lindblad_members); probabilities and Jacobian must equal the host-packed path and the
+    reference's Matrix simulator."""
+    model = smq1Q_XYI.target_model("CPTPLND")
+    rng = np.random.default_rng(9)
+    model.from_vector(model.to_vector() + 1e-2 * rng.standard_normal(model.num_params))
+    circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data
+    res = {}
+    for name, sim in (("dev", B200ForwardSimulator(device_lindblad=True)), ("host", B200ForwardSimulator()),
+                      ("matrix", MatrixForwardSimulator())):
+        res[name] = _bulk_arrays(model, sim, circuits)
+    assert np.max(np.abs(res["dev"][0] - res["host"][0])) <= 1e-12 and np.max(np.abs(res["dev"][0] - res["matrix"][0])) <= 1e-12
+    assert np.max(np.abs(res["dev"][1] - res["host"][1])) <= 1e-10 and np.max(np.abs(res["dev"][1] - res["matrix"][1])) <= 1e-10

@@ -135,3 +135,18 @@ def test_lindblad_inputs_reassemble_model_and_derivative_map(pack, param, n_lind
         Dd[lm.w_offset:lm.w_offset + val.size][:, lm.gpindices] += dval
     assert np.max(np.abs(M - M_ref)) <= 1e-12
     assert np.max(np.abs(Dd - D_dense)) <= 1e-10
+    # packing.assemble_lindblad with the oracle standing in for the device call (engine.Context.lindblad_members)
+    outs = []
+    for lm in li.members:
+        eg = li.errgens[lm.errgen]
+        B = eg.B_re + 1j * eg.B_im
+        f = {"op": ol.composed_gate, "rho": ol.composed_state, "eff": ol.composed_effect}[lm.kind]
+        val, dval = f(eg.c, eg.dc, B, lm.static)
+        outs.append((np.ravel(val), dval))
+    for pidx in (None, slice(3, 11)):
+        mt2, D2 = packing.assemble_lindblad(li, outs, m, atom, d, pidx)
+        Dr = packing.pack_derivs(m, atom, d, pidx)
+        assert max(np.max(np.abs(mt2.G - mt.G)), np.max(np.abs(mt2.rho - mt.rho)), np.max(np.abs(mt2.E - mt.E))) <= 1e-12
+        A = np.zeros((D2.n_w, D2.n_params)); A[D2.rows, D2.cols] = D2.vals
+        R = np.zeros((Dr.n_w, Dr.n_params)); R[Dr.rows, Dr.cols] = Dr.vals
+        assert A.shape == R.shape and np.max(np.abs(A - R)) <= 1e-10
