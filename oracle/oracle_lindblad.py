@@ -1,6 +1,7 @@
 """
 ORACLE (test infrastructure only -- never imported by pygsti_b200/): numpy restatement of the host-side member update for
-Lindblad-parameterised operations, the OPEN half of SURVEY.md 8f rank 3 (on-device model update).
+Lindblad-parameterised operations, the second half of SURVEY.md 8f rank 3 (on-device model update; product side:
+b200_lindblad_members, pygsti_b200/csrc/kernels_lindblad.cuh).
 
 What the reference does per parameter-vector update of a `CPTPLND` / `H+S` / `GLND` gate  G = exp(L(theta)) . G_target
 (`ComposedOp([static target, ExpErrorgenOp(LindbladErrorgen)])`):
@@ -14,8 +15,8 @@ What the reference does per parameter-vector update of a `CPTPLND` / `H+S` / `GL
   * composition             G = E . G_target, dG = dE . G_target   -- `ComposedOp.to_dense / deriv_wrt_params` (composedop.py)
 
 At BASELINE config 4 the three lower items cost 0.27 s (11 expm) + 0.8 s (einsum + checks) per update on the host against ~10 ms of GPU
-work per Jacobian.  The device version will take (B, c, dc/dtheta, G_target) and produce G and dG/dtheta; this file states the
-arithmetic it has to reproduce (Frechet derivative by the block-triangular exponential, an algorithm independent of the reference's
+work per Jacobian.  The device version takes (B, c, dc/dtheta, static parts) and produces the members and their derivatives; this file
+states the arithmetic it has to reproduce (Frechet derivative by the block-triangular exponential, an algorithm independent of the reference's
 commutator series) and `tests/test_oracle_cpu.py::test_lindblad_oracle_*` pins it against the reference run in this container.
 """
 import numpy as np

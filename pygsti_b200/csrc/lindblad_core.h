@@ -1,4 +1,4 @@
-// lindblad_core.h -- arithmetic core of the NEXT on-device row (second part): the dense exponential of an
+// lindblad_core.h -- arithmetic core of the Lindblad row (second part): the dense exponential of an
 // error generator and its Frechet derivative, as plain per-thread C++ that compiles for the host and for the device.
 //
 // Reference: ExpErrorgenOp._update_rep (scipy.linalg.expm, pygsti/modelmembers/operations/experrorgenop.py:114-125) and
@@ -7,9 +7,9 @@
 // exponential is [[E, dE], [0, E]], and pairs multiply as (A, D)(B, F) = (AB, AF + DB) -- three d x d products instead of the eight of a
 // 2d x 2d product.  Scaling: X = L / 2^s with ||X||_1 <= 1/2; Taylor to order LB_TAYLOR_ORDER (remainder < 1e-18 relative); s squarings.
 //
-// STATUS: validated on the HOST only (tests/test_lindblad_core.py: against scipy.linalg.expm / expm_frechet on random matrices and against
-// the reference's own CPTPLND members through oracle/oracle_lindblad.py).  It is not yet called by any kernel: the kernel wrapper
-// (one thread per (member, parameter), outputs written into the device copies of M and D) and its integration are next round's work.
+// Validation: on the host (tests/test_lindblad_core.py: against scipy.linalg.expm / expm_frechet on random matrices with 1-norms up to
+// 12, and against the reference's own CPTPLND gate through oracle/oracle_lindblad.py) and on the device through
+// csrc/kernels_lindblad.cuh (b200_lindblad_members; tests/test_gpu_synthetic.py, tests/test_gpu_pygsti_dropin.py).
 #pragma once
 #include <math.h>
 

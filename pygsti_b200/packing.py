@@ -272,11 +272,11 @@ def pack_hessians(model, atom, dim, param_indices1=None, param_indices2=None):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Lindblad-parameterised members (second part -- host side of the planned on-device model update).
+# Lindblad-parameterised members (second part -- host side of the on-device model update, `device_lindblad`).
 # A `CPTPLND` / `H+S` / `GLND` member is  exp(L(theta))  composed with a static object, L = Re sum_i c_i(theta) B_i.
 # What stays on the host is cheap and parameterisation-specific (c, dc/dtheta: LindbladCoefficientBlock.from_vector /
-# deriv_wrt_params, lindbladcoefficients.py:897-926); what the device will take over is the dense algebra that dominates an
-# update today (the 240-term contractions, expm, its Frechet derivative: csrc/lindblad_core.h).  This packer extracts exactly
+# deriv_wrt_params, lindbladcoefficients.py:897-926); the device takes over the dense algebra that dominates an update on the
+# host (the 240-term contractions, expm, its Frechet derivative: b200_lindblad_members, csrc/kernels_lindblad.cuh).  This packer extracts exactly
 # the inputs of that algebra; tests/test_plugin_cpu.py assembles M and D from them with the oracle and compares with
 # pack_model / pack_derivs.
 # ---------------------------------------------------------------------------------------------------------------------
