@@ -20,6 +20,7 @@ Index conventions ("W space", one column per dense member element):
     prep r, element i      ->  n_ops*d*d + r*d + i
     effect e, element i    ->  n_ops*d*d + n_rho*d + e*d + i
 """
+import weakref
 from dataclasses import dataclass, field
 import numpy as np
 
@@ -237,6 +238,33 @@ class HessMap:
         return int(self.rows.size)
 
 
+# A member's `hessian_wrt_params` costs the same whether a rectangle or the whole (n_p x n_p) Hessian is asked for (9.9 s for a
+# 64 x 64 rectangle of a 2-qubit CPTPLND gate, Np = 240), and the MLE Hessian walks over ~16 rectangles inside every member's
+# parameter block (`_iter_atom_hprobs_by_rectangle`, distforwardsim.py:304-340): the full member Hessian is computed once per
+# parameter vector and the rectangles are sliced from it.  Bounded cache (bytes), keyed by the member object and its parameters.
+_HESS_CACHE = {}
+_HESS_CACHE_MAX_BYTES = 2 << 30
+
+
+def _member_hessian(m, size, n_p):
+    key = id(m)
+    pv = np.asarray(m.to_vector(), dtype=np.float64).tobytes()
+    ent = _HESS_CACHE.get(key)
+    if ent is not None and ent[0] == pv and ent[1]() is m:
+        return ent[2]
+    H = np.asarray(m.hessian_wrt_params())
+    if np.iscomplexobj(H):
+        H = H.real
+    H = np.ascontiguousarray(H, dtype=np.float64).reshape(size, n_p, n_p)
+    _HESS_CACHE[key] = (pv, weakref.ref(m), H)
+    total = sum(e[2].nbytes for e in _HESS_CACHE.values())
+    for k in list(_HESS_CACHE):                       # oldest first (insertion order) until under the cap
+        if total <= _HESS_CACHE_MAX_BYTES or k == key:
+            continue
+        total -= _HESS_CACHE.pop(k)[2].nbytes
+    return H
+
+
 def pack_hessians(model, atom, dim, param_indices1=None, param_indices2=None):
     """Second derivatives of every member with ``has_nonzero_hessian()`` through its own ``hessian_wrt_params`` -- the
     quantity MatrixForwardSimulator._hoperation / _hprobs_from_rho_e read (matrixforwardsim.py:172-218, 1196-1237) --
@@ -260,10 +288,7 @@ def pack_hessians(model, atom, dim, param_indices1=None, param_indices2=None):
             if gp.size and m.has_nonzero_hessian():
                 l1 = np.flatnonzero(pos1[gp] >= 0); l2 = np.flatnonzero(pos2[gp] >= 0)
                 if l1.size and l2.size:
-                    H = np.asarray(m.hessian_wrt_params(list(l1), list(l2)))
-                    if np.iscomplexobj(H):
-                        H = H.real
-                    H = H.reshape(size, l1.size, l2.size)
+                    H = _member_hessian(m, size, gp.size)[:, l1][:, :, l2]
                     r, i, j = np.nonzero(H)
                     rows.append(off + r); aa.append(pos1[gp[l1[i]]]); bb.append(pos2[gp[l2[j]]]); vals.append(H[r, i, j])
             off += size

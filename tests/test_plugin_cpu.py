@@ -150,3 +150,28 @@ def test_lindblad_inputs_reassemble_model_and_derivative_map(pack, param, n_lind
         A = np.zeros((D2.n_w, D2.n_params)); A[D2.rows, D2.cols] = D2.vals
         R = np.zeros((Dr.n_w, Dr.n_params)); R[Dr.rows, Dr.cols] = Dr.vals
         assert A.shape == R.shape and np.max(np.abs(A - R)) <= 1e-10
+
+
+def test_member_hessian_cache_equals_filtered_calls_and_follows_the_parameters():
+    """pack_hessians slices rectangles out of each member's full Hessian, computed once per parameter vector: same numbers as the
+    members' own filtered `hessian_wrt_params(l1, l2)`, recomputed when the parameters change."""
+    m = smq1Q_XYI.target_model('CPTPLND')
+    rng = np.random.default_rng(0)
+    m.sim = B200ForwardSimulator()
+    atom = m.sim.create_layout(smq1Q_XYI.create_gst_experiment_design(1).all_circuits_needing_data, array_types=('e', 'ep')).atoms[0]
+    ops, rhos, effs = packing._members(m, atom)
+    lo1, hi1, lo2, hi2 = 3, 20, 10, 40
+    for step in range(2):
+        m.from_vector(m.to_vector() + 1e-2 * rng.standard_normal(m.num_params))
+        H = packing.pack_hessians(m, atom, 4, slice(lo1, hi1), slice(lo2, hi2))
+        dense = np.zeros((H.n_w, H.n1, H.n2)); dense[H.rows, H.a, H.b] = H.vals
+        ref = np.zeros_like(dense); off = 0
+        for group, size in ((ops, 16), (rhos, 4), (effs, 4)):
+            for mem in group:
+                gp = packing._gp_array(mem.gpindices)
+                l1 = [i for i, g in enumerate(gp) if lo1 <= g < hi1]; l2 = [i for i, g in enumerate(gp) if lo2 <= g < hi2]
+                if gp.size and mem.has_nonzero_hessian() and l1 and l2:
+                    Hm = np.real(np.asarray(mem.hessian_wrt_params(l1, l2))).reshape(size, len(l1), len(l2))
+                    ref[off:off + size][:, (gp[l1] - lo1)[:, None], (gp[l2] - lo2)[None, :]] += Hm
+                off += size
+        assert np.max(np.abs(ref)) > 0 and np.max(np.abs(dense - ref)) <= 1e-14
