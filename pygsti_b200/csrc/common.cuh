@@ -31,3 +31,22 @@ struct ModelDev {
 __device__ __forceinline__ double shfl_xor_f64(double v, int mask) {
     return __shfl_xor_sync(0xffffffffu, v, mask);
 }
+
+// FP64 tensor-core MMA (there is no FP64 kind of tcgen05.mma: DMMA m8n8k4 is the FP64 tensor path on sm_100a)
+__device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Where the d = 16 Jacobian kernel stores its accumulators
+#define D16_SPAM_MAX 512  // SPAM/unmapped column list entries staged in shared memory
+struct D16Args {
+    const int32_t* colmap;    // [n_w]  J column of W index w (gate part used by the register epilogue), -1 = none
+    const int32_t* spam_col;  // [n_spam] columns NOT fed by a gate element ...
+    const int32_t* spam_w;    // [n_spam] ... and the rho/effect W index feeding each (or -1 -> zero)
+    int n_spam;
+    double* J;                // [n_elements][ld]
+    int64_t ld;
+    double* probs;            // [n_elements] or nullptr
+    const double* row_scale;  // [n_elements] or nullptr: J row el is multiplied by row_scale[el] in the store epilogue
+};

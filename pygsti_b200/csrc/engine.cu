@@ -4,8 +4,6 @@
 #include "../../include/b200_fwdsim.h"
 #include "common.cuh"
 #include "kernels_generic.cuh"
-#include "kernels_d16.cuh"
-#include "kernels_d16_2p.cuh"
 #include "kernels_d16_trie.cuh"
 #include "kernels_level.cuh"
 #include "kernels_levelj.cuh"
@@ -62,19 +60,15 @@ struct b200_ctx {
     DevBuf probs_buf;
     DevBuf w_buf;        // W matrix of the general path
     DevBuf scratch;      // forward-state scratch of the generic kernels
-    DevBuf scratch2p;    // chain-vector scratch of the two-phase d16 path
     DevBuf lvl_states;   // ping-pong state buffers of the level-batched dense path
     DevBuf lj_fs, lj_bh; // level-batched Jacobian path: state table / adjoint table (all levels kept)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     cublasHandle_t cublas = nullptr;
     DevBuf fd_models, fd_gt, fd_probs;
-    long long l2_persist_max = -1, l2_window_max = -1, l2_persist_cur = 0;   // device limits (queried on first use), current set-aside
-    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_copy = nullptr;   // split device->host copies
     DevBuf lind[20];                                     // b200_lindblad_members: inputs, intermediates, outputs
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
     std::vector<cudaEvent_t> phase_events;               // 4 per call: start, after prepare, after chains, after accumulate
-    const void* l2_window_atom = nullptr;                // atom whose trie tables hold the stream's persisting L2 window
 };
 
 struct b200_atom {
@@ -85,8 +79,7 @@ struct b200_atom {
     int64_t n_w = 0, off_rho = 0, off_eff = 0;
     // device tables
     DevBuf circ_ptr, circ_ops, circ_prep, out_ptr, out_eff, out_el;
-    DevBuf srow, bperm, bcnt;          // two-phase d16 path: scratch row offsets, per-circuit gate buckets
-    int64_t scratch_rows = 0;
+    DevBuf bperm, bcnt;                // per circuit: step indices sorted by gate (bucket order), bucket sizes [n_ops]
     // level-batched dense path (d >= 64)
     bool has_levels = false;
     DevBuf lvl_circ, lvl_tiles;
@@ -106,7 +99,7 @@ struct b200_atom {
     size_t t_S_bytes = 0, t_H_bytes = 0;
     double* tH() { return t_SH.as<double>(); }
     double* tS() { return reinterpret_cast<double*>(reinterpret_cast<char*>(t_SH.p) + t_H_bytes); }
-    int n_units = 0, unit_outcomes = 4;
+    int n_units = 0;
     int n_fchains = 0, n_bchains = 0; uint32_t n_fnodes = 0, n_bnodes = 0;
     // model
     bool has_model = false;
@@ -182,15 +175,13 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     if (!c) return B200_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->scratch2p.release(); c->lvl_states.release();
+    c->out_buf.release(); c->probs_buf.release(); c->w_buf.release(); c->scratch.release(); c->lvl_states.release();
     c->lj_fs.release(); c->lj_bh.release();
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     phase_clear(c);
     for (DevBuf& b : c->lind) b.release();
-    for (cudaStream_t& st : c->copy_streams) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); st = nullptr; }
-    if (c->ev_copy) cudaEventDestroy(c->ev_copy);
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     if (c->cublas) cublasDestroy(c->cublas);
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
@@ -350,29 +341,23 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
         coptr[i + 1] = coptr[i] + no;
     }
 
-    // two-phase d16 tables: scratch rows per circuit = (L+1)*(1+n_out); steps of each circuit sorted by gate
-    std::vector<uint32_t> srow; std::vector<uint16_t> bperm, bcnt;
-    int64_t scratch_rows = 0;
+    // per circuit: the steps sorted by gate ("gate buckets") -- the order the accumulate kernels (d = 16 trie path, d >= 64
+    // level path) walk them in
+    std::vector<uint16_t> bperm, bcnt;
     if ((dim == 16 || dim >= 64) && max_depth < 65535) {
-        srow.resize((size_t)n_rows + 1); bperm.resize(cops.size()); bcnt.assign((size_t)n_rows * std::max(n_ops, 1), 0);
-        uint64_t acc_rows = 0;
+        bperm.resize(cops.size()); bcnt.assign((size_t)n_rows * std::max(n_ops, 1), 0);
         std::vector<uint32_t> off((size_t)std::max(n_ops, 1) + 1);
         for (int64_t i = 0; i < n_rows; ++i) {
             const uint32_t b0 = cptr[i], L = cptr[i + 1] - b0;
-            srow[i] = (uint32_t)acc_rows;
-            acc_rows += (uint64_t)(L + 1) * (1 + (uint64_t)(coptr[i + 1] - coptr[i]));
             uint16_t* cn = bcnt.data() + (size_t)i * std::max(n_ops, 1);
             for (uint32_t k = 0; k < L; ++k) cn[cops[b0 + k]]++;
             off[0] = 0;
             for (int g = 0; g < n_ops; ++g) off[g + 1] = off[g] + cn[g];
             for (uint32_t k = 0; k < L; ++k) bperm[b0 + off[cops[b0 + k]]++] = (uint16_t)k;
         }
-        srow[n_rows] = (uint32_t)acc_rows;
-        scratch_rows = (dim == 16 && acc_rows < ((uint64_t)1 << 32)) ? (int64_t)acc_rows : 0;   // 0 disables the two-phase path
     }
 
     b200_atom* a = new b200_atom();
-    a->scratch_rows = scratch_rows;
     a->ctx = ctx; a->dim = dim; a->n_ops = n_ops; a->n_rho = n_rho; a->n_eff = n_eff;
     a->n_rows = n_rows; a->n_elements = n_elements;
     a->n_prop_table = n_rows ? row_ptr[n_rows] : 0;
@@ -385,7 +370,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
     if ((rc = upload_vec(a->circ_ptr, cptr, ctx->stream)) || (rc = upload_vec(a->circ_ops, cops, ctx->stream)) ||
         (rc = upload_vec(a->circ_prep, cprep, ctx->stream)) || (rc = upload_vec(a->out_ptr, coptr, ctx->stream)) ||
         (rc = upload_vec(a->out_eff, coeff, ctx->stream)) || (rc = upload_vec(a->out_el, coel, ctx->stream)) ||
-        (rc = upload_vec(a->srow, srow, ctx->stream)) || (rc = upload_vec(a->bperm, bperm, ctx->stream)) ||
+        (rc = upload_vec(a->bperm, bperm, ctx->stream)) ||
         (rc = upload_vec(a->bcnt, bcnt, ctx->stream))) {
         b200_atom_free(ctx, a); return rc;
     }
@@ -469,7 +454,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
         }
     }
     // trie path tables (d = 16, <= 8 effects, <= 255 ops): prefix trie of (prep, ops), suffix trie of reversed ops
-    if (dim == 16 && n_eff <= 8 && n_ops <= 255 && n_ops >= 1 && scratch_rows > 0 && xptr[n_rows] < ((uint64_t)1 << 31)) {
+    if (dim == 16 && n_eff <= 8 && n_ops <= 255 && n_ops >= 1 && !bperm.empty() && xptr[n_rows] < ((uint64_t)1 << 31)) {
         TrieHost TF, TB;
         std::vector<int32_t> zero_root((size_t)n_rows, 0);
         build_trie(n_rows, cprep, cptr, cops, false, TF);
@@ -493,18 +478,11 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
             // offsets of the all-zero rows.
             const uint32_t zf_node = (uint32_t)TF.node_op.size(), zb_node = (uint32_t)TB.node_op.size();   // all-zero rows
             const uint32_t ne16 = (uint32_t)n_eff * 16u;
-            const int gsz = (getenv("B200_UNIT_OUTCOMES") && atoi(getenv("B200_UNIT_OUTCOMES")) == 2) ? 2 : 4;   // outcomes per phase-B unit
-            a->unit_outcomes = gsz;
+            const int gsz = AT_NO;                                         // outcomes per phase-B unit
             std::vector<UnitRec> units; std::vector<uint2> uidx;
             bool trie_ok = ((uint64_t)(zb_node + 2) * ne16 < ((uint64_t)1 << 32)) && ((uint64_t)(zf_node + 2) * 16 < ((uint64_t)1 << 32));
-            // unit order: suffix-lexicographic (default) or, dev knob B200_UNIT_ORDER=el, by Jacobian row (sequential stores)
-            std::vector<int64_t> uorder(TB.sorted);
-            if (getenv("B200_UNIT_ORDER") && !strcmp(getenv("B200_UNIT_ORDER"), "el")) {
-                std::vector<int32_t> first_el((size_t)n_rows, INT32_MAX);
-                for (int64_t i = 0; i < n_rows; ++i)
-                    for (int32_t oq = coptr[i]; oq < coptr[i + 1]; ++oq) first_el[i] = std::min(first_el[i], coel[oq]);
-                std::stable_sort(uorder.begin(), uorder.end(), [&](int64_t x, int64_t y) { return first_el[x] < first_el[y]; });
-            }
+            // unit order: suffix-lexicographic (consecutive units gather from the same region of H)
+            const std::vector<int64_t>& uorder = TB.sorted;
             for (int64_t si = 0; si < n_rows; ++si) {
                 const int64_t i = uorder[si];
                 const uint32_t b0 = cptr[i];
@@ -585,14 +563,8 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
 extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    if (ctx && ctx->l2_window_atom == a) {       // drop the stream's persisting-L2 window over this atom's tables
-        cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
-        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaCtxResetPersistingL2Cache();
-        ctx->l2_window_atom = nullptr;
-    }
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
-                      &a->srow, &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
+                      &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
                       &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
                       &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
                       &a->t_counters, &a->t_units, &a->t_uidx,
@@ -1016,89 +988,17 @@ static int launch_w_generic(b200_ctx* c, b200_atom* a, double* W, int64_t ldw, d
     return B200_OK;
 }
 
-template <int NG>
-static int launch_d16_t(b200_ctx* c, b200_atom* a, const D16Args& args) {
-    size_t smem = d16_smem_bytes(NG, a->max_depth);
-    CU(cudaFuncSetAttribute(k_dprobs_d16<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (size_t)(227u * 1024u) / (smem + 1024)));
-    int gx = grid_for(c, a->n_rows, per_sm);
-    k_dprobs_d16<NG><<<gx, D16_THREADS, smem, c->stream>>>(atom_dev(a), model_dev(a), args);
-    c->launches++;
-    CU(cudaGetLastError());
-    return B200_OK;
+// d = 16 Jacobian: the trie path (prefix + suffix sharing).  B200_D16_MODE=generic (test knob) forces the generic kernels.
+static bool d16_generic_forced() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("B200_D16_MODE"); v = (e && !strcmp(e, "generic")) ? 1 : 0; }
+    return v == 1;
 }
-static bool d16_2p_ok(b200_ctx* c, b200_atom* a);
-static int d16_mode();
 static bool d16_ok(b200_ctx* c, b200_atom* a) {
-    if (d16_mode() >= 1 && d16_2p_ok(c, a)) return true;
-    return a->dim == 16 && a->n_ops >= 1 && a->n_ops <= 8 &&
-           d16_smem_bytes(a->n_ops, a->max_depth) + 1024 <= c->smem_optin;
+    return a->dim == 16 && a->has_trie && a->n_ops >= 1 && a->n_ops <= 255 && !d16_generic_forced() &&
+           (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin;
 }
-static int d16_mode() {   // 0 = fused kernel, 1 = two-phase per-circuit chains, 2 = trie (prefix+suffix sharing; default)
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("B200_D16_MODE");
-        mode = (e && !strcmp(e, "fused")) ? 0 : (e && !strcmp(e, "2p")) ? 1 : 2;
-    }
-    return mode;
-}
-// Optional L2 set-aside for the trie value tables (dev knob B200_L2_PERSIST_MB=<n>, default off).  MEASURED HARMFUL on the
-// BASELINE layout: a persisting carve-out (cudaLimitPersistingL2CacheSize) of 79 MB slowed the Jacobian from 0.86 to
-// 1.44 ms, and the stores alone from ~0.55 to ~1.1 ms -- the 3 GB write stream needs the L2 capacity as its write-back
-// buffer more than the gathers need the tables resident.  Kept for experiments only.
-static int trie_l2_window(b200_ctx* c, b200_atom* a) {
-    const char* ef = getenv("B200_L2_PERSIST_MB");
-    const long long want = (ef && atoi(ef) > 0) ? (long long)atoi(ef) << 20 : 0;
-    if (want == 0 && c->l2_persist_cur <= 0) return B200_OK;               // never enabled: nothing to do
-    if (c->l2_persist_max < 0) {
-        cudaDeviceProp prop;
-        CU(cudaGetDeviceProperties(&prop, c->device));
-        c->l2_persist_max = (long long)prop.persistingL2CacheMaxSize;
-        c->l2_window_max = (long long)prop.accessPolicyMaxWindowSize;
-    }
-    const long long lim = std::min(want, c->l2_persist_max);
-    if (lim != c->l2_persist_cur || c->l2_window_atom != a) {
-        CU(cudaStreamSynchronize(c->stream));
-        cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
-        CU(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-        CU(cudaCtxResetPersistingL2Cache());
-        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)std::max<long long>(lim, 0)));
-        c->l2_persist_cur = lim; c->l2_window_atom = nullptr;
-        if (lim <= 0) return B200_OK;
-        // the allocation is [H | S]: S is gathered from during the whole accumulate kernel, H is consumed front to back
-        // (its node ids follow the suffix order of the units): the window is the last `lim` bytes, all of them persisting
-        const size_t total = a->t_S_bytes + a->t_H_bytes;
-        const size_t bytes = std::min(std::min<size_t>(total, (size_t)c->l2_window_max), (size_t)lim) & ~(size_t)4095;
-        if (bytes == 0) return B200_OK;
-        attr.accessPolicyWindow.base_ptr = reinterpret_cast<char*>(a->t_SH.p) + (total - bytes);
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = 1.0f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-        CU(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-        c->l2_window_atom = a;
-        if (getenv("B200_VERBOSE")) fprintf(stderr, "[b200] L2 persisting window %.1f MB of %.1f MB tables (device set-aside max %.1f MB)\n", bytes / 1048576.0, total / 1048576.0, c->l2_persist_max / 1048576.0);
-    }
-    return B200_OK;
-}
-
-// phase A of the trie path: KG = chains per atomic grab (template: the per-batch loop is fully unrolled)
-static int launch_trie_chains(b200_ctx* c, b200_atom* a, const TrieDev& t, int grid, size_t smem, int kg, int fwd_only) {
-    const char* es = getenv("B200_CHAIN_SLEEP");
-    const unsigned sleep_ns = (es && atoi(es) > 0) ? (unsigned)atoi(es) : 100u;      // dev knob: poll interval of a waiting chain
-    auto go = [&](auto kern) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TRIE_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), t, fwd_only, sleep_ns);
-        return B200_OK;
-    };
-    const char* ee = getenv("B200_CHAIN_EARLY");
-    const bool early = !(ee && *ee == '0');                 // dev knob: issue the next atomic before a short last chain is walked
-    if (t.prof) return kg >= 2 ? go(k_trie_chains<2, true, true>) : go(k_trie_chains<1, true, true>);
-    if (kg >= 3) return early ? go(k_trie_chains<3, true, false>) : go(k_trie_chains<3, false, false>);
-    if (kg >= 2) return early ? go(k_trie_chains<2, true, false>) : go(k_trie_chains<2, false, false>);
-    return early ? go(k_trie_chains<1, true, false>) : go(k_trie_chains<1, false, false>);
-}
-static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
+static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
     if (a->n_rows == 0) return B200_OK;
     TrieDev t;
     t.f_meta = a->tf_meta.as<int4>();
@@ -1109,136 +1009,24 @@ static int launch_d16_trie(b200_ctx* c, b200_atom* a, const D16Args& args) {
     t.bcnt = a->bcnt.as<uint16_t>();
     t.S = a->tS(); t.H = a->tH();
     t.counters = a->t_counters.as<unsigned>();
-    { int rcW = trie_l2_window(c, a); if (rcW) return rcW; }
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     k_trie_prepare<<<c->sm_count * 8, 256, 0, c->stream>>>(a->tS(), a->tf_par.as<uint32_t>(), a->n_fpar, a->tH(), a->tb_par.as<uint32_t>(), a->n_bpar,
                                                          (uint32_t)a->n_eff * 16u, a->t_counters.as<unsigned>());
-    c->launches += 1;
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    const size_t smemB = (size_t)AT_WARPS * 5 * 16 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + (size_t)a->n_ops * 4 + 16;
-    // dev knobs (read on every call so that one process can sweep them): chain CTAs per SM and role, chains per atomic
-    // grab (2/4/8), 256-bit stores (measured: 0.914 ms with, 0.891 ms without)
-    auto knob = [](const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; };
-    const int chain_ctas = std::max(1, knob("B200_CHAIN_CTAS", 3)), chain_k = std::max(1, knob("B200_CHAIN_K", 1));
-    const int st256 = knob("B200_ACC_ST256", 0);
-    int gA = 2 * c->sm_count * chain_ctas;         // even = forward trie, odd = backward trie
-    const bool chain_prof = knob("B200_CHAIN_PROF", 0) != 0;
-    t.prof = nullptr;
-    if (chain_prof) {
-        CU(c->f_buf.ensure(std::max<size_t>(c->f_buf.cap, 128)));
-        t.prof = c->f_buf.as<unsigned long long>(); CU(cudaMemsetAsync(t.prof, 0, 128, c->stream));
-    }
-    { int rcA = launch_trie_chains(c, a, t, gA, smemA, chain_k, 0); if (rcA) return rcA; }
+    const size_t smemB = (size_t)AT_WARPS * 5 * 16 * 8 + (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4 + 16;
+    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    // 3 chain CTAs per SM and role (even blocks = forward trie, odd = backward trie), 100 ns poll interval of a waiting chain
+    k_trie_chains<<<2 * c->sm_count * 3, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, 0, 100u);
     { int rcP = phase_mark(c); if (rcP) return rcP; }
-    if (t.prof) {
-        unsigned long long h[8];
-        CU(cudaMemcpyAsync(h, t.prof, 64, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
-        const double nw = (double)gA / 2 * TRIE_WARPS;
-        for (int r = 0; r < 2; ++r)
-            fprintf(stderr, "[chain prof] role %d (%d chains): per-warp mean cycles: hand-out %.0f, parent wait %.0f, steps %.0f, total %.0f\n",
-                    r, r ? a->n_bchains : a->n_fchains, h[r * 4] / nw, h[r * 4 + 1] / nw, h[r * 4 + 2] / nw, h[r * 4 + 3] / nw);
-    }
-    const int dbg = knob("B200_DBG", 0);
-    const bool w256 = st256 && (((uintptr_t)args.J & 31) == 0);        // 32-byte stores need 32-byte aligned rows
-    // phase-B hand-out (see next_chunk in k_accum_trie_d16): chunk = units per warp grab, rsub = sub-chunks per CTA range
-    // (0 = every warp grabs from the global counter).  Dev knobs B200_ACC_CHUNK / B200_ACC_RSUB.
-    const int units_per_circ = std::max(1, a->n_ops);
-    int acc_rsub = std::max(0, knob("B200_ACC_RSUB", 0));
-    int acc_chunk = knob("B200_ACC_CHUNK", acc_rsub > 0 ? 2 * units_per_circ : AT_CHUNK);
-    if (acc_chunk < 1) acc_chunk = AT_CHUNK;
-    auto launchB = [&](auto kern, int per_sm) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * acc_chunk - 1) / (AT_WARPS * acc_chunk), per_sm);
-        kern<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                      a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, dbg,
-                                                      acc_chunk, acc_rsub);
-        return B200_OK;
-    };
-    // (a cp.async ring variant with three groups of gathers in flight per warp was measured SLOWER, 1.015 vs 0.894 ms per
-    // Jacobian, and removed: the loop is not bound by the latency of the table gathers -- profiles/README.md)
-    int rcB = 1;
-    {
-        const bool tma = knob("B200_ACC_TMA", 0) != 0 && a->unit_outcomes != 2 && !w256;   // bulk-store epilogue (dev knob)
-        if (tma) {
-            auto kern = k_accum_trie_d16<4, false, false, true>;
-            const size_t smemT = smemB + (size_t)AT_WARPS * 4 * 256 * 8;
-            if (smemT + 1024 > c->smem_optin) return fail(B200_E_UNSUPPORTED, "TMA epilogue: shared memory");
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemT));
-            const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * acc_chunk - 1) / (AT_WARPS * acc_chunk), 2);
-            kern<<<gB, AT_WARPS * 32, smemT, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                          a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, dbg, acc_chunk, acc_rsub);
-            rcB = B200_OK;
-        } else
-        if (t.prof && a->unit_outcomes != 2 && !w256) rcB = launchB(k_accum_trie_d16<4, false, true>, 2);      // phase profiler (dev)
-        else if (a->unit_outcomes == 2) rcB = w256 ? launchB(k_accum_trie_d16<2, true>, 3) : launchB(k_accum_trie_d16<2, false>, 3);
-        else rcB = w256 ? launchB(k_accum_trie_d16<4, true>, 2) : launchB(k_accum_trie_d16<4, false>, 2);
-    }
-    if (rcB) return rcB;
+    CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+    const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
+    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                             a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, AT_CHUNK);
     { int rcP = phase_mark(c); if (rcP) return rcP; }
-    if (t.prof) {
-        unsigned long long h[4];
-        CU(cudaMemcpyAsync(h, t.prof + 8, 32, cudaMemcpyDeviceToHost, c->stream)); CU(cudaStreamSynchronize(c->stream));
-        const double nw = (double)grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), a->unit_outcomes == 2 ? 3 : 2) * AT_WARPS;
-        fprintf(stderr, "[accum prof] %d units: per-warp mean cycles: chunk prologue %.0f, group loop %.0f, epilogue %.0f, total %.0f\n",
-                a->n_units, h[0] / nw, h[1] / nw, h[2] / nw, h[3] / nw);
-    }
-    c->launches += 2;
+    c->launches += 3;
     CU(cudaGetLastError());
     return B200_OK;
-}
-static bool d16_2p_ok(b200_ctx* c, b200_atom* a) {
-    return a->dim == 16 && a->n_ops >= 1 && a->scratch_rows > 0 &&
-           (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin && a->n_ops <= 255;
-}
-static int launch_d16_2p(b200_ctx* c, b200_atom* a, const D16Args& args) {
-    if (a->n_rows == 0) return B200_OK;
-    CU(c->scratch2p.ensure((size_t)a->scratch_rows * 128));
-    TwoPhaseDev tp;
-    tp.srow = a->srow.as<uint32_t>(); tp.bperm = a->bperm.as<uint16_t>(); tp.bcnt = a->bcnt.as<uint16_t>();
-    tp.scratch = c->scratch2p.as<double>();
-    const size_t smemA = (size_t)a->n_ops * 256 * 2 * 8 + (size_t)C2P_WARPS * 32 * 8;
-    const size_t smemB = (size_t)a->n_ops * 4 * 32 * 8 + (size_t)2 * D16_SPAM_MAX * 4;
-    CU(cudaFuncSetAttribute(k_chain_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    CU(cudaFuncSetAttribute(k_accum_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-    static int batch_rows = -1;
-    if (batch_rows < 0) { const char* e = getenv("B200_2P_BATCH_MB"); batch_rows = e ? atoi(e) * 8192 : 0; }
-    // batches of whole circuits (longest first); 0 = single batch
-    std::vector<int> cuts; cuts.push_back(0);
-    if (batch_rows > 0) {
-        // host copy of srow is not kept: approximate equal-row batches through max_depth bound is not exact, so
-        // we split by circuit count proportionally (rows are dominated by depth; circuits are depth-sorted)
-        int nb = (int)((a->scratch_rows + batch_rows - 1) / batch_rows);
-        for (int i = 1; i < nb; ++i) cuts.push_back((int)((int64_t)a->n_rows * i / nb));
-    }
-    cuts.push_back((int)a->n_rows);
-    for (size_t bi = 0; bi + 1 < cuts.size(); ++bi) {
-        const int c0 = cuts[bi], c1 = cuts[bi + 1];
-        if (c1 <= c0) continue;
-        int gA = grid_for(c, ((int64_t)(c1 - c0) + C2P_WARPS - 1) / C2P_WARPS, 4);
-        k_chain_d16<<<gA, C2P_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), tp, args.probs, c0, c1);
-        int gB = grid_for(c, ((int64_t)(c1 - c0) + 1) / 2, 6);
-        k_accum_d16<<<gB, A2P_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), tp, args, c0, c1);
-        c->launches += 2;
-    }
-    CU(cudaGetLastError());
-    return B200_OK;
-}
-static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
-    if (a->n_rows == 0) return B200_OK;
-    if (d16_mode() == 2 && a->has_trie && d16_2p_ok(c, a)) return launch_d16_trie(c, a, args);
-    if (d16_mode() >= 1 && d16_2p_ok(c, a)) return launch_d16_2p(c, a, args);
-    switch (a->n_ops) {
-        case 1: return launch_d16_t<1>(c, a, args);
-        case 2: return launch_d16_t<2>(c, a, args);
-        case 3: return launch_d16_t<3>(c, a, args);
-        case 4: return launch_d16_t<4>(c, a, args);
-        case 5: return launch_d16_t<5>(c, a, args);
-        case 6: return launch_d16_t<6>(c, a, args);
-        case 7: return launch_d16_t<7>(c, a, args);
-        case 8: return launch_d16_t<8>(c, a, args);
-    }
-    return fail(B200_E_UNSUPPORTED, "d16 kernel: n_ops=%d", a->n_ops);
 }
 
 // W[el][w] for the whole atom (general path)
@@ -1287,14 +1075,15 @@ static int launch_probs_level(b200_ctx* c, b200_atom* a, double* d_out) {
 }
 
 static int launch_probs_trie(b200_ctx* c, b200_atom* a, double* d_out) {
-    TrieDev t; memset(&t, 0, sizeof t);      // (prof = nullptr)
+    TrieDev t; memset(&t, 0, sizeof t);
     t.f_meta = a->tf_meta.as<int4>();
     t.f_op = a->tf_op.as<uint8_t>(); t.n_fchains = a->n_fchains; t.n_fnodes = a->n_fnodes;
     t.S = a->tS(); t.counters = a->t_counters.as<unsigned>();
     k_trie_prepare<<<c->sm_count * 4, 256, 0, c->stream>>>(a->tS(), a->tf_par.as<uint32_t>(), a->n_fpar, nullptr, nullptr, 0u, 0u, a->t_counters.as<unsigned>());
     c->launches++;
     const size_t smemA = (size_t)a->n_ops * 256 * 8 + (size_t)TRIE_WARPS * 32 * 8;
-    { int rcA = launch_trie_chains(c, a, t, c->sm_count * 4, smemA, std::max(1, getenv("B200_CHAIN_K") ? atoi(getenv("B200_CHAIN_K")) : 1), 1); if (rcA) return rcA; }
+    CU(cudaFuncSetAttribute(k_trie_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    k_trie_chains<<<c->sm_count * 4, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, 1, 100u);
     int gp = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 15) / 16, (int64_t)c->sm_count * 8));
     k_probs_trie_d16<<<gp, 256, 0, c->stream>>>(atom_dev(a), model_dev(a), a->t_fend.as<uint32_t>(), a->tS(), d_out, 1);
     c->launches += 2;
@@ -1306,8 +1095,7 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     CU(cudaSetDevice(c->device));
-    if (a->has_trie && a->n_rows > 0 && d16_mode() == 2 && (size_t)a->n_ops * 4096 + 4096 <= c->smem_optin)
-        return launch_probs_trie(c, a, d_out);
+    if (a->n_rows > 0 && d16_ok(c, a)) return launch_probs_trie(c, a, d_out);
     if (a->has_levels && a->n_rows > 0 && !getenv("B200_NO_LEVELS")) {
         if (a->dim == 64) return launch_probs_level<64>(c, a, d_out);
         if (a->dim == 256) return launch_probs_level<256>(c, a, d_out);
@@ -1412,16 +1200,8 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
         args.colmap = a->colmap.as<int32_t>(); args.spam_col = a->spam_col.as<int32_t>();
         args.spam_w = a->spam_w.as<int32_t>(); args.n_spam = a->n_spam;
         args.J = d_out; args.ld = ld; args.probs = d_probs;
-        const bool fused_scale = (d16_mode() == 2 && a->has_trie && d16_2p_ok(c, a));   // trie epilogue applies the scale itself
-        args.row_scale = fused_scale ? d_scale : nullptr;
-        int rc = launch_d16(c, a, args);
-        if (rc) return rc;
-        if (d_scale && !fused_scale) {
-            k_scale_rows<<<(unsigned)std::min<int64_t>(a->n_elements, 65535 * 4), 256, 0, c->stream>>>(d_out, ld, a->n_elements, a->n_params, d_scale);
-            c->launches++;
-            CU(cudaGetLastError());
-        }
-        return B200_OK;
+        args.row_scale = d_scale;                  // applied in the store epilogue
+        return launch_d16(c, a, args);
     }
     if (levelj_ok(c, a))
         return a->dim == 64 ? launch_levelj<64>(c, a, d_out, ld, d_probs, d_scale) : launch_levelj<256>(c, a, d_out, ld, d_probs, d_scale);
@@ -1444,36 +1224,12 @@ extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, in
 // ------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ------------------------------------------------------------------------------------------------
-// device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles.  Large results are split into row blocks
-// that travel on separate streams (one DMA engine does not saturate the PCIe link on its own); a contiguous destination is
-// copied with plain 1-D copies.
+// device [n_rows x width] (ld = width) -> host with row stride `hstride` doubles (a contiguous destination is one 1-D copy).
+// One copy stream: 1..4 concurrent streams all landed at 53-56 GB/s (PCIe-bound) in round 1.
 static int copy_out_2d(b200_ctx* c, const double* d_src, int64_t width, int64_t n_rows, double* h_dst, int64_t hstride) {
     if (n_rows == 0 || width == 0) return B200_OK;
-    const size_t bytes = (size_t)n_rows * (size_t)width * 8;
-    const char* es = getenv("B200_D2H_SPLIT");
-    int nsplit = (es && atoi(es) > 0) ? atoi(es) : 1;   // measured: 1..4 streams all land at 53-56 GB/s (PCIe-bound), so one copy is the default
-    if (nsplit > 4) nsplit = 4;
-    if (bytes < ((size_t)64 << 20) || n_rows < nsplit) nsplit = 1;
-    auto copy_rows = [&](int64_t r0, int64_t r1, cudaStream_t st) -> int {
-        const double* src = d_src + (size_t)r0 * width; double* dst = h_dst + (size_t)r0 * hstride;
-        if (hstride == width) { CU(cudaMemcpyAsync(dst, src, (size_t)(r1 - r0) * width * 8, cudaMemcpyDeviceToHost, st)); }
-        else CU(cudaMemcpy2DAsync(dst, (size_t)hstride * 8, src, (size_t)width * 8, (size_t)width * 8, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
-        return B200_OK;
-    };
-    if (nsplit == 1) {
-        int rc = copy_rows(0, n_rows, c->stream); if (rc) return rc;
-        CU(cudaStreamSynchronize(c->stream));
-        return B200_OK;
-    }
-    if (!c->ev_copy) CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-    CU(cudaEventRecord(c->ev_copy, c->stream));                        // the result is complete on the main stream
-    for (int k = 1; k < nsplit; ++k) {
-        if (!c->copy_streams[k - 1]) CU(cudaStreamCreateWithFlags(&c->copy_streams[k - 1], cudaStreamNonBlocking));
-        CU(cudaStreamWaitEvent(c->copy_streams[k - 1], c->ev_copy, 0));
-        int rc = copy_rows(n_rows * k / nsplit, n_rows * (k + 1) / nsplit, c->copy_streams[k - 1]); if (rc) return rc;
-    }
-    { int rc = copy_rows(0, n_rows / nsplit, c->stream); if (rc) return rc; }
-    for (int k = 1; k < nsplit; ++k) CU(cudaStreamSynchronize(c->copy_streams[k - 1]));
+    if (hstride == width) { CU(cudaMemcpyAsync(h_dst, d_src, (size_t)n_rows * width * 8, cudaMemcpyDeviceToHost, c->stream)); }
+    else CU(cudaMemcpy2DAsync(h_dst, (size_t)hstride * 8, d_src, (size_t)width * 8, (size_t)width * 8, (size_t)n_rows, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return B200_OK;
 }

@@ -19,7 +19,6 @@
 //            entries and is stored at once.  This kernel is the whole HBM-write-bound cost (0.68 ms, 0.67 of HBM peak).
 #pragma once
 #include "common.cuh"
-#include "kernels_d16.cuh"   // dmma884, D16Args, D16_SPAM_MAX
 
 struct TrieDev {
     // forward trie (node value = state after the prefix; depth 0 = the prep itself)
@@ -39,7 +38,6 @@ struct TrieDev {
     double* S;                 // [n_fnodes][16]
     double* H;                 // [n_bnodes][n_eff][16]
     unsigned* counters;        // [4] work counters: forward chains, backward chains, accumulate chunks (zeroed before launch)
-    unsigned long long* prof;  // dev knob B200_CHAIN_PROF: [2 roles][4] warp-cycles in hand-out, parent wait, steps, total; [8..11] accumulate (or nullptr)
 };
 
 #define TRIE_WARPS 4
@@ -71,24 +69,16 @@ __global__ void k_trie_prepare(double* __restrict__ S, const uint32_t* __restric
     }
 }
 
-// Work hand-out: a warp takes KG consecutive chains per atomicAdd (same-address L2 atomics serialise: ~136 k of them
-// per Jacobian were a measurable part of the kernel) and reads one 16-byte record per chain; the ops of a chain are
+// Work hand-out: a warp takes ONE chain per atomicAdd and reads one 16-byte record for it; the ops of a chain are
 // consecutive bytes and are fetched 32 at a time (one coalesced load, then a shuffle per step) so that no global load
-// sits on the per-step critical path.  A warp processes the chains it holds in increasing index order and a chain only
-// waits for a chain with a smaller index, handed out earlier: the spin-waits cannot deadlock.
-//
-// Latency hiding (version 2): a chain is only 2.8 nodes long on average, and version 1 spent 75 % of its warp cycles in
-// dependent L2 round trips, atomic -> chain record -> (parent row, ops), once per chain.  Now the records of a batch are
-// loaded together, the parent rows + ops of ALL chains of the batch are requested before the first chain is walked, and
-// (EARLY) the atomic for the next batch is issued before the last chain of this one is walked if that chain is short.
-// Claiming chains any earlier than that was measured to be much WORSE (a warp that holds 16 claimed chains makes every
-// other warp wait for parents that sit in its queue: 1.34 ms per Jacobian instead of 0.90): the hand-out must stay
-// just-in-time, and with the long chains of the heavy-path decomposition a warp must not hold a second chain at all
-// while it walks one (KG = 1 is the default).
-// A prefetched parent row that is not complete yet (sentinel) falls back to the polling loop.
+// sits on the per-step critical path.  Chains are handed out by start depth and a chain only waits for a chain with a
+// smaller index, handed out earlier: the spin-waits cannot deadlock.  The parent row and the ops of the chain are
+// requested before the chain is walked, and the atomic for the next chain is issued before a SHORT chain (<= 4 nodes) is
+// walked.  Claiming chains any earlier than that was measured to be much worse (a warp that holds several claimed
+// chains makes every other warp wait for parents that sit in its queue): the hand-out stays just-in-time
+// (profiles/README.md, round 1).  A prefetched parent row that is not complete yet (sentinel) falls back to polling.
 // dynamic smem: n_ops*256 doubles (the CTA's role: backward B fragments or forward fragments)
 //               + TRIE_WARPS*2*16 doubles (forward exchange)
-template <int KG, bool EARLY, bool PROF>
 __global__ void __launch_bounds__(TRIE_WARPS * 32, TRIE_MIN_CTAS)
 k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int fwd_only, unsigned sleep_ns)
 {
@@ -112,13 +102,12 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int fwd_only, unsigned sleep_ns)
     }
     __syncthreads();
 
-    long long pr_grab = 0, pr_wait = 0, pr_step = 0; const long long pr_t0 = PROF ? clock64() : 0;
     unsigned* ctr = t.counters + role;
     const int n_chains = role ? t.n_bchains : t.n_fchains;
     const int4* meta = role ? t.b_meta : t.f_meta;
     const uint8_t* ops = role ? t.b_op : t.f_op;
     constexpr unsigned FULL = 0xffffffffu;
-    auto grab = [&]() -> int { int c = n_chains; if (lane == 0) c = (int)atomicAdd(ctr, (unsigned)KG); return c; };   // valid in lane 0
+    auto grab = [&]() -> int { int c = n_chains; if (lane == 0) c = (int)atomicAdd(ctr, 1u); return c; };   // valid in lane 0
     int c_next = grab();
 
     if (role == 0) {
@@ -126,64 +115,47 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int fwd_only, unsigned sleep_ns)
         double* fx = fx_all + warp * 32;
         const int half = lane >> 4;
         for (;;) {
-            const long long tq0 = PROF ? clock64() : 0;
             const int c0 = __shfl_sync(FULL, c_next, 0);
             if (c0 >= n_chains) break;
-            int4 mt = make_int4(0, 0, 0, 0);                // lane i < KG: record of chain c0 + i (len 0 = none)
-            if (lane < KG && c0 + lane < n_chains) mt = __ldg(meta + c0 + lane);
-            double pv[KG]; int opr[KG];
-#pragma unroll
-            for (int ci = 0; ci < KG; ++ci) {               // request parent row + first 32 ops of every chain of the batch
-                const int parent = __shfl_sync(FULL, mt.x, ci);
-                const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, ci), len = (uint32_t)__shfl_sync(FULL, mt.z, ci);
-                opr[ci] = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
-                pv[ci] = 0.0;
-                if (len && lane < 16) pv[ci] = (parent < 0) ? rho[(-1 - parent) * 16 + lane] : __ldcg(t.S + (size_t)parent * 16 + lane);
-            }
-            if (PROF) pr_grab += clock64() - tq0;
+            int4 mt = make_int4(0, 0, 0, 0);                // lane 0: record of chain c0
+            if (lane == 0) mt = __ldg(meta + c0);
+            const int parent = __shfl_sync(FULL, mt.x, 0);
+            const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, 0), len = (uint32_t)__shfl_sync(FULL, mt.z, 0);
+            int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;      // parent row + first 32 ops
+            double v = 0.0;
+            if (len && lane < 16) v = (parent < 0) ? rho[(-1 - parent) * 16 + lane] : __ldcg(t.S + (size_t)parent * 16 + lane);
             bool grabbed = false;
-#pragma unroll
-            for (int ci = 0; ci < KG; ++ci) {
-                const int parent = __shfl_sync(FULL, mt.x, ci);
-                const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, ci), len = (uint32_t)__shfl_sync(FULL, mt.z, ci);
-                if (ci == KG - 1 && EARLY && len <= 4u) { c_next = grab(); grabbed = true; }   // (never while a long chain is walked)
-                const long long tq1 = PROF ? clock64() : 0;
-                double v = pv[ci];
-                int opv = opr[ci];
-                uint32_t i0 = 0;
-                if (len) {
-                    if (parent < 0) {                       // root chain: first node is the prep itself
-                        if (lane < 16) __stcg(t.S + (size_t)first * 16 + lane, v);
-                        i0 = 1;
-                    } else {
-                        if (lane < 16) {
-                            const double* pp = t.S + (size_t)parent * 16 + lane;
-                            while (is_sent(v)) { __nanosleep(sleep_ns); v = __ldcg(pp); }
-                        }
-                        __syncwarp();
+            if (len <= 4u) { c_next = grab(); grabbed = true; }                    // (never while a long chain is walked)
+            uint32_t i0 = 0;
+            if (len) {
+                if (parent < 0) {                           // root chain: first node is the prep itself
+                    if (lane < 16) __stcg(t.S + (size_t)first * 16 + lane, v);
+                    i0 = 1;
+                } else {
+                    if (lane < 16) {
+                        const double* pp = t.S + (size_t)parent * 16 + lane;
+                        while (is_sent(v)) { __nanosleep(sleep_ns); v = __ldcg(pp); }
                     }
-                }
-                const long long tq2 = PROF ? clock64() : 0;
-                if (PROF) pr_wait += tq2 - tq1;
-                int cur = 0;
-                if (lane < 16) fx[lane] = v;
-                __syncwarp();
-                for (uint32_t i = i0; i < len; ++i) {
-                    if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
-                    const int g = __shfl_sync(FULL, opv, (int)(i & 31u));
-                    const double2* s2 = reinterpret_cast<const double2*>(fx + cur * 16 + half * 8);
-                    const double2 s0 = s2[0], s1 = s2[1], s2v = s2[2], s3 = s2[3];
-                    const double* fp = ffrag + g * 256 + lane;
-                    double f0 = fp[0] * s0.x, f1 = fp[32] * s0.y, f2 = fp[64] * s1.x, f3 = fp[96] * s1.y;
-                    f0 = fma(fp[128], s2v.x, f0); f1 = fma(fp[160], s2v.y, f1);
-                    f2 = fma(fp[192], s3.x, f2); f3 = fma(fp[224], s3.y, f3);
-                    double w = (f0 + f1) + (f2 + f3);
-                    w += shfl_xor_f64(w, 16);
-                    cur ^= 1;
-                    if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
                     __syncwarp();
                 }
-                if (PROF) pr_step += clock64() - tq2;
+            }
+            int cur = 0;
+            if (lane < 16) fx[lane] = v;
+            __syncwarp();
+            for (uint32_t i = i0; i < len; ++i) {
+                if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
+                const int g = __shfl_sync(FULL, opv, (int)(i & 31u));
+                const double2* s2 = reinterpret_cast<const double2*>(fx + cur * 16 + half * 8);
+                const double2 s0 = s2[0], s1 = s2[1], s2v = s2[2], s3 = s2[3];
+                const double* fp = ffrag + g * 256 + lane;
+                double f0 = fp[0] * s0.x, f1 = fp[32] * s0.y, f2 = fp[64] * s1.x, f3 = fp[96] * s1.y;
+                f0 = fma(fp[128], s2v.x, f0); f1 = fma(fp[160], s2v.y, f1);
+                f2 = fma(fp[192], s3.x, f2); f3 = fma(fp[224], s3.y, f3);
+                double w = (f0 + f1) + (f2 + f3);
+                w += shfl_xor_f64(w, 16);
+                cur ^= 1;
+                if (lane < 16) { fx[cur * 16 + lane] = w; __stcg(t.S + (size_t)(first + i) * 16 + lane, w); }
+                __syncwarp();
             }
             if (!grabbed) c_next = grab();
         }
@@ -193,84 +165,63 @@ k_trie_chains(AtomDev a, ModelDev m, TrieDev t, int fwd_only, unsigned sleep_ns)
         const int ne = a.n_eff;
         const bool rowok = mrow < ne;
         for (;;) {
-            const long long tq0 = PROF ? clock64() : 0;
             const int c0 = __shfl_sync(FULL, c_next, 0);
             if (c0 >= n_chains) break;
             int4 mt = make_int4(0, 0, 0, 0);
-            if (lane < KG && c0 + lane < n_chains) mt = __ldg(meta + c0 + lane);
-            double2 px[KG], py[KG]; int opr[KG];
-#pragma unroll
-            for (int ci = 0; ci < KG; ++ci) {
-                const int parent = __shfl_sync(FULL, mt.x, ci);
-                const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, ci), len = (uint32_t)__shfl_sync(FULL, mt.z, ci);
-                opr[ci] = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
-                px[ci] = make_double2(0.0, 0.0); py[ci] = px[ci];
-                if (len && rowok) {
-                    if (parent < 0) {                       // root: E itself
-                        const double* Er = E + mrow * 16;
-                        px[ci] = make_double2(Er[2 * q], Er[2 * q + 1]); py[ci] = make_double2(Er[8 + 2 * q], Er[9 + 2 * q]);
-                    } else {
-                        const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
-                        px[ci] = __ldcg(reinterpret_cast<const double2*>(hp)); py[ci] = __ldcg(reinterpret_cast<const double2*>(hp + 8));
-                    }
+            if (lane == 0) mt = __ldg(meta + c0);
+            const int parent = __shfl_sync(FULL, mt.x, 0);
+            const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, 0), len = (uint32_t)__shfl_sync(FULL, mt.z, 0);
+            int opv = (lane < (int)len) ? (int)__ldg(ops + first + lane) : 0;
+            double2 x = make_double2(0.0, 0.0), y = x;
+            if (len && rowok) {
+                if (parent < 0) {                           // root: E itself
+                    const double* Er = E + mrow * 16;
+                    x = make_double2(Er[2 * q], Er[2 * q + 1]); y = make_double2(Er[8 + 2 * q], Er[9 + 2 * q]);
+                } else {
+                    const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
+                    x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
                 }
             }
-            if (PROF) pr_grab += clock64() - tq0;
             bool grabbed = false;
-#pragma unroll
-            for (int ci = 0; ci < KG; ++ci) {
-                const int parent = __shfl_sync(FULL, mt.x, ci);
-                const uint32_t first = (uint32_t)__shfl_sync(FULL, mt.y, ci), len = (uint32_t)__shfl_sync(FULL, mt.z, ci);
-                if (ci == KG - 1 && EARLY && len <= 4u) { c_next = grab(); grabbed = true; }   // (never while a long chain is walked)
-                const long long tq1 = PROF ? clock64() : 0;
-                double2 x = px[ci], y = py[ci];
-                int opv = opr[ci];
-                uint32_t i0 = 0;
-                if (len) {
-                    if (parent < 0) {
-                        if (rowok) {
-                            double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
-                            __stcg(reinterpret_cast<double2*>(hp), x); __stcg(reinterpret_cast<double2*>(hp + 8), y);
-                        }
-                        i0 = 1;
-                    } else {
-                        if (rowok) {
-                            const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
-                            while (is_sent(x.x) || is_sent(x.y) || is_sent(y.x) || is_sent(y.y)) {
-                                __nanosleep(sleep_ns);
-                                x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                const long long tq2 = PROF ? clock64() : 0;
-                if (PROF) pr_wait += tq2 - tq1;
-                double a0 = x.x, a1 = x.y, a2 = y.x, a3 = y.y;
-                for (uint32_t i = i0; i < len; ++i) {
-                    if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
-                    const int g = __shfl_sync(FULL, opv, (int)(i & 31u));
-                    const double* bp = bfrag + g * 256 + lane;
-                    double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
-                    dmma884(d00, d01, a0, bp[0]);   dmma884(d10, d11, a0, bp[32]);
-                    dmma884(x00, x01, a1, bp[64]);  dmma884(x10, x11, a1, bp[96]);
-                    dmma884(d00, d01, a2, bp[128]); dmma884(d10, d11, a2, bp[160]);
-                    dmma884(x00, x01, a3, bp[192]); dmma884(x10, x11, a3, bp[224]);
-                    a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
+            if (len <= 4u) { c_next = grab(); grabbed = true; }
+            uint32_t i0 = 0;
+            if (len) {
+                if (parent < 0) {
                     if (rowok) {
-                        double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
-                        __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
-                        __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
+                        double* hp = t.H + ((size_t)first * ne + mrow) * 16 + 2 * q;
+                        __stcg(reinterpret_cast<double2*>(hp), x); __stcg(reinterpret_cast<double2*>(hp + 8), y);
                     }
+                    i0 = 1;
+                } else {
+                    if (rowok) {
+                        const double* hp = t.H + ((size_t)parent * ne + mrow) * 16 + 2 * q;
+                        while (is_sent(x.x) || is_sent(x.y) || is_sent(y.x) || is_sent(y.y)) {
+                            __nanosleep(sleep_ns);
+                            x = __ldcg(reinterpret_cast<const double2*>(hp)); y = __ldcg(reinterpret_cast<const double2*>(hp + 8));
+                        }
+                    }
+                    __syncwarp();
                 }
-                if (PROF) pr_step += clock64() - tq2;
+            }
+            double a0 = x.x, a1 = x.y, a2 = y.x, a3 = y.y;
+            for (uint32_t i = i0; i < len; ++i) {
+                if ((i & 31u) == 0u && i) opv = (i + lane < len) ? (int)__ldg(ops + first + i + lane) : 0;
+                const int g = __shfl_sync(FULL, opv, (int)(i & 31u));
+                const double* bp = bfrag + g * 256 + lane;
+                double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0, x00 = 0.0, x01 = 0.0, x10 = 0.0, x11 = 0.0;
+                dmma884(d00, d01, a0, bp[0]);   dmma884(d10, d11, a0, bp[32]);
+                dmma884(x00, x01, a1, bp[64]);  dmma884(x10, x11, a1, bp[96]);
+                dmma884(d00, d01, a2, bp[128]); dmma884(d10, d11, a2, bp[160]);
+                dmma884(x00, x01, a3, bp[192]); dmma884(x10, x11, a3, bp[224]);
+                a0 = d00 + x00; a1 = d01 + x01; a2 = d10 + x10; a3 = d11 + x11;
+                if (rowok) {
+                    double* hp = t.H + ((size_t)(first + i) * ne + mrow) * 16 + 2 * q;
+                    __stcg(reinterpret_cast<double2*>(hp), make_double2(a0, a1));
+                    __stcg(reinterpret_cast<double2*>(hp + 8), make_double2(a2, a3));
+                }
             }
             if (!grabbed) c_next = grab();
         }
-    }
-    if (PROF && t.prof && lane == 0) {
-        atomicAdd(t.prof + role * 4 + 0, (unsigned long long)pr_grab); atomicAdd(t.prof + role * 4 + 1, (unsigned long long)pr_wait);
-        atomicAdd(t.prof + role * 4 + 2, (unsigned long long)pr_step); atomicAdd(t.prof + role * 4 + 3, (unsigned long long)(clock64() - pr_t0));
     }
 }
 
@@ -319,74 +270,31 @@ struct UnitRec {           // 32 bytes
 #define UNIT_MAX_GROUPS 16383u
 #define UNIT_MAX_PREP 127u
 
-// Fragment layout "W256" (version 8): the DMMA tiles are interleaved instead of blocked -- M tile h holds the block
-// rows i = 2*mrow + h, N tile z the columns j = 2*n + z -- so that
-//   * a lane's two A elements of one outcome, e[2*mrow], e[2*mrow+1], and its two B elements, s[2*mrow], s[2*mrow+1],
-//     are ADJACENT in the table rows: one 128-bit load each (5 LDG.128 per group of 4 steps instead of 10 LDG.64, every
-//     warp instruction reading whole 128-byte rows: half the L1 wavefronts, which ran at 63 % of peak in version 6);
-//   * a lane's four accumulators of block row i are the four CONSECUTIVE columns 4q..4q+3 (j = 4q + 2c + z): one
-//     st.global.v4.f64 per lane writes 8 full 128-byte lines per warp instruction (SASS STG.E.256) instead of two
-//     instructions that each touch half of 8 lines.
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void st256_cs(double* p, double a, double b, double c, double d) {
-    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
 
-// TMA (bulk-store) epilogue, template flag TMA (dev knob B200_ACC_TMA=1, OFF by default): the finished blocks go registers ->
-// shared staging (one 2 KB row-major 16x16 block per outcome) -> cp.async.bulk to the Jacobian rows, so that the warp's LSU is
-// free for the next unit's gathers while the bulk engine drains the stores.  The staging writes are bank-conflict free (in one
-// STS.128 the even block rows of a quarter-warp store their left half-row, N tile 0, and the odd rows their right half-row).
-// MEASURED (C2 layout): 0.852 ms per Jacobian against 0.810 ms with plain st.cs stores, and 0.685 against 0.670 ms with the
-// gathers switched off -- taking the stores off the LSU does not help, so the loop's long-scoreboard stalls are not gathers
-// queueing behind stalled stores.  (A first version with 8-way conflicted staging had also measured "no gain".)
-// dynamic smem: AT_WARPS * (1 + NO) * 16 doubles (SPAM slots) [+ with TMA: AT_WARPS * NO * 256 doubles of staging], then the
-// column-map fragments, SPAM lists and gate bases.
-template <int NO, bool W256, bool PROF = false, bool TMA = false>   // outcomes (consecutive effects) per unit: 4 (16 warps/SM) or 2 (24 warps/SM)
-__global__ void __launch_bounds__(AT_WARPS * 32, (NO == 4 ? 2 : 3))
+// Variants of this kernel that were built, measured on the BASELINE layout and REMOVED because they lost (round 1,
+// profiles/README.md): interleaved fragments with 128-bit gathers / 256-bit stores (+3.5 %), a cp.async.bulk (TMA)
+// store epilogue through conflict-free shared staging (+5 %), CTA-level unit ranges for L1 reuse of the H gathers (+1 %),
+// 2-outcome units at 24 warps/SM (+2 %), a cp.async gather ring (+13 %), next-chunk look-ahead (+6 %).
+// dynamic smem: AT_WARPS * 5 * 16 doubles (SPAM slots), then the column-map fragments and the SPAM lists.
+constexpr int AT_NO = 4;   // outcomes (consecutive effects) per unit
+__global__ void __launch_bounds__(AT_WARPS * 32, 2)
 k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
-                 const uint2* __restrict__ uidx, unsigned* __restrict__ counter, int dbg,
-                 int chunk, int rsub)
+                 const uint2* __restrict__ uidx, unsigned* __restrict__ counter, int chunk)
 {
-    // Work hand-out.  rsub == 0: every warp takes `chunk` consecutive units per global atomic.  rsub > 0: the CTA takes a RANGE
-    // of rsub sub-chunks per global atomic and its warps take the sub-chunks of the range one by one from a shared-memory
-    // counter, so that the 8 warps of a CTA work on neighbouring circuits at the same time: the units are in suffix order,
-    // neighbouring circuits (same germ power and measurement fiducial, different preparation fiducial) gather the SAME
-    // rows of the backward table H, and those gathers then hit in L1 instead of going to L2 once per circuit.
-    __shared__ unsigned long long s_pack;                               // (first sub-chunk of the range) << 32 | next sub-chunk
+    constexpr int NO = AT_NO;
     extern __shared__ __align__(128) unsigned char smb[];
     constexpr int SPS = (1 + NO) * 16;                                  // per-warp slot: s_L row + the e_0 rows of the unit's outcomes
     double* spam_stage = reinterpret_cast<double*>(smb);                // [AT_WARPS][SPS]
-    double* stage_all = spam_stage + AT_WARPS * SPS;                    // [AT_WARPS][NO][256] (TMA only)
-    int2* cm_s = reinterpret_cast<int2*>(stage_all + (TMA ? AT_WARPS * NO * 256 : 0));   // [n_ops*4][32]
+    int2* cm_s = reinterpret_cast<int2*>(spam_stage + AT_WARPS * SPS);  // [n_ops*4][32]
     int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
     int* spamw_s = spamc_s + D16_SPAM_MAX;
-    int* gbase_s = spamw_s + D16_SPAM_MAX;                              // [n_ops] first column of a gate's block if the 256 columns are
-                                                                        // consecutive and 16-byte aligned in every row, else -1 (TMA only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (TMA) {
-        for (int g = threadIdx.x; g < a.n_ops; g += blockDim.x) {
-            const int* cp = args.colmap + g * 256;
-            int gb = cp[0];
-            bool ok = gb >= 0 && (gb & 1) == 0 && (args.ld & 1) == 0 && ((uintptr_t)args.J & 15) == 0;
-            for (int k = 1; k < 256 && ok; ++k) ok = cp[k] == gb + k;
-            gbase_s[g] = ok ? gb : -1;
-        }
-    }
     for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
         const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
-        if (W256) {
-            // tile = 2*h + z: z = 0 -> .x = first of the 4 consecutive columns of block row 2*mrow + h (or -1), .y unused
-            const int i = 2 * (l >> 2) + (tile >> 1), j0 = 4 * (l & 3);
-            const int* cp = args.colmap + g * 256 + i * 16 + j0;
-            int2 cc = make_int2(-1, -1);
-            if ((tile & 1) == 0 && cp[0] >= 0 && (cp[0] & 3) == 0 && (args.ld & 3) == 0 && cp[1] == cp[0] + 1 && cp[2] == cp[0] + 2 &&
-                cp[3] == cp[0] + 3) cc.x = cp[0];
-            cm_s[idx] = cc;
-            continue;
-        }
         const int i = 8 * (tile >> 1) + (l >> 2), jc = 8 * (tile & 1) + 2 * (l & 3);
         int2 cc = *reinterpret_cast<const int2*>(args.colmap + g * 256 + i * 16 + jc);
         if (cc.y == cc.x + 1 && cc.x >= 0 && ((cc.x | (int)(args.ld & 1)) & 1) == 0) cc.y = -2;
@@ -394,24 +302,10 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     }
     const int n_spam_s = args.n_spam < D16_SPAM_MAX ? args.n_spam : D16_SPAM_MAX;
     for (int tt = threadIdx.x; tt < n_spam_s; tt += blockDim.x) { spamc_s[tt] = args.spam_col[tt]; spamw_s[tt] = args.spam_w[tt]; }
-    if (rsub > 0 && threadIdx.x == 0) s_pack = (unsigned long long)(atomicAdd(counter, 1u) * (unsigned)rsub) << 32;
     __syncthreads();
     auto next_chunk = [&]() -> int {                                    // first unit of this warp's next chunk (all lanes)
         unsigned sc = 0;
-        if (lane == 0) {
-            if (rsub <= 0) sc = atomicAdd(counter, 1u);
-            else for (;;) {
-                const unsigned long long old = atomicAdd(&s_pack, 1ull);
-                const unsigned kk = (unsigned)old, base = (unsigned)(old >> 32);
-                if (kk < (unsigned)rsub) { sc = base + kk; break; }
-                if (kk == (unsigned)rsub) {                              // first warp past the end: fetch the next range, take its sub-chunk 0
-                    const unsigned nb = atomicAdd(counter, 1u) * (unsigned)rsub;
-                    atomicExch(&s_pack, ((unsigned long long)nb << 32) | 1ull);
-                    sc = nb; break;
-                }
-                while ((unsigned)(*(volatile unsigned long long*)&s_pack >> 32) == base) __nanosleep(20);   // another warp is fetching
-            }
-        }
+        if (lane == 0) sc = atomicAdd(counter, 1u);
         sc = __shfl_sync(0xffffffffu, sc, 0);
         const long long u = (long long)sc * chunk;
         return u < (long long)n_units ? (int)u : n_units;
@@ -419,45 +313,31 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
 
     // L2 policies of the gathers: S rows (24 MB, reused during the whole kernel) evict_last; H rows (78 MB, consumed front to back
     // in unit order) no hint -- evict_last on both was measured 4 % slower (0.858 vs 0.825 ms), evict_first on H 10 % slower
-    uint64_t pol_keep, pol_stream = 0;
+    uint64_t pol_keep;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-    if (TMA) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
     auto ldk = [&](const double* p) -> double {
         double v; asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol_keep)); return v; };
-    auto ldk2 = [&](const double* p) -> double2 {
-        double2 v; asm volatile("ld.global.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol_keep)); return v; };
     auto ldn = [](const double* p) -> double { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; };
-    auto ldn2 = [](const double* p) -> double2 { double2 v; asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p)); return v; };
     // one group of 4 steps: fr[0..1] = B elements (N tiles 0, 1), fr[2+2o], fr[3+2o] = A elements of outcome o (M tiles 0, 1)
     auto fetch = [&](const double* sp, const double* hp, double* fr) {
-        if (W256) {
-            const double2 sv = ldk2(sp); fr[0] = sv.x; fr[1] = sv.y;
+        fr[0] = ldk(sp); fr[1] = ldk(sp + 8);
 #pragma unroll
-            for (int o = 0; o < NO; ++o) { const double2 hv = ldn2(hp + 16 * o); fr[2 + 2 * o] = hv.x; fr[3 + 2 * o] = hv.y; }
-        } else {
-            fr[0] = ldk(sp); fr[1] = ldk(sp + 8);
-#pragma unroll
-            for (int k = 0; k < 2 * NO; ++k) fr[2 + k] = ldn(hp + 8 * k);
-        }
+        for (int k = 0; k < 2 * NO; ++k) fr[2 + k] = ldn(hp + 8 * k);
     };
     const unsigned mrow = lane >> 2, q = lane & 3;
     const unsigned ne16 = (unsigned)a.n_eff * 16u;
     const double* E = m.M + m.off_eff;
-    const double* Sb = t.S + (W256 ? 2 * mrow : mrow);
-    const double* Hb = t.H + (W256 ? 2 * mrow : mrow);
+    const double* Sb = t.S + mrow;
+    const double* Hb = t.H + mrow;
 
-    long long pr_pro = 0, pr_grp = 0, pr_epi = 0; const long long pr_t0 = PROF ? clock64() : 0;   // dev knob B200_CHAIN_PROF
     for (;;) {
-        const long long tq0 = PROF ? clock64() : 0;
         const int u0 = next_chunk();
         if (u0 >= n_units) break;
         const int u1 = (u0 + chunk < n_units) ? u0 + chunk : n_units;
         // ---- chunk prologue: the only exposed latency ----
         uint4 ra = __ldg(reinterpret_cast<const uint4*>(units + u0));        // el[4]
         uint4 rb = __ldg(reinterpret_cast<const uint4*>(units + u0) + 1);    // off, g_ng, f_end, b_end
-        // Index stream: every lane loads its own entry (q) of the group after next, used one iteration later.  (Loading it 32
-        // entries at a time into register windows and handing the entries out by shuffle -- 8..16 iterations of lead -- was
-        // measured 16 % SLOWER, 0.968 vs 0.832 ms: the extra shuffles and window registers cost more than the latency hidden.)
+        // Index stream: every lane loads its own entry (q) of the group after next, used one iteration later.
         const uint2* ip = uidx + rb.x + q;
         uint2 nd1 = __ldg(ip + 4);
         double r[2 + 2 * NO];
@@ -466,14 +346,12 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             fetch(Sb + nd0.x, Hb + nd0.y, r);
         }
         ip += 8;
-        if (PROF) pr_pro += clock64() - tq0;
         for (int u = u0; u < u1; ++u) {
-            const long long tq1 = PROF ? clock64() : 0;
             // next unit's record (needed only after this unit's groups)
             const int un = (u + 1 < u1) ? u + 1 : u;
             const uint4 ran = __ldg(reinterpret_cast<const uint4*>(units + un));
             const uint4 rbn = __ldg(reinterpret_cast<const uint4*>(units + un) + 1);
-            const int g = (int)(rb.y & 0xffu), ngroups = (dbg == 1) ? 0 : (int)((rb.y >> 8) & 0x3fffu);
+            const int g = (int)(rb.y & 0xffu), ngroups = (int)((rb.y >> 8) & 0x3fffu);
             if (g == 0) {
                 // gate-0 unit: it also writes the SPAM columns / probabilities, from s_L and the e_0 rows.  They are copied to a
                 // shared slot NOW (cp.async, no registers) so that their latency hides behind the group loop.
@@ -505,17 +383,13 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 for (int k = 0; k < 2 + 2 * NO; ++k) r[k] = n[k];
                 nd1 = nd2;
             }
-            const long long tq2 = PROF ? clock64() : 0;
-            if (PROF) pr_grp += tq2 - tq1;
-            if (dbg == 2) { if (acc[0][0] + acc[NO - 1][1] == 1.2345e300) args.J[0] = 1.0; ra = ran; rb = rbn; continue; }
             // ---------------- epilogue: the finished 16x16 blocks are Jacobian entries ----------------
             const int2* cm = cm_s + g * 128 + lane;
             int2 cc[4];
 #pragma unroll
             for (int tile = 0; tile < 4; ++tile) cc[tile] = cm[tile * 32];
             const int els[4] = {(int)ra.x, (int)ra.y, (int)ra.z, (int)ra.w};
-            const bool fast = W256 ? __all_sync(0xffffffffu, (cc[0].x >= 0) & (cc[2].x >= 0))
-                                   : __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
+            const bool fast = __all_sync(0xffffffffu, (cc[0].y == -2) & (cc[1].y == -2) & (cc[2].y == -2) & (cc[3].y == -2));
             if (args.row_scale) {          // objective-function row scaling fused into the epilogue
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
@@ -524,57 +398,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                     for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
                 }
             }
-            const int gb_tma = TMA ? gbase_s[g] : -1;
-            if (TMA && !W256 && gb_tma >= 0) {
-                double* stg = stage_all + warp * (NO * 256);
-                if (lane < NO) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous unit's blocks have left the staging
-                __syncwarp();
-                const bool odd = (mrow & 1u) != 0u;
-                const int ca = odd ? 8 + 2 * (int)q : 2 * (int)q, cb = odd ? 2 * (int)q : 8 + 2 * (int)q;
-#pragma unroll
-                for (int o = 0; o < NO; ++o)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        double* row = stg + o * 256 + (8 * h + (int)mrow) * 16;
-                        const double2 z0 = make_double2(acc[o][4 * h], acc[o][4 * h + 1]), z1 = make_double2(acc[o][4 * h + 2], acc[o][4 * h + 3]);
-                        *reinterpret_cast<double2*>(row + ca) = odd ? z1 : z0;
-                        *reinterpret_cast<double2*>(row + cb) = odd ? z0 : z1;
-                    }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane < NO) {
-                    const int my_el = lane == 0 ? els[0] : lane == 1 ? els[1] : lane == 2 ? els[2] : els[3];
-                    if (my_el >= 0) {
-                        double* dst = args.J + (int64_t)my_el * args.ld + gb_tma;
-                        const unsigned src = (unsigned)__cvta_generic_to_shared(stg + lane * 256);
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], 2048, %2;"
-                                     ::"l"(dst), "r"(src), "l"(pol_stream) : "memory");
-                    }
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-            } else if (W256) {
-                if (fast) {
-#pragma unroll
-                    for (int o = 0; o < NO; ++o) {
-                        if (els[o] >= 0) {
-                            double* Jr = args.J + (int64_t)els[o] * args.ld;
-                            st256_cs(Jr + cc[0].x, acc[o][0], acc[o][2], acc[o][1], acc[o][3]);
-                            st256_cs(Jr + cc[2].x, acc[o][4], acc[o][6], acc[o][5], acc[o][7]);
-                        }
-                    }
-                } else {                       // arbitrary column map: scalar stores through the map itself
-                    for (int o = 0; o < NO; ++o) {
-                        if (els[o] < 0) continue;
-                        double* Jr = args.J + (int64_t)els[o] * args.ld;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int* cp = args.colmap + g * 256 + (2 * (int)mrow + h) * 16 + 4 * (int)q;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) { const int col = __ldg(cp + k); if (col >= 0) Jr[col] = acc[o][4 * h + 2 * (k & 1) + (k >> 1)]; }
-                        }
-                    }
-                }
-            } else if (fast) {
+            if (fast) {
 #pragma unroll
                 for (int o = 0; o < NO; ++o) {
                     if (els[o] >= 0) {
@@ -604,9 +428,8 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
             }
             if (g == 0) {
                 // SPAM / unmapped columns and probabilities of the group's outcomes.  The rows they come from (s_L and e_0 of every
-                // outcome) are requested all at once -- the unit record carries their node ids -- and handed around with
-                // shuffles (the first version chased circuit-group record -> row -> element: 12 dependent round trips per
-                // gate-0 unit, 20 % of the kernel's stall samples).
+                // outcome) were requested at the top of the unit -- the unit record carries their node ids -- and are handed around
+                // with shuffles.
                 const int l16 = lane & 15;
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
@@ -644,14 +467,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 }
             }
             ra = ran; rb = rbn;
-            if (PROF) pr_epi += clock64() - tq2;
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this thread are complete
-    if (PROF && t.prof && lane == 0) {
-        atomicAdd(t.prof + 8, (unsigned long long)pr_pro); atomicAdd(t.prof + 9, (unsigned long long)pr_grp);
-        atomicAdd(t.prof + 10, (unsigned long long)pr_epi); atomicAdd(t.prof + 11, (unsigned long long)(clock64() - pr_t0));
-    }
 }
-

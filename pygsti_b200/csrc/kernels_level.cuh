@@ -16,7 +16,6 @@
 //   k_level_probs<D>: p = E . s_final (one warp per circuit), final state in buffer (L & 1).
 #pragma once
 #include "common.cuh"
-#include "kernels_d16.cuh"   // dmma884
 
 struct LevelTile { uint32_t first; uint16_t count; uint16_t gate; };   // entries [first, first+count) of lvl_circ
 

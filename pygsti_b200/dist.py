@@ -93,6 +93,101 @@ def shard_tables(t: AtomTables, rank: int, world: int, rows=None):
     return local, glob
 
 
+def expanded_rows(t: AtomTables):
+    """(prep [n_rows], list of full op sequences) with every cache link followed."""
+    slot_row = {}
+    prep = np.empty(t.n_rows, dtype=np.int32)
+    seqs = [None] * t.n_rows
+    for k in range(t.n_rows):
+        rem = t.row_ops[t.row_ptr[k]:t.row_ptr[k + 1]]
+        if t.row_istart[k] >= 0:
+            src = slot_row[int(t.row_istart[k])]
+            prep[k] = prep[src]
+            seqs[k] = np.concatenate([seqs[src], rem]) if len(rem) else seqs[src]
+        else:
+            prep[k] = t.row_prep[k]
+            seqs[k] = rem
+        if t.row_icache[k] >= 0:
+            slot_row[int(t.row_icache[k])] = k
+    return prep, seqs
+
+
+class ShardPlan:
+    """A layout atom cut into ``world`` shards the way the reference cuts a layout into atoms
+    (``MapCOPALayout`` with ``num_atoms = world``: pygsti/layouts/maplayout.py:296-303 -> ``PrefixTable.find_splitting_new``,
+    prefixtable.py:154-290): rows are ordered by circuit prefix (prep, ops...) and cut into CONTIGUOUS blocks, so that the
+    circuits of a shard keep sharing their prefixes, balanced by an HBM-write + gather work estimate.  Like the reference's
+    atoms, every shard owns a contiguous ``element_slice`` of the sharded layout's element axis
+    (distlayout.py:326-415): shard r owns global rows [r * slot, r * slot + n_local[r]) where ``slot`` = the largest shard
+    rounded up (equal slots make the exchange ONE in-place ncclAllGather; the <= few padding rows at the end of a slot
+    belong to no element).  ``to_original[r]`` maps a shard's local element index to the element index of the un-sharded
+    atom, ``position`` is the inverse map (original element -> row of the sharded element axis)."""
+
+    def __init__(self, t: AtomTables, world: int, work_per_outcome=77.0):
+        self.world = int(world)
+        prep, seqs = expanded_rows(t)
+        order = sorted(range(t.n_rows), key=lambda k: (int(prep[k]), seqs[k].tolist()))
+        nout = (t.out_ptr[1:] - t.out_ptr[:-1]).astype(np.float64)
+        L = np.array([len(s) for s in seqs], dtype=np.float64)
+        work = nout * (work_per_outcome + L)              # stores ~ outcomes, table gathers ~ outcomes x depth
+        cw = np.cumsum(work[order]) if t.n_rows else np.zeros(0)
+        total = cw[-1] if t.n_rows else 0.0
+        cuts = [0]
+        for r in range(1, self.world):
+            cuts.append(int(np.searchsorted(cw, total * r / self.world, side="left")))
+        cuts.append(t.n_rows)
+        cuts = np.maximum.accumulate(np.asarray(cuts))
+        self.rows = [np.asarray(order[cuts[r]:cuts[r + 1]], dtype=np.int64) for r in range(self.world)]
+        self.tables, self.to_original = [], []
+        for r in range(self.world):
+            rows = self.rows[r]
+            ops = [seqs[k] for k in rows]
+            ptr = np.zeros(len(rows) + 1, np.int64)
+            if len(rows):
+                ptr[1:] = np.cumsum([len(o) for o in ops])
+            oe = [t.out_eff[t.out_ptr[k]:t.out_ptr[k + 1]] for k in rows]
+            ol = [t.out_el[t.out_ptr[k]:t.out_ptr[k + 1]] for k in rows]
+            optr = np.zeros(len(rows) + 1, np.int64)
+            if len(rows):
+                optr[1:] = np.cumsum([len(o) for o in oe])
+            glob = np.concatenate(ol).astype(np.int64) if len(rows) else np.zeros(0, np.int64)
+            n_local = int(glob.shape[0])
+            self.tables.append(AtomTables(
+                dim=t.dim, n_ops=t.n_ops, n_rho=t.n_rho, n_eff=t.n_eff, n_elements=n_local, cache_size=0,
+                row_dest=np.arange(len(rows), dtype=np.int32), row_istart=np.full(len(rows), -1, np.int32),
+                row_icache=np.full(len(rows), -1, np.int32), row_prep=prep[rows].astype(np.int32),
+                row_ptr=ptr.astype(np.int32),
+                row_ops=(np.concatenate(ops).astype(np.int32) if len(rows) else np.zeros(0, np.int32)),
+                out_ptr=optr.astype(np.int32),
+                out_eff=(np.concatenate(oe).astype(np.int32) if len(rows) else np.zeros(0, np.int32)),
+                out_el=np.arange(n_local, dtype=np.int32)))
+            self.to_original.append(glob)
+        self.n_local = [tb.n_elements for tb in self.tables]
+        self.n_elements = int(t.n_elements)
+        self.slot = max(1, -(-max(self.n_local) // 8) * 8)        # rows per slot (multiple of 8 rows)
+        self.n_rows_padded = self.slot * self.world
+        self.position = np.full(self.n_elements, -1, dtype=np.int64)
+        for r in range(self.world):
+            self.position[self.to_original[r]] = r * self.slot + np.arange(self.n_local[r])
+
+    def element_slice(self, rank):
+        return slice(rank * self.slot, rank * self.slot + self.n_local[rank])
+
+
+def allgather_slots(full, group=None):
+    """ONE in-place all-gather over equal slots: ``full`` is the (world * slot, ...) array of the sharded layout, of which
+    this rank has filled its own slot ``full[rank * slot:(rank + 1) * slot]``; on return every rank holds every slot.
+    NCCL: a single ncclAllGather with the send buffer inside the receive buffer (no staging, no copies); gloo on CPU.
+    The analogue of ``gather_local_array`` -> ``Allgatherv`` (pygsti/baseobjs/resourceallocation.py:323-329)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    slot = full.shape[0] // world
+    assert slot * world == full.shape[0] and full.is_contiguous()
+    dist.all_gather_into_tensor(full, full[rank * slot:(rank + 1) * slot], group=group)
+    return full
+
+
 def allgather_rows(local, global_index, n_total, group=None):
     """All-gather row shards of a (n_local, ...) torch tensor into the full (n_total, ...) tensor on every rank.
 

@@ -89,12 +89,11 @@ def test_probs_d256(gpu_ctx):
     assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
 
 
-@pytest.mark.parametrize("mode", ["fused", "2p", "trie", "trie:B200_ACC_CPASYNC=1", "trie:B200_UNIT_OUTCOMES=2",
-                                  "trie:B200_ACC_CPASYNC=1,B200_UNIT_OUTCOMES=2", "trie:B200_ACC_ST256=1"])
+@pytest.mark.parametrize("mode", ["trie", "generic"])
 def test_every_d16_code_path(mode):
-    """The d = 16 Jacobian implementations (B200_D16_MODE; for the trie path also the accumulate-kernel variants:
-    register pipeline (default) / cp.async ring, 4 / 2 outcomes per unit, 256-bit stores) give the same answers; run in
-    a subprocess because the knobs are latched at first use."""
+    """The two d = 16 Jacobian implementations -- the trie kernels (default) and the generic W . D kernels that take over
+    for layouts the trie path rejects (B200_D16_MODE=generic forces them) -- give the same answers; run in a subprocess
+    because the knob is latched at first use."""
     code = r'''
 import sys, numpy as np
 sys.path.insert(0, %r)
