@@ -2,27 +2,29 @@
 """
 bench.py -- BASELINE.json metric: circuit-outcomes/sec of bulk_fill_dprobs (Jacobian + probabilities).
 
-Workload (configs[1] of BASELINE.json, the configuration the metric is quoted on): smq2Q_XYCNOT `full`
-model (d = 16, Np = 1360), long-sequence GST design maxL = 128 (`lite=False`): 68 335 circuits,
-273 340 circuit outcomes.  The layout tables and model tensors were produced by the reference itself
-(tests/golden/make_golden.py c2_full_layout) and are read from tests/golden/c2_full_layout.npz, so nothing
-here needs pyGSTi or /root/reference at run time.
+Headline workload (configs[1] of BASELINE.json, the configuration the metric is quoted on): smq2Q_XYCNOT `full`
+model (d = 16, Np = 1360), long-sequence GST design maxL = 128 (`lite=False`): 68 335 circuits, 273 340 circuit
+outcomes.  The layout tables and model tensors were produced by the reference itself (tests/golden/make_golden.py
+c2_full_layout) and are read from tests/golden/c2_full_layout.npz: nothing here needs pyGSTi or /root/reference.
 
-A "step" = one bulk_fill_dprobs over the whole layout = one Jacobian (273 340 x 1360 f64 = 2.97 GB) plus
-the probability vector.
+A "step" = one bulk_fill_dprobs over the WHOLE layout = one Jacobian (273 340 x 1360 f64 = 2.97 GB) + the probabilities.
 
-  value   : outcomes/s with inputs resident in HBM and the Jacobian left in HBM (device-timed, CUDA events on
-            the launching stream, max over ranks)
-  e2e     : the same metric through the C ABI with HOST buffers: every step uploads the model tensors
-            (b200_atom_set_model) and lands Jacobian + probs in (pinned) host memory (b200_fill_dprobs)
-  --impl reference : the reference's own CPU algorithm for this path -- forward-difference Jacobian, one
-            prefix-table pass per parameter (mapforwardsim_calc_densitymx.pyx:290-383) -- executed by the
-            reference's own C++ reps (oracle/_ref) on all host cores, on a bounded sample of parameters and
-            extrapolated by (Np+1)/(n+1) (every parameter is an identical full table pass).
+N > 1 (torchrun, one rank per GPU): STRONG scaling of ONE layout.  The layout is cut into N shards the way the reference
+cuts it into atoms (pygsti_b200.dist.ShardPlan; reference: maplayout.py:296-303, distlayout.py:326-415); each rank fills
+its shard into its slot of the sharded element axis and the timed step ends after ONE in-place NCCL all-gather of the
+device-resident Jacobian and probability shards (the reference's gather_local_array -> Allgatherv,
+resourceallocation.py:323-329).  `value` = all outcomes / max-over-ranks device time.  The line also carries
+  * `multi_gpu.fill_only` / `multi_gpu.allgather` : the two halves of the step, timed separately;
+  * `jtj` : the exchange the optimizer actually needs (fill_jtj / fill_jtf, distlayout.py:1220-1359): per-rank J^T J, J^T f of
+    the shard (hand-written DMMA kernel, no cuBLAS) + ONE all-reduce of Np^2 + Np doubles -- the Jacobian never moves;
+  * `e2e` : the same step through the C ABI with HOST buffers: model upload (H2D) + shard fill + D2H of every rank's rows
+    into ONE host array (POSIX shared memory, page-locked by every rank; N PCIe links in parallel);
+  * `extra_configs` : BASELINE configs 3 (d = 64 Jacobian, sharded like the headline), 4 (CPTPLND Hessian rectangle) and
+    5 (d = 256 probabilities) with their own roofline fraction and CPU baseline.
 
-Multi-GPU (torchrun): the path shards over independent circuits with no data-path collective
-(SURVEY.md 8e); every rank simulates its own replica of the layout ("weak" scaling) and `value` is the
-whole-job aggregate.
+--impl reference : the reference's own CPU algorithm for the headline path -- forward-difference Jacobian, one prefix-table
+pass per parameter (mapforwardsim_calc_densitymx.pyx:290-383) -- executed by the reference's own C++ reps (oracle/_ref)
+on all host cores, on a bounded sample of parameters and extrapolated by (Np+1)/(n+1).
 """
 import argparse
 import json
@@ -45,6 +47,7 @@ METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel k_accum_trie_d16 (ncu --set full,
 # profiles/r01_accum_final_ncu_raw.csv): 0.165 GB read + 2.929 GB written
 NCU_TRAFFIC_BYTES = 3.094e9
+DMMA_PEAK_TFLOPS = 37.2     # measured on this part with tools/ubench_fp64.cu (mma.sync m8n8k4 f64); DFMA 36.6
 
 
 def _peaks():
@@ -111,6 +114,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baselines (the reference's algorithm on the host cores; oracle/ is executed ONLY here and in --impl reference)
+# ------------------------------------------------------------------------------------------------------------------
 def cpu_reference_sample(case, threads, core_seconds=20.0):
     """Reference algorithm (FD Jacobian, pyx:290-383) on the host cores; returns dict for the JSON line.
 
@@ -142,6 +148,29 @@ def cpu_reference_sample(case, threads, core_seconds=20.0):
             "seconds_full_jacobian_extrapolated": full}
 
 
+def _oracle(prefer_ref=True):
+    from oracle import oracle_c
+    oracle_c.build()
+    kind = "reference" if (prefer_ref and os.path.exists(oracle_c.LIB_REF)) else "port"
+    return oracle_c.Oracle(kind), kind, oracle_c
+
+
+def cpu_fd_jacobian_sample(t_sub, G, rho, E, D, threads, n_params_sample):
+    """FD Jacobian of the reference on a sub-layout and a block of parameters; returns (outcomes/s extrapolated to all
+    parameters, description)."""
+    orc, kind, oc = _oracle()
+    csc = oc.csc_of(D)
+    Np = D.n_params
+    t0 = time.time(); orc.mapfill_probs(t_sub, G, rho, E); t_base = time.time() - t0
+    n = min(Np, max(threads, n_params_sample // threads * threads))
+    t0 = time.time()
+    orc.dprobs_fd(t_sub, G, rho, E, D, p_lo=0, p_hi=n, eps=1e-7, n_threads=threads, csc=csc)
+    dt = max(time.time() - t0 - t_base, 1e-6)
+    full = t_base + dt * Np / n
+    return t_sub.n_elements / full, kind, ("%d-circuit sample: base pass %.3f s + %d of %d FD parameter passes in %.2f s on %d "
+                                           "threads, extrapolated x Np/n" % (t_sub.n_rows, t_base, n, Np, dt, threads))
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -159,7 +188,7 @@ def run_reference_arm(args, rank, world):
     cb = dict(vals[-1]); cb["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "circuit-outcomes/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * case.n_elements / v, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * case.n_elements / v, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (reference-generated layout + depolarized target model)",
             "config": {"workload": WORKLOAD_DESC, "algorithm": "reference Map simulator: forward-difference Jacobian "
                        "(eps=1e-7), one prefix-table pass per parameter, prefix cache unlimited",
@@ -170,6 +199,506 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+class Dist:
+    """The little of torch.distributed the bench needs (identity at world size 1)."""
+
+    def __init__(self, torch, dist, world, rank):
+        self.torch, self.dist, self.world, self.rank = torch, dist, world, rank
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def maxv(self, xs):
+        t = self.torch.tensor([float(x) for x in xs], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def bcast_obj(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+
+def timed(D, stream, fn, steps, warmup):
+    """ms per call of fn(): `warmup` untimed calls, then exactly `steps` calls bracketed by barrier + synchronize,
+    CUDA events on the launching stream, max over ranks."""
+    torch = D.torch
+    for _ in range(warmup):
+        fn()
+    D.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    D.barrier()
+    return D.max(e0.elapsed_time(e1)) / steps
+
+
+class HostArray:
+    """ONE host array for all ranks: POSIX shared memory created by rank 0, mapped by every rank, and page-locked
+    (cudaHostRegister) so that every GPU DMAs its rows straight into it.  Falls back to a private pinned buffer per rank
+    (the rows still land in page-locked host memory, but not in one array) if shared memory is unavailable."""
+
+    def __init__(self, D, engine, n_rows, n_cols, tag):
+        from multiprocessing import shared_memory
+        self.D = D
+        self.shm = None
+        nbytes = max(int(n_rows) * int(n_cols) * 8, 8)
+        name = None
+        if D.world > 1:
+            if D.rank == 0:
+                try:
+                    st = os.statvfs("/dev/shm")                      # a tmpfs smaller than the array would SIGBUS on first touch
+                    if st.f_bavail * st.f_frsize > nbytes + (256 << 20):
+                        self.shm = shared_memory.SharedMemory(create=True, size=nbytes)
+                        name = self.shm.name
+                except Exception:
+                    name = None
+            name = D.bcast_obj(name)
+            if name is not None and D.rank != 0:
+                try:
+                    self.shm = shared_memory.SharedMemory(name=name)
+                except Exception:
+                    self.shm = None
+            ok = D.max(0.0 if self.shm is not None else 1.0) == 0.0
+            if not ok and self.shm is not None:
+                self._close()
+        if self.shm is not None:
+            self.arr = np.ndarray((n_rows, n_cols), dtype=np.float64, buffer=self.shm.buf)
+            self.kind = "one POSIX shared-memory array mapped and page-locked by every rank"
+            from pygsti_b200 import _lib
+            import ctypes as C
+            self._lib = _lib.load()
+            self._ptr = C.c_void_p(self.arr.ctypes.data)
+            _lib.check(self._lib.b200_host_register(self._ptr, nbytes))
+        else:
+            self.arr = engine.pinned_empty((n_rows, n_cols))
+            self.kind = "pinned host array" if D.world == 1 else "private pinned buffer per rank (shared memory unavailable)"
+
+    def _close(self):
+        try:
+            self.shm.close()
+            if self.D.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+        self.shm = None
+
+    def close(self):
+        if self.shm is not None:
+            try:
+                self._lib.b200_host_unregister(self._ptr)
+            except Exception:
+                pass
+            self.arr = None
+            self.D.barrier()
+            self._close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def bench_c2(args, D, engine, stream, ctx, sampler):
+    """Headline: BASELINE config 2, sharded over the ranks."""
+    torch, dist = D.torch, D.dist
+    from pygsti_b200.fixtures import Case
+    from pygsti_b200 import dist as bd
+    world, rank = D.world, D.rank
+    case = Case(WORKLOAD)
+    a = case.atoms[0]
+    nE, Np = case.n_elements, case.num_params
+    plan = bd.ShardPlan(a["tables"], world)
+    slot, n_loc = plan.slot, plan.n_local[rank]
+    atom = ctx.upload_atom(plan.tables[rank])
+    atom.set_model(a["G"], a["rho"], a["E"])
+    atom.set_derivs(a["D"])
+    info = atom.info()
+
+    J = torch.empty((plan.n_rows_padded, Np), dtype=torch.float64, device="cuda")     # the sharded layout's element axis
+    P = torch.empty(plan.n_rows_padded, dtype=torch.float64, device="cuda")
+    J.zero_(); P.zero_()
+    Jmine, Pmine = J[rank * slot:(rank + 1) * slot], P[rank * slot:(rank + 1) * slot]
+
+    def fill():
+        atom.fill_dprobs_dev(Jmine.data_ptr(), Np, Pmine.data_ptr())
+
+    def gather():
+        if world > 1:
+            dist.all_gather_into_tensor(J, Jmine)
+            dist.all_gather_into_tensor(P, Pmine)
+
+    def step():
+        fill(); gather()
+
+    # ---------------- the timed region (value) ----------------
+    for _ in range(args.warmup):
+        step()
+    D.barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = ctx.launch_count
+    D.barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    D.barrier()
+    t_wall1 = time.time()
+    launches = (ctx.launch_count - l0) + (2 * args.steps if world > 1 else 0)     # + the two NCCL all-gather kernels per step
+    ms_per_step = D.max(e0.elapsed_time(e1)) / args.steps
+    value = nE / (ms_per_step * 1e-3)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # parity of what was just timed: every rank holds the whole sharded Jacobian
+    pos = plan.position
+    st = int(case["probs_map_stride"])
+    p_host = P.cpu().numpy()[pos]
+    assert np.max(np.abs(p_host[::st] - case["probs_map_sample"])) <= 1e-10
+    rows = torch.as_tensor(pos[case["dprobs_matrix_sample_elements"]], device="cuda")
+    jerr = float(np.max(np.abs(J[rows].cpu().numpy() - case["dprobs_matrix_sample_rows"])))
+    assert jerr <= 1e-10, jerr
+
+    # ---------------- the two halves, separately ----------------
+    short = max(5, min(args.steps, 20))
+    ms_fill = timed(D, stream, fill, short, 1)
+    ms_gather = timed(D, stream, gather, short, 1) if world > 1 else 0.0
+
+    # ---------------- dominant kernel alone (roofline.achieved): CUDA events around the phases ----------------
+    ctx.phase_timing(True)
+    for _ in range(short):
+        fill()
+    (ms_prep, ms_chains, ms_accum), n_ph = ctx.phase_ms()
+    ctx.phase_timing(False)
+    ms_prep, ms_chains, ms_accum = D.maxv([ms_prep / max(n_ph, 1), ms_chains / max(n_ph, 1), ms_accum / max(n_ph, 1)])
+
+    # ---------------- J^T J + J^T f: per-rank DMMA SYRK of the shard + ONE all-reduce ----------------
+    rs = torch.from_numpy(np.random.default_rng(0).uniform(0.5, 1.5, nE)[plan.to_original[rank]]).cuda()
+    fv = torch.from_numpy(np.random.default_rng(1).standard_normal(nE)[plan.to_original[rank]]).cuda()
+    jj = torch.empty(Np * Np + Np, dtype=torch.float64, device="cuda")          # [J^T J | J^T f]: one buffer, one collective
+
+    def jtj_local():
+        atom.jtj_dev(jj.data_ptr(), rs.data_ptr(), fv.data_ptr(), jj.data_ptr() + Np * Np * 8)
+
+    def jtj_step():
+        jtj_local()
+        if world > 1:
+            dist.all_reduce(jj)
+
+    ms_jtj = timed(D, stream, jtj_step, max(3, min(args.steps, 10)), 2)
+    ms_jtj_local = timed(D, stream, jtj_local, max(3, min(args.steps, 10)), 1)
+    # parity: against the same product formed from the gathered, scaled Jacobian by a library GEMM (outside any timed region)
+    if world > 1:
+        rs_all = torch.zeros(plan.n_rows_padded, dtype=torch.float64, device="cuda"); fv_all = torch.zeros_like(rs_all)
+        rs_all[rank * slot:rank * slot + n_loc] = rs; fv_all[rank * slot:rank * slot + n_loc] = fv
+        dist.all_reduce(rs_all); dist.all_reduce(fv_all)
+    else:
+        rs_all = torch.zeros(plan.n_rows_padded, dtype=torch.float64, device="cuda"); fv_all = torch.zeros_like(rs_all)
+        rs_all[:n_loc] = rs; fv_all[:n_loc] = fv
+    step()
+    jtj_step()
+    torch.cuda.synchronize()
+    blk = 32768
+    ref = torch.zeros((Np, Np), dtype=torch.float64, device="cuda"); reff = torch.zeros(Np, dtype=torch.float64, device="cuda")
+    for r0 in range(0, plan.n_rows_padded, blk):
+        Js = J[r0:r0 + blk] * rs_all[r0:r0 + blk, None]
+        ref += Js.T @ Js; reff += Js.T @ fv_all[r0:r0 + blk]
+    jtj_err = float((jj[:Np * Np].reshape(Np, Np) - ref).abs().max() / ref.abs().max())
+    jtf_err = float((jj[Np * Np:] - reff).abs().max() / reff.abs().max())
+    assert jtj_err <= 1e-11 and jtf_err <= 1e-11, (jtj_err, jtf_err)
+    del ref, reff, rs_all, fv_all
+    jtj_flops = float(nE) * Np * (Np + 1)                      # the lower triangle of J^T J over all elements (2 flop per MAC)
+    ms_syrk = max(ms_jtj_local - ms_fill, 1e-6)
+
+    # ---------------- end to end through the C ABI with HOST buffers (e2e) ----------------
+    Jh = HostArray(D, engine, plan.n_rows_padded, Np, "J")
+    Ph = HostArray(D, engine, plan.n_rows_padded, 1, "P")
+    G_h, rho_h, E_h = (engine.pinned_empty(x.shape) for x in (a["G"], a["rho"], a["E"]))
+    G_h[...] = a["G"]; rho_h[...] = a["rho"]; E_h[...] = a["E"]
+    Jloc = Jh.arr[rank * slot:rank * slot + n_loc] if Jh.shm is not None else Jh.arr[:n_loc]
+    Ploc = (Ph.arr[rank * slot:rank * slot + n_loc] if Ph.shm is not None else Ph.arr[:n_loc]).reshape(-1)
+
+    def e2e_step():
+        atom.set_model(G_h, rho_h, E_h)        # H2D of this step's inputs
+        atom.fill_dprobs(Jloc, Ploc)           # kernels + D2H of this rank's Jacobian rows and probabilities into host memory
+
+    for _ in range(2):
+        e2e_step()
+    D.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.sync()
+    D.barrier()
+    t_e2e = D.max((time.time() - t0) / e2e_steps)
+    if Jh.shm is not None or world == 1:        # one array: check rows that other ranks wrote
+        ph = Ph.arr.reshape(-1)[pos]
+        assert np.max(np.abs(ph[::st] - case["probs_map_sample"])) <= 1e-10
+        je = float(np.max(np.abs(Jh.arr[pos[case["dprobs_matrix_sample_elements"]]] - case["dprobs_matrix_sample_rows"])))
+        assert je <= 1e-10, je
+    h2d = int((a["G"].size + a["rho"].size + a["E"].size) * 8)
+    d2h = int(n_loc * (Np + 1) * 8)
+
+    # e2e of the J^T J path: model upload + shard J^T J + all-reduce + D2H of Np^2 + Np doubles on rank 0
+    jj_h = engine.pinned_empty((Np * Np + Np,))
+    jj_hm = torch.from_numpy(jj_h)
+
+    def e2e_jtj_step():
+        atom.set_model(G_h, rho_h, E_h)
+        jtj_step()
+        if rank == 0:
+            jj_hm.copy_(jj, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_jtj_step()
+    D.barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        e2e_jtj_step()
+    D.barrier()
+    t_e2e_jtj = D.max((time.time() - t0) / e2e_steps)
+    host_kind = Jh.kind
+    Jh.close(); Ph.close()
+    atom.free()
+    del J, P
+
+    peak, peak_src = _peaks()
+    alg_bytes = nE * (Np + 1) * 8                                        # whole job
+    shard_bytes = max(plan.n_local) * (Np + 1) * 8                       # what the slowest rank's kernel writes
+    achieved = shard_bytes / (ms_accum * 1e-3) / 1e9                     # dominant kernel alone, per GPU
+    achieved_step = alg_bytes / (ms_per_step * 1e-3) / 1e9 / world       # whole step, per GPU
+    ag_bytes = (world - 1) * slot * (Np + 1) * 8                         # received by every rank
+    line = {
+        "metric": METRIC, "value": value, "unit": "circuit-outcomes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (reference-generated GST layout + depolarized target model; no dataset needed)",
+        "config": {"workload": WORKLOAD_DESC, "derivative": "analytic adjoint (== reference MatrixForwardSimulator)",
+                   "kernel": ("k_trie_prepare + k_trie_chains (prefix/suffix-trie chains, heavy-path decomposition) + "
+                              "k_accum_trie_d16 (DMMA gather-accumulate, fused Jacobian store)") if info["fused_path"] else "general W.D path",
+                   "parallelism": ("shard: ONE layout cut into %d contiguous prefix-ordered shards (ShardPlan), one per GPU; every step ends "
+                                   "with ONE in-place NCCL all-gather of the Jacobian + probability shards" % world) if world > 1
+                   else "1 GPU, whole layout (no collective)",
+                   "l2": "each step writes a %.2f GB Jacobian shard (>> 126 MB L2); no explicit flush needed" % (shard_bytes / 1e9),
+                   "dprobs_elements_per_s": value * Np},
+        "multi_gpu": {"shard_outcomes": plan.n_local, "slot_rows": slot,
+                      "fill_only": {"ms": ms_fill, "outcomes_per_s": nE / (ms_fill * 1e-3)},
+                      "allgather": {"ms": ms_gather, "bytes_received_per_rank": ag_bytes,
+                                    "GBps_per_rank": (ag_bytes / (ms_gather * 1e-3) / 1e9) if ms_gather > 0 else None,
+                                    "collective": "ncclAllGather, in place (send buffer = own slot of the receive buffer)" if world > 1 else None},
+                      "note": "the all-gather moves (N-1)/N of a 2.97 GB Jacobian INTO every GPU over NVLink (<= 900 GB/s), "
+                              "while one GPU produces it at ~4 TB/s: for d = 16 the full-Jacobian exchange is NVLink-bound and "
+                              "the jtj exchange below is the one that scales"},
+        "jtj": {"ms": ms_jtj, "ms_local": ms_jtj_local, "ms_syrk_kernel": ms_syrk,
+                "tflops": jtj_flops / world / (ms_syrk * 1e-3) / 1e12, "frac": jtj_flops / world / (ms_syrk * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+                "peak": DMMA_PEAK_TFLOPS, "peak_source": "measured DMMA rate, tools/ubench_fp64.cu",
+                "allreduce_bytes": (Np * Np + Np) * 8 if world > 1 else 0,
+                "outcomes_per_s": nE / (ms_jtj * 1e-3), "e2e_ms": t_e2e_jtj * 1e3, "e2e_outcomes_per_s": nE / t_e2e_jtj,
+                "parity": {"jtj_rel": jtj_err, "jtf_rel": jtf_err},
+                "what": "scaled Jacobian fill + k_atb_dmma (hand-written FP64 tensor-core SYRK, lower-triangle tiles, split over "
+                        "elements, deterministic reduction) + J^T f in the same kernel%s; flops = nE*Np*(Np+1)" %
+                        (" + ONE all-reduce of Np^2+Np doubles" if world > 1 else "")},
+        "e2e": {"value": nE / t_e2e, "unit": "circuit-outcomes/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3, "host_array": host_kind,
+                "d2h_bytes_all_ranks": int(nE * (Np + 1) * 8),
+                "path": "b200_atom_set_model + b200_fill_dprobs (C ABI), every rank lands its rows in the host array"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if world == 1 else None, "peak_source": peak_src,
+                     "kernel": "k_accum_trie_d16", "kernel_ms": ms_accum,
+                     "algorithmic_bytes_per_launch": shard_bytes,
+                     "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 at N=1 (profiles/r01_accum_final_ncu_raw.csv): dram "
+                                       "read 0.165 GB + write 2.929 GB = 1.04 x the algorithmic bytes",
+                     "step": {"ms": ms_per_step, "achieved": achieved_step, "frac": achieved_step / peak,
+                              "phases_ms": {"k_trie_prepare": ms_prep, "k_trie_chains": ms_chains,
+                                            "k_accum_trie_d16": ms_accum}},
+                     "note": "achieved = 8*nE_shard*(Np+1) bytes / average duration of the dominant kernel on the slowest rank, CUDA "
+                             "events on the launching stream (b200_ctx_phase_timing, a separate loop after the timed region); "
+                             "'step' is the same quantity over the whole timed step, per GPU"},
+        "clocks": clocks,
+        "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
+    }
+    return line, case
+
+
+def bench_c3(args, D, engine, stream, ctx):
+    """BASELINE config 3: 3-qubit crosstalk-free `full TP` model (d = 64, Np = 775; tensors from the reference,
+    tests/golden/c3_3q_localnoise_sub.npz), 50 000 random circuits of depth U{1..256}, 8 outcomes each,
+    bulk_fill_dprobs + probs, sharded over the ranks with one all-gather -- the configuration BASELINE names for 8 GPUs."""
+    torch, dist = D.torch, D.dist
+    from pygsti_b200 import fixtures as fx
+    world, rank = D.world, D.rank
+    n_circ = int(os.environ.get("B200_BENCH_C3_CIRCUITS", "50000"))
+    c = fx.Case("c3_3q_localnoise_sub"); a = c.atoms[0]
+    n_ops, n_eff, Np = a["tables"].n_ops, a["tables"].n_eff, a["D"].n_params
+    _, circs = fx.random_layout(64, n_ops, n_eff, n_circ, 256, seed=0, rows=(0, 0))
+    blocks = fx.balanced_blocks(circs, world, n_eff)
+    t, _ = fx.random_layout(64, n_ops, n_eff, n_circ, 256, seed=0, rows=blocks[rank])
+    n_loc_all = [(hi - lo) * n_eff for lo, hi in blocks]
+    slot = -(-max(n_loc_all) // 8) * 8
+    nE = n_circ * n_eff
+    atom = ctx.upload_atom(t); atom.set_model(a["G"], a["rho"], a["E"]); atom.set_derivs(a["D"])
+    info = atom.info()
+    J = torch.empty((slot * world, Np), dtype=torch.float64, device="cuda"); P = torch.empty(slot * world, dtype=torch.float64, device="cuda")
+    Jm, Pm = J[rank * slot:(rank + 1) * slot], P[rank * slot:(rank + 1) * slot]
+
+    def fill():
+        atom.fill_dprobs_dev(Jm.data_ptr(), Np, Pm.data_ptr())
+
+    def step():
+        fill()
+        if world > 1:
+            dist.all_gather_into_tensor(J, Jm); dist.all_gather_into_tensor(P, Pm)
+
+    steps = max(3, min(args.steps, 5))
+    ms = timed(D, stream, step, steps, 2)
+    ms_fill = timed(D, stream, fill, steps, 0) if world > 1 else ms
+    # parity: first circuits of rank 0's shard against the C oracle (checker only)
+    par = None
+    if rank == 0:
+        orc, kind, _ = _oracle(prefer_ref=False)
+        sub, _ = fx.random_layout(64, n_ops, n_eff, n_circ, 256, seed=0, rows=(0, 6))
+        Jo, po = orc.dprobs_analytic(sub, a["G"], a["rho"], a["E"], a["D"])
+        par = {"dprobs_max_abs_vs_oracle_first_6_circuits": float(np.max(np.abs(J[:sub.n_elements].cpu().numpy() - Jo))),
+               "probs_max_abs": float(np.max(np.abs(P[:sub.n_elements].cpu().numpy() - po)))}
+        assert par["dprobs_max_abs_vs_oracle_first_6_circuits"] <= 1e-10 and par["probs_max_abs"] <= 1e-12, par
+    n_prop = sum(len(x) for x in circs)
+    sweep_flops = 2.0 * 64 * 64 * n_prop * (1 + n_eff)                   # forward + one backward sweep per outcome
+    accum_flops = 2.0 * 64 * 64 * n_prop * n_eff                         # W_g = sum_k e_k (x) s_k, every outcome
+    alg_bytes = nE * (Np + 1) * 8
+    peak, _ = _peaks()
+    out = {"config": "BASELINE configs[2]: 3Q XYCNOT full TP (d=64, Np=775), %d random circuits depth U{1..256}, %d outcomes" % (n_circ, nE),
+           "ms": ms, "ms_fill_only": ms_fill, "outcomes_per_s": nE / (ms * 1e-3), "dprobs_elements_per_s": nE * Np / (ms * 1e-3),
+           "parallelism": ("shard x%d + ONE ncclAllGather of %.2f GB shards" % (world, slot * (Np + 1) * 8 / 1e9)) if world > 1 else "1 GPU",
+           "algorithmic": {"sweep_flops": sweep_flops, "accumulate_flops": accum_flops, "jacobian_bytes": alg_bytes},
+           "tflops": (sweep_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12,
+           "frac": (sweep_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+           "bound": "tensor (FP64 DMMA %.1f TFLOP/s measured); HBM floor of the output %.2f ms" % (DMMA_PEAK_TFLOPS, alg_bytes / world / peak / 1e6),
+           "atom": {k: int(v) for k, v in info.items()}, "parity": par}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sub, _ = fx.random_layout(64, n_ops, n_eff, n_circ, 256, seed=0, rows=(0, 200))
+        threads = os.cpu_count() or 1
+        v, kind, desc = cpu_fd_jacobian_sample(sub, a["G"], a["rho"], a["E"], a["D"], threads, 2 * threads)
+        out["cpu_baseline"] = {"value": v, "unit": "circuit-outcomes/s", "cores": threads, "kind": kind, "sample": desc}
+    atom.free()
+    del J, P
+    return out
+
+
+def bench_c5(args, D, engine, stream, ctx):
+    """BASELINE config 5: d = 256 dense model (14 layer labels, 16 outcomes), 5000 random circuits of depth U{1..128},
+    probabilities only -- the FP64 tensor-core roofline run.  Replicated on every rank (2.9 ms of work)."""
+    torch = D.torch
+    from pygsti_b200 import fixtures as fx
+    n_circ = 5000
+    G, rho, E = fx.random_dense_model(256, 14, 1, 16, seed=1)
+    t, circs = fx.random_layout(256, 14, 16, n_circ, 128, seed=0)
+    atom = ctx.upload_atom(t); atom.set_model(G, rho, E)
+    P = torch.empty(t.n_elements, dtype=torch.float64, device="cuda")
+    ms = timed(D, stream, lambda: atom.fill_probs_dev(P.data_ptr()), max(5, min(args.steps, 20)), 3)
+    n_prop = sum(len(x) for x in circs)
+    flops = 2.0 * 256 * 256 * n_prop
+    par = None
+    if D.rank == 0:
+        orc, kind, _ = _oracle(prefer_ref=False)
+        sub, _ = fx.random_layout(256, 14, 16, n_circ, 128, seed=0, rows=(0, 40))
+        po = orc.mapfill_probs(sub, G, rho, E)
+        par = {"probs_max_abs_vs_oracle_first_40_circuits": float(np.max(np.abs(P[:po.size].cpu().numpy() - po)))}
+        assert par["probs_max_abs_vs_oracle_first_40_circuits"] <= 1e-12, par
+    out = {"config": "BASELINE configs[4]: d=256 dense model, 14 layer labels, 5000 random circuits depth U{1..128}, 80000 outcomes, probs only",
+           "ms": ms, "outcomes_per_s": D.world * t.n_elements / (ms * 1e-3), "parallelism": "replica per GPU" if D.world > 1 else "1 GPU",
+           "algorithmic": {"flops": flops}, "tflops": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+           "bound": "tensor (FP64 DMMA %.1f TFLOP/s measured)" % DMMA_PEAK_TFLOPS, "parity": par}
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        orc, kind, _ = _oracle()
+        sub, _ = fx.random_layout(256, 14, 16, n_circ, 128, seed=0, rows=(0, 250))
+        t0 = time.time(); orc.mapfill_probs(sub, G, rho, E); dt = time.time() - t0
+        out["cpu_baseline"] = {"value": sub.n_elements / dt, "unit": "circuit-outcomes/s", "cores": 1, "kind": kind,
+                               "sample": "250 of the 5000 circuits, one bulk_fill_probs table pass, %.2f s (the reference's pass is serial)" % dt}
+    atom.free()
+    return out
+
+
+def bench_c4(args, D, engine, stream, ctx):
+    """BASELINE config 4: smq2Q_XYCNOT CPTPLND (d = 16, Np = 1680), GST design maxL = 16 (7860 circuits, 31 440 outcomes; tables,
+    tensors, derivative and second-derivative maps from the reference, tests/golden/c4_gst16_layout.npz).  Unit of work = one
+    64 x 64 rectangle of the MLE Hessian (`iter_hprobs_by_rectangle` + `_hessian_from_block`): the analytic hprobs block is
+    evaluated and reduced on the device.  Rectangles are independent: every rank times the same rectangle (replicas)."""
+    from pygsti_b200.fixtures import Case
+    path = os.path.join(REPO, "tests", "golden", "c4_gst16_layout.npz")
+    if not os.path.exists(path):
+        return {"unavailable": "tests/golden/c4_gst16_layout.npz missing"}
+    c = Case("c4_gst16_layout"); a = c.atoms[0]
+    nE, Np = c.n_elements, c.num_params
+    atom = ctx.upload_atom(a["tables"]); atom.set_model(a["G"], a["rho"], a["E"]); atom.set_derivs(a["D"])
+    r = c["hess_rects"][0]
+    p1, p2 = np.arange(r[0], r[1]), np.arange(r[2], r[3])
+    H2 = c.hess_map("H2r0")
+    rng = np.random.default_rng(0)
+    w_h, w_d = rng.standard_normal(nE), rng.uniform(0.5, 1.5, nE)
+
+    def wall(fn, n, warm=1):
+        for _ in range(warm):
+            fn()
+        D.barrier()
+        t0 = time.time()
+        for _ in range(n):
+            fn()
+        ctx.sync()
+        return D.max((time.time() - t0) / n)
+
+    Jh = engine.pinned_empty((nE, Np)); ph = np.empty(nE)
+    t_j = wall(lambda: atom.fill_dprobs(Jh, ph), 3)
+    rows = c["dprobs_matrix_sample_elements"]
+    jerr = float(np.max(np.abs(Jh[rows] - c["dprobs_matrix_sample_rows"])))
+    hb = atom.hessian_block(p1, p2, w_h, w_d, H2)
+    t_h = wall(lambda: atom.hessian_block(p1, p2, w_h, w_d, H2), 2, warm=0)
+    # parity of the rectangle on the sampled elements (hprobs materialised only for the check)
+    hp = np.empty((nE, p1.size, p2.size))
+    atom.fill_hprobs(p1, p2, hp, H2)
+    herr = float(np.max(np.abs(hp[rows] - c["hprobs_matrix_rect0_sample_rows"])))
+    red = np.einsum("e,eab->ab", w_h, hp) + np.einsum("e,ea,eb->ab", w_d, Jh[:, p1], Jh[:, p2])
+    rerr = float(np.max(np.abs(hb - red)) / np.max(np.abs(red)))
+    assert jerr <= 1e-10 and herr <= 1e-9 and rerr <= 1e-10, (jerr, herr, rerr)
+    n_rect = ((Np + 63) // 64) * ((Np + 63) // 64 + 1) // 2
+    out = {"config": "BASELINE configs[3]: smq2Q_XYCNOT CPTPLND (d=16, Np=1680), GST maxL=16: 7860 circuits, %d outcomes" % nE,
+           "dprobs": {"e2e_ms": t_j * 1e3, "outcomes_per_s": nE / t_j, "max_abs_vs_reference_matrix_sample": jerr,
+                      "path": "general W.D path (D is not a permutation), C ABI with pinned host buffers"},
+           "hessian_rectangle": {"block": [int(p1.size), int(p2.size)], "e2e_ms": t_h * 1e3,
+                                 "hprobs_elements_per_s": nE * p1.size * p2.size / t_h,
+                                 "rectangles_per_s_all_gpus": D.world / t_h,
+                                 "full_hessian_s_extrapolated": n_rect * t_h / D.world, "n_rectangles_upper_triangle": n_rect,
+                                 "hprobs_max_abs_vs_reference_matrix_sample": herr, "reduction_rel_err": rerr,
+                                 "what": "b200_hessian_block: analytic hprobs rectangle (first + second derivative terms) evaluated and "
+                                         "reduced with w_h / w_d on the device; only 64 x 64 doubles return"},
+           "parallelism": "independent rectangles: replica per GPU" if D.world > 1 else "1 GPU"}
+    if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
+        orc, kind, _ = _oracle()
+        t0 = time.time(); orc.mapfill_probs(a["tables"], a["G"], a["rho"], a["E"]); t_pass = time.time() - t0
+        threads = os.cpu_count() or 1
+        t_ref = t_pass * (p1.size + 1) * (p2.size + 1) / threads
+        out["cpu_baseline"] = {"value": nE * p1.size * p2.size / t_ref, "unit": "hprobs-elements/s", "cores": threads, "kind": kind,
+                               "sample": "one prefix-table pass %.3f s on 1 core; the reference's FD-of-FD rectangle (mapforwardsim.py:394-438) is "
+                                         "(B1+1)(B2+1) = %d such passes, assumed perfectly parallel over %d threads; the members' expm per FD "
+                                         "step is NOT included (conservative)" % (t_pass, (p1.size + 1) * (p2.size + 1), threads)}
+    atom.free()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,6 +706,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip BASELINE configs 3-5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
 
@@ -197,142 +727,36 @@ def main():
     import torch
     import torch.distributed as dist
     from pygsti_b200 import engine
-    from pygsti_b200.fixtures import Case
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    case = Case(WORKLOAD)
-    a = case.atoms[0]
-    nE, Np = case.n_elements, case.num_params
+    D = Dist(torch, dist, world, rank)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = engine.Context(local_rank, stream=stream.cuda_stream)
-    atom = ctx.upload_atom(a["tables"])
-    atom.set_model(a["G"], a["rho"], a["E"])
-    atom.set_derivs(a["D"])
-    info = atom.info()
-
-    J = torch.empty((nE, Np), dtype=torch.float64, device="cuda")
-    P = torch.empty(nE, dtype=torch.float64, device="cuda")
-
-    # ---------------- device-resident throughput (value) ----------------
-    for _ in range(args.warmup):
-        atom.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
-    barrier()
     sampler = ClockSampler(local_rank)
+
+    line, case = bench_c2(args, D, engine, stream, ctx, sampler)
+    if not args.no_extra:
+        extra = {}
+        for name, fn in (("c3_d64_dprobs", bench_c3), ("c4_cptplnd_hessian", bench_c4), ("c5_d256_probs", bench_c5)):
+            torch.cuda.empty_cache()
+            try:
+                extra[name] = fn(args, D, engine, stream, ctx)
+            except AssertionError:
+                raise
+            except Exception as e:          # an extra workload must not take the headline line down with it
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        line["extra_configs"] = extra
     if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    l0 = ctx.launch_count
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record(stream)
-    for _ in range(args.steps):
-        atom.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
-    e1.record(stream)
-    barrier()
-    t_wall1 = time.time()
-    launches = ctx.launch_count - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    ms_per_step = ms_total / args.steps
-    value = world * nE / (ms_per_step * 1e-3)
-
-    # ---------------- dominant kernel alone (roofline.achieved): CUDA events around the phases, on the launching stream ----
-    ctx.phase_timing(True)
-    for _ in range(max(5, min(args.steps, 20))):
-        atom.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
-    (ms_prep, ms_chains, ms_accum), n_ph = ctx.phase_ms()
-    ctx.phase_timing(False)
-    ph = torch.tensor([ms_prep / max(n_ph, 1), ms_chains / max(n_ph, 1), ms_accum / max(n_ph, 1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
-    ms_prep, ms_chains, ms_accum = (float(x) for x in ph.tolist())
-
-    # quick on-device sanity of what was just timed (not part of the timed region)
-    st = int(case["probs_map_stride"])
-    p_host = P.cpu().numpy()
-    assert np.max(np.abs(p_host[::st] - case["probs_map_sample"])) <= 1e-10
-    rows = torch.as_tensor(case["dprobs_matrix_sample_elements"], device="cuda")
-    jerr = float(np.max(np.abs(J[rows].cpu().numpy() - case["dprobs_matrix_sample_rows"])))
-    assert jerr <= 1e-10, jerr
-
-    # ---------------- end-to-end through the C ABI with host buffers (e2e) ----------------
-    Jh = engine.pinned_empty((nE, Np))
-    Ph = engine.pinned_empty((nE,))
-    G_h, rho_h, E_h = (engine.pinned_empty(x.shape) for x in (a["G"], a["rho"], a["E"]))
-    G_h[...] = a["G"]; rho_h[...] = a["rho"]; E_h[...] = a["E"]
-    for _ in range(2):
-        atom.set_model(G_h, rho_h, E_h); atom.fill_dprobs(Jh, Ph)
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        atom.set_model(G_h, rho_h, E_h)        # H2D of this step's inputs
-        atom.fill_dprobs(Jh, Ph)               # kernel + D2H of Jacobian and probs into host memory
-    ctx.sync()
-    t_e2e = torch.tensor([(time.time() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-    barrier()
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * nE / float(t_e2e.item())
-    assert np.max(np.abs(Ph[::st] - case["probs_map_sample"])) <= 1e-10
-    h2d = int((a["G"].size + a["rho"].size + a["E"].size) * 8)
-    d2h = int(nE * (Np + 1) * 8)
-
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-
-    if rank == 0:
-        peak, peak_src = _peaks()
-        alg_bytes = nE * (Np + 1) * 8
-        achieved = alg_bytes / (ms_accum * 1e-3) / 1e9          # dominant kernel alone
-        achieved_step = alg_bytes / (ms_per_step * 1e-3) / 1e9  # whole step (prepare + chains + accumulate)
-        line = {
-            "metric": METRIC, "value": value, "unit": "circuit-outcomes/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic (reference-generated GST layout + depolarized target model; no dataset needed)",
-            "config": {"workload": WORKLOAD_DESC, "derivative": "analytic adjoint (== reference MatrixForwardSimulator)",
-                       "kernel": ("k_trie_prepare + k_trie_chains (prefix/suffix-trie chains, heavy-path decomposition) + "
-                                  "k_accum_trie_d16 (DMMA gather-accumulate, fused Jacobian store)") if info["fused_path"] else "general W.D path",
-                       "parallelism": "dp%d: one replica of the layout per GPU, no data-path collective" % world,
-                       "l2": "each step writes a 2.97 GB Jacobian (>> 126 MB L2); no explicit flush needed",
-                       "dprobs_elements_per_s": value * Np},
-            "e2e": {"value": e2e_value, "unit": "circuit-outcomes/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": float(t_e2e.item()) * 1e3,
-                    "path": "b200_atom_set_model + b200_fill_dprobs (C ABI), pinned host buffers"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
-                         "kernel": "k_accum_trie_d16", "kernel_ms": ms_accum,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 (profiles/r01_accum_final_ncu_raw.csv): dram "
-                                           "read 0.165 GB + write 2.929 GB = 1.04 x the algorithmic bytes",
-                         "step": {"ms": ms_per_step, "achieved": achieved_step, "frac": achieved_step / peak,
-                                  "phases_ms": {"k_trie_prepare": ms_prep, "k_trie_chains": ms_chains,
-                                                "k_accum_trie_d16": ms_accum}},
-                         "note": "achieved = 8*nE*(Np+1) bytes / average duration of the dominant kernel, CUDA events on the "
-                                 "launching stream (b200_ctx_phase_timing, a separate loop after the timed region); 'step' "
-                                 "is the same quantity over the whole timed step (all three kernels), i.e. value * 10888 B"},
-            "clocks": clocks,
-            "parity_check": {"probs_vs_reference_map_sample": "<=1e-10", "dprobs_vs_reference_matrix_sample_max_abs": jerr},
-        }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_sample(case, os.cpu_count() or 1, core_seconds=20.0)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200fwdsim.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "trie_host.h", "lindblad_core.h", "kernels_lindblad.cuh", "kernels_generic.cuh", "kernels_d16_trie.cuh", "kernels_level.cuh", os.path.join("..", "..", "include", "b200_fwdsim.h")]
+HEADERS = ["common.cuh", "trie_host.h", "lindblad_core.h", "kernels_lindblad.cuh", "kernels_generic.cuh", "kernels_d16_trie.cuh", "kernels_jtj.cuh", "kernels_levelj.cuh", "kernels_level.cuh", os.path.join("..", "..", "include", "b200_fwdsim.h")]
 
 
 def _nvcc():
@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart", "-lcublas"]
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(r.stderr)

@@ -96,6 +96,10 @@ def _pin_destination(arr):
         lib = _lib.load()
         rc = lib.b200_host_register(C.c_void_p(key), int(base.nbytes))
         _REGISTERED[key] = base.nbytes if rc == 0 else (1 << 62)     # do not retry a buffer that cannot be pinned
+        if rc != 0:
+            import warnings
+            warnings.warn("B200 engine: cudaHostRegister refused the destination array; device-to-host copies of this array "
+                          "run through pageable memory (~3x slower)", RuntimeWarning)
         if rc == 0:   # un-pin when the owner array is garbage collected (before its pages go back to the allocator)
             def _unpin(k=key):
                 _REGISTERED.pop(k, None)
@@ -106,8 +110,10 @@ def _pin_destination(arr):
                 if _REGISTERED[k] < (1 << 62):
                     _lib.load().b200_host_unregister(C.c_void_p(k))
                 del _REGISTERED[k]
-    except Exception:
-        pass
+    except Exception as e:                                           # pageable destination: correct, but ~3x slower D2H
+        import warnings
+        warnings.warn("B200 engine: could not page-lock the destination array (%s: %s); the copy will be staged" %
+                      (type(e).__name__, e), RuntimeWarning)
 
 
 def _to_index_array(idx, n):
@@ -317,7 +323,11 @@ def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     ops, rhos, effs = packing._members(model, layout_atom)
     linear = all(type(m).__name__ in _LINEAR_MEMBERS for m in ops + rhos + effs) \
         and getattr(model, "_param_interposer", None) is None
-    key = (pidx.tobytes(), model.num_params) if linear else None
+    # D is constant only for THIS model's members and parameter allocation: the key names them (a layout re-used with another
+    # or re-parameterised model of equal size must not hit a stale map)
+    key = (pidx.tobytes(), model.num_params, id(model),
+           tuple((id(m), getattr(m.gpindices, "start", None), getattr(m.gpindices, "stop", None)) if isinstance(m.gpindices, slice)
+                 else (id(m), bytes(np.asarray(m.gpindices).tobytes())) for m in ops + rhos + effs)) if linear else None
     if key is not None and ent["deriv_key"] == key:
         return pidx
     D = packing.pack_derivs(model, layout_atom, model.dim, pidx)

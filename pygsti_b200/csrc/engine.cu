@@ -7,8 +7,8 @@
 #include "kernels_d16_trie.cuh"
 #include "kernels_level.cuh"
 #include "kernels_levelj.cuh"
+#include "kernels_jtj.cuh"
 #include <cstdlib>
-#include <cublas_v2.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -64,7 +64,7 @@ struct b200_ctx {
     DevBuf lj_fs, lj_bh; // level-batched Jacobian path: state table / adjoint table (all levels kept)
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
-    cublasHandle_t cublas = nullptr;
+    DevBuf atb_part, atb_part_f;                 // partial tiles of the A^T B reductions (k_atb_dmma)
     DevBuf fd_models, fd_gt, fd_probs;
     DevBuf lind[20];                                     // b200_lindblad_members: inputs, intermediates, outputs
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
@@ -183,7 +183,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     phase_clear(c);
     for (DevBuf& b : c->lind) b.release();
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
-    if (c->cublas) cublasDestroy(c->cublas);
+    c->atb_part.release(); c->atb_part_f.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1292,41 +1292,48 @@ extern "C" int b200_fill_dprobs_scaled(b200_ctx* c, b200_atom* a, const double* 
     return B200_OK;
 }
 
-#define CB(x) do { cublasStatus_t s_ = (x); if (s_ != CUBLAS_STATUS_SUCCESS) \
-    return fail(B200_E_CUDA, "%s failed: cublas status %d (%s:%d)", #x, (int)s_, __FILE__, __LINE__); } while (0)
+// C [na x nb] (+)= A^T B over nE rows on the FP64 tensor cores (kernels_jtj.cuh); tri: A == B, symmetric result.  atf = A^T f.
+static int atb_device(b200_ctx* c, const double* A, int64_t lda, int na, const double* B, int64_t ldb, int nb, int64_t nE,
+                      bool tri, const double* f, double* C, int64_t ldc, double* atf, bool accumulate) {
+    if (na <= 0 || nb <= 0) return B200_OK;
+    if ((lda & 1) || (ldb & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+        return fail(B200_E_INVALID, "A^T B: operands must be 16-byte aligned with even row strides");
+    AtbArgs p;
+    p.A = A; p.lda = lda; p.na = na; p.B = B; p.ldb = ldb; p.nb = nb; p.nE = nE; p.tri = tri ? 1 : 0;
+    p.n_bi = (na + JT_T - 1) / JT_T; p.n_bj = (nb + JT_T - 1) / JT_T;
+    p.n_tiles = tri ? p.n_bi * (p.n_bi + 1) / 2 : p.n_bi * p.n_bj;
+    // K slices: about four waves of CTAs, at least 128 rows each; partial tiles are summed in slice order afterwards
+    int64_t S = ((int64_t)c->sm_count * 4 + p.n_tiles / 2) / p.n_tiles;
+    S = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(S, 256), (nE + 127) / 128));
+    p.rows_per_slice = std::max<int64_t>(JT_KC, ((nE + S - 1) / S + JT_KC - 1) / JT_KC * JT_KC);
+    p.n_slices = (int)std::max<int64_t>(1, (nE + p.rows_per_slice - 1) / p.rows_per_slice);
+    p.f = (atf && f) ? f : nullptr;
+    CU(c->atb_part.ensure((size_t)p.n_slices * p.n_tiles * JT_T * JT_T * 8));
+    CU(c->atb_part_f.ensure((size_t)p.n_slices * p.n_bi * JT_T * 8));
+    p.part = c->atb_part.as<double>(); p.part_f = c->atb_part_f.as<double>();
+    const size_t smem = (size_t)JT_ST * JT_STAGE_DOUBLES * 8;
+    CU(cudaFuncSetAttribute(k_atb_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_atb_dmma<<<(unsigned)(p.n_slices * p.n_tiles), 256, smem, c->stream>>>(p);
+    k_atb_reduce<<<(unsigned)p.n_tiles, 256, 0, c->stream>>>(p, C, ldc, atf, accumulate ? 1 : 0);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
 
 // J^T J (full symmetric, row-major) and J^T f into DEVICE buffers; everything asynchronous on the ctx stream
 static int jtj_device(b200_ctx* c, b200_atom* a, const double* d_scale, const double* d_f, double* d_jtj, double* d_jtf) {
     const int Np = a->n_params; const int64_t nE = a->n_elements;
     if (Np == 0) return B200_OK;
-    if (nE >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "too many elements for the BLAS call");
-    CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * Np * 8, 16)));
-    int rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), Np, nullptr, d_scale);
+    const int64_t ldj = (Np + 1) & ~1;                  // even row stride: 16-byte aligned cp.async rows
+    CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * ldj * 8, 16)));
+    int rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), ldj, nullptr, d_scale);
     if (rc) return rc;
-    if (!c->cublas) { CB(cublasCreate(&c->cublas)); }
-    CB(cublasSetStream(c->cublas, c->stream));
-    // J is row-major [nE x Np] = column-major A [Np x nE] (lda = Np):  J^T J = A A^T  (plain library SYRK)
-    const double one = 1.0, zero = 0.0;
-    if (nE > 0) {
-        CB(cublasDsyrk(c->cublas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, &zero,
-                       d_jtj, Np));
-        dim3 blk(16, 16), grd((Np + 15) / 16, (Np + 15) / 16);
-        // column-major lower triangle == row-major upper triangle: mirror it
-        k_symmetrize<<<grd, blk, 0, c->stream>>>(d_jtj, Np);
-        c->launches += 2;
-    } else {
+    if (nE == 0) {
         CU(cudaMemsetAsync(d_jtj, 0, (size_t)Np * Np * 8, c->stream));
+        if (d_jtf) CU(cudaMemsetAsync(d_jtf, 0, (size_t)Np * 8, c->stream));
+        return B200_OK;
     }
-    if (d_jtf) {
-        if (nE > 0) {
-            CB(cublasDgemv(c->cublas, CUBLAS_OP_N, Np, (int)nE, &one, c->out_buf.as<double>(), Np, d_f, 1, &zero, d_jtf, 1));
-            c->launches++;
-        } else {
-            CU(cudaMemsetAsync(d_jtf, 0, (size_t)Np * 8, c->stream));
-        }
-    }
-    CU(cudaGetLastError());
-    return B200_OK;
+    return atb_device(c, c->out_buf.as<double>(), ldj, Np, c->out_buf.as<double>(), ldj, Np, nE, true, d_f, d_jtj, Np, d_jtf, false);
 }
 
 extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, const double* f, double* jtj_out, double* jtf_out) {
@@ -1450,15 +1457,15 @@ extern "C" int b200_hessian_block(b200_ctx* c, b200_atom* a, int32_t n1, const i
     return fill_hprobs_impl(c, a, n1, p1, n2, p2, nnz2, h_rows, h_a, h_b, h_vals, nullptr, w_h, w_d, out);
 }
 
-// column gather with optional row weights: out[el][k] = (w ? w[el] : 1) * J[el][cols[k]]
+// column gather with optional row weights: out[el][k] = (w ? w[el] : 1) * J[el][cols[k]]   (out row stride ldo)
 __global__ void __launch_bounds__(256)
 k_gather_cols(const double* __restrict__ J, int64_t ld, int64_t n_el, int n, const int32_t* __restrict__ cols,
-              const double* __restrict__ w, double* __restrict__ out)
+              const double* __restrict__ w, double* __restrict__ out, int64_t ldo)
 {
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < n_el * n; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t el = idx / n; const int k = (int)(idx - el * n);
         const double v = J[el * ld + cols[k]];
-        out[idx] = w ? v * w[el] : v;
+        out[el * ldo + k] = w ? v * w[el] : v;
     }
 }
 
@@ -1554,33 +1561,34 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
     if (red_out) {
         // MLE Hessian block (objectivefns.py:4914-4990 `_hessian_from_block` without omitted-outcome rows):
         //   red[a][b] = sum_el w_h[el] H[el][a][b] + w_d[el] J[el][p1[a]] J[el][p2[b]]      -- only n1 x n2 doubles leave the device
-        if (nE >= ((int64_t)1 << 31) || (int64_t)n1 * n2 >= ((int64_t)1 << 31)) return fail(B200_E_UNSUPPORTED, "block too large for the BLAS calls");
-        DevBuf d_wh, d_wd, d_red, d_j1, d_j2;
-        CU(d_wh.ensure((size_t)nE * 8)); CU(d_wd.ensure((size_t)nE * 8)); CU(d_red.ensure((size_t)n1 * n2 * 8));
-        CU(d_j1.ensure((size_t)nE * n1 * 8)); CU(d_j2.ensure((size_t)nE * n2 * 8));
+        DevBuf d_wh, d_wd, d_red, d_j1, d_j2, d_cs;
+        const int64_t ld1 = (n1 + 1) & ~1, ld2 = (n2 + 1) & ~1, n12 = (int64_t)n1 * n2;
+        CU(d_wh.ensure((size_t)nE * 8)); CU(d_wd.ensure((size_t)nE * 8)); CU(d_red.ensure((size_t)n12 * 8));
+        CU(d_j1.ensure((size_t)nE * ld1 * 8)); CU(d_j2.ensure((size_t)nE * ld2 * 8));
         CU(cudaMemcpyAsync(d_wh.p, w_h, (size_t)nE * 8, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d_wd.p, w_d, (size_t)nE * 8, cudaMemcpyHostToDevice, c->stream));
         CU(c->out_buf.ensure(std::max<size_t>((size_t)nE * a->n_params * 8, 16)));
         rc = fill_dprobs_device(c, a, c->out_buf.as<double>(), a->n_params, nullptr, nullptr);
         if (rc) return rc;
         const int gg = (int)std::min<int64_t>((nE * std::max(n1, n2) + 255) / 256, (int64_t)c->sm_count * 16);
-        k_gather_cols<<<gg, 256, 0, c->stream>>>(c->out_buf.as<double>(), a->n_params, nE, n1, d_p1.as<int32_t>(), d_wd.as<double>(), d_j1.as<double>());
-        k_gather_cols<<<gg, 256, 0, c->stream>>>(c->out_buf.as<double>(), a->n_params, nE, n2, d_p2.as<int32_t>(), nullptr, d_j2.as<double>());
+        k_gather_cols<<<gg, 256, 0, c->stream>>>(c->out_buf.as<double>(), a->n_params, nE, n1, d_p1.as<int32_t>(), d_wd.as<double>(), d_j1.as<double>(), ld1);
+        k_gather_cols<<<gg, 256, 0, c->stream>>>(c->out_buf.as<double>(), a->n_params, nE, n2, d_p2.as<int32_t>(), nullptr, d_j2.as<double>(), ld2);
         c->launches += 2;
         CU(cudaGetLastError());
-        if (!c->cublas) { CB(cublasCreate(&c->cublas)); }
-        CB(cublasSetStream(c->cublas, c->stream));
-        const double one = 1.0, zero = 0.0;
-        // H block: row-major [nE x n1 n2] = column-major [n1 n2 x nE]:  red = A w_h
-        CB(cublasDgemv(c->cublas, CUBLAS_OP_N, n1 * n2, (int)nE, &one, d_out.as<double>(), n1 * n2, d_wh.as<double>(), 1, &zero,
-                       d_red.as<double>(), 1));
-        // row-major red [n1 x n2] = column-major [n2 x n1] += J2^T-layout [n2 x nE] . (w_d J1)[n1 x nE]^T
-        CB(cublasDgemm(c->cublas, CUBLAS_OP_N, CUBLAS_OP_T, n2, n1, (int)nE, &one, d_j2.as<double>(), n2, d_j1.as<double>(), n1, &one,
-                       d_red.as<double>(), n2));
+        // red = sum_el w_h[el] H[el]  (weighted column sums of the [nE x n1 n2] block, two deterministic passes) ...
+        const int ns = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c->sm_count * 8 * 256 + n12 - 1) / n12, (nE + 63) / 64));
+        const int64_t rps = (nE + ns - 1) / ns;
+        CU(d_cs.ensure((size_t)ns * n12 * 8));
+        k_wcolsum<<<dim3((unsigned)((n12 + 255) / 256), (unsigned)ns), 256, 0, c->stream>>>(d_out.as<double>(), n12, nE, d_wh.as<double>(), rps, d_cs.as<double>());
+        k_wcolsum_reduce<<<(unsigned)((n12 + 255) / 256), 256, 0, c->stream>>>(d_cs.as<double>(), n12, ns, d_red.as<double>());
         c->launches += 2;
+        CU(cudaGetLastError());
+        // ... += (w_d J1)^T J2 on the FP64 tensor cores
+        rc = atb_device(c, d_j1.as<double>(), ld1, n1, d_j2.as<double>(), ld2, n2, nE, false, nullptr, d_red.as<double>(), n2, nullptr, true);
+        if (rc) return rc;
         CU(cudaMemcpyAsync(red_out, d_red.p, (size_t)n1 * n2 * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        d_wh.release(); d_wd.release(); d_red.release(); d_j1.release(); d_j2.release();
+        d_wh.release(); d_wd.release(); d_red.release(); d_j1.release(); d_j2.release(); d_cs.release();
     } else {
         CU(cudaMemcpyAsync(out, d_out.p, (size_t)nE * n1 * n2 * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));

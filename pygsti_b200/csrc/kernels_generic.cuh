@@ -314,24 +314,6 @@ k_contract_csc(const double* __restrict__ W, int64_t ldw, int64_t n_el, int n_pa
     }
 }
 
-// J[el][:] *= row_scale[el]   (d = 16 kernels other than the trie path)
-__global__ void __launch_bounds__(256)
-k_scale_rows(double* __restrict__ J, int64_t ld, int64_t n_el, int n_params, const double* __restrict__ row_scale)
-{
-    for (int64_t el = blockIdx.x; el < n_el; el += gridDim.x) {
-        const double sc = row_scale[el];
-        double* Jr = J + el * ld;
-        for (int p = threadIdx.x; p < n_params; p += blockDim.x) Jr[p] *= sc;
-    }
-}
-
-// C[i][j] = C[j][i] for i < j (cublasDsyrk fills one triangle)
-__global__ void k_symmetrize(double* __restrict__ C, int n)
-{
-    const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && j < n && j > i) C[(size_t)j * n + i] = C[(size_t)i * n + j];
-}
-
 // ---------------------------------------------------------------------------------------------
 // forward-difference helpers (reference semantics, pyx:349-378)
 // ---------------------------------------------------------------------------------------------

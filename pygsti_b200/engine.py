@@ -32,7 +32,8 @@ def device_count():
 
 
 class Context:
-    """One engine context per GPU (mirrors one MPI rank's ResourceAllocation in the reference)."""
+    """One engine context per GPU (mirrors one MPI rank's ResourceAllocation in the reference).  A context and its atoms share
+    scratch buffers: calls on one context must not overlap (use one context per thread / per GPU)."""
 
     def __init__(self, device=0, stream=None):
         self._lib = _lib.load()
@@ -289,25 +290,13 @@ class Atom:
 
 
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by cudaHostAlloc memory (freed when the array is garbage collected)."""
+    """numpy array backed by cudaHostAlloc memory; the pages are released (cudaFreeHost) when the array and every view of it
+    have been garbage collected."""
+    import weakref
     lib = _lib.load()
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p(0)
     _lib.check(lib.b200_host_alloc(C.byref(p), nbytes))
-    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib.b200_host_free(C.c_void_p(self.ptr))
-            except Exception:
-                pass
-    _OWNERS[arr.ctypes.data] = _Owner(p.value)
-    return arr
-
-
-_OWNERS = {}
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)       # numpy keeps `buf` alive as the base of the array
+    weakref.finalize(buf, lib.b200_host_free, C.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)

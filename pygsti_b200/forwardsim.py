@@ -28,7 +28,9 @@ class B200ForwardSimulator(_MapForwardSimulator):
     derivative_mode : 'analytic' (default) or 'fd'
         'analytic': adjoint Jacobian, equal to the reference's MatrixForwardSimulator to ~1e-14.
         'fd': the reference Map simulator's forward differences (pyx:349-378) evaluated on the GPU with
-        ``derivative_eps``.
+        ``derivative_eps``.  Members are perturbed to ``M + eps * dM/dtheta_p``: the reference's own values for members linear
+        in their parameters (full / TP / static), first-order-linearised (difference O(eps * d2M)) for CPTPLND / H+S members.
+        The fused objective-function fills (``pygsti_b200.objective``) delegate to the stock methods in this mode.
     device : int or None
         CUDA device of this process (default: ``LOCAL_RANK`` modulo the device count, else 0).  With
         ``num_atoms > 1`` and no MPI communicator, atoms are spread round-robin over ``devices``.
@@ -133,6 +135,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
         """``bulk_fill_dprobs`` with every row multiplied by ``row_scale[el]`` on the device: the
         `dprobs *= dg_probs[:, None]` / `jac *= p5over_lsvec[:, None]` passes of the objective functions
         (objectivefns.py:4609-4616, 4644-4649) fused into the kernel epilogue."""
+        self._require_local(layout, "bulk_fill_dprobs_scaled")
         if pr_array_to_fill is not None:
             self.bulk_fill_probs(pr_array_to_fill, layout)
         ralloc = layout.resource_alloc('param-processing')
@@ -146,6 +149,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
     def bulk_jtj(self, layout, row_scale=None, f=None):
         """(J^T J, J^T f) for J = diag(row_scale) . dprobs without the Jacobian leaving the device (what
         `fill_jtj` / `fill_jtf` hand the Levenberg-Marquardt step, distlayout.py:1220-1359)."""
+        self._require_local(layout, "bulk_jtj")
         JTJ, JTf = None, None
         for atom in layout.atoms:
             sl = atom.element_slice
@@ -161,6 +165,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
         the device: the per-rectangle work of the MLE Hessian (`_construct_hessian` / `_hessian_from_block`,
         objectivefns.py:1576-1693, 4914-4990) without moving (nE x B1 x B2) arrays to the host.  Returns None if a member
         has no analytic second derivative."""
+        self._require_local(layout, "bulk_hessian_block")
         total = None
         for atom in layout.atoms:
             sl = atom.element_slice
@@ -169,6 +174,17 @@ class B200ForwardSimulator(_MapForwardSimulator):
                 return None
             total = blk if total is None else total + blk
         return total
+
+    @staticmethod
+    def _require_local(layout, what):
+        """The fused reductions sum over the atoms of THIS process only.  With a layout split over MPI processors the reference
+        all-reduces over atom processors (fill_jtj / _gather_hessian, distlayout.py:1220-1359, objectivefns.py:1698-1737); use the
+        stock objective-function methods there (pygsti_b200.objective delegates automatically) or, with one process per GPU
+        under torch.distributed, pygsti_b200.dist.allreduce_jtj."""
+        from .objective import _distributed
+        if _distributed(layout):
+            raise NotImplementedError("%s: layout is distributed over MPI processors; use the objective function's own "
+                                      "dterms/dlsvec/hessian (they run on this simulator) or pygsti_b200.dist" % what)
 
     def __getstate__(self):
         state = super().__getstate__()

@@ -14,9 +14,35 @@ anything else is delegated to the objective function's own (reference) method, w
 import numpy as np
 
 
+def _distributed(layout):
+    """True for layouts split over MPI processors: the fused reductions below only see the local atoms, so those cases go to
+    the objective function's own methods (which gather / all-reduce through the layout, distlayout.py:1220-1359)."""
+    try:
+        if layout.resource_alloc().comm is not None:
+            return True
+    except Exception:
+        pass
+    gps = getattr(layout, "global_param_slice", None)
+    n = getattr(layout, "global_num_params", None)
+    if gps is not None and n is not None and (gps.start or 0, gps.stop) != (0, n):
+        return True
+    gne, ne = getattr(layout, "global_num_elements", None), getattr(layout, "num_elements", None)
+    return gne is not None and ne is not None and gne != ne
+
+
 def _plain(objfn):
+    sim = objfn.model.sim
     return getattr(objfn, "firsts", None) is None and not getattr(objfn, "_process_penalties", False) \
-        and hasattr(objfn.model.sim, "bulk_fill_dprobs_scaled") and objfn.local_ex == 0
+        and hasattr(sim, "bulk_fill_dprobs_scaled") and objfn.local_ex == 0 \
+        and getattr(sim, "derivative_mode", "analytic") == "analytic" and not _distributed(objfn.layout)
+
+
+def _term_weights(objfn):
+    """Row weights a TermWeighted objective (TVD, ...) applies in `_reweight_jac` (objectivefns.py:5148-5152); ones otherwise.
+    Obtained by letting the objective reweight a column of ones, so any subclass is covered."""
+    w = np.ones((objfn.nelements, 1))
+    objfn._reweight_jac(w)
+    return w[:, 0]
 
 
 def _row_scale_terms(objfn):
@@ -32,16 +58,15 @@ def fused_dterms(objfn, paramvec=None):
         return objfn.dterms(paramvec)
     if paramvec is not None:
         objfn.model.from_vector(paramvec)
-    dg = _row_scale_terms(objfn)
+    dg = _row_scale_terms(objfn) * _term_weights(objfn)
     jac = objfn.jac[0:objfn.nelements, :]
     objfn.model.sim.bulk_fill_dprobs_scaled(jac, objfn.layout, dg)
-    objfn._reweight_jac(jac)
     return objfn.jac
 
 
 def _lsvec_scale(objfn, paramvec):
-    """dg_probs * 0.5 / lsvec  and lsvec, following dlsvec (objectivefns.py:4633-4653)."""
-    dg = _row_scale_terms(objfn)
+    """term weight * dg_probs * 0.5 / lsvec  and lsvec, following dterms + dlsvec (objectivefns.py:4609-4624, 4644-4649)."""
+    dg = _row_scale_terms(objfn) * _term_weights(objfn)
     lsvec = objfn.lsvec(paramvec).copy()
     with np.errstate(divide='ignore', invalid='ignore'):
         p5 = 0.5 / lsvec
@@ -58,7 +83,6 @@ def fused_dlsvec(objfn, paramvec=None):
     scale, _ = _lsvec_scale(objfn, paramvec)
     jac = objfn.jac[0:objfn.nelements, :]
     objfn.model.sim.bulk_fill_dprobs_scaled(jac, objfn.layout, scale)
-    objfn._reweight_jac(jac)
     return objfn.jac
 
 

@@ -277,6 +277,69 @@ def case_c2_full_layout(lite=False, name="c2_full_layout"):
     print("%s: %.1fs  %.2f MB (ref probs %.3fs)" % (name, time.time() - t0, os.path.getsize(path) / 1e6, t_probs))
 
 
+def case_c4_gst16_layout():
+    """BASELINE config 4 at the size SURVEY 8d names: smq2Q_XYCNOT `CPTPLND` model (Np = 1680; parameter vector perturbed by
+    1e-3 N(0,1), seed 0), GST design maxL = 16 (7860 circuits, 31 440 outcomes).  Stored: tables, dense model tensors, the
+    (general, non-permutation) derivative map, the members' second derivatives for ONE 64 x 64 Hessian rectangle inside a gate's
+    parameter block (the unit of work of the MLE Hessian, `iter_hprobs_by_rectangle`), and reference outputs for a sample of
+    circuits: probabilities of the Map simulator (every 8th element), and Jacobian rows + that Hessian rectangle from the
+    Matrix simulator."""
+    from pygsti.modelpacks import smq2Q_XYCNOT as mp
+    t0 = time.time()
+    m = mp.target_model('CPTPLND')
+    v = m.to_vector(); rng = np.random.default_rng(0)
+    m.from_vector(v + 1e-3 * rng.standard_normal(v.size))
+    circs = list(mp.create_gst_experiment_design(16).all_circuits_needing_data)
+    m.sim = MapForwardSimulator()
+    layout = m.sim.create_layout(circs, array_types=('e', 'ep'))
+    atom = layout.atoms[0]
+    d = m.dim
+    print("layout built: %.1fs  nE=%d circuits=%d" % (time.time() - t0, layout.num_elements, len(circs)))
+    tabs = packing.pack_atom(atom, d)
+    mt = packing.pack_model(m, atom, d)
+    D = packing.pack_derivs(m, atom, d)
+    rect = (slice(700, 764), slice(690, 754))
+    H2 = packing.pack_hessians(m, atom, d, rect[0], rect[1])
+    out = {"n_atoms": np.array(1), "dim": np.array(d), "num_params": np.array(m.num_params),
+           "n_elements": np.array(layout.num_elements), "n_circuits": np.array(len(circs)), "param_vec": m.to_vector().copy()}
+    out.update(tabs.to_dict("a0_"))
+    out["a0_G"] = mt.G; out["a0_rho"] = mt.rho; out["a0_E"] = mt.E
+    out["a0_D_rows"] = D.rows; out["a0_D_cols"] = D.cols; out["a0_D_vals"] = D.vals
+    out["a0_D_shape"] = np.array([D.n_w, D.n_params])
+    out["a0_element_slice"] = np.array([0, layout.num_elements])
+    out["a0_H2r0_rows"] = H2.rows; out["a0_H2r0_a"] = H2.a; out["a0_H2r0_b"] = H2.b; out["a0_H2r0_vals"] = H2.vals
+    out["a0_H2r0_shape"] = np.array([H2.n_w, H2.n1, H2.n2])
+    out["hess_rects"] = np.array([[rect[0].start, rect[0].stop, rect[1].start, rect[1].stop]])
+    probs = np.empty(layout.num_elements)
+    t1 = time.time(); m.sim.bulk_fill_probs(probs, layout); t_probs = time.time() - t1
+    out["probs_map_stride"] = np.array(8)
+    out["probs_map_sample"] = probs[::8].copy()
+    out["probs_map_sum"] = np.array(probs.sum())
+    out["ref_probs_seconds_1core"] = np.array(t_probs)
+    sample = np.sort(rng.choice(len(circs), size=12, replace=False))
+    mm = m.copy(); mm.sim = MatrixForwardSimulator()
+    sc = [circs[i] for i in sample]
+    ml = mm.sim.create_layout(sc, array_types=('e', 'ep', 'epp'))
+    dpm = np.empty((ml.num_elements, m.num_params)); mm.sim.bulk_fill_dprobs(dpm, ml)
+    blocks = list(mm.sim.iter_hprobs_by_rectangle(ml, [rect], False))
+    hp = np.array(blocks[0][2])
+    el_idx, rows, hrows = [], [], []
+    for k, ci in enumerate(sample):
+        mi, mo = layout.indices_and_outcomes_for_index(int(ci))
+        oi, oo = ml.indices_and_outcomes_for_index(k)
+        mi = np.arange(mi.start, mi.stop) if isinstance(mi, slice) else np.asarray(mi)
+        oi = np.arange(oi.start, oi.stop) if isinstance(oi, slice) else np.asarray(oi)
+        lut = {o: int(ix) for o, ix in zip(oo, oi)}
+        for o, ix in zip(mo, mi):
+            el_idx.append(int(ix)); rows.append(dpm[lut[o]]); hrows.append(hp[lut[o]])
+    out["dprobs_matrix_sample_elements"] = np.array(el_idx)
+    out["dprobs_matrix_sample_rows"] = np.array(rows)
+    out["hprobs_matrix_rect0_sample_rows"] = np.array(hrows)
+    path = os.path.join(HERE, "c4_gst16_layout.npz")
+    np.savez_compressed(path, **out)
+    print("c4_gst16_layout: %.1fs  %.2f MB (ref probs %.3fs, H2 nnz %d)" % (time.time() - t0, os.path.getsize(path) / 1e6, t_probs, H2.rows.size))
+
+
 def case_c2_lite_layout():
     case_c2_full_layout(lite=True, name="c2_lite_layout")
 

@@ -106,3 +106,74 @@ def test_two_rank_jtj_allreduce():
         assert p.exitcode == 0
     for rank, e1, e2 in res:
         assert e1 <= 1e-12 and e2 <= 1e-12, res
+
+
+def _worker_plan(rank, world, port, name, q):
+    sys.path.insert(0, REPO)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pygsti_b200.fixtures import Case
+    from pygsti_b200 import dist as bd
+    from oracle import oracle_np as onp
+    c = Case(name)
+    a = c.atoms[0]
+    plan = bd.ShardPlan(a["tables"], world)
+    slot, n_loc = plan.slot, plan.n_local[rank]
+    J = torch.zeros((plan.n_rows_padded, c.num_params), dtype=torch.float64)
+    P = torch.zeros(plan.n_rows_padded, dtype=torch.float64)
+    local = plan.tables[rank]
+    J[rank * slot:rank * slot + n_loc] = torch.from_numpy(onp.dprobs_analytic(local, a["G"], a["rho"], a["E"], a["D"]))
+    P[rank * slot:rank * slot + n_loc] = torch.from_numpy(onp.mapfill_probs(local, a["G"], a["rho"], a["E"]))
+    bd.allgather_slots(J); bd.allgather_slots(P)
+    pos = plan.position
+    ok = (np.max(np.abs(P.numpy()[pos] - c["probs_map"])) <= 1e-14) and (np.max(np.abs(J.numpy()[pos] - c["dprobs_matrix"])) <= 1e-12)
+    q.put((rank, bool(ok), plan.n_local, [t.num_state_propagations() for t in plan.tables]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c1_1q_full", "c2_2q_full_sub"])
+def test_shard_plan_and_in_place_allgather(name):
+    """The bench's multi-GPU step on CPU: contiguous prefix-ordered shards (ShardPlan), every rank fills its slot of the sharded
+    element axis, ONE in-place all-gather over equal slots, results equal the un-sharded reference arrays
+    (serial == N ranks, as test/unit/mpi/run_me_with_mpiexec.py:186-261 checks for the reference)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30700 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_worker_plan, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+
+
+def test_shard_plan_full_layout_keeps_prefix_sharing():
+    """8 shards of the C2-lite layout: every element exactly once, balanced, and the shards together need barely more
+    propagations WITH prefix sharing than the un-sharded table (the cut costs ~nothing)."""
+    sys.path.insert(0, REPO)
+    from pygsti_b200.fixtures import Case
+    from pygsti_b200 import dist as bd
+    t = Case("c2_lite_layout").atoms[0]["tables"]
+    plan = bd.ShardPlan(t, 8)
+    assert sum(plan.n_local) == t.n_elements and len(np.unique(plan.position)) == t.n_elements
+    assert plan.position.min() >= 0 and plan.position.max() < plan.n_rows_padded
+    assert max(plan.n_local) <= 1.1 * t.n_elements / 8
+    for r in range(8):
+        sl = plan.element_slice(r)
+        assert np.array_equal(np.sort(plan.position[plan.to_original[r]]), np.arange(sl.start, sl.stop))
+
+    def shared_props(tab):                                   # distinct (prep, prefix) pairs = propagations with full prefix sharing
+        seen = set()
+        for k in range(tab.n_rows):
+            ops = tab.row_ops[tab.row_ptr[k]:tab.row_ptr[k + 1]].tolist()
+            key = (int(tab.row_prep[k]),)
+            for o in ops:
+                key = key + (o,)
+                seen.add(hash(key))
+        return len(seen)
+    total = sum(shared_props(tb) for tb in plan.tables)
+    assert total <= 1.02 * 38677 + 8 * 134, total            # 38 677 = the reference's own count for the un-sharded lite layout

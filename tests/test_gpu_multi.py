@@ -1,5 +1,7 @@
-"""Multi-GPU path on real devices (skipped with < 2 GPUs): ranks shard a layout, fill their shard on their GPU
-through the C ABI (device-buffer entry points) and reassemble it with one NCCL all-gather."""
+"""Multi-GPU path on real devices (skipped with < 2 GPUs): ranks shard ONE layout (ShardPlan), fill their shard on their GPU
+through the C ABI (device-buffer entry points) into their slot of the sharded element axis, and reassemble it with ONE
+in-place NCCL all-gather; the sharded J^T J / J^T f take one NCCL all-reduce.  Serial == N ranks, as the reference checks in
+test/unit/mpi/run_me_with_mpiexec.py:186-261."""
 import os
 import sys
 
@@ -22,31 +24,34 @@ def _worker(rank, world, port, name, q):
     from pygsti_b200 import dist as bd, engine
     c = Case(name)
     a = c.atoms[0]
-    local, glob = bd.shard_tables(a["tables"], rank, world)
+    plan = bd.ShardPlan(a["tables"], world)
+    slot, n_loc = plan.slot, plan.n_local[rank]
     stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
     ctx = engine.Context(rank, stream=stream.cuda_stream)
-    at = ctx.upload_atom(local); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
+    at = ctx.upload_atom(plan.tables[rank]); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
     Np = c.num_params
-    J = torch.empty((local.n_elements, Np), dtype=torch.float64, device="cuda")
-    P = torch.empty(local.n_elements, dtype=torch.float64, device="cuda")
-    at.fill_dprobs_dev(J.data_ptr(), Np, P.data_ptr())
-    gi = torch.from_numpy(glob).cuda()
-    Pf = bd.allgather_rows(P, gi, c.n_elements)
-    Jf = bd.allgather_rows(J, gi, c.n_elements)
+    J = torch.zeros((plan.n_rows_padded, Np), dtype=torch.float64, device="cuda")
+    P = torch.zeros(plan.n_rows_padded, dtype=torch.float64, device="cuda")
+    at.fill_dprobs_dev(J[rank * slot:].data_ptr(), Np, P[rank * slot:].data_ptr())
+    bd.allgather_slots(J); bd.allgather_slots(P)
     torch.cuda.synchronize()
+    pos = plan.position
     st = int(c["probs_map_stride"])
-    e1 = float(np.max(np.abs(Pf.cpu().numpy()[::st] - c["probs_map_sample"])))
-    rows = torch.as_tensor(c["dprobs_matrix_sample_elements"], device="cuda")
-    e2 = float(np.max(np.abs(Jf[rows].cpu().numpy() - c["dprobs_matrix_sample_rows"])))
+    e1 = float(np.max(np.abs(P.cpu().numpy()[pos][::st] - c["probs_map_sample"])))
+    rows = torch.as_tensor(pos[c["dprobs_matrix_sample_elements"]], device="cuda")
+    e2 = float(np.max(np.abs(J[rows].cpu().numpy() - c["dprobs_matrix_sample_rows"])))
     # sharded J^T J / J^T f: per-rank b200_jtj_dev on the element shard + ONE NCCL all-reduce
     rs = np.random.default_rng(0).uniform(0.5, 1.5, c.n_elements); fv = np.random.default_rng(1).standard_normal(c.n_elements)
+    glob = plan.to_original[rank]
     d_rs = torch.from_numpy(rs[glob]).cuda(); d_f = torch.from_numpy(fv[glob]).cuda()
     jtj = torch.empty((Np, Np), dtype=torch.float64, device="cuda"); jtf = torch.empty(Np, dtype=torch.float64, device="cuda")
     at.jtj_dev(jtj.data_ptr(), d_rs.data_ptr(), d_f.data_ptr(), jtf.data_ptr())
     bd.allreduce_jtj(jtj, jtf)
     torch.cuda.synchronize()
-    Js = Jf * torch.from_numpy(rs).cuda()[:, None]
-    ref_jtj = Js.T @ Js; ref_jtf = Js.T @ torch.from_numpy(fv).cuda()
+    rs_s = torch.zeros(plan.n_rows_padded, dtype=torch.float64, device="cuda"); fv_s = torch.zeros_like(rs_s)
+    rs_s[torch.from_numpy(pos).cuda()] = torch.from_numpy(rs).cuda(); fv_s[torch.from_numpy(pos).cuda()] = torch.from_numpy(fv).cuda()
+    Js = J * rs_s[:, None]
+    ref_jtj = Js.T @ Js; ref_jtf = Js.T @ fv_s
     e3 = float((jtj - ref_jtj).abs().max() / ref_jtj.abs().max())
     e4 = float((jtf - ref_jtf).abs().max() / ref_jtf.abs().max())
     q.put((rank, e1, e2, e3, e4))

@@ -113,12 +113,121 @@ def test_full_size_layout_properties(gpu_ctx, load_case):
     # per-circuit sums: rows of the prefix table own consecutive out entries
     sums = np.add.reduceat(p[t.out_el], t.out_ptr[:-1])
     assert np.max(np.abs(sums - 1.0)) <= 1e-12
-    jsum = np.add.reduceat(J[t.out_el[:4000]], t.out_ptr[:1000], axis=0)
-    # d/dtheta of sum_j p_j = d/dtheta (sum_j E_j) . s : nonzero only through the effect parameters
-    eff_cols = np.unique(a["D"].cols[a["D"].rows >= t.n_ops * 256 + t.n_rho * 16])
-    mask = np.ones(Np, bool); mask[eff_cols] = False
-    # model is depolarized (not exactly TP) so only check the linear-algebra identity on a sample vs oracle
-    assert np.all(np.isfinite(jsum))
+    # Size-independent identity checked on ALL 273 340 rows.  Every member of this model is `full`: its parameters ARE its
+    # elements, and p is homogeneous of degree (number of occurrences) in each member, so by Euler's theorem
+    #     sum_{params of gate g} theta * dp/dtheta = count_g(circuit) * p,   and = p for the prep and for the effect of the row.
+    D = a["D"]
+    M = np.concatenate([a["G"].ravel(), a["rho"].ravel(), a["E"].ravel()])
+    theta = np.zeros(Np); theta[D.cols] = M[D.rows]
+    counts = _gate_counts(t)                                             # [n_rows, n_ops]
+    row_of_el = np.empty(nE, np.int64); eff_of_el = np.empty(nE, np.int64)
+    row_of_el[t.out_el] = np.repeat(np.arange(t.n_rows), np.diff(t.out_ptr)); eff_of_el[t.out_el] = t.out_eff
+    scale = max(1.0, float(np.max(np.abs(p))))
+    for g in range(t.n_ops):
+        cols = D.cols[(D.rows >= g * 256) & (D.rows < (g + 1) * 256)]
+        lhs = J[:, cols] @ theta[cols]
+        assert np.max(np.abs(lhs - counts[row_of_el, g] * p)) <= 1e-10 * scale * max(1, counts.max()), g
+    off_rho, off_eff = t.n_ops * 256, t.n_ops * 256 + t.n_rho * 16
+    cols = D.cols[(D.rows >= off_rho) & (D.rows < off_eff)]
+    assert np.max(np.abs(J[:, cols] @ theta[cols] - p)) <= 1e-10 * scale
+    for e in range(t.n_eff):
+        cols = D.cols[(D.rows >= off_eff + e * 16) & (D.rows < off_eff + (e + 1) * 16)]
+        lhs = J[:, cols] @ theta[cols]
+        assert np.max(np.abs(lhs - np.where(eff_of_el == e, p, 0.0))) <= 1e-10 * scale, e
+    at.free()
+
+
+def _gate_counts(t):
+    """Occurrences of every gate in the FULL circuit of every prefix-table row (cache links followed)."""
+    counts = np.zeros((t.n_rows, t.n_ops), np.int64)
+    slot = {}
+    for k in range(t.n_rows):
+        c = np.bincount(t.row_ops[t.row_ptr[k]:t.row_ptr[k + 1]], minlength=t.n_ops)
+        if t.row_istart[k] >= 0:
+            c = c + counts[slot[int(t.row_istart[k])]]
+        counts[k] = c
+        if t.row_icache[k] >= 0:
+            slot[int(t.row_icache[k])] = k
+    return counts
+
+
+def test_full_size_config4_cptplnd(gpu_ctx, load_case):
+    """BASELINE config 4 at the size SURVEY 8d names (CPTPLND, Np = 1680, 7860 circuits / 31 440 outcomes): probabilities
+    against the reference's Map simulator, sampled Jacobian rows and a sampled 64 x 64 Hessian rectangle against the
+    reference's Matrix simulator (goldens: make_golden.py c4_gst16_layout), plus the TP property on all circuits."""
+    c = load_case("c4_gst16_layout")
+    a = c.atoms[0]
+    at = _atom(gpu_ctx, a)
+    nE, Np = c.n_elements, c.num_params
+    J = engine.pinned_empty((nE, Np)); p = np.empty(nE)
+    at.fill_dprobs(J, p)
+    st = int(c["probs_map_stride"])
+    assert np.max(np.abs(p[::st] - c["probs_map_sample"])) <= PROBS_TOL
+    assert abs(p.sum() - float(c["probs_map_sum"])) <= 1e-9
+    rows = c["dprobs_matrix_sample_elements"]
+    assert np.max(np.abs(J[rows] - c["dprobs_matrix_sample_rows"])) <= DPROBS_TOL
+    t = a["tables"]
+    # CPTP model: every circuit's probabilities sum to 1 and every circuit's Jacobian rows sum to 0, for ALL circuits
+    assert np.max(np.abs(np.add.reduceat(p[t.out_el], t.out_ptr[:-1]) - 1.0)) <= 1e-12
+    assert np.max(np.abs(np.add.reduceat(J[t.out_el], t.out_ptr[:-1], axis=0))) <= 1e-10
+    r = c["hess_rects"][0]
+    p1, p2 = np.arange(r[0], r[1]), np.arange(r[2], r[3])
+    H = np.empty((nE, p1.size, p2.size))
+    at.fill_hprobs(p1, p2, H, c.hess_map("H2r0"))
+    assert np.max(np.abs(H[rows] - c["hprobs_matrix_rect0_sample_rows"])) <= 1e-9
+    assert np.max(np.abs(np.add.reduceat(H[t.out_el], t.out_ptr[:-1], axis=0))) <= 1e-9     # second derivative of sum_j p_j = 1
+    at.free()
+
+
+def test_full_size_config3_d64(gpu_ctx, load_case):
+    """BASELINE config 3 on one GPU, 5000 of the 50 000 random circuits of the bench stream (d = 64, Np = 775, depth U{1..256}; model
+    tensors from the reference): sampled circuits against the oracle (itself pinned to the reference's Matrix goldens for this
+    model, tests/test_oracle_cpu.py), and for ALL rows the size-independent TP property: sum_j p_j = 1, sum_j dp_j = 0."""
+    from pygsti_b200 import fixtures as fx
+    from oracle import oracle_c
+    c = load_case("c3_3q_localnoise_sub"); a = c.atoms[0]
+    n_ops, n_eff, Np = a["tables"].n_ops, a["tables"].n_eff, a["D"].n_params
+    t, circs = fx.random_layout(64, n_ops, n_eff, 50000, 256, seed=0, rows=(0, 5000))
+    at = gpu_ctx.upload_atom(t); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
+    J = engine.pinned_empty((t.n_elements, Np)); p = np.empty(t.n_elements)
+    at.fill_dprobs(J, p)
+    assert np.max(np.abs(p.reshape(-1, n_eff).sum(axis=1) - 1.0)) <= 1e-12
+    assert np.max(np.abs(J.reshape(-1, n_eff, Np).sum(axis=1))) <= 1e-10
+    orc = oracle_c.Oracle("port")
+    for lo in (0, 2497, 4990):
+        sub, _ = fx.random_layout(64, n_ops, n_eff, 50000, 256, seed=0, rows=(lo, lo + 6))
+        Jo, po = orc.dprobs_analytic(sub, a["G"], a["rho"], a["E"], a["D"])
+        sl = slice(lo * n_eff, (lo + 6) * n_eff)
+        assert np.max(np.abs(p[sl] - po)) <= PROBS_TOL
+        assert np.max(np.abs(J[sl] - Jo)) <= DPROBS_TOL
+    # J^T J / J^T f with an ODD number of parameters (775): the hand-written DMMA reduction against numpy
+    rs = np.random.default_rng(0).uniform(0.5, 1.5, t.n_elements); f = np.random.default_rng(1).standard_normal(t.n_elements)
+    JTJ, JTf = at.jtj(rs, f)
+    Js = J * rs[:, None]
+    ref = Js.T @ Js
+    assert np.max(np.abs(JTJ - ref)) <= 1e-11 * np.max(np.abs(ref)) and np.array_equal(JTJ, JTJ.T)
+    assert np.max(np.abs(JTf - Js.T @ f)) <= 1e-11 * np.max(np.abs(Js.T @ f))
+    at.free()
+
+
+def test_full_size_config5_d256(gpu_ctx):
+    """BASELINE config 5 at full size (d = 256, 14 layer labels, 5000 random circuits of depth U{1..128}, 16 outcomes): sampled
+    circuits against the oracle and, for ALL circuits, linearity in the effects: with E_15 := sum of the other effects the
+    last outcome's probability must equal the sum of the others."""
+    from pygsti_b200 import fixtures as fx
+    from oracle import oracle_c
+    G, rho, E = fx.random_dense_model(256, 14, 1, 16, seed=1)
+    E = E.copy(); E[15] = E[:15].sum(axis=0)
+    t, circs = fx.random_layout(256, 14, 16, 5000, 128, seed=0)
+    at = gpu_ctx.upload_atom(t); at.set_model(G, rho, E)
+    p = np.empty(t.n_elements); at.fill_probs(p)
+    P = p.reshape(-1, 16)
+    assert np.max(np.abs(P[:, :15].sum(axis=1) - P[:, 15])) <= 1e-12 * max(1.0, np.max(np.abs(P)))
+    orc = oracle_c.Oracle("port")
+    for lo in (0, 2500, 4980):
+        sub, _ = fx.random_layout(256, 14, 16, 5000, 128, seed=0, rows=(lo, lo + 20))
+        po = orc.mapfill_probs(sub, G, rho, E)
+        assert np.max(np.abs(p[lo * 16:(lo + 20) * 16] - po)) <= PROBS_TOL * max(1.0, np.max(np.abs(po)))
     at.free()
 
 

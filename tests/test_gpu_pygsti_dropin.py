@@ -239,6 +239,36 @@ def test_four_qubit_cloud_crosstalk_model_d256():
     assert np.max(np.abs(pmap - pb)) <= 1e-10
 
 
+def test_fused_objective_with_term_weights():
+    """A TermWeighted objective ('normalized tvd': rows weighted by 1 / circuit size, objectivefns.py:5175-5192): the weights
+    must reach the fused row scale -- dterms, dlsvec AND J^T J / J^T f -- exactly as `_reweight_jac` applies them."""
+    from pygsti.data import simulate_data
+    from pygsti.objectivefns import objectivefns as _objfns
+    from pygsti_b200 import objective as fused
+    target = smq1Q_XYI.target_model("full TP")
+    datagen = target.depolarize(op_noise=0.1, spam_noise=0.05)
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    ds = simulate_data(datagen, circuits, 1000, seed=1234)
+    start = target.depolarize(op_noise=0.06, spam_noise=0.03)
+
+    def make():
+        m = start.copy(); m.sim = B200ForwardSimulator()
+        return _objfns.TVDFunction.create_from(m, ds, circuits, name='normalized tvd', method_names=('lsvec', 'dlsvec', 'dterms'))
+
+    ours, same = make(), make()
+    v = start.to_vector()
+    w = fused._term_weights(ours)
+    assert w.shape == (ours.nelements,) and np.ptp(w) > 0.1                 # genuinely non-trivial weights
+    Jsame = same.dlsvec(v).copy(); Dsame = same.dterms(v).copy(); fsame = same.lsvec(v).copy()
+    Df = fused.fused_dterms(ours, v).copy(); Jf = fused.fused_dlsvec(ours, v).copy()
+    assert np.max(np.abs(Df - Dsame)) <= 1e-11 * max(1.0, np.max(np.abs(Dsame)))
+    assert np.max(np.abs(Jf - Jsame)) <= 1e-11 * max(1.0, np.max(np.abs(Jsame)))
+    JTJ, JTf = fused.fused_jtj(ours, v)
+    R = Jsame.T @ Jsame
+    assert np.max(np.abs(JTJ - R)) <= 1e-10 * np.max(np.abs(R))
+    assert np.max(np.abs(JTf - Jsame.T @ fsame)) <= 1e-10 * max(1.0, np.max(np.abs(Jsame.T @ fsame)))
+
+
 @pytest.mark.parametrize("objname", ["chi2", "logl"])
 def test_fused_objective_jacobian_and_jtj(objname):
     """'next' row 8f-1: dterms / dlsvec with the row scaling fused into the kernel epilogue, and J^T J / J^T f without
