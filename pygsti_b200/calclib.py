@@ -337,32 +337,37 @@ def _deriv_map(fwdsim, layout_atom, ent, param_indices):
     return pidx
 
 
-def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices, layout_atom, param_indices,
-                        resource_alloc, eps, row_scale=None):
-    """array_to_fill[dest_indices, dest_param_indices] = d(probabilities)/d(params[param_indices])
-    (replaces pyx:290-383).  ``eps`` is used only in 'fd' mode.  ``row_scale`` (extension, length = number of
-    elements of the atom): every Jacobian row is multiplied by its entry on the device (objective-function fill)."""
-    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+def prepare_dprobs_atom(fwdsim, layout_atom, param_indices):
+    """Host half of a Jacobian fill: bring the device copy of the model tensors and of the derivative map for this parameter block
+    up to date (host packing + small uploads).  Returns (engine atom, parameter index array).  Runs on the calling thread only:
+    it walks pyGSTi model objects."""
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
-    atom = ent["atom"]
     if getattr(fwdsim, "device_lindblad", False) and _lindblad_model_and_derivs(fwdsim, layout_atom, ent, param_indices, ctx):
         pidx = packing.param_slice_to_array(param_indices, model.num_params)
     else:
         _upload_model(fwdsim, layout_atom, ent)
         pidx = _deriv_map(fwdsim, layout_atom, ent, param_indices)
         _maybe_bind(fwdsim, layout_atom, ent, pidx)
-    if not shared_mem_leader:
-        return
+    return ent["atom"], pidx
+
+
+def run_dprobs_atom(fwdsim, atom, pidx, array_to_fill, dest_indices, dest_param_indices, layout_atom, eps, row_scale=None,
+                    pr_array_to_fill=None):
+    """Device half of a Jacobian fill: kernels + device-to-host copy into ``array_to_fill[dest_indices, dest_param_indices]``
+    (and, if given, the probabilities into ``pr_array_to_fill``, a view of exactly this atom's elements).  Touches only the
+    engine (the C calls release the GIL): atoms that live on different GPUs can run from different threads."""
     nE = layout_atom.num_elements
     nP = int(pidx.size)
     mode = getattr(fwdsim, "derivative_mode", "analytic")
+    pr = pr_array_to_fill if (pr_array_to_fill is not None and pr_array_to_fill.dtype == np.float64
+                              and pr_array_to_fill.ndim == 1 and pr_array_to_fill.shape[0] == nE) else None
     if mode == "fd":
         if row_scale is not None:
             raise ValueError("row_scale is only supported with derivative_mode='analytic'")
-        fill = (lambda out: atom.fill_dprobs_fd(out, eps=eps))
+        fill = (lambda out: atom.fill_dprobs_fd(out, eps=eps, probs_out=pr))
     else:
-        fill = (lambda out: atom.fill_dprobs(out, row_scale=row_scale))
+        fill = (lambda out: atom.fill_dprobs(out, probs_out=pr, row_scale=row_scale))
 
     rblk = _contiguous_block(dest_indices, array_to_fill.shape[0])
     if dest_param_indices is None:
@@ -372,7 +377,11 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
     direct = (rblk is not None and cblk is not None and rblk[1] - rblk[0] == nE and cblk[1] - cblk[0] == nP
               and array_to_fill.dtype == np.float64
               and (array_to_fill.shape[1] <= 1 or array_to_fill.strides[1] == 8))
-    if nE == 0 or nP == 0:
+    if nE == 0:
+        return
+    if nP == 0:
+        if pr is not None:
+            atom.fill_probs(pr)
         return
     if direct:
         _pin_destination(array_to_fill)
@@ -383,6 +392,20 @@ def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices,
         r = _to_index_array(dest_indices, array_to_fill.shape[0])
         c = np.arange(nP) if dest_param_indices is None else _to_index_array(dest_param_indices, array_to_fill.shape[1])
         array_to_fill[np.ix_(r, c)] = tmp
+    if pr_array_to_fill is not None and pr is None:          # unusual destination: separate fill
+        tmp = np.empty(nE); atom.fill_probs(tmp); pr_array_to_fill[...] = tmp
+
+
+def mapfill_dprobs_atom(fwdsim, array_to_fill, dest_indices, dest_param_indices, layout_atom, param_indices,
+                        resource_alloc, eps, row_scale=None):
+    """array_to_fill[dest_indices, dest_param_indices] = d(probabilities)/d(params[param_indices])
+    (replaces pyx:290-383).  ``eps`` is used only in 'fd' mode.  ``row_scale`` (extension, length = number of
+    elements of the atom): every Jacobian row is multiplied by its entry on the device (objective-function fill)."""
+    shared_mem_leader = resource_alloc.is_host_leader if (resource_alloc is not None) else True
+    atom, pidx = prepare_dprobs_atom(fwdsim, layout_atom, param_indices)
+    if not shared_mem_leader:
+        return
+    run_dprobs_atom(fwdsim, atom, pidx, array_to_fill, dest_indices, dest_param_indices, layout_atom, eps, row_scale)
 
 
 def atom_jtj(fwdsim, layout_atom, row_scale=None, f=None):

@@ -8,6 +8,7 @@
 #include "kernels_level.cuh"
 #include "kernels_levelj.cuh"
 #include "kernels_jtj.cuh"
+#include "kernels_gemm.cuh"
 #include <cstdlib>
 
 #include <algorithm>
@@ -88,6 +89,7 @@ struct b200_atom {
     bool has_lj = false;
     DevBuf lj_fbase, lj_bbase, lj_frow, lj_brow, lj_btiles, lj_ti_ptr, lj_items;
     DevBuf lj2_ti_ptr, lj2_mask, lj2_items, lj2_ij, lj2_v;       // DMMA accumulate (k_level_accum2): per (tile, gate, sub-block)
+    DevBuf lj3_tp, lj3_mask, lj3_items, lj3_ij, lj3_v;           // warp-per-outcome accumulate (k_level_accum3): per (gate, sub-block, M half)
     std::vector<uint32_t> lj_btile_ptr;     // [max_depth+1]
     uint64_t lj_rows_f = 0, lj_rows_b = 0;
     int lj_no_max = 0, lj_n_tiles = 0, lj_pt = LJ_PT_MIN;   // lj_pt: parameters per accumulate tile (chosen in set_derivs)
@@ -109,6 +111,8 @@ struct b200_atom {
     int32_t n_params = 0;
     bool unit_perm = false;
     DevBuf cptr, crow, cval;               // CSC of D
+    bool has_dense = false; int64_t ldD = 0;   // general path: D also DENSE [n_w x ldD] + per 128-column tile the 16-row K chunks with non-zeros
+    DevBuf Dd, kt_ptr, kt_idx;
     DevBuf colmap, spam_col, spam_w;       // fused-path maps (unit partial permutation)
     int n_spam = 0;
     DevBuf id_colmap, id_spam_col, id_spam_w;  // identity maps: d16 kernel writing W for the general path
@@ -566,9 +570,9 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
                       &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
                       &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
-                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
+                      &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->lj3_tp, &a->lj3_mask, &a->lj3_items, &a->lj3_ij, &a->lj3_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
                       &a->t_counters, &a->t_units, &a->t_uidx,
-                      &a->cptr, &a->crow, &a->cval, &a->colmap, &a->spam_col, &a->spam_w,
+                      &a->cptr, &a->crow, &a->cval, &a->Dd, &a->kt_ptr, &a->kt_idx, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->aff_rptr, &a->aff_rcol, &a->aff_rval, &a->aff_const, &a->aff_theta,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
     for (DevBuf* b : bufs) b->release();
@@ -783,6 +787,23 @@ extern "C" int b200_atom_set_params(b200_ctx* ctx, b200_atom* a, int32_t n_param
     return B200_OK;
 }
 
+// Per tile of GM_TN columns: the sorted list of GM_KC-row chunks of the right-hand side that contain a non-zero (host side).
+// `col_rows(c, fn)` calls fn(row) for every non-zero row of column c.
+template <class F>
+static void build_kt_lists(int n_cols, F col_rows, std::vector<int32_t>& kt_ptr, std::vector<int32_t>& kt_idx) {
+    const int n_tiles = std::max(1, (n_cols + GM_TN - 1) / GM_TN);
+    kt_ptr.assign((size_t)n_tiles + 1, 0); kt_idx.clear();
+    std::vector<int32_t> tmp;
+    for (int tl = 0; tl < n_tiles; ++tl) {
+        tmp.clear();
+        for (int c = tl * GM_TN; c < std::min(n_cols, (tl + 1) * GM_TN); ++c) col_rows(c, [&](int64_t r) { tmp.push_back((int32_t)(r / GM_KC)); });
+        std::sort(tmp.begin(), tmp.end()); tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        kt_idx.insert(kt_idx.end(), tmp.begin(), tmp.end());
+        kt_ptr[tl + 1] = (int32_t)kt_idx.size();
+    }
+    if (kt_idx.empty()) kt_idx.push_back(0);
+}
+
 extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, int32_t n_params,
                                     int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals)
 {
@@ -840,6 +861,24 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
         a->n_spam = (int)spam_col.size();
         if ((rc = upload_vec(a->colmap, colmap, ctx->stream)) || (rc = upload_vec(a->spam_col, spam_col, ctx->stream)) ||
             (rc = upload_vec(a->spam_w, spam_w, ctx->stream))) return rc;
+    }
+    a->has_dense = false;
+    if (!unit && !a->has_lj && n_params > 0) {
+        // general path: J = W . D as a DMMA GEMM -- D dense on the device + K-chunk lists (kernels_gemm.cuh)
+        const int64_t ldD = (n_params + 1) & ~1;
+        if ((double)n_w * (double)ldD * 8.0 <= 2.0e9) {
+            std::vector<int32_t> ktp, kti;
+            build_kt_lists(n_params, [&](int col, auto fn) { for (int t = cptr[col]; t < cptr[col + 1]; ++t) fn(crow[t]); }, ktp, kti);
+            if ((rc = upload_vec(a->kt_ptr, ktp, ctx->stream)) || (rc = upload_vec(a->kt_idx, kti, ctx->stream))) return rc;
+            CU(a->Dd.ensure((size_t)n_w * ldD * 8));
+            CU(cudaMemsetAsync(a->Dd.p, 0, (size_t)n_w * ldD * 8, ctx->stream));
+            k_csc_to_dense<<<(unsigned)std::min(n_params, 4096), 128, 0, ctx->stream>>>(a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
+                                                                                     nullptr, n_params, a->Dd.as<double>(), ldD);
+            ctx->launches++;
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(ctx->stream));
+            a->ldD = ldD; a->has_dense = true;
+        }
     }
     if (a->has_lj) {
         // tile plan of the level-batched Jacobian path: per (tile of LJ_PT parameters, W-space block) the columns that
@@ -923,9 +962,72 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
                 (rc = upload_vec(a->lj2_v, nz_v, ctx->stream))) return rc;
             CU(cudaStreamSynchronize(ctx->stream));
         }
+        // plan of the warp-per-outcome accumulate (k_level_accum3): gate-block non-zeros regrouped by (gate, 64 x 64 sub-block,
+        // M half of 32 rows), ALL parameters together, with the 8 x 8 tiles (4 x 8 per half) each group touches
+        {
+            const int d = a->dim, sbd = d / 64, nsb = sbd * sbd;
+            struct Rec3 { uint32_t key; uint32_t p; uint16_t ij; double v; };
+            std::vector<Rec3> recs;
+            for (int p = 0; p < n_params; ++p)
+                for (int t = cptr[p]; t < cptr[p + 1]; ++t) {
+                    if (crow[t] >= a->off_rho) break;
+                    const int g = (int)(crow[t] / dd); const int wl = (int)(crow[t] - (int64_t)g * dd);
+                    const int i = wl / d, j = wl - i * d;
+                    const int sb = (i / 64) * sbd + (j / 64), mh = (i & 63) / 32;
+                    Rec3 r; r.key = (uint32_t)((g * nsb + sb) * 2 + mh); r.p = (uint32_t)p;
+                    r.ij = (uint16_t)(((i & 31) << 8) | (j & 63)); r.v = cval[t];
+                    recs.push_back(r);
+                }
+            std::stable_sort(recs.begin(), recs.end(), [](const Rec3& x, const Rec3& y) { return x.key != y.key ? x.key < y.key : x.p < y.p; });
+            const size_t n_keys = (size_t)a->n_ops * nsb * 2;
+            std::vector<uint32_t> tp3(n_keys + 1, 0), mask3(std::max<size_t>(n_keys, 1), 0);
+            std::vector<uint4> items3; std::vector<uint16_t> ij3(recs.size()); std::vector<double> v3(recs.size());
+            size_t r = 0;
+            for (size_t key = 0; key < n_keys; ++key) {
+                tp3[key] = (uint32_t)items3.size();
+                while (r < recs.size() && recs[r].key == key) {
+                    uint4 it = make_uint4(recs[r].p, (unsigned)r, (unsigned)r, 0u);
+                    while (r < recs.size() && recs[r].key == key && recs[r].p == it.x) {
+                        ij3[r] = recs[r].ij; v3[r] = recs[r].v;
+                        mask3[key] |= 1u << (8 * ((recs[r].ij >> 8) / 8) + (recs[r].ij & 0xff) / 8);
+                        ++r;
+                    }
+                    it.z = (unsigned)r;
+                    items3.push_back(it);
+                }
+            }
+            tp3[n_keys] = (uint32_t)items3.size();
+            if (items3.empty()) items3.push_back(make_uint4(0, 0, 0, 0));
+            if (ij3.empty()) { ij3.push_back(0); v3.push_back(0.0); }
+            if ((rc = upload_vec(a->lj3_tp, tp3, ctx->stream)) || (rc = upload_vec(a->lj3_mask, mask3, ctx->stream)) ||
+                (rc = upload_vec(a->lj3_items, items3, ctx->stream)) || (rc = upload_vec(a->lj3_ij, ij3, ctx->stream)) ||
+                (rc = upload_vec(a->lj3_v, v3, ctx->stream))) return rc;
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_derivs = true;
+    return B200_OK;
+}
+
+// C (+)= A . B  (kernels_gemm.cuh); `batch` entries of A / C share B
+static int ab_device(b200_ctx* c, const double* A, int64_t lda, int64_t strideA, const double* B, int64_t ldb,
+                     double* C, int64_t ldc, int64_t strideC, int64_t M, int N, int K,
+                     const int32_t* kt_ptr, const int32_t* kt_idx, const double* row_scale, bool accumulate, int batch) {
+    if (M <= 0 || N <= 0 || batch <= 0) return B200_OK;
+    if ((lda & 1) || (ldb & 1) || (strideA & 1) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15))
+        return fail(B200_E_INVALID, "A . B: operands must be 16-byte aligned with even row strides");
+    AbArgs p;
+    p.A = A; p.lda = lda; p.strideA = strideA; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.strideC = strideC;
+    p.M = M; p.N = N; p.K = K; p.kt_ptr = kt_ptr; p.kt_idx = kt_idx; p.row_scale = row_scale; p.accumulate = accumulate ? 1 : 0;
+    const size_t smem = (size_t)GM_ST * GM_STAGE_DOUBLES * 8;
+    CU(cudaFuncSetAttribute(k_ab_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t gm = (M + GM_TM - 1) / GM_TM;
+    if (gm >= ((int64_t)1 << 31) || batch > 65535) return fail(B200_E_UNSUPPORTED, "A . B: grid too large");
+    dim3 grid((unsigned)gm, (unsigned)((N + GM_TN - 1) / GM_TN), (unsigned)batch);
+    k_ab_dmma<<<grid, 256, smem, c->stream>>>(p);
+    c->launches++;
+    CU(cudaGetLastError());
     return B200_OK;
 }
 
@@ -1166,8 +1268,20 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
         k_levelj_probs<D><<<gi, 128, 0, c->stream>>>(ad, md, lj, d_probs);
         c->launches++;
     }
-    static const bool accum_v1 = getenv("B200_LJ_ACCUM_V1") != nullptr;      // dev knob: scalar shared-memory contraction
+    static const bool accum_v1 = getenv("B200_LJ_ACCUM_V1") != nullptr;      // test knobs: scalar shared-memory contraction (v1),
+    static const bool accum_v2 = getenv("B200_LJ_ACCUM_V2") != nullptr;      // CTA-per-(circuit, parameter tile) DMMA accumulate (v2)
     const size_t smemC2 = ((size_t)a->lj_no_max * a->lj_pt + 64 * LJ_LDW) * 8 + LJ_KMAX * 4 + 16;
+    const int np_pad = (a->n_params + 7) & ~7;
+    const size_t smemC3 = ((size_t)LJ3_WARPS * np_pad + (size_t)LJ3_WARPS * 32 * LJ3_LDW) * 8;
+    const int n_og = (a->lj_no_max + LJ3_WARPS - 1) / LJ3_WARPS;
+    if (!accum_v1 && !accum_v2 && smemC3 + 1024 <= c->smem_optin && (int64_t)a->n_rows * n_og < ((int64_t)1 << 31)) {
+        LevelJ3Dev l3;
+        l3.tp3 = a->lj3_tp.as<uint32_t>(); l3.mask3 = a->lj3_mask.as<uint32_t>(); l3.items3 = a->lj3_items.as<uint4>();
+        l3.nz_ij = a->lj3_ij.as<uint16_t>(); l3.nz_v = a->lj3_v.as<double>();
+        l3.zrow_f = (uint32_t)a->lj_rows_f; l3.zrow_b = (uint32_t)a->lj_rows_b; l3.nsb = (D / 64) * (D / 64); l3.np_pad = np_pad; l3.n_og = n_og;
+        CU(cudaFuncSetAttribute(k_level_accum3<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC3));
+        k_level_accum3<D><<<(unsigned)(a->n_rows * n_og), LJ3_WARPS * 32, smemC3, c->stream>>>(ad, md, lj, l3, d_out, ld, d_scale);
+    } else
     if (accum_v1 || smemC2 + 1024 > c->smem_optin) {
         CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         k_level_accum<D><<<(unsigned)(a->n_rows * a->lj_n_tiles), LJ_THREADS, smemC, c->stream>>>(ad, md, lj, d_out, ld, d_scale);
@@ -1209,6 +1323,9 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
     CU(c->w_buf.ensure((size_t)a->n_elements * a->n_w * sizeof(double)));
     int rc = compute_w(c, a, c->w_buf.as<double>(), d_probs);
     if (rc) return rc;
+    if (a->has_dense)
+        return ab_device(c, c->w_buf.as<double>(), a->n_w, 0, a->Dd.as<double>(), a->ldD, d_out, ld, 0, a->n_elements, a->n_params, (int)a->n_w,
+                         a->kt_ptr.as<int32_t>(), a->kt_idx.as<int32_t>(), d_scale, false, 1);
     dim3 grid((a->n_params + 127) / 128, (unsigned)std::min<int64_t>(a->n_elements, 65535));
     k_contract_csc<<<grid, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, a->n_elements, a->n_params,
                                                  a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(), d_out, ld, d_scale);
@@ -1302,9 +1419,21 @@ static int atb_device(b200_ctx* c, const double* A, int64_t lda, int na, const d
     p.A = A; p.lda = lda; p.na = na; p.B = B; p.ldb = ldb; p.nb = nb; p.nE = nE; p.tri = tri ? 1 : 0;
     p.n_bi = (na + JT_T - 1) / JT_T; p.n_bj = (nb + JT_T - 1) / JT_T;
     p.n_tiles = tri ? p.n_bi * (p.n_bi + 1) / 2 : p.n_bi * p.n_bj;
-    // K slices: about four waves of CTAs, at least 128 rows each; partial tiles are summed in slice order afterwards
-    int64_t S = ((int64_t)c->sm_count * 4 + p.n_tiles / 2) / p.n_tiles;
-    S = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(S, 256), (nE + 127) / 128));
+    // K slices (partial tiles are summed in slice order afterwards): one CTA per (slice, tile) and one CTA per SM, so the
+    // slice count is chosen to fill whole waves of SMs -- 9 slices x 66 tiles = 594 CTAs on 148 SMs ran 5 waves for 4.01 waves
+    // of work (measured: 0.57 of the DMMA peak with the pipe 84 % busy while active).  Search 3..10 waves, >= 256 rows a slice.
+    int64_t S = 1;
+    {
+        const int64_t s_max = std::max<int64_t>(1, std::min<int64_t>(256, nE / 256));
+        double best = -1.0;
+        for (int64_t cand = 1; cand <= s_max; ++cand) {
+            const int64_t ctas = cand * p.n_tiles, waves = (ctas + c->sm_count - 1) / c->sm_count;
+            if (waves > 10 && best > 0) break;
+            double eff = (double)ctas / (double)(waves * c->sm_count);
+            if (waves < 3) eff *= 0.9;                       // few long CTAs: the tail of the last wave is not hidden
+            if (eff > best + 1e-9) { best = eff; S = cand; }
+        }
+    }
     p.rows_per_slice = std::max<int64_t>(JT_KC, ((nE + S - 1) / S + JT_KC - 1) / JT_KC * JT_KC);
     p.n_slices = (int)std::max<int64_t>(1, (nE + p.rows_per_slice - 1) / p.rows_per_slice);
     p.f = (atf && f) ? f : nullptr;
@@ -1507,25 +1636,73 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
             krow[t] = h_rows[i]; kval[t] = h_vals[i];
         }
         kptr.push_back((int32_t)nnz2);
-        DevBuf d_ukey, d_kptr, d_krow, d_kval;
-        if ((rc = upload_vec(d_ukey, ukey, c->stream)) || (rc = upload_vec(d_kptr, kptr, c->stream)) ||
-            (rc = upload_vec(d_krow, krow, c->stream)) || (rc = upload_vec(d_kval, kval, c->stream))) return rc;
         CU(c->w_buf.ensure((size_t)per));
-        CU(cudaMemsetAsync(d_out.p, 0, (size_t)nE * n1 * n2 * 8, c->stream));
         rc = compute_w(c, a, c->w_buf.as<double>(), nullptr);
         if (rc) return rc;
-        const int nk = (int)ukey.size();
-        dim3 gk((nk + 127) / 128, (unsigned)std::min<int64_t>(nE, 65535));
-        k_hess_d2<<<gk, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, n1, n2, nk, d_ukey.as<int64_t>(), d_kptr.as<int32_t>(),
-                                            d_krow.as<int32_t>(), d_kval.as<double>(), d_out.as<double>());
-        c->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->stream));
-        d_ukey.release(); d_kptr.release(); d_krow.release(); d_kval.release();
+        const int64_t n12 = (int64_t)n1 * n2, ld12 = (n12 + 1) & ~(int64_t)1;
+        if ((double)a->n_w * (double)ld12 * 8.0 <= 2.0e9 && n12 < ((int64_t)1 << 31)) {
+            // out = W . D2 as a DMMA GEMM: D2 dense [n_w x n1 n2] (duplicates merged on the host) + K-chunk lists per column tile
+            std::vector<int32_t> mrow; std::vector<int64_t> mcol; std::vector<double> mval;
+            mrow.reserve((size_t)nnz2); mcol.reserve((size_t)nnz2); mval.reserve((size_t)nnz2);
+            for (size_t k = 0; k < ukey.size(); ++k)
+                for (int32_t t = kptr[k]; t < kptr[k + 1]; ++t) {
+                    if (t > kptr[k] && krow[t] == mrow.back()) { mval.back() += kval[t]; continue; }
+                    mrow.push_back(krow[t]); mcol.push_back(ukey[k]); mval.push_back(kval[t]);
+                }
+            std::vector<int32_t> ktp, kti;
+            {   // entries are sorted by key = column: walk them tile by tile
+                size_t pos = 0;
+                build_kt_lists((int)n12, [&](int col, auto fn) {
+                    while (pos < mcol.size() && mcol[pos] < col) ++pos;
+                    for (size_t q = pos; q < mcol.size() && mcol[q] == col; ++q) fn(mrow[q]); }, ktp, kti);
+            }
+            DevBuf d_mrow, d_mcol, d_mval, d_ktp, d_kti, d_D2;
+            if ((rc = upload_vec(d_mrow, mrow, c->stream)) || (rc = upload_vec(d_mcol, mcol, c->stream)) || (rc = upload_vec(d_mval, mval, c->stream)) ||
+                (rc = upload_vec(d_ktp, ktp, c->stream)) || (rc = upload_vec(d_kti, kti, c->stream))) return rc;
+            CU(d_D2.ensure((size_t)a->n_w * ld12 * 8));
+            CU(cudaMemsetAsync(d_D2.p, 0, (size_t)a->n_w * ld12 * 8, c->stream));
+            k_coo_to_dense<<<(unsigned)std::min<int64_t>(((int64_t)mrow.size() + 255) / 256 + 1, 4096), 256, 0, c->stream>>>(
+                (int64_t)mrow.size(), d_mrow.as<int32_t>(), d_mcol.as<int64_t>(), d_mval.as<double>(), d_D2.as<double>(), ld12);
+            c->launches++;
+            rc = ab_device(c, c->w_buf.as<double>(), a->n_w, 0, d_D2.as<double>(), ld12, d_out.as<double>(), n12, 0, nE, (int)n12, (int)a->n_w,
+                           d_ktp.as<int32_t>(), d_kti.as<int32_t>(), nullptr, false, 1);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(c->stream));
+            d_mrow.release(); d_mcol.release(); d_mval.release(); d_ktp.release(); d_kti.release(); d_D2.release();
+        } else {
+            DevBuf d_ukey, d_kptr, d_krow, d_kval;
+            if ((rc = upload_vec(d_ukey, ukey, c->stream)) || (rc = upload_vec(d_kptr, kptr, c->stream)) ||
+                (rc = upload_vec(d_krow, krow, c->stream)) || (rc = upload_vec(d_kval, kval, c->stream))) return rc;
+            CU(cudaMemsetAsync(d_out.p, 0, (size_t)nE * n1 * n2 * 8, c->stream));
+            const int nk = (int)ukey.size();
+            dim3 gk((nk + 127) / 128, (unsigned)std::min<int64_t>(nE, 65535));
+            k_hess_d2<<<gk, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, n1, n2, nk, d_ukey.as<int64_t>(), d_kptr.as<int32_t>(),
+                                                d_krow.as<int32_t>(), d_kval.as<double>(), d_out.as<double>());
+            c->launches++;
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+            d_ukey.release(); d_kptr.release(); d_krow.release(); d_kval.release();
+        }
         accumulate = 1;
     }
-    // batch of tangent directions bounded by ~1 GB of W scratch
-    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n1, ((int64_t)1 << 30) / std::max<int64_t>(per, 1)));
+    // first-order part: out[:, a, :] (+)= Wp_a . D[:, p2] per tangent direction a -- dense D[:, p2] + K-chunk lists for the DMMA GEMM
+    DevBuf d_Dsel, d_ktp2, d_kti2;
+    const int64_t ld2 = (n2 + 1) & ~1;
+    const bool dense2 = (double)a->n_w * (double)ld2 * 8.0 <= 2.0e9;
+    if (dense2) {
+        std::vector<int32_t> ktp, kti;
+        build_kt_lists(n2, [&](int col, auto fn) { for (int t = a->h_cptr[p2[col]]; t < a->h_cptr[p2[col] + 1]; ++t) fn(a->h_crow[t]); }, ktp, kti);
+        if ((rc = upload_vec(d_ktp2, ktp, c->stream)) || (rc = upload_vec(d_kti2, kti, c->stream))) return rc;
+        CU(d_Dsel.ensure((size_t)a->n_w * ld2 * 8));
+        CU(cudaMemsetAsync(d_Dsel.p, 0, (size_t)a->n_w * ld2 * 8, c->stream));
+        k_csc_to_dense<<<(unsigned)std::min(n2, 4096), 128, 0, c->stream>>>(a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
+                                                                           d_p2.as<int32_t>(), n2, d_Dsel.as<double>(), ld2);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));          // the host K-chunk lists go out of scope
+    }
+    // batch of tangent directions bounded by ~8 GB of W scratch
+    const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n1, ((int64_t)8 << 30) / std::max<int64_t>(per, 1)));
     CU(c->w_buf.ensure((size_t)B * per));
     CU(c->fd_models.ensure((size_t)B * a->n_w * 8));
     CU(c->fd_gt.ensure(std::max<size_t>((size_t)B * a->off_rho * 8, 16)));
@@ -1551,13 +1728,21 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
             default: rc = fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
         }
         if (rc) return rc;
-        dim3 g4((n2 + 127) / 128, (unsigned)std::min<int64_t>(nE * nb, 65535));
-        k_contract_hess<<<g4, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, nb, a0, n1, n2, d_p2.as<int32_t>(),
-                                                   a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
-                                                   d_out.as<double>(), accumulate);
-        c->launches++;
-        CU(cudaGetLastError());
+        if (dense2) {
+            rc = ab_device(c, c->w_buf.as<double>(), a->n_w, nE * a->n_w, d_Dsel.as<double>(), ld2, d_out.as<double>() + (size_t)a0 * n2,
+                           (int64_t)n1 * n2, n2, nE, n2, (int)a->n_w, d_ktp2.as<int32_t>(), d_kti2.as<int32_t>(), nullptr, accumulate != 0, nb);
+            if (rc) return rc;
+        } else {
+            dim3 g4((n2 + 127) / 128, (unsigned)std::min<int64_t>(nE * nb, 65535));
+            k_contract_hess<<<g4, 128, 0, c->stream>>>(c->w_buf.as<double>(), a->n_w, nE, nb, a0, n1, n2, d_p2.as<int32_t>(),
+                                                       a->cptr.as<int32_t>(), a->crow.as<int32_t>(), a->cval.as<double>(),
+                                                       d_out.as<double>(), accumulate);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
     }
+    CU(cudaStreamSynchronize(c->stream));
+    d_Dsel.release(); d_ktp2.release(); d_kti2.release();
     if (red_out) {
         // MLE Hessian block (objectivefns.py:4914-4990 `_hessian_from_block` without omitted-outcome rows):
         //   red[a][b] = sum_el w_h[el] H[el][a][b] + w_d[el] J[el][p1[a]] J[el][p2[b]]      -- only n1 x n2 doubles leave the device

@@ -391,3 +391,154 @@ k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __res
         for (int p = tid; p < tile_np; p += LJ_THREADS) __stcs(Jr + p, Jacc[o * LJ_PT + p] * sc);
     }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// phase C, version 3 (round 2, default): no CTA barriers, one WARP per (circuit, outcome).
+// Version 2 ran 10 gates x 8 outcomes = 80 serial phases per CTA, each a few DMMA between two __syncthreads and a
+// dependent gather (ncu: DMMA waiting on the long scoreboard 24 % of the samples, barrier 17 %, DMMA pipe 25 %; 66 of the
+// 85 ms of BASELINE config 3).  Here a warp owns one outcome of one circuit for the whole kernel:
+//   * its adjoint rows e^(k+1) (the 26 GB table BH at config 3) are read exactly once, half a row (32 components = one M
+//     half of the 64 x 64 block) per pass; the state rows s_k are shared by the warps of the CTA through L1;
+//   * per (gate, 64 x 64 sub-block, M half): W[i][j] = sum_k e^(k+1)[i] s_k[j] on DMMA (M = 32, N = 64, K = the bucket's
+//     steps, only the 8 x 8 tiles the derivative map needs: 32-bit tile mask from the host), software-pipelined one group
+//     of 4 steps ahead, parked in a WARP-PRIVATE shared tile and contracted with the sparse map by the same warp (one lane
+//     per parameter) into the warp's own accumulator row: only __syncwarp, no atomics, fixed order (deterministic);
+//   * the finished row is stored coalesced with the objective-function row scale applied.
+// One CTA = 4 warps = 4 outcomes of one circuit; all parameters at once (no parameter tiles).
+// dynamic smem (doubles): LJ3_WARPS * np_pad (accumulator rows) + LJ3_WARPS * 32 * LJ3_LDW (W tiles)
+// ------------------------------------------------------------------------------------------------------------
+#define LJ3_WARPS 4
+#define LJ3_LDW 66
+
+struct LevelJ3Dev {
+    const uint32_t* tp3;       // [n_ops * nsb * 2 + 1] item ranges per (gate, sub-block, M half)
+    const uint32_t* mask3;     // [n_ops * nsb * 2] needed 8x8 tiles of the half block (bit 8*mt + nt, mt < 4)
+    const uint4* items3;       // (parameter, nz lo, nz hi, 0)
+    const uint16_t* nz_ij;     // (i_local << 8) | j_local, i_local < 32, j_local < 64
+    const double* nz_v;
+    uint32_t zrow_f, zrow_b;   // all-zero rows of FS / BH
+    int nsb, np_pad, n_og;     // sub-blocks per matrix; padded accumulator row length; outcome groups per circuit
+};
+
+template <int D>
+__global__ void __launch_bounds__(LJ3_WARPS * 32, 2)
+k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __restrict__ J, int64_t ld,
+               const double* __restrict__ row_scale)
+{
+    constexpr int SBD = D / 64;
+    extern __shared__ __align__(16) double sml[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mrow = lane >> 2, q = lane & 3;
+    const int c = blockIdx.x / l3.n_og, og = blockIdx.x - c * l3.n_og;
+    const int q0 = a.out_ptr[c], nout = a.out_ptr[c + 1] - q0;
+    const int o = og * LJ3_WARPS + warp;
+    if (o >= nout) return;                              // (no CTA-wide barrier anywhere below)
+    double* Jacc = sml + (size_t)warp * l3.np_pad;
+    double* Wt = sml + (size_t)LJ3_WARPS * l3.np_pad + (size_t)warp * (32 * LJ3_LDW);
+    const uint32_t p0 = a.circ_ptr[c], Lc = a.circ_ptr[c + 1] - p0;
+    const size_t fb = lj.fbase[c];
+    const size_t brow0 = (size_t)lj.bbase[c] + (size_t)o * (Lc + 1) + 1;       // row of e^(k+1) for step k = brow0 + k
+    const uint16_t* cn = lj.bcnt + (size_t)c * a.n_ops;
+    const uint16_t* perm = lj.bperm + p0;
+
+    for (int p = lane; p < lj.n_params; p += 32) Jacc[p] = 0.0;
+    __syncwarp();
+    uint32_t tb = 0;
+    for (int g = 0; g < a.n_ops; ++g) {
+        const int cnt = cn[g];
+        if (cnt > 0) {
+            const int ns4 = (cnt + 3) & ~3;
+            for (int sb = 0; sb < l3.nsb; ++sb) {
+                const int jb = (sb % SBD) * 64;
+#pragma unroll 1
+                for (int mh = 0; mh < 2; ++mh) {
+                    const int key = (g * l3.nsb + sb) * 2 + mh;
+                    const uint32_t it0 = __ldg(l3.tp3 + key), it1 = __ldg(l3.tp3 + key + 1);
+                    if (it1 == it0) continue;
+                    const unsigned mask = __ldg(l3.mask3 + key);
+                    const unsigned need_n = (mask | (mask >> 8) | (mask >> 16) | (mask >> 24)) & 0xffu;
+                    const int ib = (sb / SBD) * 64 + mh * 32;
+                    double acc[4][8][2];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+                    double fa[4], fbv[8], na[4], nb[8];
+                    auto fetch = [&](int k0, double (&xa)[4], double (&xb)[8]) {
+                        const int t = k0 + q;
+                        const int k = (t < cnt) ? (int)__ldg(perm + tb + t) : -1;
+                        const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l3.zrow_b) * D + ib + mrow;
+                        const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l3.zrow_f) * D + jb + mrow;
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) xa[mt] = ((mask >> (8 * mt)) & 0xffu) ? __ldg(er + 8 * mt) : 0.0;
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) xb[nt] = (need_n & (1u << nt)) ? __ldg(sr + 8 * nt) : 0.0;
+                    };
+                    fetch(0, fa, fbv);
+                    for (int k0 = 0; k0 < ns4; k0 += 4) {
+                        if (k0 + 4 < ns4) fetch(k0 + 4, na, nb);
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 8; ++nt)
+                                if (mask & (1u << (8 * mt + nt))) dmma884(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fbv[nt]);   // warp-uniform
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt) fbv[nt] = nb[nt];
+                    }
+                    __syncwarp();                               // the previous contraction has read Wt
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 8; ++nt)
+                            if (mask & (1u << (8 * mt + nt)))
+                                *reinterpret_cast<double2*>(Wt + (mt * 8 + mrow) * LJ3_LDW + nt * 8 + 2 * q) =
+                                    make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                    __syncwarp();
+                    for (uint32_t it = it0 + lane; it < it1; it += 32) {
+                        const uint4 item = __ldg(l3.items3 + it);
+                        double s = 0.0;
+                        for (uint32_t t = item.y; t < item.z; ++t) {
+                            const unsigned ij = __ldg(l3.nz_ij + t);
+                            s = fma(__ldg(l3.nz_v + t), Wt[(ij >> 8) * LJ3_LDW + (ij & 0xffu)], s);
+                        }
+                        Jacc[item.x] += s;                      // a parameter occurs once per (gate, sub-block, half) list
+                    }
+                }
+            }
+        }
+        tb += cnt;
+    }
+    __syncwarp();
+    {   // state-preparation and effect rows of D (item lists per parameter tile, as in versions 1 / 2)
+        const int prep = a.circ_prep[c];
+        const int eff = a.out_eff[q0 + o];
+        const double* sL = lj.FS + (fb + Lc) * D;
+        const double* e0 = lj.BH + (brow0 - 1) * D;
+        for (int tile = 0; tile < lj.n_tiles; ++tile) {
+            const uint32_t* tp = lj.ti_ptr + (size_t)tile * (a.n_ops + 2);
+            const uint32_t it0 = tp[a.n_ops], it1 = tp[a.n_ops + 1];
+            for (uint32_t it = it0 + lane; it < it1; it += 32) {
+                const uint4 item = __ldg(lj.items + it);
+                double acc = 0.0;
+                for (uint32_t t = item.y; t < item.z; ++t) {
+                    const int64_t wl = __ldg(lj.crow + t);
+                    if (wl < m.off_eff) {
+                        const int r = (int)((wl - m.off_rho) / D), i = (int)((wl - m.off_rho) - (int64_t)r * D);
+                        if (r == prep) acc = fma(__ldg(lj.cval + t), e0[i], acc);
+                    } else {
+                        const int r = (int)((wl - m.off_eff) / D), i = (int)((wl - m.off_eff) - (int64_t)r * D);
+                        if (r == eff) acc = fma(__ldg(lj.cval + t), sL[i], acc);
+                    }
+                }
+                Jacc[tile * lj.pt + item.x] += acc;
+            }
+        }
+    }
+    __syncwarp();
+    const int64_t el = a.out_el[q0 + o];
+    const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
+    double* Jr = J + el * ld;
+    for (int p = lane; p < lj.n_params; p += 32) __stcs(Jr + p, Jacc[p] * sc);
+}

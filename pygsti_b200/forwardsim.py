@@ -110,6 +110,77 @@ class B200ForwardSimulator(_MapForwardSimulator):
                 atom._b200_device = devs[i % len(devs)]
         return layout
 
+    # ---- single-process multi-GPU: atoms on different GPUs run CONCURRENTLY --------------------------------------------
+    def _device_groups(self, layout):
+        """[[atoms of GPU 0], [atoms of GPU 1], ...] when this process drives several GPUs and nothing is distributed over MPI
+        (the reference then loops over the local atoms one after another, distforwardsim.py:98-99, 123-144); else None."""
+        devs = self._b200_devices
+        if not devs or len(set(devs)) < 2 or len(layout.atoms) < 2:
+            return None
+        from .objective import _distributed
+        if _distributed(layout):
+            return None
+        groups = {}
+        for atom in layout.atoms:
+            groups.setdefault(getattr(atom, "_b200_device", devs[0]), []).append(atom)
+        return list(groups.values()) if len(groups) > 1 else None
+
+    @staticmethod
+    def _run_groups(groups, work):
+        """One host thread per GPU; a GPU's atoms run in order on its own engine context (the C calls release the GIL, so the
+        kernels and the device-to-host copies of different GPUs overlap).  Exceptions are re-raised on the caller."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(group):
+            for item in group:
+                work(item)
+        with ThreadPoolExecutor(max_workers=len(groups)) as ex:
+            for fut in [ex.submit(run, g) for g in groups]:
+                fut.result()
+
+    def _bulk_fill_probs(self, array_to_fill, layout):
+        """Replaces distforwardsim.py:92-103 when atoms live on several GPUs of this process: same result, atoms of
+        different GPUs filled concurrently into their disjoint ``atom.element_slice`` rows."""
+        groups = self._device_groups(layout)
+        if groups is None:
+            return super()._bulk_fill_probs(array_to_fill, layout)
+        ralloc = layout.resource_alloc('atom-processing')
+        ralloc.host_comm_barrier()
+        prepared = {}
+        for atom in layout.atoms:                       # host packing + uploads: serial (pyGSTi objects are not thread-safe)
+            ctx, ent = _b200_calclib._engine_atom(self, atom)
+            _b200_calclib._upload_model(self, atom, ent)
+            prepared[id(atom)] = ent["atom"]
+
+        def work(atom):
+            dst = array_to_fill[atom.element_slice]
+            if dst.dtype == _np.float64 and dst.ndim == 1 and dst.shape[0] == atom.num_elements:
+                prepared[id(atom)].fill_probs(dst)
+            else:
+                tmp = _np.empty(atom.num_elements); prepared[id(atom)].fill_probs(tmp); dst[...] = tmp
+        self._run_groups(groups, work)
+        ralloc.host_comm_barrier()
+
+    def _bulk_fill_dprobs(self, array_to_fill, layout, pr_array_to_fill):
+        """Replaces distforwardsim.py:110-146 in the same situation (no parameter blocks requested): every atom's Jacobian rows
+        and probabilities are produced on its GPU and copied into the caller's arrays while the other GPUs do the same."""
+        groups = self._device_groups(layout)
+        if groups is None or layout.param_dimension_blk_sizes[0] is not None:
+            return super()._bulk_fill_dprobs(array_to_fill, layout, pr_array_to_fill)
+        ralloc = layout.resource_alloc('atom-processing')
+        ralloc.host_comm_barrier()
+        prepared = {}
+        for atom in layout.atoms:
+            prepared[id(atom)] = _b200_calclib.prepare_dprobs_atom(self, atom, layout.global_param_slice)
+
+        def work(atom):
+            eng_atom, pidx = prepared[id(atom)]
+            pr = None if pr_array_to_fill is None else pr_array_to_fill[atom.element_slice]
+            _b200_calclib.run_dprobs_atom(self, eng_atom, pidx, array_to_fill[atom.element_slice, :], None, None, atom,
+                                          self.derivative_eps, pr_array_to_fill=pr)
+        self._run_groups(groups, work)
+        ralloc.host_comm_barrier()
+
     # ---- hessian ------------------------------------------------------------------------------------
     def _bulk_fill_hprobs_atom(self, array_to_fill, dest_param_slice1, dest_param_slice2, layout_atom,
                                param_slice1, param_slice2, resource_alloc):

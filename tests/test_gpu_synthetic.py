@@ -199,7 +199,7 @@ np.save(sys.argv[1], J); print("ok", ctx.launch_count)
     import tempfile
     outs = []
     with tempfile.TemporaryDirectory() as td:
-        for tag, extra in (("lj", {}), ("gen", {"B200_NO_LEVELJ": "1"}), ("lj_v1", {"B200_LJ_ACCUM_V1": "1"})):
+        for tag, extra in (("lj", {}), ("gen", {"B200_NO_LEVELJ": "1"}), ("lj_v1", {"B200_LJ_ACCUM_V1": "1"}), ("lj_v2", {"B200_LJ_ACCUM_V2": "1"})):
             f = os.path.join(td, tag + ".npy")
             r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **extra), capture_output=True, text=True, timeout=600)
             assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
@@ -207,6 +207,7 @@ np.save(sys.argv[1], J); print("ok", ctx.launch_count)
     assert np.all(np.isfinite(outs[0]))
     assert np.max(np.abs(outs[0] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # DMMA accumulate vs W-matrix path
     assert np.max(np.abs(outs[2] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # scalar accumulate vs W-matrix path
+    assert np.max(np.abs(outs[3] - outs[1])) <= 1e-11 * max(1.0, np.max(np.abs(outs[1])))   # CTA-per-tile DMMA accumulate (v2)
 
 
 def test_repeated_calls_with_changing_models(gpu_ctx):
