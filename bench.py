@@ -377,6 +377,35 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
     ms_fill = timed(D, stream, fill, short, 1)
     ms_gather = timed(D, stream, gather, short, 1) if world > 1 else 0.0
 
+    # ---------------- the exchange FUSED into the fill: peer stores over NVLink from the kernel epilogue ----------------
+    fused = None
+    if world > 1:
+        try:
+            JP = bd.PeerArray(ctx, plan.n_rows_padded, Np); PP = bd.PeerArray(ctx, plan.n_rows_padded, 1)
+            Jt, Pt = JP.tensor(), PP.tensor()
+            Jt.zero_(); Pt.zero_()
+            D.barrier()
+            peers = [r for r in range(world) if r != rank]
+            jo = [JP.row_ptr(r, rank * slot) for r in peers]; po = [PP.row_ptr(r, rank * slot) for r in peers]
+            jm, pm = JP.row_ptr(rank, rank * slot), PP.row_ptr(rank, rank * slot)
+            tick = torch.zeros(1, device="cuda")
+
+            def fused_step():
+                atom.fill_dprobs_bcast_dev(jm, Np, pm, jo, po)
+                dist.all_reduce(tick)                  # stream-ordered barrier: every rank's stores have been issued and completed
+
+            ms_fused = timed(D, stream, fused_step, short, 2)
+            same = bool(torch.equal(Jt, J)) and bool(torch.equal(Pt, P))
+            fused = {"ms": ms_fused, "outcomes_per_s": nE / (ms_fused * 1e-3), "bitwise_equal_to_nccl_result": same,
+                     "bytes_sent_per_rank": (world - 1) * plan.n_local[rank] * (Np + 1) * 8,
+                     "what": "b200_fill_dprobs_bcast_dev: k_accum_trie_d16<PEERS> stores every finished Jacobian block into the local array "
+                             "and into the CUDA-IPC-mapped arrays of the %d peers (plain st.global over NVLink), then one 4-byte all-reduce "
+                             "as the barrier; no separate all-gather pass" % (world - 1)}
+            del Jt, Pt
+            JP.close(); PP.close()
+        except Exception as e:            # CUDA IPC unavailable in this container, ...: the NCCL step above stands
+            fused = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
     # ---------------- dominant kernel alone (roofline.achieved): CUDA events around the phases ----------------
     ctx.phase_timing(True)
     for _ in range(short):
@@ -500,6 +529,7 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
                       "allgather": {"ms": ms_gather, "bytes_received_per_rank": ag_bytes,
                                     "GBps_per_rank": (ag_bytes / (ms_gather * 1e-3) / 1e9) if ms_gather > 0 else None,
                                     "collective": "ncclAllGather, in place (send buffer = own slot of the receive buffer)" if world > 1 else None},
+                      "fused_fill_allgather": fused,
                       "note": "the all-gather moves (N-1)/N of a 2.97 GB Jacobian INTO every GPU over NVLink (<= 900 GB/s), "
                               "while one GPU produces it at ~4 TB/s: for d = 16 the full-Jacobian exchange is NVLink-bound and "
                               "the jtj exchange below is the one that scales"},

@@ -181,6 +181,25 @@ int b200_hessian_block(b200_ctx* ctx, b200_atom* atom, int32_t n1, const int32_t
 int b200_fill_probs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out);
 int b200_fill_dprobs_dev(b200_ctx* ctx, b200_atom* atom, double* d_out, int64_t ld, double* d_probs);
 
+/* ---- multi-GPU, one process per GPU: Jacobian fill FUSED with the exchange over NVLink peer memory ------------------
+ * The reference reassembles per-rank shards with gather_local_array -> Allgatherv (pygsti/baseobjs/resourceallocation.py:
+ * 323-329) after every rank has filled its own rows.  Here the rows can travel while they are produced: every rank holds the
+ * whole sharded array (b200_peer_alloc, a cudaMalloc'd buffer exported through CUDA IPC), maps the arrays of its peers
+ * (b200_peer_open) and b200_fill_dprobs_bcast_dev makes the kernel epilogue store each finished Jacobian row / probability
+ * into the local array AND, at the same offset, into every peer's array (plain stores over NVLink / NVSwitch).  After a
+ * stream synchronisation on every rank plus one barrier, every rank holds every row -- no separate all-gather pass.
+ *   d_out / d_probs        : this rank's slot inside ITS OWN array (as for b200_fill_dprobs_dev)
+ *   d_out_peers[i] / d_probs_peers[i] : the address of the SAME slot inside peer i's array (n_peers <= 7; d_probs_peers may be NULL)
+ * Kernels without a fused peer epilogue (the general W.D path) fill locally and forward the slot with asynchronous
+ * peer-to-peer copies on the same stream: same result, same call. */
+#define B200_MAX_PEERS 7
+int b200_peer_alloc(b200_ctx* ctx, int64_t bytes, void** d_ptr_out, unsigned char handle_out[64]);
+int b200_peer_open(b200_ctx* ctx, const unsigned char handle[64], void** d_ptr_out);
+int b200_peer_close(b200_ctx* ctx, void* d_ptr);
+int b200_peer_free(b200_ctx* ctx, void* d_ptr);
+int b200_fill_dprobs_bcast_dev(b200_ctx* ctx, b200_atom* atom, double* d_out, int64_t ld, double* d_probs,
+                               int n_peers, double* const* d_out_peers, double* const* d_probs_peers);
+
 /* ---- "next" row: the objective-function Jacobian fill, fused ------------------------------
  * b200_fill_dprobs_scaled  = b200_fill_dprobs followed by the row scaling the objective functions apply to it,
  *     out[el, p] = row_scale[el] * d p_el / d theta_p

@@ -52,6 +52,11 @@ SIGNATURES = {
     "b200_jtj_dev": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "b200_fill_probs_dev": (C.c_int, [vp, vp, vp]),
     "b200_fill_dprobs_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp]),
+    "b200_peer_alloc": (C.c_int, [vp, C.c_int64, C.POINTER(vp), vp]),
+    "b200_peer_open": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "b200_peer_close": (C.c_int, [vp, vp]),
+    "b200_peer_free": (C.c_int, [vp, vp]),
+    "b200_fill_dprobs_bcast_dev": (C.c_int, [vp, vp, vp, C.c_int64, vp, C.c_int, vp, vp]),
     "b200_host_alloc": (C.c_int, [C.POINTER(vp), C.c_int64]),
     "b200_host_free": (C.c_int, [vp]),
     "b200_host_register": (C.c_int, [vp, C.c_int64]),

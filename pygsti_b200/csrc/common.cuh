@@ -38,6 +38,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, const double a, 
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+#define B200_PEERS_MAX 7
 // Where the d = 16 Jacobian kernel stores its accumulators
 #define D16_SPAM_MAX 512  // SPAM/unmapped column list entries staged in shared memory
 struct D16Args {
@@ -49,4 +50,8 @@ struct D16Args {
     int64_t ld;
     double* probs;            // [n_elements] or nullptr
     const double* row_scale;  // [n_elements] or nullptr: J row el is multiplied by row_scale[el] in the store epilogue
+    // fused exchange (b200_fill_dprobs_bcast_dev): the same rows are also stored at the same offsets of the peers' arrays
+    int n_peers;
+    double* peerJ[B200_PEERS_MAX];
+    double* peerP[B200_PEERS_MAX];
 };

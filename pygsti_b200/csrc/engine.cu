@@ -1121,10 +1121,16 @@ static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
     // 3 chain CTAs per SM and role (even blocks = forward trie, odd = backward trie), 100 ns poll interval of a waiting chain
     k_trie_chains<<<2 * c->sm_count * 3, TRIE_WARPS * 32, smemA, c->stream>>>(atom_dev(a), model_dev(a), t, 0, 100u);
     { int rcP = phase_mark(c); if (rcP) return rcP; }
-    CU(cudaFuncSetAttribute(k_accum_trie_d16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
     const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
-    k_accum_trie_d16<<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
-                                                             a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, AT_CHUNK);
+    if (args.n_peers > 0) {
+        CU(cudaFuncSetAttribute(k_accum_trie_d16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        k_accum_trie_d16<true><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                                       a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, AT_CHUNK);
+    } else {
+        CU(cudaFuncSetAttribute(k_accum_trie_d16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
+        k_accum_trie_d16<false><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+                                                                        a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, AT_CHUNK);
+    }
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     c->launches += 3;
     CU(cudaGetLastError());
@@ -1139,7 +1145,7 @@ static int compute_w(b200_ctx* c, b200_atom* a, double* W, double* probs) {
         D16Args args;
         args.colmap = a->id_colmap.as<int32_t>(); args.spam_col = a->id_spam_col.as<int32_t>();
         args.spam_w = a->id_spam_w.as<int32_t>(); args.n_spam = a->id_n_spam;
-        args.J = W; args.ld = a->n_w; args.probs = probs; args.row_scale = nullptr;
+        args.J = W; args.ld = a->n_w; args.probs = probs; args.row_scale = nullptr; args.n_peers = 0;
         return launch_d16(c, a, args);
     }
     CU(cudaMemsetAsync(W, 0, (size_t)a->n_elements * a->n_w * sizeof(double), c->stream));
@@ -1222,7 +1228,8 @@ static bool levelj_ok(b200_ctx* c, b200_atom* a) {
            (int64_t)a->n_rows * std::max(a->lj_n_tiles, 1) < ((int64_t)1 << 31) && levelj_ts(c, a, nullptr) > 0;
 }
 template <int D>
-static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
+static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale,
+                         const PeerOut& peers, bool* peers_done) {
     if (a->n_rows == 0) return B200_OK;
     CU(c->lj_fs.ensure(((size_t)a->lj_rows_f + 1) * D * 8));      // + one all-zero row each (bucket padding of the DMMA accumulate)
     CU(c->lj_bh.ensure(((size_t)a->lj_rows_b + 1) * D * 8));
@@ -1280,7 +1287,8 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
         l3.nz_ij = a->lj3_ij.as<uint16_t>(); l3.nz_v = a->lj3_v.as<double>();
         l3.zrow_f = (uint32_t)a->lj_rows_f; l3.zrow_b = (uint32_t)a->lj_rows_b; l3.nsb = (D / 64) * (D / 64); l3.np_pad = np_pad; l3.n_og = n_og;
         CU(cudaFuncSetAttribute(k_level_accum3<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC3));
-        k_level_accum3<D><<<(unsigned)(a->n_rows * n_og), LJ3_WARPS * 32, smemC3, c->stream>>>(ad, md, lj, l3, d_out, ld, d_scale);
+        k_level_accum3<D><<<(unsigned)(a->n_rows * n_og), LJ3_WARPS * 32, smemC3, c->stream>>>(ad, md, lj, l3, d_out, ld, d_scale, peers);
+        if (peers_done) *peers_done = true;
     } else
     if (accum_v1 || smemC2 + 1024 > c->smem_optin) {
         CU(cudaFuncSetAttribute(k_level_accum<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
@@ -1298,8 +1306,13 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
     return B200_OK;
 }
 
-// Jacobian into a device buffer; d_scale (device, [n_elements]) or nullptr
-static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
+// destinations of the fused exchange (b200_fill_dprobs_bcast_dev): the same slot inside the arrays of the peer GPUs
+struct PeerSpec { int n = 0; double* J[B200_PEERS_MAX]; double* P[B200_PEERS_MAX]; bool j_done = false, p_done = false; };
+
+// Jacobian into a device buffer; d_scale (device, [n_elements]) or nullptr.  `ps` (optional): kernels with a fused peer epilogue
+// also store into the peers' arrays and mark ps->j_done / ps->p_done.
+static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale,
+                              PeerSpec* ps = nullptr) {
     if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
@@ -1315,10 +1328,23 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
         args.spam_w = a->spam_w.as<int32_t>(); args.n_spam = a->n_spam;
         args.J = d_out; args.ld = ld; args.probs = d_probs;
         args.row_scale = d_scale;                  // applied in the store epilogue
+        args.n_peers = 0;
+        if (ps && ps->n > 0) {
+            args.n_peers = ps->n;
+            for (int r = 0; r < ps->n; ++r) { args.peerJ[r] = ps->J[r]; args.peerP[r] = d_probs ? ps->P[r] : nullptr; }
+            ps->j_done = true; ps->p_done = true;
+        }
         return launch_d16(c, a, args);
     }
-    if (levelj_ok(c, a))
-        return a->dim == 64 ? launch_levelj<64>(c, a, d_out, ld, d_probs, d_scale) : launch_levelj<256>(c, a, d_out, ld, d_probs, d_scale);
+    if (levelj_ok(c, a)) {
+        PeerOut po; po.n = 0;
+        if (ps) { po.n = ps->n; for (int r = 0; r < ps->n; ++r) po.J[r] = ps->J[r]; }
+        bool done = false;
+        int rc = a->dim == 64 ? launch_levelj<64>(c, a, d_out, ld, d_probs, d_scale, po, &done)
+                              : launch_levelj<256>(c, a, d_out, ld, d_probs, d_scale, po, &done);
+        if (ps && done) ps->j_done = true;
+        return rc;
+    }
     // general path: W then J = W . D
     CU(c->w_buf.ensure((size_t)a->n_elements * a->n_w * sizeof(double)));
     int rc = compute_w(c, a, c->w_buf.as<double>(), d_probs);
@@ -1336,6 +1362,66 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
 
 extern "C" int b200_fill_dprobs_dev(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs) {
     return fill_dprobs_device(c, a, d_out, ld, d_probs, nullptr);
+}
+
+// ---- peer memory: fused fill + exchange (one process per GPU) ---------------------------------------------------------
+extern "C" int b200_peer_alloc(b200_ctx* c, int64_t bytes, void** d_ptr_out, unsigned char handle_out[64]) {
+    if (!c || !d_ptr_out || !handle_out || bytes <= 0) return fail(B200_E_INVALID, "bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CU(cudaSetDevice(c->device));
+    *d_ptr_out = nullptr;
+    void* p = nullptr;
+    CU(cudaMalloc(&p, (size_t)bytes));                  // (a plain cudaMalloc allocation: the kind CUDA IPC can export)
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); return fail(B200_E_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    *d_ptr_out = p;
+    return B200_OK;
+}
+extern "C" int b200_peer_open(b200_ctx* c, const unsigned char handle[64], void** d_ptr_out) {
+    if (!c || !handle || !d_ptr_out) return fail(B200_E_INVALID, "bad argument");
+    CU(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h; memcpy(&h, handle, 64);
+    *d_ptr_out = nullptr;
+    CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200_OK;
+}
+extern "C" int b200_peer_close(b200_ctx* c, void* d_ptr) {
+    if (!c || !d_ptr) return B200_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return B200_OK;
+}
+extern "C" int b200_peer_free(b200_ctx* c, void* d_ptr) {
+    if (!c || !d_ptr) return B200_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_ptr));
+    return B200_OK;
+}
+
+extern "C" int b200_fill_dprobs_bcast_dev(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs,
+                                          int n_peers, double* const* d_out_peers, double* const* d_probs_peers) {
+    if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
+    if (n_peers < 0 || n_peers > B200_MAX_PEERS) return fail(B200_E_INVALID, "n_peers must be in [0, %d]", B200_MAX_PEERS);
+    if (n_peers > 0 && !d_out_peers) return fail(B200_E_INVALID, "d_out_peers is NULL");
+    PeerSpec ps; ps.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!d_out_peers[r]) return fail(B200_E_INVALID, "d_out_peers[%d] is NULL", r);
+        ps.J[r] = d_out_peers[r]; ps.P[r] = d_probs_peers ? d_probs_peers[r] : nullptr;
+    }
+    int rc = fill_dprobs_device(c, a, d_out, ld, d_probs, nullptr, &ps);
+    if (rc) return rc;
+    // kernels without a fused peer epilogue: forward the finished slot with asynchronous peer copies on the same stream
+    for (int r = 0; r < n_peers; ++r) {
+        if (!ps.j_done && a->n_elements > 0 && a->n_params > 0)
+            CU(cudaMemcpy2DAsync(ps.J[r], (size_t)ld * 8, d_out, (size_t)ld * 8, (size_t)a->n_params * 8, (size_t)a->n_elements, cudaMemcpyDefault, c->stream));
+        if (!ps.p_done && d_probs && ps.P[r] && a->n_elements > 0)
+            CU(cudaMemcpyAsync(ps.P[r], d_probs, (size_t)a->n_elements * 8, cudaMemcpyDefault, c->stream));
+    }
+    return B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1549,14 +1635,14 @@ extern "C" int b200_fill_dprobs_fd(b200_ctx* c, b200_atom* a, double eps, double
 }
 
 template <int D>
-static int launch_w_tangent(b200_ctx* c, b200_atom* a, int nb, const double* dMb, const double* dGtb, double* Wb) {
+static int launch_w_tangent(b200_ctx* c, b200_atom* a, int nb, const double* dMb, const double* dGtb, double* Wb, const unsigned char* need) {
     int gx = grid_for(c, (a->n_rows + GEN_WARPS - 1) / GEN_WARPS, 4);
-    size_t need = (size_t)nb * gx * GEN_WARPS * 2 * (size_t)(a->max_depth + 1) * D * sizeof(double);
-    CU(c->scratch.ensure(need));
+    const size_t scratch_bytes = (size_t)nb * gx * GEN_WARPS * 2 * (size_t)(a->max_depth + 1) * D * sizeof(double);
+    CU(c->scratch.ensure(scratch_bytes));
     size_t smem = (size_t)GEN_WARPS * 4 * D * sizeof(double);
     dim3 grid(gx, nb);
     k_w_tangent_generic<D><<<grid, GEN_WARPS * 32, smem, c->stream>>>(atom_dev(a), model_dev(a), dMb, dGtb, Wb, a->n_w,
-                                                                       c->scratch.as<double>());
+                                                                       c->scratch.as<double>(), need);
     c->launches++;
     CU(cudaGetLastError());
     return B200_OK;
@@ -1623,12 +1709,20 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
             if (h_rows[t] < 0 || h_rows[t] >= a->n_w) return fail(B200_E_INVALID, "D2 row %d out of range", h_rows[t]);
             if (h_a[t] < 0 || h_a[t] >= n1 || h_b[t] < 0 || h_b[t] >= n2) return fail(B200_E_INVALID, "D2 index out of range");
         }
-        std::vector<int64_t> idx((size_t)nnz2);
-        std::iota(idx.begin(), idx.end(), 0);
+        // order the entries by key = a * n2 + b, then by W row: counting sort over the n1 n2 keys + a short sort inside each key
+        // (a comparison sort of all 5e5 entries of a CPTPLND rectangle was 40 of the 93 ms of a rectangle)
         auto keyof = [&](int64_t t) { return (int64_t)h_a[t] * n2 + h_b[t]; };
-        std::sort(idx.begin(), idx.end(), [&](int64_t x, int64_t y) {
-            const int64_t kx = keyof(x), ky = keyof(y);
-            return kx != ky ? kx < ky : h_rows[x] < h_rows[y]; });
+        std::vector<int64_t> idx((size_t)nnz2);
+        {
+            std::vector<int64_t> cnt((size_t)n1 * n2 + 1, 0);
+            for (int64_t t = 0; t < nnz2; ++t) cnt[(size_t)keyof(t) + 1]++;
+            for (size_t k = 0; k + 1 < cnt.size(); ++k) cnt[k + 1] += cnt[k];
+            std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+            for (int64_t t = 0; t < nnz2; ++t) idx[(size_t)pos[(size_t)keyof(t)]++] = t;
+            for (size_t k = 0; k + 1 < cnt.size(); ++k)
+                if (cnt[k + 1] - cnt[k] > 1 && !std::is_sorted(idx.begin() + cnt[k], idx.begin() + cnt[k + 1], [&](int64_t x, int64_t y) { return h_rows[x] < h_rows[y]; }))
+                    std::stable_sort(idx.begin() + cnt[k], idx.begin() + cnt[k + 1], [&](int64_t x, int64_t y) { return h_rows[x] < h_rows[y]; });
+        }
         std::vector<int64_t> ukey; std::vector<int32_t> kptr, krow((size_t)nnz2); std::vector<double> kval((size_t)nnz2);
         for (int64_t t = 0; t < nnz2; ++t) {
             const int64_t i = idx[t];
@@ -1701,6 +1795,18 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));          // the host K-chunk lists go out of scope
     }
+    // blocks of the W row the contraction reads (rows of D[:, p2] with a non-zero): gates / state preparations / effects
+    DevBuf d_need;
+    std::vector<unsigned char> need((size_t)a->n_ops + 2, 0);
+    {
+        const int64_t dd = (int64_t)a->dim * a->dim;
+        for (int b2 = 0; b2 < n2; ++b2)
+            for (int t = a->h_cptr[p2[b2]]; t < a->h_cptr[p2[b2] + 1]; ++t) {
+                const int64_t w = a->h_crow[t];
+                need[w < a->off_rho ? (size_t)(w / dd) : (w < a->off_eff ? (size_t)a->n_ops : (size_t)a->n_ops + 1)] = 1;
+            }
+        if ((rc = upload_vec(d_need, need, c->stream))) return rc;
+    }
     // batch of tangent directions bounded by ~8 GB of W scratch
     const int B = (int)std::max<int64_t>(1, std::min<int64_t>(n1, ((int64_t)8 << 30) / std::max<int64_t>(per, 1)));
     CU(c->w_buf.ensure((size_t)B * per));
@@ -1709,7 +1815,15 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
     for (int a0 = 0; a0 < n1; a0 += B) {
         const int nb = std::min(B, n1 - a0);
         CU(cudaMemsetAsync(c->fd_models.p, 0, (size_t)nb * a->n_w * 8, c->stream));
-        CU(cudaMemsetAsync(c->w_buf.p, 0, (size_t)nb * per, c->stream));
+        {   // zero only the blocks that are accumulated (and read)
+            const int64_t dd = (int64_t)a->dim * a->dim;
+            auto zero_cols = [&](int64_t col0, int64_t ncols) -> int {
+                CU(cudaMemset2DAsync(c->w_buf.as<double>() + col0, (size_t)a->n_w * 8, 0, (size_t)ncols * 8, (size_t)nb * nE, c->stream));
+                return B200_OK; };
+            for (int g = 0; g < a->n_ops; ++g) if (need[g] && (rc = zero_cols(g * dd, dd))) return rc;
+            if (need[a->n_ops] && (rc = zero_cols(a->off_rho, a->off_eff - a->off_rho))) return rc;
+            if (need[a->n_ops + 1] && (rc = zero_cols(a->off_eff, a->n_w - a->off_eff))) return rc;
+        }
         dim3 g1(4, nb);
         k_tangent_models<<<g1, 128, 0, c->stream>>>(a->n_w, d_p1.as<int32_t>(), a0, a->cptr.as<int32_t>(),
                                                     a->crow.as<int32_t>(), a->cval.as<double>(), c->fd_models.as<double>());
@@ -1721,10 +1835,10 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         }
         CU(cudaGetLastError());
         switch (a->dim) {
-            case 4: rc = launch_w_tangent<4>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
-            case 16: rc = launch_w_tangent<16>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
-            case 64: rc = launch_w_tangent<64>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
-            case 256: rc = launch_w_tangent<256>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>()); break;
+            case 4: rc = launch_w_tangent<4>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>(), d_need.as<unsigned char>()); break;
+            case 16: rc = launch_w_tangent<16>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>(), d_need.as<unsigned char>()); break;
+            case 64: rc = launch_w_tangent<64>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>(), d_need.as<unsigned char>()); break;
+            case 256: rc = launch_w_tangent<256>(c, a, nb, c->fd_models.as<double>(), c->fd_gt.as<double>(), c->w_buf.as<double>(), d_need.as<unsigned char>()); break;
             default: rc = fail(B200_E_UNSUPPORTED, "dim %d", a->dim);
         }
         if (rc) return rc;
@@ -1742,7 +1856,7 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         }
     }
     CU(cudaStreamSynchronize(c->stream));
-    d_Dsel.release(); d_ktp2.release(); d_kti2.release();
+    d_Dsel.release(); d_ktp2.release(); d_kti2.release(); d_need.release();
     if (red_out) {
         // MLE Hessian block (objectivefns.py:4914-4990 `_hessian_from_block` without omitted-outcome rows):
         //   red[a][b] = sum_el w_h[el] H[el][a][b] + w_d[el] J[el][p1[a]] J[el][p2[b]]      -- only n1 x n2 doubles leave the device

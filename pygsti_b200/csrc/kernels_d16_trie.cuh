@@ -280,7 +280,10 @@ __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc)
 // store epilogue through conflict-free shared staging (+5 %), CTA-level unit ranges for L1 reuse of the H gathers (+1 %),
 // 2-outcome units at 24 warps/SM (+2 %), a cp.async gather ring (+13 %), next-chunk look-ahead (+6 %).
 // dynamic smem: AT_WARPS * 5 * 16 doubles (SPAM slots), then the column-map fragments and the SPAM lists.
+// PEERS (b200_fill_dprobs_bcast_dev): every store of the epilogue is repeated, at the same offset, into the arrays of the
+// peer GPUs (NVLink peer memory): the exchange of the sharded Jacobian overlaps its production instead of following it.
 constexpr int AT_NO = 4;   // outcomes (consecutive effects) per unit
+template <bool PEERS>
 __global__ void __launch_bounds__(AT_WARPS * 32, 2)
 k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* __restrict__ units, int n_units,
                  const uint2* __restrict__ uidx, unsigned* __restrict__ counter, int chunk)
@@ -398,29 +401,34 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                     for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
                 }
             }
-            if (fast) {
+            const int n_dst = PEERS ? 1 + args.n_peers : 1;
+#pragma unroll 1
+            for (int dst = 0; dst < n_dst; ++dst) {
+                double* Jb = (!PEERS || dst == 0) ? args.J : args.peerJ[dst - 1];
+                if (fast) {
 #pragma unroll
-                for (int o = 0; o < NO; ++o) {
-                    if (els[o] >= 0) {
-                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] >= 0) {
+                            double* Jr = Jb + (int64_t)els[o] * args.ld;
 #pragma unroll
-                        for (int tile = 0; tile < 4; ++tile)
-                            __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                            for (int tile = 0; tile < 4; ++tile)
+                                __stcs(reinterpret_cast<double2*>(Jr + cc[tile].x), make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]));
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int o = 0; o < NO; ++o) {
-                    if (els[o] >= 0) {
-                        double* Jr = args.J + (int64_t)els[o] * args.ld;
+                    for (int o = 0; o < NO; ++o) {
+                        if (els[o] >= 0) {
+                            double* Jr = Jb + (int64_t)els[o] * args.ld;
 #pragma unroll
-                        for (int tile = 0; tile < 4; ++tile) {
-                            const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
-                            if (cc[tile].y == -2) {
-                                *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
-                            } else {
-                                if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
-                                if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                            for (int tile = 0; tile < 4; ++tile) {
+                                const double v0 = acc[o][tile * 2], v1 = acc[o][tile * 2 + 1];
+                                if (cc[tile].y == -2) {
+                                    *reinterpret_cast<double2*>(Jr + cc[tile].x) = make_double2(v0, v1);
+                                } else {
+                                    if (cc[tile].x >= 0) Jr[cc[tile].x] = v0;
+                                    if (cc[tile].y >= 0) Jr[cc[tile].y] = v1;
+                                }
                             }
                         }
                     }
@@ -443,12 +451,16 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                 for (int o = 0; o < NO; ++o) {
                     if (els[o] < 0) continue;                                   // (warp-uniform)
                     const int ei = e_base + o;
-                    double* Jr = args.J + (int64_t)els[o] * args.ld;
+                    const int64_t roff = (int64_t)els[o] * args.ld;
+                    double* Jr = args.J + roff;
                     if (args.probs) {
                         double pr = (lane < 16) ? E[ei * 16 + lane] * sLv : 0.0;
 #pragma unroll
                         for (int mk = 8; mk > 0; mk >>= 1) pr += shfl_xor_f64(pr, mk);
-                        if (lane == 0) args.probs[els[o]] = pr;
+                        if (lane == 0) {
+                            args.probs[els[o]] = pr;
+                            if (PEERS) for (int r = 0; r < args.n_peers; ++r) if (args.peerP[r]) args.peerP[r][els[o]] = pr;
+                        }
                     }
                     const int w_rho0 = (int)m.off_rho + prep * 16, w_eff0 = (int)m.off_eff + ei * 16;
                     const double sc = args.row_scale ? __ldg(args.row_scale + els[o]) : 1.0;
@@ -462,7 +474,10 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                         double val = 0.0;
                         if (ir >= 0 && ir < 16) val = vr * sc;
                         else if (ie >= 0 && ie < 16) val = ve * sc;
-                        if (ok) Jr[col] = val;
+                        if (ok) {
+                            Jr[col] = val;
+                            if (PEERS) for (int r = 0; r < args.n_peers; ++r) args.peerJ[r][roff + col] = val;
+                        }
                     }
                 }
             }

@@ -165,8 +165,11 @@ k_w_generic(AtomDev a, ModelDev m, double* __restrict__ W, int64_t ldw, double* 
 template <int D>
 __global__ void __launch_bounds__(GEN_WARPS * 32)
 k_w_tangent_generic(AtomDev a, ModelDev m, const double* __restrict__ dMb, const double* __restrict__ dGtb,
-                    double* __restrict__ Wb, int64_t ldw, double* __restrict__ scratch)
+                    double* __restrict__ Wb, int64_t ldw, double* __restrict__ scratch, const unsigned char* __restrict__ need)
 {
+    // need[g] (g < n_ops), need[n_ops] (state preparations), need[n_ops + 1] (effects): only these blocks of the W row are
+    // read by the contraction that follows (the rectangle's second parameter axis touches one or two members), so only
+    // these are accumulated; nullptr = all.
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* eb0 = smem + (size_t)warp * 4 * D;
@@ -210,16 +213,18 @@ k_w_tangent_generic(AtomDev a, ModelDev m, const double* __restrict__ dMb, const
             double* e = eb0; double* en = eb1; double* de = db0; double* den = db1;
             for (int i = lane; i < D; i += 32) {
                 e[i] = E[(int64_t)ei * D + i]; de[i] = dE[(int64_t)ei * D + i];
-                Wr[m.off_eff + (int64_t)ei * D + i] += dsL[i];
+                if (!need || need[a.n_ops + 1]) Wr[m.off_eff + (int64_t)ei * D + i] += dsL[i];
             }
             __syncwarp();
             for (int k = L - 1; k >= 0; --k) {
                 const int g = ops[k];
                 const double* s = st + (int64_t)k * D; const double* ds = dst + (int64_t)k * D;
                 double* Wg = Wr + (int64_t)g * D * D;
-                for (int idx = lane; idx < D * D; idx += 32) {
-                    const int i = idx / D, j = idx - i * D;
-                    Wg[idx] += de[i] * s[j] + e[i] * ds[j];
+                if (!need || need[g]) {
+                    for (int idx = lane; idx < D * D; idx += 32) {
+                        const int i = idx / D, j = idx - i * D;
+                        Wg[idx] += de[i] * s[j] + e[i] * ds[j];
+                    }
                 }
                 const double* Gg = G + (int64_t)g * D * D;
                 const double* dGg = dG + (int64_t)g * D * D;
@@ -234,7 +239,7 @@ k_w_tangent_generic(AtomDev a, ModelDev m, const double* __restrict__ dMb, const
                 __syncwarp();
                 double* x = e; e = en; en = x; x = de; de = den; den = x;
             }
-            for (int i = lane; i < D; i += 32) Wr[m.off_rho + (int64_t)prep * D + i] += de[i];
+            if (!need || need[a.n_ops]) for (int i = lane; i < D; i += 32) Wr[m.off_rho + (int64_t)prep * D + i] += de[i];
             __syncwarp();
         }
     }

@@ -420,10 +420,12 @@ struct LevelJ3Dev {
     int nsb, np_pad, n_og;     // sub-blocks per matrix; padded accumulator row length; outcome groups per circuit
 };
 
+struct PeerOut { int n; double* J[B200_PEERS_MAX]; };     // fused exchange: the same rows also go to the peers' arrays
+
 template <int D>
 __global__ void __launch_bounds__(LJ3_WARPS * 32, 2)
 k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __restrict__ J, int64_t ld,
-               const double* __restrict__ row_scale)
+               const double* __restrict__ row_scale, PeerOut peers)
 {
     constexpr int SBD = D / 64;
     extern __shared__ __align__(16) double sml[];
@@ -443,72 +445,95 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
 
     for (int p = lane; p < lj.n_params; p += 32) Jacc[p] = 0.0;
     __syncwarp();
-    uint32_t tb = 0;
-    for (int g = 0; g < a.n_ops; ++g) {
-        const int cnt = cn[g];
-        if (cnt > 0) {
-            const int ns4 = (cnt + 3) & ~3;
-            for (int sb = 0; sb < l3.nsb; ++sb) {
-                const int jb = (sb % SBD) * 64;
-#pragma unroll 1
-                for (int mh = 0; mh < 2; ++mh) {
-                    const int key = (g * l3.nsb + sb) * 2 + mh;
-                    const uint32_t it0 = __ldg(l3.tp3 + key), it1 = __ldg(l3.tp3 + key + 1);
-                    if (it1 == it0) continue;
-                    const unsigned mask = __ldg(l3.mask3 + key);
-                    const unsigned need_n = (mask | (mask >> 8) | (mask >> 16) | (mask >> 24)) & 0xffu;
-                    const int ib = (sb / SBD) * 64 + mh * 32;
-                    double acc[4][8][2];
+
+    // The passes (gate, sub-block, M half) of this warp as a flat sequence, so that the first fragments of pass n + 1 can be
+    // requested before pass n is parked and contracted (one exposed round trip per warp instead of one per pass).
+    int g = -1, sb = 0, mh = 0, cnt = 0;
+    uint32_t tb = 0, it0 = 0, it1 = 0;
+    unsigned mask = 0;
+    auto advance = [&]() -> bool {
+        for (;;) {
+            bool next_gate = (g < 0) || (cnt == 0);
+            if (!next_gate) {
+                if (mh == 0) mh = 1; else { mh = 0; ++sb; }
+                if (sb >= l3.nsb) next_gate = true;
+            }
+            if (next_gate) {
+                if (g >= 0) tb += cnt;
+                ++g;
+                if (g >= a.n_ops) return false;
+                cnt = cn[g]; sb = 0; mh = 0;
+                if (cnt == 0) continue;
+            }
+            const int key = (g * l3.nsb + sb) * 2 + mh;
+            it0 = __ldg(l3.tp3 + key); it1 = __ldg(l3.tp3 + key + 1);
+            if (it1 == it0) continue;
+            mask = __ldg(l3.mask3 + key);
+            return true;
+        }
+    };
+    // fragments of the group of 4 steps starting at k0 of the CURRENT iterator position; the bucket's step indices come 32 at a
+    // time through one coalesced load + a shuffle (no dependent index load per group)
+    int pk = -1;
+    auto fetch = [&](int k0, double (&xa)[4], double (&xb)[8]) {
+        if ((k0 & 31) == 0) { const int t = k0 + lane; pk = (t < cnt) ? (int)__ldg(perm + tb + t) : -1; }
+        const int k = __shfl_sync(0xffffffffu, pk, (k0 & 31) + q);
+        const unsigned need_n = (mask | (mask >> 8) | (mask >> 16) | (mask >> 24)) & 0xffu;
+        const int ib = (sb / SBD) * 64 + mh * 32, jb = (sb % SBD) * 64;
+        const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l3.zrow_b) * D + ib + mrow;
+        const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l3.zrow_f) * D + jb + mrow;
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
+        for (int mt = 0; mt < 4; ++mt) xa[mt] = ((mask >> (8 * mt)) & 0xffu) ? __ldg(er + 8 * mt) : 0.0;
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
-                    double fa[4], fbv[8], na[4], nb[8];
-                    auto fetch = [&](int k0, double (&xa)[4], double (&xb)[8]) {
-                        const int t = k0 + q;
-                        const int k = (t < cnt) ? (int)__ldg(perm + tb + t) : -1;
-                        const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l3.zrow_b) * D + ib + mrow;
-                        const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l3.zrow_f) * D + jb + mrow;
+        for (int nt = 0; nt < 8; ++nt) xb[nt] = (need_n & (1u << nt)) ? __ldg(sr + 8 * nt) : 0.0;
+    };
+    double fa[4], fbv[8];
+    bool have = advance();
+    if (have) fetch(0, fa, fbv);
+    while (have) {
+        const unsigned cmask = mask;
+        const uint32_t cit0 = it0, cit1 = it1;
+        const int ns4 = (cnt + 3) & ~3;
+        double acc[4][8][2];
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) xa[mt] = ((mask >> (8 * mt)) & 0xffu) ? __ldg(er + 8 * mt) : 0.0;
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) xb[nt] = (need_n & (1u << nt)) ? __ldg(sr + 8 * nt) : 0.0;
-                    };
-                    fetch(0, fa, fbv);
-                    for (int k0 = 0; k0 < ns4; k0 += 4) {
-                        if (k0 + 4 < ns4) fetch(k0 + 4, na, nb);
+            for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+        for (int k0 = 0; k0 < ns4; k0 += 4) {
+            double na[4], nb[8];
+            if (k0 + 4 < ns4) fetch(k0 + 4, na, nb);
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt)
+            for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-                            for (int nt = 0; nt < 8; ++nt)
-                                if (mask & (1u << (8 * mt + nt))) dmma884(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fbv[nt]);   // warp-uniform
+                for (int nt = 0; nt < 8; ++nt)
+                    if (cmask & (1u << (8 * mt + nt))) dmma884(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fbv[nt]);   // warp-uniform
+            if (k0 + 4 < ns4) {
 #pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
+                for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
 #pragma unroll
-                        for (int nt = 0; nt < 8; ++nt) fbv[nt] = nb[nt];
-                    }
-                    __syncwarp();                               // the previous contraction has read Wt
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                        for (int nt = 0; nt < 8; ++nt)
-                            if (mask & (1u << (8 * mt + nt)))
-                                *reinterpret_cast<double2*>(Wt + (mt * 8 + mrow) * LJ3_LDW + nt * 8 + 2 * q) =
-                                    make_double2(acc[mt][nt][0], acc[mt][nt][1]);
-                    __syncwarp();
-                    for (uint32_t it = it0 + lane; it < it1; it += 32) {
-                        const uint4 item = __ldg(l3.items3 + it);
-                        double s = 0.0;
-                        for (uint32_t t = item.y; t < item.z; ++t) {
-                            const unsigned ij = __ldg(l3.nz_ij + t);
-                            s = fma(__ldg(l3.nz_v + t), Wt[(ij >> 8) * LJ3_LDW + (ij & 0xffu)], s);
-                        }
-                        Jacc[item.x] += s;                      // a parameter occurs once per (gate, sub-block, half) list
-                    }
-                }
+                for (int nt = 0; nt < 8; ++nt) fbv[nt] = nb[nt];
             }
         }
-        tb += cnt;
+        have = advance();                               // iterator now at the NEXT pass: request its first fragments
+        if (have) fetch(0, fa, fbv);
+        __syncwarp();                                   // the previous contraction has read Wt
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt)
+                if (cmask & (1u << (8 * mt + nt)))
+                    *reinterpret_cast<double2*>(Wt + (mt * 8 + mrow) * LJ3_LDW + nt * 8 + 2 * q) =
+                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+        __syncwarp();
+        for (uint32_t it = cit0 + lane; it < cit1; it += 32) {
+            const uint4 item = __ldg(l3.items3 + it);
+            double s = 0.0;
+            for (uint32_t t = item.y; t < item.z; ++t) {
+                const unsigned ij = __ldg(l3.nz_ij + t);
+                s = fma(__ldg(l3.nz_v + t), Wt[(ij >> 8) * LJ3_LDW + (ij & 0xffu)], s);
+            }
+            Jacc[item.x] += s;                          // a parameter occurs once per (gate, sub-block, half) list
+        }
     }
     __syncwarp();
     {   // state-preparation and effect rows of D (item lists per parameter tile, as in versions 1 / 2)
@@ -541,4 +566,8 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
     const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
     double* Jr = J + el * ld;
     for (int p = lane; p < lj.n_params; p += 32) __stcs(Jr + p, Jacc[p] * sc);
+    for (int r = 0; r < peers.n; ++r) {
+        double* Jp = peers.J[r] + el * ld;
+        for (int p = lane; p < lj.n_params; p += 32) __stcs(Jp + p, Jacc[p] * sc);
+    }
 }

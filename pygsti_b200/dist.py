@@ -236,3 +236,56 @@ def allreduce_jtj(jtj, jtf=None, group=None):
     jtj.copy_(flat[:n * n].reshape(n, n))
     jtf.copy_(flat[n * n:])
     return jtj, jtf
+
+
+class PeerArray:
+    """A (n_rows, n_cols) float64 device array that exists on EVERY rank and that every rank can store into directly: each
+    rank allocates its copy through the engine (``b200_peer_alloc``: cudaMalloc + CUDA IPC handle), the handles are exchanged
+    once (``all_gather_object``) and every rank maps the copies of its peers (``b200_peer_open``, NVLink peer access).  With
+    ``Atom.fill_dprobs_bcast_dev`` the Jacobian kernel of rank r then writes rank r's slot of the sharded element axis into all
+    copies while it produces it -- the all-gather of ``allgather_slots`` without a separate pass.
+    ``sync()`` = stream synchronisation + barrier: afterwards every copy is complete."""
+
+    def __init__(self, ctx, n_rows, n_cols, group=None):
+        import torch.distributed as dist
+        self.ctx, self.group = ctx, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nbytes = max(self.n_rows * self.n_cols * 8, 8)
+        ptr, handle = ctx.peer_alloc(self.nbytes)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self.ptrs = [ptr if r == self.rank else ctx.peer_open(handles[r]) for r in range(self.world)]
+        dist.barrier(group=group)
+
+    @property
+    def __cuda_array_interface__(self):
+        shape = (self.n_rows, self.n_cols) if self.n_cols > 1 else (self.n_rows,)
+        return {"shape": shape, "typestr": "<f8", "data": (self.ptrs[self.rank], False), "version": 3, "strides": None}
+
+    def tensor(self):
+        """torch view of THIS rank's copy (no copy)."""
+        import torch
+        return torch.as_tensor(self, device="cuda:%d" % self.ctx.device)
+
+    def row_ptr(self, owner, row):
+        """Device pointer (valid in this process) of row ``row`` inside the copy held by rank ``owner``."""
+        return self.ptrs[owner] + int(row) * self.n_cols * 8
+
+    def sync(self):
+        import torch.distributed as dist
+        self.ctx.sync()
+        dist.barrier(group=self.group)
+
+    def close(self):
+        import torch.distributed as dist
+        if self.ptrs is None:
+            return
+        self.ctx.sync()
+        dist.barrier(group=self.group)                   # nobody stores into a copy that is about to go away
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.ctx.peer_close(p)
+        dist.barrier(group=self.group)
+        self.ctx.peer_free(self.ptrs[self.rank])
+        self.ptrs = None

@@ -106,6 +106,27 @@ class Context:
     def upload_atom(self, t: AtomTables):
         return Atom(self, t)
 
+    # ---- peer memory (one process per GPU): arrays that the kernels of OTHER ranks store into over NVLink ----------------
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte CUDA IPC handle) of a new device buffer that peers can map (``b200_peer_alloc``)."""
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64)()
+        _lib.check(self._lib.b200_peer_alloc(self._h, int(nbytes), C.byref(p), C.cast(h, C.c_void_p)))
+        return int(p.value), bytes(h)
+
+    def peer_open(self, handle):
+        """Map a peer's buffer from its IPC handle; returns the device pointer valid in THIS process."""
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _lib.check(self._lib.b200_peer_open(self._h, C.cast(h, C.c_void_p), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr):
+        _lib.check(self._lib.b200_peer_close(self._h, C.c_void_p(int(ptr))))
+
+    def peer_free(self, ptr):
+        _lib.check(self._lib.b200_peer_free(self._h, C.c_void_p(int(ptr))))
+
 
 class Atom:
     def __init__(self, ctx: Context, t: AtomTables):
@@ -287,6 +308,21 @@ class Atom:
     def fill_dprobs_dev(self, d_out_ptr, ld, d_probs_ptr=0):
         _lib.check(self._lib.b200_fill_dprobs_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr)), int(ld),
                                                   C.c_void_p(int(d_probs_ptr))))
+
+
+def _atom_fill_dprobs_bcast_dev(self, d_out_ptr, ld, d_probs_ptr, peer_out_ptrs, peer_probs_ptrs=None):
+    """Jacobian fill FUSED with the exchange (``b200_fill_dprobs_bcast_dev``): rows are stored into this rank's slot at
+    ``d_out_ptr`` and, at the same time, into the same slot of every peer's array (``peer_out_ptrs``).  Asynchronous."""
+    n = len(peer_out_ptrs)
+    arr_t = C.c_void_p * max(n, 1)
+    jo = arr_t(*[C.c_void_p(int(x)) for x in peer_out_ptrs])
+    po = arr_t(*[C.c_void_p(int(x)) for x in peer_probs_ptrs]) if peer_probs_ptrs else None
+    _lib.check(self._lib.b200_fill_dprobs_bcast_dev(self.ctx._h, self._h, C.c_void_p(int(d_out_ptr)), int(ld),
+                                                    C.c_void_p(int(d_probs_ptr)), n, C.cast(jo, C.c_void_p),
+                                                    C.cast(po, C.c_void_p) if po is not None else None))
+
+
+Atom.fill_dprobs_bcast_dev = _atom_fill_dprobs_bcast_dev
 
 
 def pinned_empty(shape, dtype=np.float64):

@@ -36,6 +36,9 @@ class B200ForwardSimulator(_MapForwardSimulator):
         ``num_atoms > 1`` and no MPI communicator, atoms are spread round-robin over ``devices``.
     devices : sequence of int or None
         GPUs to spread a single process's atoms over (default: just ``device``).
+    fused_objective : bool
+        True (default): a stock pyGSTi objective function / Levenberg-Marquardt run on this simulator uses the fused row scaling
+        and the on-device J^T J / J^T f (``pygsti_b200.objective.install_hooks``); False: pyGSTi's own host-side passes.
     analytic_hessian : bool
         True (default): `bulk_fill_hprobs` is fully analytic on the device for every member that provides
         `hessian_wrt_params`.  False: members not linear in their parameters go through the reference's own
@@ -44,7 +47,8 @@ class B200ForwardSimulator(_MapForwardSimulator):
 
     def __init__(self, model=None, max_cache_size=None, num_atoms=None, processor_grid=None, param_blk_sizes=None,
                  derivative_eps=1e-7, hessian_eps=1e-5, derivative_mode='analytic', device=None, devices=None,
-                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False, device_lindblad=False):
+                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False, device_lindblad=False,
+                 fused_objective=True):
         if derivative_mode not in ('analytic', 'fd'):
             raise ValueError("derivative_mode must be 'analytic' or 'fd'")
         self.derivative_mode = derivative_mode
@@ -52,6 +56,10 @@ class B200ForwardSimulator(_MapForwardSimulator):
         self.device_model_update = bool(device_model_update)
         self.host_prefix_cache = bool(host_prefix_cache)
         self.device_lindblad = bool(device_lindblad)
+        self.fused_objective = bool(fused_objective)
+        if self.fused_objective:                       # stock dterms / dlsvec / LM normal equations reach the fused kernels
+            from . import objective as _objective
+            _objective.install_hooks()
         if max_cache_size is None and not self.host_prefix_cache:
             max_cache_size = 0                             # SURVEY 8f rank 4 (layout construction): no host-side cache plan
         self._b200_device = device
@@ -76,7 +84,8 @@ class B200ForwardSimulator(_MapForwardSimulator):
         state = super()._to_nice_serialization()
         state.update({'derivative_mode': self.derivative_mode, 'device': self._b200_device,
                       'analytic_hessian': self.analytic_hessian, 'device_model_update': self.device_model_update,
-                      'host_prefix_cache': self.host_prefix_cache, 'device_lindblad': self.device_lindblad})
+                      'host_prefix_cache': self.host_prefix_cache, 'device_lindblad': self.device_lindblad,
+                      'fused_objective': self.fused_objective})
         return state
 
     @classmethod
@@ -88,7 +97,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
                    device=state.get('device', None), analytic_hessian=state.get('analytic_hessian', True),
                    device_model_update=state.get('device_model_update', False),
                    host_prefix_cache=state.get('host_prefix_cache', False),
-                   device_lindblad=state.get('device_lindblad', False))
+                   device_lindblad=state.get('device_lindblad', False), fused_objective=state.get('fused_objective', True))
 
     def copy(self, keep_model_attached=True):
         # MapForwardSimulator.copy hard-codes its own class (mapforwardsim.py:190-204) -> must override,
@@ -96,7 +105,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
         out = B200ForwardSimulator(self.model, self._max_cache_size, self._num_atoms, self._processor_grid,
                                    self._pblk_sizes, self.derivative_eps, self.hessian_eps,
                                    self.derivative_mode, self._b200_device, self._b200_devices, self.analytic_hessian,
-                                   self.device_model_update, self.host_prefix_cache, self.device_lindblad)
+                                   self.device_model_update, self.host_prefix_cache, self.device_lindblad, self.fused_objective)
         if not keep_model_attached:
             out.model = None
         return out

@@ -128,3 +128,123 @@ def fused_hessian(objfn, paramvec=None, block_size=None):
             if b0 != a0:
                 H[s2, s1] = blk.T
     return H
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Drop-in for STOCK pyGSTi runs: `GateSetTomography.run(..., simulator=B200ForwardSimulator())`, `run_gst_fit`, ... reach
+# the fused kernels without any change to user code.
+#
+#   * `TimeIndependentMDCObjectiveFunction.dterms / dlsvec` (objectivefns.py:4595-4653): wrapped; for a "plain" objective on
+#     a B200ForwardSimulator the row scaling happens in the kernel epilogue (`fused_dterms / fused_dlsvec`), anything else
+#     runs the original method.  The wrapper remembers (parameter vector, row scale, lsvec) of the Jacobian it just produced.
+#   * `DistributableCOPALayout.fill_jtj / fill_jtf` and `DistributedArraysInterface.norm2_jac` -- what Levenberg-Marquardt
+#     calls right after `dlsvec` (simplerlm.py:663-678; distlayout.py:1220-1359) -- wrapped: when the array handed in IS that
+#     Jacobian (same memory, model still at the same parameters) the products come from the device
+#     (`B200ForwardSimulator.bulk_jtj`: scaled Jacobian re-filled in HBM + hand-written DMMA SYRK, ~25 ms at BASELINE config 2
+#     instead of a 1 TFLOP numpy `dot` over a 2.97 GB host array); otherwise the original method runs.
+# Installed once per process by `B200ForwardSimulator(fused_objective=True)` (the default); `uninstall_hooks()` restores pyGSTi.
+# ----------------------------------------------------------------------------------------------------------------------
+_HOOKS = {}
+_LAST = {}            # Jacobian base address -> record of the fused fill that produced it
+
+
+def _sim_wants_hooks(objfn):
+    sim = getattr(getattr(objfn, "model", None), "sim", None)
+    return sim is not None and getattr(sim, "fused_objective", False) and hasattr(sim, "bulk_fill_dprobs_scaled")
+
+
+def _remember(objfn, kind, scale, lsvec):
+    jac = objfn.jac
+    _LAST.clear()      # one live record: the LM loop consumes a Jacobian before it asks for the next
+    _LAST[jac.ctypes.data] = dict(objfn=objfn, kind=kind, x=objfn.model.to_vector().copy(), scale=np.array(scale, copy=True),
+                                  lsvec=None if lsvec is None else np.array(lsvec[:objfn.nelements], copy=True),
+                                  shape=jac.shape, jtj=None, jtf=None)
+
+
+def _record_for(j):
+    try:
+        rec = _LAST.get(j.ctypes.data)
+    except Exception:
+        return None
+    if rec is None or tuple(j.shape) != tuple(rec["shape"]):
+        return None
+    objfn = rec["objfn"]
+    if not np.array_equal(objfn.model.to_vector(), rec["x"]) or _distributed(objfn.layout):
+        return None
+    return rec
+
+
+def _device_products(rec):
+    if rec["jtj"] is None:
+        objfn = rec["objfn"]
+        f = rec["lsvec"] if rec["lsvec"] is not None else np.zeros(objfn.nelements)
+        rec["jtj"], rec["jtf"] = objfn.model.sim.bulk_jtj(objfn.layout, rec["scale"], f)
+    return rec
+
+
+def install_hooks():
+    """Idempotent.  Needs pyGSTi importable (it is the host application)."""
+    if _HOOKS:
+        return
+    from pygsti.objectivefns import objectivefns as _of
+    from pygsti.layouts.distlayout import DistributableCOPALayout as _DL
+    from pygsti.optimize import arraysinterface as _ari
+    cls = _of.TimeIndependentMDCObjectiveFunction
+    orig_dterms, orig_dlsvec = cls.dterms, cls.dlsvec
+    orig_jtj, orig_jtf = _DL.fill_jtj, _DL.fill_jtf
+    orig_norm2 = _ari.DistributedArraysInterface.norm2_jac
+
+    def dterms(self, paramvec=None):
+        if type(self).dterms is not dterms or not (_sim_wants_hooks(self) and _plain(self)):
+            return orig_dterms(self, paramvec)
+        if paramvec is not None:
+            self.model.from_vector(paramvec)
+        scale = _row_scale_terms(self) * _term_weights(self)
+        self.model.sim.bulk_fill_dprobs_scaled(self.jac[0:self.nelements, :], self.layout, scale)
+        _remember(self, "dterms", scale, None)
+        return self.jac
+
+    def dlsvec(self, paramvec=None):
+        if type(self).dlsvec is not dlsvec or type(self).dterms is not dterms or not (_sim_wants_hooks(self) and _plain(self)):
+            return orig_dlsvec(self, paramvec)
+        if paramvec is not None:
+            self.model.from_vector(paramvec)
+        scale, lsvec = _lsvec_scale(self, paramvec)
+        self.model.sim.bulk_fill_dprobs_scaled(self.jac[0:self.nelements, :], self.layout, scale)
+        _remember(self, "dlsvec", scale, lsvec)
+        return self.jac
+
+    def fill_jtj(self, j, jtj, shared_mem_buf=None):
+        rec = _record_for(j)
+        if rec is None or rec["objfn"].layout is not self or tuple(jtj.shape) != (j.shape[1], j.shape[1]):
+            return orig_jtj(self, j, jtj, shared_mem_buf)
+        jtj[:, :] = _device_products(rec)["jtj"]
+
+    def fill_jtf(self, j, f, jtf):
+        rec = _record_for(j)
+        if rec is None or rec["objfn"].layout is not self or rec["lsvec"] is None or jtf.shape != (j.shape[1],) \
+                or not np.array_equal(np.asarray(f)[:rec["lsvec"].shape[0]], rec["lsvec"]) or f.shape[0] != rec["lsvec"].shape[0]:
+            return orig_jtf(self, j, f, jtf)
+        jtf[:] = _device_products(rec)["jtf"]
+
+    def norm2_jac(self, j):
+        rec = _record_for(j)
+        if rec is None or rec["objfn"].layout is not self.layout:
+            return orig_norm2(self, j)
+        return float(np.trace(_device_products(rec)["jtj"]))          # ||J||_F^2 = tr(J^T J)
+
+    cls.dterms, cls.dlsvec = dterms, dlsvec
+    _DL.fill_jtj, _DL.fill_jtf = fill_jtj, fill_jtf
+    _ari.DistributedArraysInterface.norm2_jac = norm2_jac
+    _HOOKS.update(cls=cls, dterms=orig_dterms, dlsvec=orig_dlsvec, DL=_DL, jtj=orig_jtj, jtf=orig_jtf,
+                  ari=_ari.DistributedArraysInterface, norm2=orig_norm2)
+
+
+def uninstall_hooks():
+    if not _HOOKS:
+        return
+    _HOOKS["cls"].dterms, _HOOKS["cls"].dlsvec = _HOOKS["dterms"], _HOOKS["dlsvec"]
+    _HOOKS["DL"].fill_jtj, _HOOKS["DL"].fill_jtf = _HOOKS["jtj"], _HOOKS["jtf"]
+    _HOOKS["ari"].norm2_jac = _HOOKS["norm2"]
+    _HOOKS.clear()
+    _LAST.clear()

@@ -54,7 +54,19 @@ def _worker(rank, world, port, name, q):
     ref_jtj = Js.T @ Js; ref_jtf = Js.T @ fv_s
     e3 = float((jtj - ref_jtj).abs().max() / ref_jtj.abs().max())
     e4 = float((jtf - ref_jtf).abs().max() / ref_jtf.abs().max())
-    q.put((rank, e1, e2, e3, e4))
+    # the same exchange FUSED into the fill: every rank's kernel stores its rows into all copies of a peer-mapped array
+    JP = bd.PeerArray(ctx, plan.n_rows_padded, Np); PP = bd.PeerArray(ctx, plan.n_rows_padded, 1)
+    Jt, Pt = JP.tensor(), PP.tensor()
+    Jt.zero_(); Pt.zero_()
+    torch.cuda.synchronize(); dist.barrier()
+    peers = [r for r in range(world) if r != rank]
+    at.fill_dprobs_bcast_dev(JP.row_ptr(rank, rank * slot), Np, PP.row_ptr(rank, rank * slot),
+                             [JP.row_ptr(r, rank * slot) for r in peers], [PP.row_ptr(r, rank * slot) for r in peers])
+    JP.sync()
+    e5 = float((Jt - J).abs().max()); e6 = float((Pt - P).abs().max())         # bitwise the NCCL result
+    del Jt, Pt
+    JP.close(); PP.close()
+    q.put((rank, e1, e2, e3, e4, e5, e6))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,8 +86,8 @@ def test_two_gpu_shard_fill_allgather():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    for rank, e1, e2, e3, e4 in res:
-        assert e1 <= 1e-12 and e2 <= 1e-10 and e3 <= 1e-10 and e4 <= 1e-10, res
+    for rank, e1, e2, e3, e4, e5, e6 in res:
+        assert e1 <= 1e-12 and e2 <= 1e-10 and e3 <= 1e-10 and e4 <= 1e-10 and e5 == 0.0 and e6 == 0.0, res
 
 
 def test_single_process_two_gpus_concurrent():

@@ -239,6 +239,51 @@ def test_four_qubit_cloud_crosstalk_model_d256():
     assert np.max(np.abs(pmap - pb)) <= 1e-10
 
 
+def test_stock_objective_and_lm_use_the_fused_path():
+    """Missing-drop-in row of round 1: a STOCK objective function (`objfn.dlsvec`, `objfn.dterms`) and the products LM forms right
+    after it (`layout.fill_jtj / fill_jtf`, `ari.norm2_jac`; simplerlm.py:663-678) on a B200ForwardSimulator go through the fused
+    kernels (hooks installed by the simulator), and give what pyGSTi's own host code gives."""
+    from pygsti.data import simulate_data
+    from pygsti.objectivefns import objectivefns as _objfns
+    from pygsti.optimize import arraysinterface as _ari
+    from pygsti_b200 import objective as fused
+    target = smq1Q_XYI.target_model("full TP")
+    datagen = target.depolarize(op_noise=0.1, spam_noise=0.05)
+    circuits = smq1Q_XYI.create_gst_experiment_design(4).all_circuits_needing_data
+    ds = simulate_data(datagen, circuits, 1000, seed=1234)
+    start = target.depolarize(op_noise=0.06, spam_noise=0.03)
+
+    def make(**kw):
+        m = start.copy(); m.sim = B200ForwardSimulator(**kw)
+        return _objfns.Chi2Function.create_from(m, ds, circuits, method_names=('lsvec', 'dlsvec', 'dterms'))
+
+    assert fused._HOOKS, "hooks are installed by the simulator constructor"
+    hooked, plain = make(), make(fused_objective=False)
+    v = start.to_vector()
+    J1 = hooked.dlsvec(v); J0 = plain.dlsvec(v).copy()
+    assert J1.ctypes.data in fused._LAST and fused._LAST[J1.ctypes.data]["kind"] == "dlsvec"       # the fused path ran
+    assert np.max(np.abs(J1 - J0)) <= 1e-11 * max(1.0, np.max(np.abs(J0)))
+    f = hooked.lsvec(v)
+    nP = J1.shape[1]
+    ari = _ari.DistributedArraysInterface(hooked.layout, 'normal', 0)
+    jtj = np.empty((nP, nP)); jtf = np.empty(nP)
+    n2 = ari.norm2_jac(J1)
+    ari.fill_jtj(J1, jtj, None); ari.fill_jtf(J1, f, jtf)
+    assert fused._LAST[J1.ctypes.data]["jtj"] is not None                                          # ... came from the device
+    R = J0.T @ J0
+    assert np.max(np.abs(jtj - R)) <= 1e-10 * np.max(np.abs(R))
+    assert np.max(np.abs(jtf - J0.T @ plain.lsvec(v))) <= 1e-10 * max(1.0, np.max(np.abs(J0.T @ f)))
+    assert abs(n2 - np.linalg.norm(J0) ** 2) <= 1e-10 * n2
+    # a Jacobian the hooks do not know (a copy) and a model that has moved on fall back to pyGSTi's own code
+    Jc = J0.copy(); jtj2 = np.empty((nP, nP))
+    ari.fill_jtj(Jc, jtj2, None)
+    assert np.max(np.abs(jtj2 - R)) <= 1e-12 * np.max(np.abs(R))
+    hooked.model.from_vector(v + 1e-3)
+    assert fused._record_for(J1) is None
+    D1 = hooked.dterms(v); D0 = plain.dterms(v)
+    assert np.max(np.abs(D1 - D0)) <= 1e-11 * max(1.0, np.max(np.abs(D0)))
+
+
 def test_fused_objective_with_term_weights():
     """A TermWeighted objective ('normalized tvd': rows weighted by 1 / circuit size, objectivefns.py:5175-5192): the weights
     must reach the fused row scale -- dterms, dlsvec AND J^T J / J^T f -- exactly as `_reweight_jac` applies them."""
@@ -251,11 +296,11 @@ def test_fused_objective_with_term_weights():
     ds = simulate_data(datagen, circuits, 1000, seed=1234)
     start = target.depolarize(op_noise=0.06, spam_noise=0.03)
 
-    def make():
-        m = start.copy(); m.sim = B200ForwardSimulator()
+    def make(**kw):
+        m = start.copy(); m.sim = B200ForwardSimulator(**kw)
         return _objfns.TVDFunction.create_from(m, ds, circuits, name='normalized tvd', method_names=('lsvec', 'dlsvec', 'dterms'))
 
-    ours, same = make(), make()
+    ours, same = make(), make(fused_objective=False)
     v = start.to_vector()
     w = fused._term_weights(ours)
     assert w.shape == (ours.nelements,) and np.ptp(w) > 0.1                 # genuinely non-trivial weights
@@ -292,7 +337,7 @@ def test_fused_objective_jacobian_and_jtj(objname):
 
     ref = make(MatrixForwardSimulator())      # independent simulator AND independent layout (element order differs)
     ours = make(B200ForwardSimulator())
-    same = make(B200ForwardSimulator())       # reference objective-function code path on top of the GPU simulator
+    same = make(B200ForwardSimulator(fused_objective=False))   # reference objective-function code path on top of the GPU simulator
     v = start.to_vector()
     Jref = ref.dlsvec(v).copy(); fref = ref.lsvec(v).copy()
     Jsame = same.dlsvec(v).copy(); Dsame = same.dterms(v).copy()
