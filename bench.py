@@ -653,6 +653,37 @@ def bench_c5(args, D, engine, stream, ctx):
            "ms": ms, "outcomes_per_s": D.world * t.n_elements / (ms * 1e-3), "parallelism": "replica per GPU" if D.world > 1 else "1 GPU",
            "algorithmic": {"flops": flops}, "tflops": flops / (ms * 1e-3) / 1e12, "frac": flops / (ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
            "bound": "tensor (FP64 DMMA %.1f TFLOP/s measured)" % DMMA_PEAK_TFLOPS, "parity": par}
+    # The same circuits on a model of the family BASELINE names (4-qubit crosstalk: every layer = small operations embedded on 1-2
+    # qubits): the factor programs (device form of OpCRep_Composed / OpCRep_Embedded) against the dense products of the same model
+    try:
+        from pygsti_b200.packing import FactoredModel, factored_to_dense
+        rng = np.random.default_rng(5)
+        fptr, f_nq, f_t, f_off, mats, off = [0], [], [], [], [], 0
+        targets = [(q,) for q in range(4)] * 2 + [(0, 1), (1, 0), (1, 2), (2, 1), (2, 3), (3, 2)]         # 14 layer labels
+        for tg in targets:
+            for _ in range(2):                                                                           # ideal gate . local error factor
+                k = len(tg)
+                small = np.eye(4 ** k) * 0.9 + 0.2 * rng.standard_normal((4 ** k, 4 ** k)) / 2 ** k
+                f_nq.append(k); f_t.append(list(tg) + [-1] * (4 - k)); f_off.append(off); mats.append(small.ravel()); off += small.size
+            fptr.append(len(f_nq))
+        fm = FactoredModel(n_qubits=4, op_fptr=np.asarray(fptr, np.int32), f_nq=np.asarray(f_nq, np.int32),
+                           f_targets=np.asarray(f_t, np.int32).reshape(-1, 4), f_moff=np.asarray(f_off, np.int64),
+                           mats=np.concatenate(mats), rho=rho, E=E)
+        atom.set_model_factored(fm)
+        Pf = torch.empty_like(P)
+        ms_f = timed(D, stream, lambda: atom.fill_probs_dev(Pf.data_ptr()), max(5, min(args.steps, 20)), 3)
+        atom.set_model(factored_to_dense(fm, 256), rho, E)
+        ms_d = timed(D, stream, lambda: atom.fill_probs_dev(P.data_ptr()), max(5, min(args.steps, 20)), 3)
+        err = float((Pf - P).abs().max())
+        assert err <= 1e-11, err
+        out["embedded_model"] = {"what": "same 5000 circuits, 14 layer labels each = 2 factors embedded on 1-2 of 4 qubits (28 factors): "
+                                         "k_probs_factored (factor programs, no dense matrices) vs the dense level-batched DMMA path on the "
+                                         "densified model", "ms_factored": ms_f, "ms_dense": ms_d, "speedup": ms_d / ms_f,
+                                 "outcomes_per_s_factored": D.world * t.n_elements / (ms_f * 1e-3), "max_abs_diff": err}
+    except AssertionError:
+        raise
+    except Exception as e:
+        out["embedded_model"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
         orc, kind, _ = _oracle()
         sub, _ = fx.random_layout(256, 14, 16, n_circ, 128, seed=0, rows=(0, 250))

@@ -92,6 +92,18 @@ int b200_atom_info(b200_atom* atom, int64_t info[8]);
 int b200_atom_set_model(b200_ctx* ctx, b200_atom* atom,
                         const double* G, const double* rho, const double* E);
 
+/* FACTORED model: every gate (layer operation) is a product of small superoperators embedded on 1-2 qubits -- the device
+ * form of the reference's non-dense reps OpCRep_Composed / OpCRep_Embedded (pygsti/evotypes/densitymx/opcreps.cpp:242-276,
+ * 93-158; chosen by pyGSTi for dim > 64, pygsti/evotypes/evotype.py:97).  Gate g = factors [op_fptr[g], op_fptr[g+1]) applied
+ * in that order; factor f acts with the row-major (4^nq x 4^nq) matrix at mats + f_moff[f] on the f_nq[f] (1 or 2) qubits
+ * f_targets[4 f ..] (positions in state-space order, 0 = most significant base-4 digit of the state index).
+ * b200_fill_probs then applies the factors directly (4 / 16 multiply-adds per state component instead of d); the dense
+ * matrices the derivative paths need are built ON THE DEVICE from the same programs, so the host never calls to_dense on a
+ * d x d operation.  Replaces b200_atom_set_model for such models (dim = 4^n, n >= 2).  rho / E as in b200_atom_set_model. */
+int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* atom, int32_t n_factors, const int32_t* op_fptr,
+                                 const int32_t* f_nq, const int32_t* f_targets, const int64_t* f_moff,
+                                 const double* mats, int64_t n_mats, const double* rho, const double* E);
+
 /* Sparse derivative map D (COO, duplicates summed by the engine), n_params = number of Jacobian
  * columns produced (the caller has already restricted/renumbered to its param_slice,
  * distforwardsim.py:130-144).  Replaces the per-parameter `model.set_parameter_values` loop of

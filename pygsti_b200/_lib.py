@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200_atom_free": (C.c_int, [vp, vp]),
     "b200_atom_info": (C.c_int, [vp, c_i64p]),
     "b200_atom_set_model": (C.c_int, [vp, vp, vp, vp, vp]),
+    "b200_atom_set_model_factored": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp, vp]),
     "b200_atom_set_derivs": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, vp]),
     "b200_atom_bind_params": (C.c_int, [vp, vp, C.c_int32, vp]),
     "b200_atom_set_params": (C.c_int, [vp, vp, C.c_int32, vp]),

@@ -193,6 +193,13 @@ def _upload_model(fwdsim, layout_atom, ent):
     if getattr(fwdsim, "device_model_update", False) and _bound_to(ent, model):
         atom.set_params(model.to_vector())
         return
+    if model.dim >= 64 and getattr(fwdsim, "factored_reps", True):
+        # dim > 64: pyGSTi's own reps are Composed / Embedded (evotype.py:97); hand the factor programs to the engine instead of
+        # densifying every layer label on the host (packing.pack_model_factored returns None for anything else)
+        fm = packing.pack_model_factored(model, layout_atom, model.dim)
+        if fm is not None:
+            atom.set_model_factored(fm)
+            return
     atom.set_model(packing.pack_model(model, layout_atom, model.dim))
 
 

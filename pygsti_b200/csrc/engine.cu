@@ -9,6 +9,7 @@
 #include "kernels_levelj.cuh"
 #include "kernels_jtj.cuh"
 #include "kernels_gemm.cuh"
+#include "kernels_factored.cuh"
 #include <cstdlib>
 
 #include <algorithm>
@@ -66,6 +67,8 @@ struct b200_ctx {
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     DevBuf atb_part, atb_part_f;                 // partial tiles of the A^T B reductions (k_atb_dmma)
+    DevBuf hb[24];                               // scratch of the Hessian-block path (kept between calls: cudaMalloc / cudaFree per
+                                                 // rectangle cost more than the kernels once peer access is enabled)
     DevBuf fd_models, fd_gt, fd_probs;
     DevBuf lind[20];                                     // b200_lindblad_members: inputs, intermediates, outputs
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
@@ -106,6 +109,8 @@ struct b200_atom {
     // model
     bool has_model = false;
     DevBuf M, Gt;
+    bool has_factored = false;             // gates also held as factor programs (b200_atom_set_model_factored)
+    DevBuf fac_ptr, fac_rec, fac_mats; int fac_n_mats = 0;
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -188,6 +193,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     for (DevBuf& b : c->lind) b.release();
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     c->atb_part.release(); c->atb_part_f.release();
+    for (DevBuf& b : c->hb) b.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -567,7 +573,7 @@ extern "C" int b200_atom_upload(b200_ctx* ctx, int dim, int n_ops, int n_rho, in
 extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
     if (!a) return B200_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt,
+    DevBuf* bufs[] = {&a->circ_ptr, &a->circ_ops, &a->circ_prep, &a->out_ptr, &a->out_eff, &a->out_el, &a->M, &a->Gt, &a->fac_ptr, &a->fac_rec, &a->fac_mats,
                       &a->bperm, &a->bcnt, &a->lvl_circ, &a->lvl_tiles,
                       &a->lj_fbase, &a->lj_bbase, &a->lj_frow, &a->lj_brow, &a->lj_btiles, &a->lj_ti_ptr, &a->lj_items,
                       &a->lj2_ti_ptr, &a->lj2_mask, &a->lj2_items, &a->lj2_ij, &a->lj2_v, &a->lj3_tp, &a->lj3_mask, &a->lj3_items, &a->lj3_ij, &a->lj3_v, &a->tf_meta, &a->tf_op, &a->tb_meta, &a->tb_op, &a->t_fn, &a->t_bn, &a->t_fend, &a->t_bend, &a->tf_par, &a->tb_par, &a->t_SH,
@@ -608,7 +614,67 @@ extern "C" int b200_atom_set_model(b200_ctx* ctx, b200_atom* a, const double* G,
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(ctx->stream));   // caller may free/modify its host arrays on return
-    a->has_model = true;
+    a->has_model = true; a->has_factored = false;
+    return B200_OK;
+}
+
+template <int D>
+static int launch_factored_dense(b200_ctx* c, b200_atom* a, const FactoredDev& fd) {
+    const size_t smem = (size_t)FAC_WARPS * 2 * D * 8;
+    CU(cudaFuncSetAttribute(k_factored_to_dense<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)a->n_ops * D + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 8));
+    k_factored_to_dense<D><<<grid, FAC_WARPS * 32, smem, c->stream>>>(a->n_ops, fd, a->M.as<double>(), a->Gt.as<double>());
+    c->launches++;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+static FactoredDev factored_dev(b200_atom* a) {
+    FactoredDev fd; fd.op_fptr = a->fac_ptr.as<int32_t>(); fd.fac = a->fac_rec.as<FactorRec>(); fd.mats = a->fac_mats.as<double>();
+    return fd;
+}
+
+extern "C" int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* a, int32_t n_factors, const int32_t* op_fptr,
+                                            const int32_t* f_nq, const int32_t* f_targets, const int64_t* f_moff,
+                                            const double* mats, int64_t n_mats, const double* rho, const double* E) {
+    if (!ctx || !a || !op_fptr || !rho || !E || n_factors < 0 || (n_factors > 0 && (!f_nq || !f_targets || !f_moff || !mats)))
+        return fail(B200_E_INVALID, "NULL / negative argument");
+    const int d = a->dim;
+    int nq = 0; while ((1 << (2 * nq)) < d) ++nq;
+    if ((1 << (2 * nq)) != d || (d != 16 && d != 64 && d != 256)) return fail(B200_E_UNSUPPORTED, "factored models need dim = 16, 64 or 256");
+    if (op_fptr[0] != 0 || op_fptr[a->n_ops] != n_factors) return fail(B200_E_INVALID, "op_fptr must run from 0 to n_factors");
+    std::vector<FactorRec> recs((size_t)std::max(n_factors, 1));
+    for (int g = 0; g < a->n_ops; ++g) if (op_fptr[g + 1] < op_fptr[g]) return fail(B200_E_INVALID, "op_fptr not monotone");
+    for (int f = 0; f < n_factors; ++f) {
+        const int k = f_nq[f];
+        if (k < 1 || k > 2) return fail(B200_E_UNSUPPORTED, "factor %d acts on %d qubits (1 or 2 supported)", f, k);
+        const int64_t ds = (int64_t)1 << (2 * k);
+        if (f_moff[f] < 0 || f_moff[f] + ds * ds > n_mats || f_moff[f] >= ((int64_t)1 << 31)) return fail(B200_E_INVALID, "factor %d: matrix offset out of range", f);
+        FactorRec r; r.nq = k; r.shift[0] = r.shift[1] = 0; r.moff = (int32_t)f_moff[f];
+        for (int t = 0; t < k; ++t) {
+            const int q = f_targets[4 * f + t];
+            if (q < 0 || q >= nq || (t == 1 && q == f_targets[4 * f])) return fail(B200_E_INVALID, "factor %d: bad target qubit %d", f, q);
+            r.shift[t] = 2 * (nq - 1 - q);
+        }
+        recs[f] = r;
+    }
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int32_t> fptr(op_fptr, op_fptr + a->n_ops + 1);
+    std::vector<double> mv(mats, mats + std::max<int64_t>(n_mats, 0)); if (mv.empty()) mv.push_back(0.0);
+    int rc;
+    if ((rc = upload_vec(a->fac_ptr, fptr, ctx->stream)) || (rc = upload_vec(a->fac_rec, recs, ctx->stream)) ||
+        (rc = upload_vec(a->fac_mats, mv, ctx->stream))) return rc;
+    CU(a->M.ensure((size_t)a->n_w * sizeof(double)));
+    CU(a->Gt.ensure(std::max<size_t>((size_t)a->off_rho * sizeof(double), 16)));
+    double* M = a->M.as<double>();
+    CU(cudaMemcpyAsync(M + a->off_rho, rho, (size_t)a->n_rho * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(M + a->off_eff, E, (size_t)a->n_eff * d * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (a->n_ops) {
+        const FactoredDev fd = factored_dev(a);
+        rc = d == 16 ? launch_factored_dense<16>(ctx, a, fd) : d == 64 ? launch_factored_dense<64>(ctx, a, fd) : launch_factored_dense<256>(ctx, a, fd);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    a->has_model = true; a->has_factored = true; a->fac_n_mats = (int)std::min<int64_t>(n_mats, INT_MAX);
     return B200_OK;
 }
 
@@ -763,6 +829,7 @@ extern "C" int b200_atom_set_params_dev(b200_ctx* ctx, b200_atom* a, int32_t n_p
     if (n_params != a->bind_n_params) return fail(B200_E_INVALID, "n_params=%d, bound with %d", n_params, a->bind_n_params);
     CU(cudaSetDevice(ctx->device));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_w + 255) / 256, (int64_t)ctx->sm_count * 8));
+    a->has_factored = false;                  // M is about to change: the factor programs no longer describe it
     k_model_affine<<<grid, 256, 0, ctx->stream>>>(a->n_w, a->aff_rptr.as<int32_t>(), a->aff_rcol.as<int32_t>(), a->aff_rval.as<double>(),
                                                   a->aff_const.as<double>(), d_theta, a->M.as<double>());
     ctx->launches++;
@@ -1204,6 +1271,26 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     CU(cudaSetDevice(c->device));
     if (a->n_rows > 0 && d16_ok(c, a)) return launch_probs_trie(c, a, d_out);
+    if (a->has_factored && a->n_rows > 0 && a->dim >= 64 && !getenv("B200_NO_FACTORED")) {
+        // gates as factor programs (Embedded / Composed reps): no dense d x d products at all
+        const FactoredDev fd = factored_dev(a);
+        const double* M = a->M.as<double>();
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 4));
+        const int n_mats = (int)(a->fac_mats.cap / 8);
+        const int n_ms = n_mats <= 8192 ? a->fac_n_mats : 0;              // stage the factor matrices in shared memory when <= 64 KB
+        if (a->dim == 64) {
+            const size_t smem = ((size_t)FAC_WARPS * 2 * 64 + n_ms) * 8;
+            CU(cudaFuncSetAttribute(k_probs_factored<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_probs_factored<64><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, M + a->off_rho, M + a->off_eff, d_out, 1);
+        } else {
+            const size_t smem = ((size_t)FAC_WARPS * 2 * 256 + n_ms) * 8;
+            CU(cudaFuncSetAttribute(k_probs_factored<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_probs_factored<256><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, M + a->off_rho, M + a->off_eff, d_out, 1);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+        return B200_OK;
+    }
     if (a->has_levels && a->n_rows > 0 && !getenv("B200_NO_LEVELS")) {
         if (a->dim == 64) return launch_probs_level<64>(c, a, d_out);
         if (a->dim == 256) return launch_probs_level<256>(c, a, d_out);
@@ -1687,6 +1774,31 @@ k_gather_cols(const double* __restrict__ J, int64_t ld, int64_t n_el, int n, con
 static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t* p1, int32_t n2, const int32_t* p2,
                            int64_t nnz2, const int32_t* h_rows, const int32_t* h_a, const int32_t* h_b, const double* h_vals,
                            double* out, const double* w_h, const double* w_d, double* red_out) {
+    // scratch kept in the context between calls
+    DevBuf& d_p1 = c->hb[0];
+    DevBuf& d_p2 = c->hb[1];
+    DevBuf& d_out = c->hb[2];
+    DevBuf& d_mrow = c->hb[3];
+    DevBuf& d_mcol = c->hb[4];
+    DevBuf& d_mval = c->hb[5];
+    DevBuf& d_ktp = c->hb[6];
+    DevBuf& d_kti = c->hb[7];
+    DevBuf& d_D2 = c->hb[8];
+    DevBuf& d_ukey = c->hb[9];
+    DevBuf& d_kptr = c->hb[10];
+    DevBuf& d_krow = c->hb[11];
+    DevBuf& d_kval = c->hb[12];
+    DevBuf& d_Dsel = c->hb[13];
+    DevBuf& d_ktp2 = c->hb[14];
+    DevBuf& d_kti2 = c->hb[15];
+    DevBuf& d_need = c->hb[16];
+    DevBuf& d_wh = c->hb[17];
+    DevBuf& d_wd = c->hb[18];
+    DevBuf& d_red = c->hb[19];
+    DevBuf& d_j1 = c->hb[20];
+    DevBuf& d_j2 = c->hb[21];
+    DevBuf& d_cs = c->hb[22];
+
     if (!c || !a || (!out && !red_out) || (n1 > 0 && !p1) || (n2 > 0 && !p2)) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
@@ -1695,7 +1807,6 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
     CU(cudaSetDevice(c->device));
     const int64_t nE = a->n_elements;
     if (nE == 0 || n1 == 0 || n2 == 0) return B200_OK;
-    DevBuf d_p1, d_p2, d_out;
     std::vector<int32_t> v1(p1, p1 + n1), v2(p2, p2 + n2);
     int rc;
     if ((rc = upload_vec(d_p1, v1, c->stream)) || (rc = upload_vec(d_p2, v2, c->stream))) return rc;
@@ -1750,7 +1861,6 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
                     while (pos < mcol.size() && mcol[pos] < col) ++pos;
                     for (size_t q = pos; q < mcol.size() && mcol[q] == col; ++q) fn(mrow[q]); }, ktp, kti);
             }
-            DevBuf d_mrow, d_mcol, d_mval, d_ktp, d_kti, d_D2;
             if ((rc = upload_vec(d_mrow, mrow, c->stream)) || (rc = upload_vec(d_mcol, mcol, c->stream)) || (rc = upload_vec(d_mval, mval, c->stream)) ||
                 (rc = upload_vec(d_ktp, ktp, c->stream)) || (rc = upload_vec(d_kti, kti, c->stream))) return rc;
             CU(d_D2.ensure((size_t)a->n_w * ld12 * 8));
@@ -1762,9 +1872,7 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
                            d_ktp.as<int32_t>(), d_kti.as<int32_t>(), nullptr, false, 1);
             if (rc) return rc;
             CU(cudaStreamSynchronize(c->stream));
-            d_mrow.release(); d_mcol.release(); d_mval.release(); d_ktp.release(); d_kti.release(); d_D2.release();
         } else {
-            DevBuf d_ukey, d_kptr, d_krow, d_kval;
             if ((rc = upload_vec(d_ukey, ukey, c->stream)) || (rc = upload_vec(d_kptr, kptr, c->stream)) ||
                 (rc = upload_vec(d_krow, krow, c->stream)) || (rc = upload_vec(d_kval, kval, c->stream))) return rc;
             CU(cudaMemsetAsync(d_out.p, 0, (size_t)nE * n1 * n2 * 8, c->stream));
@@ -1775,12 +1883,10 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
             c->launches++;
             CU(cudaGetLastError());
             CU(cudaStreamSynchronize(c->stream));
-            d_ukey.release(); d_kptr.release(); d_krow.release(); d_kval.release();
         }
         accumulate = 1;
     }
     // first-order part: out[:, a, :] (+)= Wp_a . D[:, p2] per tangent direction a -- dense D[:, p2] + K-chunk lists for the DMMA GEMM
-    DevBuf d_Dsel, d_ktp2, d_kti2;
     const int64_t ld2 = (n2 + 1) & ~1;
     const bool dense2 = (double)a->n_w * (double)ld2 * 8.0 <= 2.0e9;
     if (dense2) {
@@ -1796,7 +1902,6 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         CU(cudaStreamSynchronize(c->stream));          // the host K-chunk lists go out of scope
     }
     // blocks of the W row the contraction reads (rows of D[:, p2] with a non-zero): gates / state preparations / effects
-    DevBuf d_need;
     std::vector<unsigned char> need((size_t)a->n_ops + 2, 0);
     {
         const int64_t dd = (int64_t)a->dim * a->dim;
@@ -1856,11 +1961,9 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         }
     }
     CU(cudaStreamSynchronize(c->stream));
-    d_Dsel.release(); d_ktp2.release(); d_kti2.release(); d_need.release();
     if (red_out) {
         // MLE Hessian block (objectivefns.py:4914-4990 `_hessian_from_block` without omitted-outcome rows):
         //   red[a][b] = sum_el w_h[el] H[el][a][b] + w_d[el] J[el][p1[a]] J[el][p2[b]]      -- only n1 x n2 doubles leave the device
-        DevBuf d_wh, d_wd, d_red, d_j1, d_j2, d_cs;
         const int64_t ld1 = (n1 + 1) & ~1, ld2 = (n2 + 1) & ~1, n12 = (int64_t)n1 * n2;
         CU(d_wh.ensure((size_t)nE * 8)); CU(d_wd.ensure((size_t)nE * 8)); CU(d_red.ensure((size_t)n12 * 8));
         CU(d_j1.ensure((size_t)nE * ld1 * 8)); CU(d_j2.ensure((size_t)nE * ld2 * 8));
@@ -1887,12 +1990,10 @@ static int fill_hprobs_impl(b200_ctx* c, b200_atom* a, int32_t n1, const int32_t
         if (rc) return rc;
         CU(cudaMemcpyAsync(red_out, d_red.p, (size_t)n1 * n2 * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        d_wh.release(); d_wd.release(); d_red.release(); d_j1.release(); d_j2.release(); d_cs.release();
     } else {
         CU(cudaMemcpyAsync(out, d_out.p, (size_t)nE * n1 * n2 * 8, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
     }
-    d_p1.release(); d_p2.release(); d_out.release();
     return B200_OK;
 }
 

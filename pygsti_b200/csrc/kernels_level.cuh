@@ -19,45 +19,44 @@
 
 struct LevelTile { uint32_t first; uint16_t count; uint16_t gate; };   // entries [first, first+count) of lvl_circ
 
+// (Round 2 measured two variants of this loop on BASELINE config 5 and reverted both: a four-block register ring for the B
+// fragments, 3.10 vs 2.93 ms, and split-K over two warp groups, 3.32 ms.  The level kernels are not bound by the L2 latency of
+// one warp or by the 64-deep DMMA chain but by how little work one depth level holds: ~0.33 GFLOP = 9 us of the whole GPU.)
 // Inner product loop shared by k_level_gemm and k_level_gemm_rows (kernels_levelj.cuh): acc[mt][nt] += A[32 x D] . B[D x 8 NT].
-// A fragments come from shared memory (row stride D + 4), B fragments (rows of G, 32 bytes per row and K step) from L2 through a
-// REGISTER RING four blocks of 16 K deep: the loads of block b + 4 are issued right after the 4 x 8 DMMA of block b, so three
-// blocks of tensor work (~1500 cycles) cover the L2 latency.  Round 1 prefetched one block ahead: with the 2 CTAs per SM a depth
-// level offers, each warp then waited on L2 between blocks and the level kernels ran at 0.39 of the DMMA peak (config 5).
+// A fragments come from shared memory (row stride D + 4), B fragments (rows of G, 32 bytes per row and K step) from L2.  The B
+// loads of the NEXT 16 K (the four sectors of one 128-byte line of each row) are issued before the 4 x 8 DMMA of the current
+// 16 K: the first version loaded B inside the step that used it (unroll 2) and left the FP64 tensor pipe waiting on L2.
 template <int D, int NT>
 __device__ __forceinline__ void level_gemm_core(const double* __restrict__ ap, const double* __restrict__ bp, double (&acc)[4][NT][2])
 {
     constexpr int LDS_ = D + 4;
-    static_assert(D % 64 == 0, "ring of four 16-K blocks");
-    double bb[4][4][NT];
+    double bb[4][NT];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
+    for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bb[s4][nt] = __ldg(bp + (size_t)nt * 8 * D + 4 * s4);
+#pragma unroll 1
+    for (int k0 = 0; k0 < D; k0 += 16) {
+        double bn[4][NT];
+        const int kn = (k0 + 16 < D) ? k0 + 16 : k0;          // (last block: reload the current one, unused)
 #pragma unroll
         for (int s4 = 0; s4 < 4; ++s4)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) bb[b][s4][nt] = __ldg(bp + (size_t)nt * 8 * D + 16 * b + 4 * s4);
-#pragma unroll 1
-    for (int k0 = 0; k0 < D; k0 += 64) {
+            for (int nt = 0; nt < NT; ++nt) bn[s4][nt] = __ldg(bp + (size_t)nt * 8 * D + kn + 4 * s4);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int kb = k0 + 16 * b;
+        for (int s4 = 0; s4 < 4; ++s4) {
+            double af[4];
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
-                double af[4];
+            for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + k0 + 4 * s4];
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) af[mt] = ap[mt * 8 * LDS_ + kb + 4 * s4];
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bb[b][s4][nt]);
-            }
-            if (kb + 64 < D) {
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) bb[b][s4][nt] = __ldg(bp + (size_t)nt * 8 * D + kb + 64 + 4 * s4);
-            }
+                for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bb[s4][nt]);
         }
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bb[s4][nt] = bn[s4][nt];
     }
 }
 

@@ -463,6 +463,18 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
                 ++g;
                 if (g >= a.n_ops) return false;
                 cnt = cn[g]; sb = 0; mh = 0;
+                {   // pull the adjoint rows of the NEXT gate's bucket (HBM: each is read by this warp only) into L2 while this
+                    // gate is processed: their later gathers then cost an L2 hit instead of a DRAM round trip
+                    const int gn = g + 1;
+                    if (gn < a.n_ops) {
+                        const int cn_next = cn[gn];
+                        for (int t = lane; t < cn_next; t += 32) {
+                            const int kk = (int)__ldg(perm + tb + cnt + t);
+                            const double* er = lj.BH + (brow0 + kk) * D;
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(er), "r"(D * 8) : "memory");
+                        }
+                    }
+                }
                 if (cnt == 0) continue;
             }
             const int key = (g * l3.nsb + sb) * 2 + mh;

@@ -174,6 +174,20 @@ class Atom:
         E = _f64(E).reshape(self.n_eff, d)
         _lib.check(self._lib.b200_atom_set_model(self.ctx._h, self._h, _ptr(G), _ptr(rho), _ptr(E)))
 
+    def set_model_factored(self, fm):
+        """Upload a ``packing.FactoredModel`` (gates as products of small operations embedded on 1-2 qubits): probabilities then
+        apply the factors directly and the dense matrices of the derivative paths are built on the device."""
+        d = self.dim
+        fptr, fnq = _i32(fm.op_fptr), _i32(fm.f_nq)
+        ftg = _i32(np.asarray(fm.f_targets).reshape(-1, 4))
+        moff = np.ascontiguousarray(fm.f_moff, dtype=np.int64)
+        mats = _f64(fm.mats)
+        rho = _f64(fm.rho).reshape(self.n_rho, d); E = _f64(fm.E).reshape(self.n_eff, d)
+        if fptr.shape[0] != self.n_ops + 1:
+            raise ValueError("op_fptr must have n_ops + 1 entries")
+        _lib.check(self._lib.b200_atom_set_model_factored(self.ctx._h, self._h, int(fnq.shape[0]), _ptr(fptr), _ptr(fnq), _ptr(ftg),
+                                                          _ptr(moff), _ptr(mats), int(mats.shape[0]), _ptr(rho), _ptr(E)))
+
     def set_derivs(self, D: DerivMap):
         rows, cols, vals = _i32(D.rows), _i32(D.cols), _f64(D.vals)
         _lib.check(self._lib.b200_atom_set_derivs(self.ctx._h, self._h, int(D.n_w), int(D.n_params),

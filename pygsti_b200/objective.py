@@ -32,8 +32,10 @@ def _distributed(layout):
 
 def _plain(objfn):
     sim = objfn.model.sim
-    return getattr(objfn, "firsts", None) is None and not getattr(objfn, "_process_penalties", False) \
-        and hasattr(sim, "bulk_fill_dprobs_scaled") and objfn.local_ex == 0 \
+    # (no omitted-outcome rows, no penalty rows: `local_ex` counts the extra rows; `_process_penalties` only says WHICH processor
+    #  would fill them and is True on a single process -- round 1 tested it and therefore always delegated)
+    return getattr(objfn, "firsts", None) is None and hasattr(sim, "bulk_fill_dprobs_scaled") \
+        and getattr(objfn, "local_ex", 0) == 0 and getattr(objfn, "ex", 0) == 0 \
         and getattr(sim, "derivative_mode", "analytic") == "analytic" and not _distributed(objfn.layout)
 
 

@@ -436,3 +436,106 @@ def assemble_lindblad(li, outs, model, atom, dim, param_indices=None):
     keep = D.data != 0.0
     return mt, DerivMap(n_w=n_w, n_params=int(pidx.size), rows=D.row[keep].astype(np.int32), cols=D.col[keep].astype(np.int32),
                         vals=D.data[keep].astype(np.float64))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Factored (non-dense) gate representation: layer operations that pyGSTi builds as products of small operations embedded
+# on 1-2 qubits (`ComposedOp` of `EmbeddedOp`; pygsti/modelmembers/operations/{composedop,embeddedop}.py -- the reference's
+# OpCRep_Composed / OpCRep_Embedded, pygsti/evotypes/densitymx/opcreps.cpp:93-158, 242-276) are handed to the engine as
+# "factor programs": per layer label a list of (small dense superoperator, target qubits).  The engine applies the factors to
+# the state directly (4 or 16 multiply-adds per component instead of d = 256) and builds the dense d x d matrices it needs
+# for the derivative paths ON THE DEVICE -- the host never calls to_dense on a d = 256 operation (0.01-0.2 s per label).
+# ----------------------------------------------------------------------------------------------------------------------
+@dataclass
+class FactoredModel:
+    n_qubits: int
+    op_fptr: np.ndarray      # int32 [n_ops + 1]  factors of op g: [op_fptr[g], op_fptr[g+1]), applied in this order
+    f_nq: np.ndarray         # int32 [n_factors]  number of target qubits (1 or 2)
+    f_targets: np.ndarray    # int32 [n_factors, 4]  qubit positions in state-space order (0 = most significant), -1 padded
+    f_moff: np.ndarray       # int64 [n_factors]  offset of the factor's (4^nq x 4^nq) row-major matrix in `mats`
+    mats: np.ndarray         # float64
+    rho: np.ndarray
+    E: np.ndarray
+
+
+def _flatten_factors(op, qubit_labels, out):
+    """Append (targets, small dense matrix) of `op` to `out`; False if `op` is not a product of embedded <= 2-qubit ops."""
+    name = type(op).__name__
+    if name == "ComposedOp":
+        return all(_flatten_factors(f, qubit_labels, out) for f in op.factorops)
+    if name == "EmbeddedOp":
+        try:
+            targets = [qubit_labels.index(t) for t in op.target_labels]
+        except ValueError:
+            return False
+        small = np.asarray(op.embedded_op.to_dense('HilbertSchmidt'), dtype=np.float64)
+        k = len(targets)
+        if k < 1 or k > 2 or small.shape != (4 ** k, 4 ** k) or len(set(targets)) != k:
+            return False
+        out.append((targets, small))
+        return True
+    return False
+
+
+def pack_model_factored(model, atom, dim):
+    """FactoredModel of the atom's layer operations, or None when some operation is not a product of embedded 1-2 qubit
+    operations on a pure n-qubit space (the caller then packs dense matrices as before)."""
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    nq = int(round(np.log(d) / np.log(4)))
+    if 4 ** nq != d or nq < 2 or not ops:
+        return None
+    try:
+        labels = list(model.state_space.sole_tensor_product_block_labels)
+    except Exception:
+        return None
+    if len(labels) != nq:
+        return None
+    fptr, f_nq, f_targets, f_moff, mats = [0], [], [], [], []
+    off = 0
+    for op in ops:
+        fac = []
+        if not _flatten_factors(op, labels, fac):
+            return None
+        for targets, small in fac:
+            f_nq.append(len(targets)); f_targets.append(list(targets) + [-1] * (4 - len(targets)))
+            f_moff.append(off); mats.append(small.ravel()); off += small.size
+        fptr.append(len(f_nq))
+    rho = np.empty((len(rhos), d)); E = np.empty((len(effs), d))
+    for i, r in enumerate(rhos):
+        rho[i] = np.asarray(r.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(d)
+    for i, e in enumerate(effs):
+        E[i] = np.asarray(e.to_dense('HilbertSchmidt'), dtype=np.float64).reshape(d)
+    return FactoredModel(n_qubits=nq, op_fptr=np.asarray(fptr, np.int32), f_nq=np.asarray(f_nq, np.int32),
+                         f_targets=np.asarray(f_targets, np.int32).reshape(-1, 4), f_moff=np.asarray(f_moff, np.int64),
+                         mats=(np.concatenate(mats) if mats else np.zeros(0)), rho=rho, E=E)
+
+
+def factored_to_dense(fm, dim):
+    """numpy restatement of what the device does with a FactoredModel (test / oracle helper): dense G [n_ops, d, d]."""
+    d = int(dim); nq = fm.n_qubits
+    n_ops = fm.op_fptr.shape[0] - 1
+    G = np.empty((n_ops, d, d))
+    idx = np.arange(d)
+    for g in range(n_ops):
+        M = np.eye(d)
+        for f in range(fm.op_fptr[g], fm.op_fptr[g + 1]):
+            k = int(fm.f_nq[f]); ds = 4 ** k
+            small = fm.mats[fm.f_moff[f]:fm.f_moff[f] + ds * ds].reshape(ds, ds)
+            shifts = [2 * (nq - 1 - int(q)) for q in fm.f_targets[f, :k]]
+            tmask = 0
+            for s in shifts:
+                tmask |= 3 << s
+            t = np.zeros(d, dtype=np.int64)
+            for s in shifts:
+                t = (t << 2) | ((idx >> s) & 3)
+            rest = idx & ~tmask
+            F = np.zeros((d, d))
+            for tp in range(ds):
+                col = rest.copy()
+                for a, s in enumerate(shifts):
+                    col |= ((tp >> (2 * (k - 1 - a))) & 3) << s
+                F[idx, col] += small[t, tp]
+            M = F @ M                                  # factors act in order: the first factor is applied first
+        G[g] = M
+    return G

@@ -310,3 +310,45 @@ def test_lindblad_members_on_device(gpu_ctx, d):
         assert val.shape == v_ref.shape and dval.shape == dv_ref.shape
         assert np.max(np.abs(val - v_ref)) <= 1e-12 * max(1.0, np.max(np.abs(v_ref)))
         assert np.max(np.abs(dval - dv_ref)) <= 1e-11 * max(1.0, np.max(np.abs(dv_ref)))
+
+
+@pytest.mark.parametrize("dim,n_ops", [(256, 9), (64, 6)])
+def test_factored_model_embedded_composed(gpu_ctx, dim, n_ops):
+    """Gates as products of small operations embedded on 1-2 qubits (the device form of OpCRep_Composed / OpCRep_Embedded,
+    opcreps.cpp:93-158, 242-276): probabilities through the factor programs equal the dense-product path and the oracle, and
+    the dense matrices built on the device equal the Kronecker construction (packing.factored_to_dense)."""
+    from pygsti_b200.packing import FactoredModel, factored_to_dense
+    nq = {64: 3, 256: 4}[dim]
+    rng = np.random.default_rng(dim)
+    fptr, f_nq, f_t, f_off, mats, off = [0], [], [], [], [], 0
+    for g in range(n_ops):
+        for _ in range(int(rng.integers(0 if g == 0 else 1, 4))):          # gate 0 may be the empty product (identity)
+            k = int(rng.integers(1, 3))
+            tg = [int(x) for x in rng.choice(nq, size=k, replace=False)]     # any order, e.g. (2, 0)
+            small = np.eye(4 ** k) * 0.8 + 0.3 * rng.standard_normal((4 ** k, 4 ** k)) / 2 ** k
+            f_nq.append(k); f_t.append(tg + [-1] * (4 - k)); f_off.append(off); mats.append(small.ravel()); off += small.size
+        fptr.append(len(f_nq))
+    n_eff = 8
+    rho = rng.standard_normal((1, dim)) / np.sqrt(dim); E = rng.standard_normal((n_eff, dim)) / np.sqrt(dim)
+    fm = FactoredModel(n_qubits=nq, op_fptr=np.asarray(fptr, np.int32), f_nq=np.asarray(f_nq, np.int32),
+                       f_targets=np.asarray(f_t, np.int32).reshape(-1, 4), f_moff=np.asarray(f_off, np.int64),
+                       mats=np.concatenate(mats), rho=rho, E=E)
+    G = factored_to_dense(fm, dim)
+    circs = synth.random_circuits(40, 30, n_ops, 1, n_eff, seed=3)
+    t = synth.make_tables(dim, n_ops, 1, n_eff, circs)
+    at = gpu_ctx.upload_atom(t); at.set_model_factored(fm)
+    p = np.full(t.n_elements, np.nan); at.fill_probs(p)
+    Md = at.get_model()
+    assert np.max(np.abs(Md[:n_ops * dim * dim].reshape(n_ops, dim, dim) - G)) <= 1e-13 * max(1.0, np.max(np.abs(G)))
+    po = onp.mapfill_probs(t, G, rho, E)
+    assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    at.set_model(G, rho, E)                                                  # the dense path on the same model
+    pd = np.full(t.n_elements, np.nan); at.fill_probs(pd)
+    assert np.max(np.abs(p - pd)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    # the derivative path on a factored model uses the device-built dense matrices
+    D = synth.random_derivs(t, 40, density=0.0005, seed=5)
+    at.set_model_factored(fm); at.set_derivs(D)
+    J = np.full((t.n_elements, 40), np.nan); at.fill_dprobs(J)
+    Jo = onp.dprobs_analytic(t, G, rho, E, D)
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    at.free()
