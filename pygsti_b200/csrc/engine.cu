@@ -110,7 +110,7 @@ struct b200_atom {
     bool has_model = false;
     DevBuf M, Gt;
     bool has_factored = false;             // gates also held as factor programs (b200_atom_set_model_factored)
-    DevBuf fac_ptr, fac_rec, fac_mats; int fac_n_mats = 0;
+    DevBuf fac_ptr, fac_rec, fac_mats; int fac_n_mats = 0, fac_n = 0; bool fac_probs_ok = false;   // (programs small enough for shared memory)
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -674,7 +674,8 @@ extern "C" int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* a, int32_t
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(ctx->stream));
-    a->has_model = true; a->has_factored = true; a->fac_n_mats = (int)std::min<int64_t>(n_mats, INT_MAX);
+    a->has_model = true; a->has_factored = true; a->fac_n_mats = (int)std::min<int64_t>(n_mats, INT_MAX); a->fac_n = n_factors;
+    a->fac_probs_ok = n_mats <= FAC_MATS_MAX && n_factors <= FAC_RECS_MAX && a->n_ops <= 4096;
     return B200_OK;
 }
 
@@ -1047,27 +1048,48 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
                 }
             std::stable_sort(recs.begin(), recs.end(), [](const Rec3& x, const Rec3& y) { return x.key != y.key ? x.key < y.key : x.p < y.p; });
             const size_t n_keys = (size_t)a->n_ops * nsb * 2;
-            std::vector<uint32_t> tp3(n_keys + 1, 0), mask3(std::max<size_t>(n_keys, 1), 0);
-            std::vector<uint4> items3; std::vector<uint16_t> ij3(recs.size()); std::vector<double> v3(recs.size());
+            std::vector<uint2> tp3(std::max<size_t>(n_keys, 1), make_uint2(0u, 0u));
+            std::vector<uint32_t> mask3(std::max<size_t>(n_keys, 1), 0);
+            std::vector<uint16_t> ij3; std::vector<int32_t> p3; std::vector<double> v3;
             size_t r = 0;
             for (size_t key = 0; key < n_keys; ++key) {
-                tp3[key] = (uint32_t)items3.size();
+                // parameters of this (gate, sub-block, half), each with its run of non-zeros [lo, hi) in recs
+                std::vector<std::pair<size_t, size_t>> runs;
                 while (r < recs.size() && recs[r].key == key) {
-                    uint4 it = make_uint4(recs[r].p, (unsigned)r, (unsigned)r, 0u);
-                    while (r < recs.size() && recs[r].key == key && recs[r].p == it.x) {
-                        ij3[r] = recs[r].ij; v3[r] = recs[r].v;
+                    const size_t lo = r; const uint32_t pcur = recs[r].p;
+                    while (r < recs.size() && recs[r].key == key && recs[r].p == pcur) {
                         mask3[key] |= 1u << (8 * ((recs[r].ij >> 8) / 8) + (recs[r].ij & 0xff) / 8);
                         ++r;
                     }
-                    it.z = (unsigned)r;
-                    items3.push_back(it);
+                    runs.emplace_back(lo, r);
                 }
+                if (runs.empty()) continue;
+                // whole parameters to lanes: longest run first onto the least loaded lane (ties: lowest lane) -- deterministic
+                std::vector<size_t> order(runs.size());
+                std::iota(order.begin(), order.end(), 0);
+                std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return runs[x].second - runs[x].first > runs[y].second - runs[y].first; });
+                std::vector<std::vector<size_t>> lane_runs(32);
+                std::vector<size_t> load(32, 0);
+                for (size_t o : order) {
+                    const int l = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+                    lane_runs[l].push_back(o); load[l] += runs[o].second - runs[o].first;
+                }
+                const size_t n_it = *std::max_element(load.begin(), load.end());
+                const size_t base = ij3.size();
+                ij3.resize(base + n_it * 32, 0); p3.resize(base + n_it * 32, -1); v3.resize(base + n_it * 32, 0.0);
+                for (int l = 0; l < 32; ++l) {
+                    size_t k = 0;
+                    for (size_t o : lane_runs[l])
+                        for (size_t q = runs[o].first; q < runs[o].second; ++q, ++k) {
+                            ij3[base + k * 32 + l] = recs[q].ij; p3[base + k * 32 + l] = (int32_t)recs[q].p; v3[base + k * 32 + l] = recs[q].v;
+                        }
+                }
+                tp3[key] = make_uint2((unsigned)base, (unsigned)n_it);
             }
-            tp3[n_keys] = (uint32_t)items3.size();
-            if (items3.empty()) items3.push_back(make_uint4(0, 0, 0, 0));
-            if (ij3.empty()) { ij3.push_back(0); v3.push_back(0.0); }
+            if (ij3.empty()) { ij3.push_back(0); p3.push_back(-1); v3.push_back(0.0); }
+            if (ij3.size() >= ((size_t)1 << 32)) return fail(B200_E_UNSUPPORTED, "derivative map too large for the level-batched Jacobian plan");
             if ((rc = upload_vec(a->lj3_tp, tp3, ctx->stream)) || (rc = upload_vec(a->lj3_mask, mask3, ctx->stream)) ||
-                (rc = upload_vec(a->lj3_items, items3, ctx->stream)) || (rc = upload_vec(a->lj3_ij, ij3, ctx->stream)) ||
+                (rc = upload_vec(a->lj3_items, p3, ctx->stream)) || (rc = upload_vec(a->lj3_ij, ij3, ctx->stream)) ||
                 (rc = upload_vec(a->lj3_v, v3, ctx->stream))) return rc;
             CU(cudaStreamSynchronize(ctx->stream));
         }
@@ -1271,21 +1293,21 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
     CU(cudaSetDevice(c->device));
     if (a->n_rows > 0 && d16_ok(c, a)) return launch_probs_trie(c, a, d_out);
-    if (a->has_factored && a->n_rows > 0 && a->dim >= 64 && !getenv("B200_NO_FACTORED")) {
+    if (a->has_factored && a->fac_probs_ok && a->n_rows > 0 && a->dim >= 64 && !getenv("B200_NO_FACTORED")) {
         // gates as factor programs (Embedded / Composed reps): no dense d x d products at all
         const FactoredDev fd = factored_dev(a);
         const double* M = a->M.as<double>();
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 4));
-        const int n_mats = (int)(a->fac_mats.cap / 8);
-        const int n_ms = n_mats <= 8192 ? a->fac_n_mats : 0;              // stage the factor matrices in shared memory when <= 64 KB
+        const int n_ms = a->fac_n_mats, n_fac = a->fac_n;
+        const size_t tail = ((size_t)((n_ms + 1) & ~1)) * 8 + (size_t)n_fac * sizeof(FactorRec) + ((size_t)a->n_ops + 1) * 4;
         if (a->dim == 64) {
-            const size_t smem = ((size_t)FAC_WARPS * 2 * 64 + n_ms) * 8;
+            const size_t smem = (size_t)FAC_WARPS * 2 * 64 * 8 + tail;
             CU(cudaFuncSetAttribute(k_probs_factored<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_probs_factored<64><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, M + a->off_rho, M + a->off_eff, d_out, 1);
+            k_probs_factored<64><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, n_fac, M + a->off_rho, M + a->off_eff, d_out, 1);
         } else {
-            const size_t smem = ((size_t)FAC_WARPS * 2 * 256 + n_ms) * 8;
+            const size_t smem = (size_t)FAC_WARPS * 2 * 256 * 8 + tail;
             CU(cudaFuncSetAttribute(k_probs_factored<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_probs_factored<256><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, M + a->off_rho, M + a->off_eff, d_out, 1);
+            k_probs_factored<256><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, n_ms, n_fac, M + a->off_rho, M + a->off_eff, d_out, 1);
         }
         c->launches++;
         CU(cudaGetLastError());
@@ -1370,7 +1392,7 @@ static int launch_levelj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, d
     const int n_og = (a->lj_no_max + LJ3_WARPS - 1) / LJ3_WARPS;
     if (!accum_v1 && !accum_v2 && smemC3 + 1024 <= c->smem_optin && (int64_t)a->n_rows * n_og < ((int64_t)1 << 31)) {
         LevelJ3Dev l3;
-        l3.tp3 = a->lj3_tp.as<uint32_t>(); l3.mask3 = a->lj3_mask.as<uint32_t>(); l3.items3 = a->lj3_items.as<uint4>();
+        l3.tp3 = a->lj3_tp.as<uint2>(); l3.mask3 = a->lj3_mask.as<uint32_t>(); l3.nz_p = a->lj3_items.as<int32_t>();
         l3.nz_ij = a->lj3_ij.as<uint16_t>(); l3.nz_v = a->lj3_v.as<double>();
         l3.zrow_f = (uint32_t)a->lj_rows_f; l3.zrow_b = (uint32_t)a->lj_rows_b; l3.nsb = (D / 64) * (D / 64); l3.np_pad = np_pad; l3.n_og = n_og;
         CU(cudaFuncSetAttribute(k_level_accum3<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC3));

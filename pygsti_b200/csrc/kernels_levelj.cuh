@@ -408,13 +408,18 @@ k_level_accum2(AtomDev a, ModelDev m, LevelJDev lj, LevelJ2Dev l2, double* __res
 // dynamic smem (doubles): LJ3_WARPS * np_pad (accumulator rows) + LJ3_WARPS * 32 * LJ3_LDW (W tiles)
 // ------------------------------------------------------------------------------------------------------------
 #define LJ3_WARPS 4
-#define LJ3_LDW 66
+#define LJ3_LDW 72       // 72 = 8 mod 32 doubles... row stride chosen so that the 128-bit accumulator stores of a quarter-warp hit 8 distinct bank groups
 
 struct LevelJ3Dev {
-    const uint32_t* tp3;       // [n_ops * nsb * 2 + 1] item ranges per (gate, sub-block, M half)
+    const uint2* tp3;          // [n_ops * nsb * 2] per (gate, sub-block, M half): (first entry, iterations) of its lane-major list
     const uint32_t* mask3;     // [n_ops * nsb * 2] needed 8x8 tiles of the half block (bit 8*mt + nt, mt < 4)
-    const uint4* items3;       // (parameter, nz lo, nz hi, 0)
+    // Non-zeros of dG/dtheta inside the half block as LANE-MAJOR lists: entry (first + 32 k + lane) is the k-th non-zero of
+    // `lane`.  Every parameter of the block lives in exactly one lane (no cross-lane conflicts, fixed summation order), the
+    // lanes are balanced by non-zero count and padded with parameter -1.  The three loads of an iteration are coalesced and
+    // independent of everything the loop computes, so they pipeline (round-2 profile of the item-list version: 25 % of the
+    // kernel's stall samples sat on the dependent item -> non-zero -> W chain).
     const uint16_t* nz_ij;     // (i_local << 8) | j_local, i_local < 32, j_local < 64
+    const int32_t* nz_p;       // parameter (column of J) or -1
     const double* nz_v;
     uint32_t zrow_f, zrow_b;   // all-zero rows of FS / BH
     int nsb, np_pad, n_og;     // sub-blocks per matrix; padded accumulator row length; outcome groups per circuit
@@ -478,30 +483,37 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
                 if (cnt == 0) continue;
             }
             const int key = (g * l3.nsb + sb) * 2 + mh;
-            it0 = __ldg(l3.tp3 + key); it1 = __ldg(l3.tp3 + key + 1);
-            if (it1 == it0) continue;
+            const uint2 tp = __ldg(l3.tp3 + key);
+            it0 = tp.x; it1 = tp.y;                     // first entry, iterations
+            if (it1 == 0) continue;
             mask = __ldg(l3.mask3 + key);
             return true;
         }
     };
-    // fragments of the group of 4 steps starting at k0 of the CURRENT iterator position; the bucket's step indices come 32 at a
-    // time through one coalesced load + a shuffle (no dependent index load per group)
-    int pk = -1;
-    auto fetch = [&](int k0, double (&xa)[4], double (&xb)[8]) {
-        if ((k0 & 31) == 0) { const int t = k0 + lane; pk = (t < cnt) ? (int)__ldg(perm + tb + t) : -1; }
-        const int k = __shfl_sync(0xffffffffu, pk, (k0 & 31) + q);
-        const unsigned need_n = (mask | (mask >> 8) | (mask >> 16) | (mask >> 24)) & 0xffu;
-        const int ib = (sb / SBD) * 64 + mh * 32, jb = (sb % SBD) * 64;
+    // fragments of the group of 4 steps starting at k0 of the CURRENT iterator position.  A (adjoint rows: streamed from HBM / L2,
+    // read by this warp only) is requested TWO groups ahead, B (state rows: shared by the warps of the CTA, L1 hits) one group
+    // ahead -- the profile of the one-group-ahead version had 20 % of its stall samples on the first DMMA of a group.
+    auto step_of = [&](int k0) -> int { const int t = k0 + q; return (t < cnt) ? (int)__ldg(perm + tb + t) : -1; };
+    auto fetchA = [&](int k0, double (&xa)[4]) {
+        const int k = step_of(k0);
+        const int ib = (sb / SBD) * 64 + mh * 32;
         const double* er = lj.BH + (k >= 0 ? (brow0 + k) : (size_t)l3.zrow_b) * D + ib + mrow;
-        const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l3.zrow_f) * D + jb + mrow;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) xa[mt] = ((mask >> (8 * mt)) & 0xffu) ? __ldg(er + 8 * mt) : 0.0;
+    };
+    auto fetchB = [&](int k0, double (&xb)[8]) {
+        const int k = step_of(k0);
+        const unsigned need_n = (mask | (mask >> 8) | (mask >> 16) | (mask >> 24)) & 0xffu;
+        const int jb = (sb % SBD) * 64;
+        const double* sr = lj.FS + (k >= 0 ? (fb + k) : (size_t)l3.zrow_f) * D + jb + mrow;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) xb[nt] = (need_n & (1u << nt)) ? __ldg(sr + 8 * nt) : 0.0;
     };
-    double fa[4], fbv[8];
+    double fa[4], fa1[4], fbv[8];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) fa1[mt] = 0.0;
     bool have = advance();
-    if (have) fetch(0, fa, fbv);
+    if (have) { fetchA(0, fa); fetchB(0, fbv); if (cnt > 4) fetchA(4, fa1); }
     while (have) {
         const unsigned cmask = mask;
         const uint32_t cit0 = it0, cit1 = it1;
@@ -512,8 +524,9 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
         for (int k0 = 0; k0 < ns4; k0 += 4) {
-            double na[4], nb[8];
-            if (k0 + 4 < ns4) fetch(k0 + 4, na, nb);
+            double fa2[4], nb[8];
+            if (k0 + 8 < ns4) fetchA(k0 + 8, fa2);
+            if (k0 + 4 < ns4) fetchB(k0 + 4, nb);
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -521,13 +534,17 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
                     if (cmask & (1u << (8 * mt + nt))) dmma884(acc[mt][nt][0], acc[mt][nt][1], fa[mt], fbv[nt]);   // warp-uniform
             if (k0 + 4 < ns4) {
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
+                for (int mt = 0; mt < 4; ++mt) fa[mt] = fa1[mt];
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) fbv[nt] = nb[nt];
             }
+            if (k0 + 8 < ns4) {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) fa1[mt] = fa2[mt];
+            }
         }
         have = advance();                               // iterator now at the NEXT pass: request its first fragments
-        if (have) fetch(0, fa, fbv);
+        if (have) { fetchA(0, fa); fetchB(0, fbv); if (cnt > 4) fetchA(4, fa1); }
         __syncwarp();                                   // the previous contraction has read Wt
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -537,14 +554,19 @@ k_level_accum3(AtomDev a, ModelDev m, LevelJDev lj, LevelJ3Dev l3, double* __res
                     *reinterpret_cast<double2*>(Wt + (mt * 8 + mrow) * LJ3_LDW + nt * 8 + 2 * q) =
                         make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         __syncwarp();
-        for (uint32_t it = cit0 + lane; it < cit1; it += 32) {
-            const uint4 item = __ldg(l3.items3 + it);
-            double s = 0.0;
-            for (uint32_t t = item.y; t < item.z; ++t) {
-                const unsigned ij = __ldg(l3.nz_ij + t);
-                s = fma(__ldg(l3.nz_v + t), Wt[(ij >> 8) * LJ3_LDW + (ij & 0xffu)], s);
+        {
+            double sacc = 0.0; int pp = -1;
+#pragma unroll 4
+            for (uint32_t k = 0; k < cit1; ++k) {
+                const uint32_t e = cit0 + k * 32 + lane;
+                const unsigned ij = __ldg(l3.nz_ij + e);
+                const int pn = __ldg(l3.nz_p + e);
+                const double v = __ldg(l3.nz_v + e);
+                const double w = Wt[(ij >> 8) * LJ3_LDW + (ij & 0xffu)];
+                if (pn != pp) { if (pp >= 0) Jacc[pp] += sacc; sacc = 0.0; pp = pn; }
+                sacc = fma(v, w, sacc);
             }
-            Jacc[item.x] += s;                          // a parameter occurs once per (gate, sub-block, half) list
+            if (pp >= 0) Jacc[pp] += sacc;
         }
     }
     __syncwarp();
