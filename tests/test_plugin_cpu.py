@@ -175,3 +175,66 @@ def test_member_hessian_cache_equals_filtered_calls_and_follows_the_parameters()
                     ref[off:off + size][:, (gp[l1] - lo1)[:, None], (gp[l2] - lo2)[None, :]] += Hm
                 off += size
         assert np.max(np.abs(ref)) > 0 and np.max(np.abs(dense - ref)) <= 1e-14
+
+
+def test_factored_packing_reproduces_to_dense():
+    """Factor programs of pyGSTi's non-dense reps (ComposedOp of EmbeddedOp; opcreps.cpp:93-158, 242-276): what the device
+    does with them (packing.factored_to_dense is the numpy restatement of k_factored_to_dense) equals the reference's own
+    to_dense for every layer label of a 4-qubit cloud-crosstalk model and of a 3-qubit local-noise model, bit for bit; models
+    whose layers are not products of embedded 1-2 qubit operations are declined (dense packing then)."""
+    from pygsti.processors import QubitProcessorSpec
+    from pygsti.models import modelconstruction as mc
+    from pygsti.forwardsims import MapForwardSimulator
+    from pygsti.circuits import Circuit
+    rng = np.random.default_rng(7)
+    for nq, build in ((4, lambda ps: mc.create_cloud_crosstalk_model(ps, lindblad_error_coeffs={
+            ('Gxpi2', 0): {('H', 'X'): 0.01, ('S', 'Z'): 0.005}, ('Gcnot', 1, 2): {('H', 'ZZ'): 0.01, ('S', 'XX'): 0.003}})),
+                      (3, lambda ps: mc.create_crosstalk_free_model(ps, ideal_gate_type='full TP', ideal_spam_type='full TP'))):
+        pspec = QubitProcessorSpec(nq, ['Gxpi2', 'Gypi2', 'Gcnot'], geometry='line')
+        model = build(pspec)
+        prim = list(model.primitive_op_labels)
+        circs = [Circuit([prim[int(rng.integers(len(prim)))] for _ in range(int(rng.integers(1, 9)))], line_labels=tuple(range(nq)))
+                 for _ in range(10)]
+        model.sim = MapForwardSimulator()
+        atom = model.sim.create_layout(circs, array_types=('e',)).atoms[0]
+        d = 4 ** nq
+        mt = packing.pack_model(model, atom, d)
+        fm = packing.pack_model_factored(model, atom, d)
+        assert fm is not None and fm.n_qubits == nq and fm.op_fptr[-1] == fm.f_nq.size >= mt.G.shape[0]
+        assert np.array_equal(packing.factored_to_dense(fm, d), mt.G)
+        assert np.array_equal(fm.rho, mt.rho) and np.array_equal(fm.E, mt.E)
+    m1 = smq1Q_XYI.target_model()                           # dense 1-qubit gates: not a factored model
+    m1.sim = MapForwardSimulator()
+    a1 = m1.sim.create_layout(smq1Q_XYI.create_gst_experiment_design(1).all_circuits_needing_data, array_types=('e',)).atoms[0]
+    assert packing.pack_model_factored(m1, a1, 4) is None
+
+
+def test_stock_objective_hooks_install_and_restore():
+    """The simulator installs the objective-function / LM hooks once; they gate on the simulator and the objective (penalty rows,
+    omitted outcomes and `derivative_mode='fd'` go to pyGSTi's own methods) and `uninstall_hooks` restores pyGSTi."""
+    from pygsti.objectivefns import objectivefns as _of
+    from pygsti.layouts.distlayout import DistributableCOPALayout as _DL
+    from pygsti.data import simulate_data
+    from pygsti_b200 import objective as fused
+    fused.uninstall_hooks()
+    orig = (_of.TimeIndependentMDCObjectiveFunction.dlsvec, _DL.fill_jtj)
+    m = smq1Q_XYI.target_model("full TP").depolarize(op_noise=0.05, spam_noise=0.02)
+    circuits = smq1Q_XYI.create_gst_experiment_design(1).all_circuits_needing_data
+    ds = simulate_data(m, circuits, 100, seed=1)
+    m.sim = B200ForwardSimulator()
+    assert fused._HOOKS and _of.TimeIndependentMDCObjectiveFunction.dlsvec is not orig[0] and _DL.fill_jtj is not orig[1]
+    o = _of.Chi2Function.create_from(m, ds, circuits, method_names=('lsvec', 'dlsvec'))
+    assert fused._sim_wants_hooks(o) and fused._plain(o)
+    o_pen = _of.Chi2Function.create_from(m, ds, circuits, method_names=('lsvec', 'dlsvec'), penalties={'cptp_penalty_factor': 1.0})
+    assert not fused._plain(o_pen)                           # penalty rows: the reference's own dlsvec
+    m2 = m.copy(); m2.sim = B200ForwardSimulator(derivative_mode='fd')
+    assert not fused._plain(_of.Chi2Function.create_from(m2, ds, circuits, method_names=('lsvec', 'dlsvec')))
+    m3 = m.copy(); m3.sim = B200ForwardSimulator(fused_objective=False)
+    assert not fused._sim_wants_hooks(_of.Chi2Function.create_from(m3, ds, circuits, method_names=('lsvec', 'dlsvec')))
+    # arrays the hooks did not produce fall through to pyGSTi's own fill_jtj
+    J = np.random.default_rng(0).standard_normal((o.layout.num_elements, m.num_params)); jtj = np.empty((m.num_params,) * 2)
+    o.layout.fill_jtj(J, jtj)
+    assert np.allclose(jtj, J.T @ J)
+    fused.uninstall_hooks()
+    assert (_of.TimeIndependentMDCObjectiveFunction.dlsvec, _DL.fill_jtj) == orig and not fused._HOOKS
+    fused.install_hooks()
