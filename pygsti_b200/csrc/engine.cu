@@ -10,6 +10,7 @@
 #include "kernels_jtj.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_factored.cuh"
+#include "kernels_ozaki.cuh"
 #include <cstdlib>
 
 #include <algorithm>
@@ -67,6 +68,7 @@ struct b200_ctx {
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     DevBuf atb_part, atb_part_f;                 // partial tiles of the A^T B reductions (k_atb_dmma)
+    DevBuf oz_S, oz_misc, oz_part;               // Ozaki J^T J: int8 digit slices, (column maxima | exponents | tile list), partial tiles
     DevBuf hb[24];                               // scratch of the Hessian-block path (kept between calls: cudaMalloc / cudaFree per
                                                  // rectangle cost more than the kernels once peer access is enabled)
     DevBuf fd_models, fd_gt, fd_probs;
@@ -194,6 +196,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     c->scale_buf.release(); c->f_buf.release(); c->jtj_buf.release(); c->jtf_buf.release();
     c->atb_part.release(); c->atb_part_f.release();
     for (DevBuf& b : c->hb) b.release();
+    c->oz_S.release(); c->oz_misc.release(); c->oz_part.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1644,6 +1647,53 @@ static int atb_device(b200_ctx* c, const double* A, int64_t lda, int na, const d
     return B200_OK;
 }
 
+// J^T J on the 5th-generation tensor cores (tcgen05.mma kind::i8 + TMEM) through the Ozaki splitting -- kernels_ozaki.cuh.
+// J [nE x ldj] on the device; result d_jtj [Np x Np] (row-major, full symmetric).  T = 8 digits (62 bits) or 7 (55 bits).
+template <int T>
+static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int Np, double* d_jtj) {
+    const int n_bi = (Np + OZ_TM - 1) / OZ_TM, n_bj = (Np + OZ_TN - 1) / OZ_TN;
+    const int64_t P_pad = (int64_t)n_bi * OZ_TM;
+    std::vector<int2> tiles;
+    for (int bi = 0; bi < n_bi; ++bi)
+        for (int bj = 0; bj < n_bj; ++bj) if ((int64_t)bj * OZ_TN <= (int64_t)bi * OZ_TM + OZ_TM - 1) tiles.push_back(make_int2(bi, bj));
+    const int n_tiles = (int)tiles.size();
+    const int64_t stages_total = (nE + OZ_KS - 1) / OZ_KS;
+    // K slices: short enough that every level's int32 sum stays exact, and as many more as fill whole waves of SMs (one CTA per SM)
+    const int64_t ksl_min = (stages_total + OZ_MAX_STAGES_PER_SLICE - 1) / OZ_MAX_STAGES_PER_SLICE;
+    int64_t ksl = ksl_min; double best = -1.0;
+    for (int64_t cand = ksl_min; cand <= ksl_min + 24 && cand <= std::max<int64_t>(1, stages_total / 64); ++cand) {
+        const int64_t ctas = cand * n_tiles, waves = (ctas + c->sm_count - 1) / c->sm_count;
+        const double eff = (double)ctas / (double)(waves * c->sm_count);
+        if (eff > best + 0.01) { best = eff; ksl = cand; }
+    }
+    const int64_t sps = (stages_total + ksl - 1) / ksl;
+    const int64_t n_stages = ksl * sps;
+    if (sps > OZ_MAX_STAGES_PER_SLICE) return fail(B200_E_UNSUPPORTED, "Ozaki J^T J: K slice too long");
+    CU(c->oz_S.ensure((size_t)n_stages * T * P_pad * OZ_KS));
+    const size_t misc_bytes = (size_t)P_pad * 8 + (size_t)P_pad * 4 + (size_t)n_tiles * sizeof(int2) + 64;
+    CU(c->oz_misc.ensure(misc_bytes));
+    CU(c->oz_part.ensure((size_t)ksl * n_tiles * OZ_TM * OZ_TN * 8));
+    unsigned long long* d_cmax = c->oz_misc.as<unsigned long long>();
+    int* d_expo = reinterpret_cast<int*>(d_cmax + P_pad);
+    int2* d_tiles = reinterpret_cast<int2*>(d_expo + P_pad);            // P_pad is a multiple of 128: 8-byte aligned
+    CU(cudaMemsetAsync(d_cmax, 0, (size_t)P_pad * 12, c->stream));
+    CU(cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)n_tiles * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    k_oz_colmax<<<dim3((unsigned)((Np + 63) / 64), (unsigned)std::min<int64_t>(512, (nE + 3) / 4)), 256, 0, c->stream>>>(J, ldj, nE, Np, d_cmax);
+    k_oz_exponents<<<(unsigned)((Np + 255) / 256), 256, 0, c->stream>>>(d_cmax, Np, d_expo);
+    k_oz_slice<T><<<dim3((unsigned)(P_pad / 64), (unsigned)((n_stages + 1) / 2)), 256, 0, c->stream>>>(J, ldj, nE, Np, d_expo, c->oz_S.as<int8_t>(), P_pad, n_stages);
+    OzArgs p;
+    p.S = c->oz_S.as<int8_t>(); p.P_pad = P_pad; p.tiles = d_tiles; p.n_tiles = n_tiles;
+    p.n_kslices = (int)ksl; p.stages_per_slice = (int)sps; p.part = c->oz_part.as<double>();
+    const size_t smem = (size_t)OZ_NST * T * (OZ_TM + OZ_TN) * OZ_KS;
+    CU(cudaFuncSetAttribute(k_oz_syrk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_oz_syrk<T><<<(unsigned)(ksl * n_tiles), 128, smem, c->stream>>>(p);
+    k_oz_reduce<<<(unsigned)n_tiles, 256, 0, c->stream>>>(p, d_expo, Np, d_jtj, Np);
+    c->launches += 5;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));          // (the host tile list goes out of scope)
+    return B200_OK;
+}
+
 // J^T J (full symmetric, row-major) and J^T f into DEVICE buffers; everything asynchronous on the ctx stream
 static int jtj_device(b200_ctx* c, b200_atom* a, const double* d_scale, const double* d_f, double* d_jtj, double* d_jtf) {
     const int Np = a->n_params; const int64_t nE = a->n_elements;
@@ -1655,6 +1705,25 @@ static int jtj_device(b200_ctx* c, b200_atom* a, const double* d_scale, const do
     if (nE == 0) {
         CU(cudaMemsetAsync(d_jtj, 0, (size_t)Np * Np * 8, c->stream));
         if (d_jtf) CU(cudaMemsetAsync(d_jtf, 0, (size_t)Np * 8, c->stream));
+        return B200_OK;
+    }
+    // B200_JTJ=ozaki: the tcgen05 (int8 Ozaki) SYRK; default: the FP64 DMMA SYRK
+    const char* mode = getenv("B200_JTJ");
+    if (mode && !strncmp(mode, "ozaki", 5) && nE >= 1024) {
+        rc = !strcmp(mode, "ozaki7") ? jtj_ozaki<7>(c, c->out_buf.as<double>(), ldj, nE, Np, d_jtj)
+                                     : jtj_ozaki<8>(c, c->out_buf.as<double>(), ldj, nE, Np, d_jtj);
+        if (rc) return rc;
+        if (d_jtf) {          // J^T f: weighted column sums of J (FP64, two deterministic passes)
+            const int ns = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c->sm_count * 8 * 256 + ldj - 1) / ldj, (nE + 63) / 64));
+            const int64_t rps = (nE + ns - 1) / ns;
+            CU(c->atb_part.ensure((size_t)ns * ldj * 8));
+            k_wcolsum<<<dim3((unsigned)((ldj + 255) / 256), (unsigned)ns), 256, 0, c->stream>>>(c->out_buf.as<double>(), ldj, nE, d_f, rps, c->atb_part.as<double>());
+            CU(c->atb_part_f.ensure((size_t)ldj * 8));
+            k_wcolsum_reduce<<<(unsigned)((ldj + 255) / 256), 256, 0, c->stream>>>(c->atb_part.as<double>(), ldj, ns, c->atb_part_f.as<double>());
+            CU(cudaMemcpyAsync(d_jtf, c->atb_part_f.p, (size_t)Np * 8, cudaMemcpyDeviceToDevice, c->stream));
+            c->launches += 2;
+            CU(cudaGetLastError());
+        }
         return B200_OK;
     }
     return atb_device(c, c->out_buf.as<double>(), ldj, Np, c->out_buf.as<double>(), ldj, Np, nE, true, d_f, d_jtj, Np, d_jtf, false);
