@@ -47,7 +47,16 @@ METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel k_accum_trie_d16 (ncu --set full,
 # profiles/r01_accum_final_ncu_raw.csv): 0.165 GB read + 2.929 GB written
 NCU_TRAFFIC_BYTES = 3.094e9
+INT8_PEAK_POPS = 4.5        # nominal dense int8 tensor rate of a B200 (tcgen05.mma kind::i8)
 DMMA_PEAK_TFLOPS = 37.2     # measured on this part with tools/ubench_fp64.cu (mma.sync m8n8k4 f64); DFMA 36.6
+
+
+def _bf16_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f).get("bf16_tflops", 0.0))
+    except Exception:
+        return 0.0
 
 
 def _peaks():
@@ -429,6 +438,12 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
 
     ms_jtj = timed(D, stream, jtj_step, max(3, min(args.steps, 10)), 2)
     ms_jtj_local = timed(D, stream, jtj_local, max(3, min(args.steps, 10)), 1)
+    # the same contraction on the FP64 tensor cores (round 1/2's k_atb_dmma), for comparison and as a second parity reference
+    ctx.set_jtj_mode(0)
+    ms_jtj_local_dmma = timed(D, stream, jtj_local, max(3, min(args.steps, 5)), 1)
+    jtj_step(); torch.cuda.synchronize()
+    jj_dmma = jj.clone()
+    ctx.set_jtj_mode(-1)
     # parity: against the same product formed from the gathered, scaled Jacobian by a library GEMM (outside any timed region)
     if world > 1:
         rs_all = torch.zeros(plan.n_rows_padded, dtype=torch.float64, device="cuda"); fv_all = torch.zeros_like(rs_all)
@@ -448,9 +463,15 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
     jtj_err = float((jj[:Np * Np].reshape(Np, Np) - ref).abs().max() / ref.abs().max())
     jtf_err = float((jj[Np * Np:] - reff).abs().max() / reff.abs().max())
     assert jtj_err <= 1e-11 and jtf_err <= 1e-11, (jtj_err, jtf_err)
+    jtj_err_dmma = float((jj_dmma[:Np * Np].reshape(Np, Np) - ref).abs().max() / ref.abs().max())
+    jtj_vs_dmma = float((jj[:Np * Np] - jj_dmma[:Np * Np]).abs().max() / ref.abs().max())
+    assert jtj_err_dmma <= 1e-11, jtj_err_dmma
+    del jj_dmma
     del ref, reff, rs_all, fv_all
     jtj_flops = float(nE) * Np * (Np + 1)                      # the lower triangle of J^T J over all elements (2 flop per MAC)
     ms_syrk = max(ms_jtj_local - ms_fill, 1e-6)
+    ms_syrk_dmma = max(ms_jtj_local_dmma - ms_fill, 1e-6)
+    oz_pairs = 36                                               # digit pairs a + b < 8 of the 8-digit splitting
 
     # ---------------- end to end through the C ABI with HOST buffers (e2e) ----------------
     Jh = HostArray(D, engine, plan.n_rows_padded, Np, "J")
@@ -541,14 +562,27 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
                       "note": "the all-gather moves (N-1)/N of a 2.97 GB Jacobian INTO every GPU over NVLink (<= 900 GB/s), "
                               "while one GPU produces it at ~4 TB/s: for d = 16 the full-Jacobian exchange is NVLink-bound and "
                               "the jtj exchange below is the one that scales"},
-        "jtj": {"ms": ms_jtj, "ms_local": ms_jtj_local, "ms_syrk_kernel": ms_syrk,
-                "tflops": jtj_flops / world / (ms_syrk * 1e-3) / 1e12, "frac": jtj_flops / world / (ms_syrk * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
-                "peak": DMMA_PEAK_TFLOPS, "peak_source": "measured DMMA rate, tools/ubench_fp64.cu",
+        "jtj": {"ms": ms_jtj, "ms_local": ms_jtj_local, "ms_contraction": ms_syrk,
+                "fp64_equiv_tflops": jtj_flops / world / (ms_syrk * 1e-3) / 1e12,
+                "int8_pops": oz_pairs * jtj_flops / world / (ms_syrk * 1e-3) / 1e15,
+                "frac": oz_pairs * jtj_flops / world / (ms_syrk * 1e-3) / 1e15 / INT8_PEAK_POPS,
+                "peak": INT8_PEAK_POPS, "peak_unit": "POP/s (int8, dense)",
+                "peak_source": "nominal B200 dense int8 rate (MEASURED_PEAKS.json holds no int8 figure; 2 x its measured bf16 burst "
+                               "of %.0f TFLOP/s would be %.2f)" % (_bf16_peak(), 2e-3 * _bf16_peak()),
+                "fp64_dmma": {"ms_local": ms_jtj_local_dmma, "ms_contraction": ms_syrk_dmma,
+                              "tflops": jtj_flops / world / (ms_syrk_dmma * 1e-3) / 1e12,
+                              "frac": jtj_flops / world / (ms_syrk_dmma * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS, "peak": DMMA_PEAK_TFLOPS,
+                              "peak_source": "measured DMMA rate, tools/ubench_fp64.cu", "parity_jtj_rel": jtj_err_dmma,
+                              "what": "k_atb_dmma (hand-written FP64 tensor-core SYRK), b200_ctx_set_jtj_mode(0)"},
+                "speedup_vs_fp64_dmma": ms_jtj_local_dmma / ms_jtj_local,
                 "allreduce_bytes": (Np * Np + Np) * 8 if world > 1 else 0,
                 "outcomes_per_s": nE / (ms_jtj * 1e-3), "e2e_ms": t_e2e_jtj * 1e3, "e2e_outcomes_per_s": nE / t_e2e_jtj,
-                "parity": {"jtj_rel": jtj_err, "jtf_rel": jtf_err},
-                "what": "scaled Jacobian fill + k_atb_dmma (hand-written FP64 tensor-core SYRK, lower-triangle tiles, split over "
-                        "elements, deterministic reduction) + J^T f in the same kernel%s; flops = nE*Np*(Np+1)" %
+                "parity": {"jtj_rel": jtj_err, "jtf_rel": jtf_err, "jtj_vs_fp64_dmma_rel": jtj_vs_dmma},
+                "what": "scaled Jacobian fill + k_oz_colstats (column exponents + J^T f in one pass) + k_oz_slice (8 int8 digits per "
+                        "entry, written as the tensor core's shared-memory image) + k_oz_syrk<8> (tcgen05.mma kind::i8, all 8 level "
+                        "accumulators resident in TMEM, digit tiles staged by cp.async.bulk, 36 digit pairs per stage as 12 "
+                        "instructions with the column digits stacked along N; exact int32 sums) + k_oz_reduce (FP64, deterministic, "
+                        "bitwise symmetric)%s; ms_contraction = everything but the fill; flops = nE*Np*(Np+1), int8 ops = 36 x that" %
                         (" + ONE all-reduce of Np^2+Np doubles" if world > 1 else "")},
         "e2e": {"value": nE / t_e2e, "unit": "circuit-outcomes/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e * 1e3, "host_array": host_kind,

@@ -62,6 +62,13 @@ int b200_ctx_launch_count(b200_ctx* ctx, int64_t* n_out);
  * made since timing was switched on (or since the last read) and their number, and clears the record. */
 int b200_ctx_phase_timing(b200_ctx* ctx, int on);
 int b200_ctx_phase_ms(b200_ctx* ctx, double ms_out[3], int64_t* n_calls_out);
+/* How b200_jtj / b200_jtj_dev contract the Jacobian (the reduction fill_jtj performs on the host, distlayout.py:1220-1359):
+ *   -1 (default) automatic: the tcgen05 path with 8 digits from 4096 rows up, the FP64 path below;
+ *    0  FP64 tensor cores (mma.sync DMMA SYRK, k_atb_dmma);
+ *    8 / 7  5th-generation tensor cores through the Ozaki splitting (tcgen05.mma kind::i8, exact int32 accumulation in
+ *       TMEM; 8 digits = 62 bits per entry relative to its column's largest magnitude, 7 digits = 55 bits).
+ * The environment variable B200_JTJ (dmma | ozaki | ozaki7) sets the initial mode of new contexts. */
+int b200_ctx_set_jtj_mode(b200_ctx* ctx, int mode);
 
 /* ---- layout atom (one-time per layout) ---------------------------------------------------------
  * Replaces convert_maplayout / convert_dict_of_intlists / create_rhocache (pyx:55-101), which the

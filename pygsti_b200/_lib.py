@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200_ctx_sync": (C.c_int, [vp]),
     "b200_ctx_launch_count": (C.c_int, [vp, c_i64p]),
     "b200_ctx_phase_timing": (C.c_int, [vp, C.c_int]),
+    "b200_ctx_set_jtj_mode": (C.c_int, [vp, C.c_int]),
     "b200_ctx_phase_ms": (C.c_int, [vp, C.POINTER(C.c_double), c_i64p]),
     "b200_atom_upload": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, vp, vp, C.c_int64,

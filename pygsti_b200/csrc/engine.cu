@@ -10,6 +10,7 @@
 #include "kernels_jtj.cuh"
 #include "kernels_gemm.cuh"
 #include "kernels_factored.cuh"
+#include "kernels_factoredj.cuh"
 #include "kernels_ozaki.cuh"
 #include <cstdlib>
 
@@ -68,11 +69,14 @@ struct b200_ctx {
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // backward sweep runs beside the forward sweep
     DevBuf scale_buf, f_buf, jtj_buf, jtf_buf;   // fused objective Jacobian / J^T J
     DevBuf atb_part, atb_part_f;                 // partial tiles of the A^T B reductions (k_atb_dmma)
+    DevBuf fj_fs, fj_counter;                    // factored Jacobian: forward states of every factor step, work counter
     DevBuf oz_S, oz_misc, oz_part;               // Ozaki J^T J: int8 digit slices, (column maxima | exponents | tile list), partial tiles
     DevBuf hb[24];                               // scratch of the Hessian-block path (kept between calls: cudaMalloc / cudaFree per
                                                  // rectangle cost more than the kernels once peer access is enabled)
     DevBuf fd_models, fd_gt, fd_probs;
     DevBuf lind[20];                                     // b200_lindblad_members: inputs, intermediates, outputs
+    int jtj_mode = -1;                                   // b200_ctx_set_jtj_mode
+    std::vector<int2> oz_tiles; int oz_tiles_np = -1;    // lower-triangle tile list of the Ozaki SYRK (host copy outlives the async upload)
     bool phase_timing = false;                           // b200_ctx_phase_timing: events around the d16 trie phases
     std::vector<cudaEvent_t> phase_events;               // 4 per call: start, after prepare, after chains, after accumulate
 };
@@ -113,6 +117,11 @@ struct b200_atom {
     DevBuf M, Gt;
     bool has_factored = false;             // gates also held as factor programs (b200_atom_set_model_factored)
     DevBuf fac_ptr, fac_rec, fac_mats; int fac_n_mats = 0, fac_n = 0; bool fac_probs_ok = false;   // (programs small enough for shared memory)
+    std::vector<FactorRec> h_fac; std::vector<int32_t> h_fptr;     // host copy of the factor programs
+    // factor-space derivative map (b200_atom_set_derivs_factored): the Jacobian straight from the factor programs (kernels_factoredj.cuh)
+    bool has_fderivs = false; int32_t fj_n_params = 0; int fj_n_acc = 0, fj_n_frag = 0; uint64_t fj_rows = 0;
+    std::vector<FactorRec> fj_fac;                                 // the factor structure the map was built for
+    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval;
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -176,6 +185,7 @@ extern "C" int b200_ctx_create(int device, void* stream, b200_ctx** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("B200_JTJ")) c->jtj_mode = !strcmp(e, "dmma") ? 0 : !strcmp(e, "ozaki7") ? 7 : !strcmp(e, "ozaki") ? 8 : -1;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     *out = c;
     return B200_OK;
@@ -197,6 +207,7 @@ extern "C" int b200_ctx_destroy(b200_ctx* c) {
     c->atb_part.release(); c->atb_part_f.release();
     for (DevBuf& b : c->hb) b.release();
     c->oz_S.release(); c->oz_misc.release(); c->oz_part.release();
+    c->fj_fs.release(); c->fj_counter.release();
     c->fd_models.release(); c->fd_gt.release(); c->fd_probs.release();
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -222,6 +233,13 @@ static void phase_clear(b200_ctx* c) {
     for (cudaEvent_t e : c->phase_events) cudaEventDestroy(e);
     c->phase_events.clear();
 }
+extern "C" int b200_ctx_set_jtj_mode(b200_ctx* c, int mode) {
+    if (!c) return fail(B200_E_INVALID, "NULL ctx");
+    if (mode != -1 && mode != 0 && mode != 7 && mode != 8) return fail(B200_E_INVALID, "jtj mode must be -1, 0, 7 or 8");
+    c->jtj_mode = mode;
+    return B200_OK;
+}
+
 extern "C" int b200_ctx_phase_timing(b200_ctx* c, int on) {
     if (!c) return fail(B200_E_INVALID, "ctx is NULL");
     CU(cudaSetDevice(c->device));
@@ -678,7 +696,102 @@ extern "C" int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* a, int32_t
     }
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_model = true; a->has_factored = true; a->fac_n_mats = (int)std::min<int64_t>(n_mats, INT_MAX); a->fac_n = n_factors;
+    a->h_fac.assign(recs.begin(), recs.begin() + n_factors); a->h_fptr = fptr;
     a->fac_probs_ok = n_mats <= FAC_MATS_MAX && n_factors <= FAC_RECS_MAX && a->n_ops <= 4096;
+    return B200_OK;
+}
+
+static bool same_factor_structure(const std::vector<FactorRec>& x, const std::vector<FactorRec>& y) {
+    if (x.size() != y.size()) return false;
+    for (size_t i = 0; i < x.size(); ++i)
+        if (x[i].nq != y[i].nq || x[i].shift[0] != y[i].shift[0] || x[i].shift[1] != y[i].shift[1] || x[i].moff != y[i].moff) return false;
+    return true;
+}
+
+// Derivative map in FACTOR space: rows index [factor matrices (the `mats` array of b200_atom_set_model_factored) | rho | E].
+extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_t n_wf, int32_t n_params, int64_t nnz,
+                                             const int32_t* rows, const int32_t* cols, const double* vals) {
+    if (!ctx || !a || n_params < 0 || nnz < 0 || (nnz > 0 && (!rows || !cols || !vals))) return fail(B200_E_INVALID, "NULL / negative argument");
+    if (!a->has_factored) return fail(B200_E_STATE, "b200_atom_set_model_factored has not been called");
+    const int d = a->dim;
+    if (d != 64 && d != 256) return fail(B200_E_UNSUPPORTED, "factor-space derivatives need dim = 64 or 256");
+    const int64_t n_mats = a->fac_n_mats;
+    if (n_wf != n_mats + (int64_t)(a->n_rho + a->n_eff) * d) return fail(B200_E_INVALID, "n_wf=%lld, expected %lld", (long long)n_wf, (long long)(n_mats + (int64_t)(a->n_rho + a->n_eff) * d));
+    if (a->n_eff >= (1 << 14) || a->n_rho >= (1 << 14)) return fail(B200_E_UNSUPPORTED, "too many preps / effects");
+    if (a->has_derivs && a->n_params != n_params) return fail(B200_E_INVALID, "factor-space map has %d parameters, the dense map %d", n_params, a->n_params);
+    const int n_fac = a->fac_n;
+    // accumulator / fragment offsets, owners of every matrix element (factors may share a matrix: their accumulators add up)
+    std::vector<int32_t> fao((size_t)std::max(n_fac, 1)), ffo((size_t)std::max(n_fac, 1)), first((size_t)std::max<int64_t>(n_mats, 1), -1), next((size_t)std::max(n_fac, 1), -1);
+    int n_acc = 0, n_frag = 0;
+    for (int f = 0; f < n_fac; ++f) {
+        const FactorRec& r = a->h_fac[f];
+        const int ds2 = r.nq == 2 ? 256 : 16;
+        fao[f] = n_acc; ffo[f] = n_frag; n_acc += ds2; n_frag += r.nq == 2 ? 256 : 32;
+        const int head = first[r.moff];
+        if (head >= 0 && (a->h_fac[head].nq != r.nq)) return fail(B200_E_UNSUPPORTED, "factors of different size share a matrix");
+        for (int i = 0; i < ds2; ++i) {
+            if (first[r.moff + i] != head) return fail(B200_E_UNSUPPORTED, "factor matrices overlap partially");
+        }
+        next[f] = head;
+        for (int i = 0; i < ds2; ++i) first[r.moff + i] = f;
+    }
+    // CSC with element codes
+    std::vector<int32_t> cptr((size_t)n_params + 1, 0);
+    auto n_owner = [&](int64_t w) { int n = 0; for (int f = first[w]; f >= 0; f = next[f]) ++n; return n; };
+    for (int64_t t = 0; t < nnz; ++t) {
+        const int64_t w = rows[t]; const int p = cols[t];
+        if (w < 0 || w >= n_wf || p < 0 || p >= n_params) return fail(B200_E_INVALID, "entry %lld out of range", (long long)t);
+        cptr[p + 1] += w < n_mats ? n_owner(w) : 1;
+    }
+    for (int p = 0; p < n_params; ++p) cptr[p + 1] += cptr[p];
+    const int64_t tot = cptr[n_params];
+    std::vector<uint32_t> ccode((size_t)std::max<int64_t>(tot, 1)); std::vector<double> cval((size_t)std::max<int64_t>(tot, 1));
+    std::vector<int32_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int64_t t = 0; t < nnz; ++t) {
+        const int64_t w = rows[t]; const int p = cols[t];
+        if (w < n_mats) {
+            for (int f = first[w]; f >= 0; f = next[f]) {
+                const FactorRec& r = a->h_fac[f];
+                const int e = (int)(w - r.moff);
+                uint32_t code;
+                if (r.nq == 2) { const int ra = e >> 4, cb = e & 15; code = (uint32_t)(fao[f] + ((((ra >> 3) * 2 + (cb >> 3)) * 32 + (((ra & 7) << 2) | ((cb & 7) >> 1))) * 2) + (cb & 1)); }
+                else code = (uint32_t)(fao[f] + e);
+                ccode[fill[p]] = code; cval[fill[p]++] = vals[t];
+            }
+        } else {
+            const int64_t v = w - n_mats;
+            const bool is_rho = v < (int64_t)a->n_rho * d;
+            const int64_t u = is_rho ? v : v - (int64_t)a->n_rho * d;
+            ccode[fill[p]] = ((is_rho ? 1u : 2u) << 30) | ((uint32_t)(u / d) << 16) | (uint32_t)(u % d);
+            cval[fill[p]++] = vals[t];
+        }
+    }
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_vec(a->fj_fao, fao, ctx->stream)) || (rc = upload_vec(a->fj_ffo, ffo, ctx->stream)) ||
+        (rc = upload_vec(a->fj_cptr, cptr, ctx->stream)) || (rc = upload_vec(a->fj_ccode, ccode, ctx->stream)) ||
+        (rc = upload_vec(a->fj_cval, cval, ctx->stream))) return rc;
+    // rows of the forward-state table: one per factor step of every circuit + the initial state
+    const int64_t n_out = a->n_elements;
+    CU(a->fj_base.ensure(((size_t)a->n_rows + 1) * 4 + 16));
+    CU(a->fj_out_circ.ensure(std::max<size_t>((size_t)n_out * 4, 16)));
+    std::vector<uint32_t> cnt((size_t)a->n_rows + 1, 0);
+    if (a->n_rows > 0) {
+        k_fj_count<<<(unsigned)std::min<int64_t>((a->n_rows + 255) / 256, 4096), 256, 0, ctx->stream>>>(atom_dev(a), a->fac_ptr.as<int32_t>(), a->fj_base.as<uint32_t>(), a->fj_out_circ.as<int32_t>());
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(cnt.data(), a->fj_base.p, (size_t)a->n_rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t run = 0;
+    for (int64_t c = 0; c < a->n_rows; ++c) { const uint32_t n = cnt[c]; cnt[c] = (uint32_t)run; run += n; }
+    cnt[a->n_rows] = (uint32_t)run;
+    if (run >= ((uint64_t)1 << 32)) return fail(B200_E_UNSUPPORTED, "forward-state table too large");
+    CU(cudaMemcpyAsync(a->fj_base.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    a->fj_rows = run; a->fj_n_acc = n_acc; a->fj_n_frag = n_frag; a->fj_n_params = n_params; a->fj_fac = a->h_fac;
+    a->has_fderivs = true;
+    if (!a->has_derivs) a->n_params = n_params;
     return B200_OK;
 }
 
@@ -1099,6 +1212,7 @@ extern "C" int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* a, int64_t n_w, in
     }
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_derivs = true;
+    a->has_fderivs = false;      // (a factor-space map of the same parameter block is set AFTER the dense one)
     return B200_OK;
 }
 
@@ -1423,11 +1537,58 @@ struct PeerSpec { int n = 0; double* J[B200_PEERS_MAX]; double* P[B200_PEERS_MAX
 
 // Jacobian into a device buffer; d_scale (device, [n_elements]) or nullptr.  `ps` (optional): kernels with a fused peer epilogue
 // also store into the peers' arrays and mark ps->j_done / ps->p_done.
+// ------------------------------------------------------------------------------------------------
+// factored Jacobian (gates as factor programs + factor-space derivative map): kernels_factoredj.cuh
+// ------------------------------------------------------------------------------------------------
+static size_t fj_smem(b200_atom* a, int warps) {
+    return (size_t)((a->fj_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * sizeof(FactorRec) + ((size_t)a->n_ops + 1 + 2 * (size_t)a->fac_n) * 4 + 16 +
+           (size_t)warps * (3 * (size_t)a->dim + a->fj_n_acc) * 8;
+}
+static int fj_warps(b200_ctx* c, b200_atom* a) {
+    for (int w = 8; w >= 1; w >>= 1) if (fj_smem(a, w) <= std::min<size_t>(c->smem_optin, (size_t)110 * 1024) || (w == 1 && fj_smem(a, 1) <= c->smem_optin)) return w;
+    return 0;
+}
+static bool factoredj_ok(b200_ctx* c, b200_atom* a) {
+    static const bool off = getenv("B200_NO_FACTOREDJ") != nullptr;
+    return !off && a->has_factored && a->has_fderivs && a->fac_probs_ok && (a->dim == 64 || a->dim == 256) && a->n_rows > 0 &&
+           a->fj_n_params == a->n_params && same_factor_structure(a->fj_fac, a->h_fac) && fj_warps(c, a) > 0;
+}
+template <int D>
+static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
+    CU(c->fj_fs.ensure((size_t)a->fj_rows * D * 8));
+    CU(c->fj_counter.ensure(16));
+    const FactoredDev fd = factored_dev(a);
+    const double* M = a->M.as<double>();
+    {
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 4));
+        const size_t smem = (size_t)FAC_WARPS * 2 * D * 8 + ((size_t)((a->fac_n_mats + 1) & ~1)) * 8 + (size_t)a->fac_n * sizeof(FactorRec) + ((size_t)a->n_ops + 1) * 4;
+        CU(cudaFuncSetAttribute(k_fj_forward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fj_forward<D><<<grid, FAC_WARPS * 32, smem, c->stream>>>(atom_dev(a), fd, a->fac_n_mats, a->fac_n, a->fj_base.as<uint32_t>(), M + a->off_rho, M + a->off_eff,
+                                                                c->fj_fs.as<double>(), d_probs);
+    }
+    CU(cudaMemsetAsync(c->fj_counter.p, 0, 4, c->stream));
+    FjDev fj;
+    fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
+    fj.n_acc = a->fj_n_acc; fj.n_frag = a->fj_n_frag; fj.cptr = a->fj_cptr.as<int32_t>(); fj.ccode = a->fj_ccode.as<uint32_t>(); fj.cval = a->fj_cval.as<double>();
+    fj.n_params = a->fj_n_params;
+    const int warps = fj_warps(c, a);
+    const size_t smem = fj_smem(a, warps);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)227 * 1024) / (smem + 1024)));
+    const int64_t n_items = a->n_elements;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_items + warps - 1) / warps, (int64_t)c->sm_count * per_sm));
+    CU(cudaFuncSetAttribute(k_fj_backward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_fj_backward<D><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_eff, c->fj_fs.as<double>(), d_out, ld, d_scale,
+                                                         c->fj_counter.as<unsigned>(), (int)n_items);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    return B200_OK;
+}
+
 static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale,
                               PeerSpec* ps = nullptr) {
     if (!c || !a || !d_out) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (!a->has_derivs && !a->has_fderivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (ld < a->n_params) return fail(B200_E_INVALID, "ld=%lld < n_params=%d", (long long)ld, a->n_params);
     CU(cudaSetDevice(c->device));
     if (a->n_elements == 0 || a->n_params == 0) {
@@ -1448,6 +1609,10 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
         }
         return launch_d16(c, a, args);
     }
+    if (factoredj_ok(c, a)) {
+        return a->dim == 64 ? launch_factoredj<64>(c, a, d_out, ld, d_probs, d_scale) : launch_factoredj<256>(c, a, d_out, ld, d_probs, d_scale);
+    }
+    if (!a->has_derivs) return fail(B200_E_STATE, "only a factor-space derivative map is set and the factored Jacobian path is unavailable for this atom");
     if (levelj_ok(c, a)) {
         PeerOut po; po.n = 0;
         if (ps) { po.n = ps->n; for (int r = 0; r < ps->n; ++r) po.J[r] = ps->J[r]; }
@@ -1562,7 +1727,7 @@ extern "C" int b200_fill_probs(b200_ctx* c, b200_atom* a, double* out, int64_t o
 extern "C" int b200_fill_dprobs(b200_ctx* c, b200_atom* a, double* out, int64_t row_stride,
                                 double* probs_out, int64_t probs_stride) {
     if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (!a->has_derivs && !a->has_fderivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (row_stride < a->n_params) return fail(B200_E_INVALID, "row_stride < n_params");
     if (probs_out && probs_stride < 1) return fail(B200_E_INVALID, "probs_stride must be >= 1");
     CU(cudaSetDevice(c->device));
@@ -1589,7 +1754,7 @@ static int upload_scale(b200_ctx* c, b200_atom* a, const double* row_scale, cons
 extern "C" int b200_fill_dprobs_scaled(b200_ctx* c, b200_atom* a, const double* row_scale, double* out, int64_t row_stride,
                                        double* probs_out, int64_t probs_stride) {
     if (!c || !a || !out) return fail(B200_E_INVALID, "NULL argument");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (!a->has_derivs && !a->has_fderivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (row_stride < a->n_params) return fail(B200_E_INVALID, "row_stride < n_params");
     if (probs_out && probs_stride < 1) return fail(B200_E_INVALID, "probs_stride must be >= 1");
     CU(cudaSetDevice(c->device));
@@ -1650,12 +1815,17 @@ static int atb_device(b200_ctx* c, const double* A, int64_t lda, int na, const d
 // J^T J on the 5th-generation tensor cores (tcgen05.mma kind::i8 + TMEM) through the Ozaki splitting -- kernels_ozaki.cuh.
 // J [nE x ldj] on the device; result d_jtj [Np x Np] (row-major, full symmetric).  T = 8 digits (62 bits) or 7 (55 bits).
 template <int T>
-static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int Np, double* d_jtj) {
+static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int Np, const double* d_f, double* d_jtj, double* d_jtf) {
     const int n_bi = (Np + OZ_TM - 1) / OZ_TM, n_bj = (Np + OZ_TN - 1) / OZ_TN;
     const int64_t P_pad = (int64_t)n_bi * OZ_TM;
-    std::vector<int2> tiles;
-    for (int bi = 0; bi < n_bi; ++bi)
-        for (int bj = 0; bj < n_bj; ++bj) if ((int64_t)bj * OZ_TN <= (int64_t)bi * OZ_TM + OZ_TM - 1) tiles.push_back(make_int2(bi, bj));
+    std::vector<int2>& tiles = c->oz_tiles;
+    if (c->oz_tiles_np != Np) {
+        CU(cudaStreamSynchronize(c->stream));       // an earlier asynchronous upload may still read the old list
+        tiles.clear();
+        for (int bi = 0; bi < n_bi; ++bi)
+            for (int bj = 0; bj < n_bj; ++bj) if ((int64_t)bj * OZ_TN <= (int64_t)bi * OZ_TM + OZ_TM - 1) tiles.push_back(make_int2(bi, bj));
+        c->oz_tiles_np = Np;
+    }
     const int n_tiles = (int)tiles.size();
     const int64_t stages_total = (nE + OZ_KS - 1) / OZ_KS;
     // K slices: short enough that every level's int32 sum stays exact, and as many more as fill whole waves of SMs (one CTA per SM)
@@ -1669,17 +1839,21 @@ static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int 
     const int64_t sps = (stages_total + ksl - 1) / ksl;
     const int64_t n_stages = ksl * sps;
     if (sps > OZ_MAX_STAGES_PER_SLICE) return fail(B200_E_UNSUPPORTED, "Ozaki J^T J: K slice too long");
+    // column statistics: one pass over J for the exponents and J^T f
+    const int ns = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c->sm_count * 8 * 256 + Np - 1) / Np, (nE + 63) / 64));
+    const int64_t rps = (nE + ns - 1) / ns;
     CU(c->oz_S.ensure((size_t)n_stages * T * P_pad * OZ_KS));
-    const size_t misc_bytes = (size_t)P_pad * 8 + (size_t)P_pad * 4 + (size_t)n_tiles * sizeof(int2) + 64;
+    const size_t misc_bytes = (size_t)2 * ns * Np * 8 + (size_t)P_pad * 4 + (size_t)n_tiles * sizeof(int2) + 64;
     CU(c->oz_misc.ensure(misc_bytes));
     CU(c->oz_part.ensure((size_t)ksl * n_tiles * OZ_TM * OZ_TN * 8));
-    unsigned long long* d_cmax = c->oz_misc.as<unsigned long long>();
-    int* d_expo = reinterpret_cast<int*>(d_cmax + P_pad);
+    double* d_psum = c->oz_misc.as<double>();
+    double* d_pmax = d_psum + (size_t)ns * Np;
+    int* d_expo = reinterpret_cast<int*>(d_pmax + (size_t)ns * Np);
     int2* d_tiles = reinterpret_cast<int2*>(d_expo + P_pad);            // P_pad is a multiple of 128: 8-byte aligned
-    CU(cudaMemsetAsync(d_cmax, 0, (size_t)P_pad * 12, c->stream));
+    CU(cudaMemsetAsync(d_expo, 0, (size_t)P_pad * 4, c->stream));
     CU(cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)n_tiles * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-    k_oz_colmax<<<dim3((unsigned)((Np + 63) / 64), (unsigned)std::min<int64_t>(512, (nE + 3) / 4)), 256, 0, c->stream>>>(J, ldj, nE, Np, d_cmax);
-    k_oz_exponents<<<(unsigned)((Np + 255) / 256), 256, 0, c->stream>>>(d_cmax, Np, d_expo);
+    k_oz_colstats<<<dim3((unsigned)((Np + 255) / 256), (unsigned)ns), 256, 0, c->stream>>>(J, ldj, nE, Np, d_jtf ? d_f : nullptr, rps, d_psum, d_pmax);
+    k_oz_colstats_reduce<<<(unsigned)((Np + 255) / 256), 256, 0, c->stream>>>(d_psum, d_pmax, Np, ns, d_jtf, d_expo);
     k_oz_slice<T><<<dim3((unsigned)(P_pad / 64), (unsigned)((n_stages + 1) / 2)), 256, 0, c->stream>>>(J, ldj, nE, Np, d_expo, c->oz_S.as<int8_t>(), P_pad, n_stages);
     OzArgs p;
     p.S = c->oz_S.as<int8_t>(); p.P_pad = P_pad; p.tiles = d_tiles; p.n_tiles = n_tiles;
@@ -1690,7 +1864,6 @@ static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int 
     k_oz_reduce<<<(unsigned)n_tiles, 256, 0, c->stream>>>(p, d_expo, Np, d_jtj, Np);
     c->launches += 5;
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));          // (the host tile list goes out of scope)
     return B200_OK;
 }
 
@@ -1707,31 +1880,16 @@ static int jtj_device(b200_ctx* c, b200_atom* a, const double* d_scale, const do
         if (d_jtf) CU(cudaMemsetAsync(d_jtf, 0, (size_t)Np * 8, c->stream));
         return B200_OK;
     }
-    // B200_JTJ=ozaki: the tcgen05 (int8 Ozaki) SYRK; default: the FP64 DMMA SYRK
-    const char* mode = getenv("B200_JTJ");
-    if (mode && !strncmp(mode, "ozaki", 5) && nE >= 1024) {
-        rc = !strcmp(mode, "ozaki7") ? jtj_ozaki<7>(c, c->out_buf.as<double>(), ldj, nE, Np, d_jtj)
-                                     : jtj_ozaki<8>(c, c->out_buf.as<double>(), ldj, nE, Np, d_jtj);
-        if (rc) return rc;
-        if (d_jtf) {          // J^T f: weighted column sums of J (FP64, two deterministic passes)
-            const int ns = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c->sm_count * 8 * 256 + ldj - 1) / ldj, (nE + 63) / 64));
-            const int64_t rps = (nE + ns - 1) / ns;
-            CU(c->atb_part.ensure((size_t)ns * ldj * 8));
-            k_wcolsum<<<dim3((unsigned)((ldj + 255) / 256), (unsigned)ns), 256, 0, c->stream>>>(c->out_buf.as<double>(), ldj, nE, d_f, rps, c->atb_part.as<double>());
-            CU(c->atb_part_f.ensure((size_t)ldj * 8));
-            k_wcolsum_reduce<<<(unsigned)((ldj + 255) / 256), 256, 0, c->stream>>>(c->atb_part.as<double>(), ldj, ns, c->atb_part_f.as<double>());
-            CU(cudaMemcpyAsync(d_jtf, c->atb_part_f.p, (size_t)Np * 8, cudaMemcpyDeviceToDevice, c->stream));
-            c->launches += 2;
-            CU(cudaGetLastError());
-        }
-        return B200_OK;
-    }
+    int mode = c->jtj_mode;
+    if (mode < 0) mode = (nE >= 4096) ? 8 : 0;
+    if (mode == 8) return jtj_ozaki<8>(c, c->out_buf.as<double>(), ldj, nE, Np, d_f, d_jtj, d_jtf);
+    if (mode == 7) return jtj_ozaki<7>(c, c->out_buf.as<double>(), ldj, nE, Np, d_f, d_jtj, d_jtf);
     return atb_device(c, c->out_buf.as<double>(), ldj, Np, c->out_buf.as<double>(), ldj, Np, nE, true, d_f, d_jtj, Np, d_jtf, false);
 }
 
 extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, const double* f, double* jtj_out, double* jtf_out) {
     if (!c || !a || !jtj_out) return fail(B200_E_INVALID, "NULL argument");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (!a->has_derivs && !a->has_fderivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (jtf_out && !f) return fail(B200_E_INVALID, "jtf_out requires f");
     CU(cudaSetDevice(c->device));
     const int Np = a->n_params; const int64_t nE = a->n_elements;
@@ -1758,7 +1916,7 @@ extern "C" int b200_jtj(b200_ctx* c, b200_atom* a, const double* row_scale, cons
 extern "C" int b200_jtj_dev(b200_ctx* c, b200_atom* a, const double* d_row_scale, const double* d_f, double* d_jtj, double* d_jtf) {
     if (!c || !a || !d_jtj) return fail(B200_E_INVALID, "NULL argument");
     if (!a->has_model) return fail(B200_E_STATE, "b200_atom_set_model has not been called");
-    if (!a->has_derivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
+    if (!a->has_derivs && !a->has_fderivs) return fail(B200_E_STATE, "b200_atom_set_derivs has not been called");
     if (d_jtf && !d_f) return fail(B200_E_INVALID, "d_jtf requires d_f");
     CU(cudaSetDevice(c->device));
     return jtj_device(c, a, d_row_scale, d_f, d_jtj, d_jtf);

@@ -10,8 +10,8 @@
 //
 // Kernel k_oz_syrk<T>: one CTA per (output tile 128 x 64 of the lower triangle, K slice).  ALL T level accumulators (level t = a + b,
 // 64 TMEM columns each: T x 64 <= 512 = the whole tensor memory of the SM) stay resident for the whole K slice, so a pipeline stage
-// carries the T digit tiles of both operands ONCE (T x (128 + 64) rows x 32 K-bytes = 48 KB at T = 8) and feeds T (T+1) / 2 = 36 MMAs
-// (M 128, N 64, K 32) from it: 196 MAC per operand byte.  (A first version kept one 128 x 256 accumulator per level and re-streamed both
+// carries the T digit tiles of both operands ONCE (T x (128 + 64) rows x 32 K-bytes = 48 KB at T = 8) and feeds all T (T+1) / 2 = 36
+// digit pairs from it: 196 MAC per operand byte.  (A first version kept one 128 x 256 accumulator per level and re-streamed both
 // operands for every digit pair: 87 MAC/B = 136 GB through L2 per J^T J of config 2 -- L2-feed-bound at the DMMA kernel's speed.)
 //   * digits live in global memory as the exact shared-memory image the tensor core wants (K-major, no swizzle: 8 x 16 B core matrices,
 //     S[k stage][digit][row group of 8][K chunk of 16][row & 7][16 B]), so one digit tile of a stage is ONE contiguous run of 4 KB /
@@ -32,59 +32,77 @@
 #define OZ_SBO 256u                    // between row groups of 8
 #define OZ_MAX_STAGES_PER_SLICE 2047   // 8 pairs x 65 504 rows x 64^2 < 2^31
 
-// ---- column exponents: e_p = smallest e with max_el |J[el][p]| < 2^e  (0 for an all-zero column) -----------------------------
+// ---- one pass over J: per column the largest magnitude (-> exponent e_p) and, with f, the weighted sum (J^T f)[p] -----------------
+// row slices -> partials [n_slices][Np], reduced in slice order by k_oz_colstats_reduce (deterministic)
 __global__ void __launch_bounds__(256)
-k_oz_colmax(const double* __restrict__ J, int64_t ld, int64_t nE, int Np, unsigned long long* __restrict__ cmax_bits)
+k_oz_colstats(const double* __restrict__ J, int64_t ld, int64_t nE, int Np, const double* __restrict__ f, int64_t rows_per_slice,
+              double* __restrict__ part_sum, double* __restrict__ part_max)
 {
-    const int p = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int64_t r0 = (int64_t)blockIdx.y * 4 + (threadIdx.x >> 6), rs = (int64_t)gridDim.y * 4;
-    if (p >= Np) return;
-    double m = 0.0;
-    for (int64_t r = r0; r < nE; r += rs) m = fmax(m, fabs(J[r * ld + p]));
-    atomicMax(cmax_bits + p, (unsigned long long)__double_as_longlong(m));        // non-negative doubles order like their bit patterns
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int64_t k_lo = blockIdx.y * rows_per_slice, k_hi = min(k_lo + rows_per_slice, nE);
+    if (c >= Np) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, m0 = 0.0, m1 = 0.0;
+    int64_t k = k_lo;
+    for (; k + 3 < k_hi; k += 4) {
+        const double v0 = J[k * ld + c], v1 = J[(k + 1) * ld + c], v2 = J[(k + 2) * ld + c], v3 = J[(k + 3) * ld + c];
+        if (f) { s0 = fma(f[k], v0, s0); s1 = fma(f[k + 1], v1, s1); s2 = fma(f[k + 2], v2, s2); s3 = fma(f[k + 3], v3, s3); }
+        m0 = fmax(m0, fmax(fabs(v0), fabs(v1))); m1 = fmax(m1, fmax(fabs(v2), fabs(v3)));
+    }
+    for (; k < k_hi; ++k) { const double v = J[k * ld + c]; if (f) s0 = fma(f[k], v, s0); m0 = fmax(m0, fabs(v)); }
+    part_sum[(size_t)blockIdx.y * Np + c] = (s0 + s1) + (s2 + s3);
+    part_max[(size_t)blockIdx.y * Np + c] = fmax(m0, m1);
 }
-__global__ void k_oz_exponents(const unsigned long long* __restrict__ cmax_bits, int Np, int* __restrict__ expo)
+// e_p = smallest e with max_el |J[el][p]| < 2^e  (0 for an all-zero column)
+__global__ void __launch_bounds__(256)
+k_oz_colstats_reduce(const double* __restrict__ part_sum, const double* __restrict__ part_max, int Np, int n_slices,
+                     double* __restrict__ jtf, int* __restrict__ expo)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= Np) return;
-    const double m = __longlong_as_double((long long)cmax_bits[p]);
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= Np) return;
+    double s = 0.0, m = 0.0;
+    for (int sl = 0; sl < n_slices; ++sl) { s += part_sum[(size_t)sl * Np + c]; m = fmax(m, part_max[(size_t)sl * Np + c]); }
+    if (jtf) jtf[c] = s;
     int e = 0;
     if (m > 0.0 && isfinite(m)) { frexp(m, &e); }                                  // m = f 2^e, f in [0.5, 1)  =>  |x| 2^-e < 1
-    expo[p] = e;
+    expo[c] = max(e, -900);
 }
 
 // ---- digits, written as the operand image:  S[stage][t][p >> 3][chunk][p & 7][16],  zero padded to P_pad x n_stages ----------
-// block (64 columns p) x (64 rows el = 2 stages): read J coalesced along p, transpose through shared memory, write 2 KB runs
+// One thread = one column p x 16 consecutive elements = one 16-byte chunk of the image per digit: no shared memory.  The loads of a
+// warp are 256 contiguous bytes of a Jacobian row; 8 neighbouring columns write 128 contiguous bytes.  Digit t is read off the low
+// mantissa bits of y + 1.5 2^(52 - 7t) (round-to-nearest at 2^-7t in one DADD), the remainder y - d_t 2^-7t is exact.
 template <int T>
 __global__ void __launch_bounds__(256)
 k_oz_slice(const double* __restrict__ J, int64_t ld, int64_t nE, int Np, const int* __restrict__ expo,
            int8_t* __restrict__ S, int64_t P_pad, int64_t n_stages)
 {
-    __shared__ __align__(16) int8_t dig[T][64][64 + 16];      // [t][p][el]
-    const int p0 = blockIdx.x * 64; const int64_t el0 = (int64_t)blockIdx.y * 64;
-    const int tp = threadIdx.x & 63, te = threadIdx.x >> 6;   // 64 columns x 4 rows per pass
-    const int p = p0 + tp;
-    const int e = (p < Np) ? expo[p] : 0;
-    for (int r = te; r < 64; r += 4) {
-        const int64_t el = el0 + r;
-        double x = (p < Np && el < nE) ? J[el * ld + p] : 0.0;
-        double y = scalbn(x, 6 - e);                          // |y| < 64
+    const int p = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int c4 = threadIdx.x >> 6;                          // which 16 of the block's 64 elements: stage 2 by + (c4 >> 1), chunk c4 & 1
+    const int64_t el0 = (int64_t)blockIdx.y * 64 + c4 * 16;
+    const int64_t stage = (int64_t)blockIdx.y * 2 + (c4 >> 1);
+    if (stage >= n_stages) return;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (p < Np && el0 + i < nE) ? J[(el0 + i) * ld + p] : 0.0;
+    const double sc = scalbn(1.0, 6 - ((p < Np) ? expo[p] : 0));          // |x| sc < 64
+    uint32_t w[T][4];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { w[t][0] = 0u; w[t][1] = 0u; w[t][2] = 0u; w[t][3] = 0u; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        double y = x[i] * sc;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            const double d = rint(y);
-            dig[t][tp][r] = (int8_t)(int)d;
-            y = (y - d) * 128.0;                              // |y - d| <= 0.5: the next digit is again in [-64, 64]
+            const double magic = 6755399441055744.0 / (double)(1ull << (7 * t));     // 1.5 2^(52 - 7t)
+            const double m = y + magic;
+            w[t][i >> 2] |= ((uint32_t)__double2loint(m) & 0xFFu) << (8 * (i & 3));
+            y -= (m - magic);                                 // |remainder| <= 2^(-7t-1): the next digit is again in [-64, 64]
         }
     }
-    __syncthreads();
-    // chunk q = ((((ks T + t) 8 + rg) 2 + c) 8 + r8): 16 bytes = 16 consecutive elements of column p0 + 8 rg + r8
-    for (int q = threadIdx.x; q < 2 * T * 8 * 16; q += 256) {
-        const int r8 = q & 7, c = (q >> 3) & 1, rg = (q >> 4) & 7, kt = q >> 7, t = kt % T, ks = kt / T;
-        const int64_t stage = (int64_t)blockIdx.y * 2 + ks;
-        if (stage >= n_stages) continue;
-        const int4 v = *reinterpret_cast<const int4*>(&dig[t][rg * 8 + r8][ks * 32 + c * 16]);
-        *reinterpret_cast<int4*>(S + ((stage * T + t) * P_pad + p0 + rg * 8) * OZ_KS + c * 128 + r8 * 16) = v;
-    }
+    int8_t* dst = S + (stage * T * P_pad + (p & ~7)) * OZ_KS + (c4 & 1) * 128 + (p & 7) * 16;
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+        *reinterpret_cast<int4*>(dst + (int64_t)t * P_pad * OZ_KS) = make_int4((int)w[t][0], (int)w[t][1], (int)w[t][2], (int)w[t][3]);
 }
 
 // ---- tcgen05 / mbarrier / bulk-copy helpers (forms as in CUTLASS cute/arch/{mma_sm100_umma,tmem_allocator_sm100,copy_sm90_tma}.hpp) --
@@ -137,7 +155,9 @@ struct OzArgs {
 };
 
 // instruction descriptor: D = S32 (bits 4-5 = 2), A = B = signed int8 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-#define OZ_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_TN >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24))
+__device__ __forceinline__ constexpr uint32_t oz_idesc(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_TM >> 4) << 24);
+}
 
 template <int T>
 __global__ void __launch_bounds__(128, 1)
@@ -194,12 +214,18 @@ k_oz_syrk(OzArgs p)
                 oz_mbar_wait(&full_bar[slot], use & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t da = oz_desc(smem0 + slot * STAGE), db = oz_desc(smem0 + slot * STAGE + T * A_T);
+                // digit a of the rows against digits 0 .. T-1-a of the columns, STACKED along N (the column digit tiles are contiguous
+                // row groups in shared memory and level a + b is accumulator column 64 (a + b)): one instruction of N = 64 (T - a)
+                // (<= 256 per instruction) instead of T - a instructions of N = 64, which re-read the 4 KB row tile each time and
+                // were shared-memory bound (ncu: tensor pipe 60 % busy, L1/shared 89 %).  T = 8: 12 instructions per stage.
 #pragma unroll
-                for (int t = 0; t < T; ++t)
+                for (int a = 0; a < T; ++a)
 #pragma unroll
-                    for (int a = 0; a <= t; ++a)
-                        oz_mma_i8(tmem + (uint32_t)(t * OZ_TN), da + (uint64_t)((a * A_T) >> 4), db + (uint64_t)(((t - a) * B_T) >> 4),
-                                  OZ_IDESC, (n > 0 || a > 0) ? 1u : 0u);
+                    for (int off = 0; off < OZ_TN * (T - a); off += 256) {
+                        const int nn = (OZ_TN * (T - a) - off) < 256 ? (OZ_TN * (T - a) - off) : 256;
+                        oz_mma_i8(tmem + (uint32_t)(a * OZ_TN + off), da + (uint64_t)((a * A_T) >> 4), db + (uint64_t)((off * OZ_KS) >> 4),
+                                  oz_idesc(nn), (n > 0 || a > 0) ? 1u : 0u);
+                    }
                 oz_commit(&empty_bar[slot]);
             }
             oz_commit(&acc_done);

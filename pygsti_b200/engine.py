@@ -62,6 +62,10 @@ class Context:
         _lib.check(self._lib.b200_ctx_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def set_jtj_mode(self, mode):
+        """-1 automatic (default), 0 FP64 DMMA SYRK, 8 / 7 tcgen05 Ozaki with 8 / 7 digits (b200_ctx_set_jtj_mode)."""
+        _lib.check(self._lib.b200_ctx_set_jtj_mode(self._h, int(mode)))
+
     def phase_timing(self, on=True):
         """Bracket the phases of the d = 16 Jacobian path with CUDA events on the launching stream (bench.py roofline)."""
         _lib.check(self._lib.b200_ctx_phase_timing(self._h, 1 if on else 0))

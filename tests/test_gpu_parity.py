@@ -308,10 +308,12 @@ def test_hessian_block_reduction(gpu_ctx, load_case):
     at.free()
 
 
+@pytest.mark.parametrize("jtj_mode", [0, 8, 7])
 @pytest.mark.parametrize("name", ["c2_2q_full_sub", "c4_2q_cptplnd_sub", "c1_1q_tp", "c3_3q_localnoise_sub"])
-def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name):
+def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name, jtj_mode):
     """b200_fill_dprobs_scaled / b200_jtj (fused objective Jacobian fill) on every kernel path: fused d=16 (trie
-    epilogue), general d=16 (W + contraction), d=4 and d=64 generic."""
+    epilogue), general d=16 (W + contraction), d=4 and d=64 generic; the contraction by the FP64 DMMA SYRK (mode 0) and by
+    the tcgen05 int8 Ozaki SYRK with 8 / 7 digits (forced here: the automatic mode uses it from 4096 rows up)."""
     c = load_case(name)
     a = c.atoms[0]
     at = _atom(gpu_ctx, a)
@@ -322,9 +324,49 @@ def test_scaled_jacobian_and_jtj(gpu_ctx, load_case, name):
     J = np.full((c.n_elements, c.num_params), np.nan)
     at.fill_dprobs(J, row_scale=w)
     assert np.max(np.abs(J - Jref)) <= 1e-10 * max(1.0, np.max(np.abs(Jref)))
-    JTJ, JTf = at.jtj(w, f)
+    gpu_ctx.set_jtj_mode(jtj_mode)
+    try:
+        JTJ, JTf = at.jtj(w, f)
+    finally:
+        gpu_ctx.set_jtj_mode(-1)
     R = Jref.T @ Jref
     assert np.max(np.abs(JTJ - R)) <= 1e-10 * max(1.0, np.max(np.abs(R)))
     assert np.max(np.abs(JTJ - JTJ.T)) == 0.0
     assert np.max(np.abs(JTf - Jref.T @ f)) <= 1e-10 * max(1.0, np.max(np.abs(Jref.T @ f)))
+    at.free()
+
+
+def test_jtj_tcgen05_full_size_vs_fp64(gpu_ctx, load_case):
+    """BASELINE config 2 at full size (273 340 x 1360): the tcgen05 Ozaki J^T J (8 and 7 digits; several K slices per tile,
+    int32 accumulators near their exactness bound) against the FP64 DMMA SYRK and against a long-double host product."""
+    c = load_case("c2_full_layout")
+    a = c.atoms[0]
+    at = _atom(gpu_ctx, a)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.5, 1.5, size=c.n_elements) * 10.0 ** rng.integers(-3, 4, size=c.n_elements)   # rows over 7 decades
+    f = rng.standard_normal(c.n_elements)
+    res = {}
+    try:
+        for mode in (0, 8, 7):
+            gpu_ctx.set_jtj_mode(mode)
+            res[mode] = at.jtj(w, f)
+    finally:
+        gpu_ctx.set_jtj_mode(-1)
+    R, Rf = res[0]
+    sc = np.max(np.abs(R))
+    for mode, tol in ((8, 1e-13), (7, 1e-12)):
+        X, Xf = res[mode]
+        assert np.isfinite(X).all()
+        assert np.max(np.abs(X - X.T)) == 0.0
+        assert np.max(np.abs(X - R)) <= tol * sc, mode
+        assert np.max(np.abs(Xf - Rf)) <= 1e-12 * np.max(np.abs(Rf)), mode
+    J = np.empty((c.n_elements, c.num_params))
+    at.fill_dprobs(J, row_scale=w)
+    cols = [0, 5, 401, c.num_params - 1]
+    ref = np.zeros((len(cols), c.num_params), dtype=np.longdouble)          # float64 products of 4096-row blocks, summed in long double
+    for r0 in range(0, c.n_elements, 4096):
+        ref += J[r0:r0 + 4096, cols].T @ J[r0:r0 + 4096]
+    ref = ref.astype(np.float64)
+    for mode, tol in ((0, 1e-13), (8, 1e-13), (7, 1e-12)):
+        assert np.max(np.abs(res[mode][0][cols] - ref)) <= tol * sc, mode
     at.free()

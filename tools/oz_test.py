@@ -17,8 +17,7 @@ rng = np.random.default_rng(0)
 w = rng.uniform(0.5, 1.5, nE); f = rng.standard_normal(nE)
 res = {}
 for mode in ("dmma", "ozaki", "ozaki7"):
-    if mode == "dmma": os.environ.pop("B200_JTJ", None)
-    else: os.environ["B200_JTJ"] = mode
+    ctx.set_jtj_mode({"dmma": 0, "ozaki": 8, "ozaki7": 7}[mode])
     ts = []
     try:
         for r in range(reps):
