@@ -118,6 +118,15 @@ int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* atom, int32_t n_facto
  * (matrixforwardsim.py:89-170). */
 int b200_atom_set_derivs(b200_ctx* ctx, b200_atom* atom, int64_t n_w, int32_t n_params,
                          int64_t nnz, const int32_t* rows, const int32_t* cols, const double* vals);
+/* Derivative map in FACTOR space for an atom whose gates were set with b200_atom_set_model_factored: rows index
+ * [mats (the factor matrices of that call) | rho (n_rho x d) | E (n_eff x d)], COO like b200_atom_set_derivs.  With it
+ * the Jacobian of d = 64 / 256 atoms is evaluated straight from the factor programs -- the device form of the
+ * reference's OpCRep_Embedded / OpCRep_Composed (opcreps.cpp:93-158, 242-276) differentiated factor by factor
+ * (EmbeddedOp.deriv_wrt_params is the embedded operation's own derivative, embeddedop.py) -- without dense d x d
+ * products.  Describes the same parameter block as the dense map, if one is set (call it AFTER b200_atom_set_derivs;
+ * that call drops a factor-space map).  Without a dense map only the Jacobian / J^T J calls are available. */
+int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* atom, int64_t n_wf, int32_t n_params, int64_t nnz,
+                                  const int32_t* rows, const int32_t* cols, const double* vals);
 
 /* ---- on-device model update for members AFFINE in their parameters (first part) ----------
  * FullArbitraryOp / FullTPOp / FullState / TPState / static members and (un)constrained POVM effects are affine in the

@@ -222,3 +222,65 @@ def hprobs_general(t, G, rho, E, D, H2=None, p1=None, p2=None):
         rows, a, b, vals = H2
         np.add.at(H, (slice(None), a, b), W[:, rows] * vals[None, :])
     return H
+
+
+# --------------------------------------------------------------------------------------
+#  factored gates: layer operations as products of small operations embedded on 1-2 qubits
+#  (OpCRep_Composed of OpCRep_Embedded, pygsti/evotypes/densitymx/opcreps.cpp:242-276, 93-158; the derivative of an
+#  EmbeddedOp is its embedded operation's own derivative, pygsti/modelmembers/operations/embeddedop.py deriv_wrt_params)
+# --------------------------------------------------------------------------------------
+def _embed(fm, f, d):
+    """dense d x d matrix of factor f and, per small-matrix entry (a, b), the (row, col) index pairs it occupies."""
+    nq = fm.n_qubits; k = int(fm.f_nq[f]); ds = 4 ** k
+    small = fm.mats[fm.f_moff[f]:fm.f_moff[f] + ds * ds].reshape(ds, ds)
+    shifts = [2 * (nq - 1 - int(q)) for q in fm.f_targets[f, :k]]
+    idx = np.arange(d)
+    tmask = 0
+    for s in shifts:
+        tmask |= 3 << s
+    t = np.zeros(d, dtype=np.int64)
+    for s in shifts:
+        t = (t << 2) | ((idx >> s) & 3)
+    rest = idx & ~tmask
+    F = np.zeros((d, d))
+    for i in range(d):
+        for j in range(d):
+            if rest[i] == rest[j]:
+                F[i, j] = small[t[i], t[j]]
+    return F, t, rest
+
+
+def w_matrix_factored(t, fm):
+    """Wf[el, w] = d p_el / d (factor-space element w), w over [fm.mats | rho | E]: for a factor F = embed(g) between the
+    forward state s (before it) and the backward vector e (after it), d p / d g[a][b] = sum_{i ~ a, j ~ b, rest(i) = rest(j)} e_i s_j."""
+    d = t.dim
+    n_mats = fm.mats.size
+    Wf = np.zeros((t.n_elements, n_mats + (t.n_rho + t.n_eff) * d))
+    off_rho = n_mats; off_eff = n_mats + t.n_rho * d
+    n_fac = fm.f_nq.shape[0]
+    emb = [_embed(fm, f, d) for f in range(n_fac)]
+    preps, seqs = expand_rows(t)
+    for k in range(t.row_dest.shape[0]):
+        steps = [f for g in seqs[k] for f in range(fm.op_fptr[g], fm.op_fptr[g + 1])]      # factors in order of application
+        s = [fm.rho[preps[k]]]
+        for f in steps:
+            s.append(emb[f][0] @ s[-1])
+        for j in range(t.out_ptr[k], t.out_ptr[k + 1]):
+            el = t.out_el[j]; ei = t.out_eff[j]
+            Wf[el, off_eff + ei * d: off_eff + (ei + 1) * d] += s[-1]
+            e = fm.E[ei].copy()
+            for m in range(len(steps) - 1, -1, -1):
+                f = steps[m]; F, tt, rest = emb[f]
+                ds = 4 ** int(fm.f_nq[f])
+                outer = np.outer(e, s[m]) * (rest[:, None] == rest[None, :])
+                blk = np.zeros((ds, ds))
+                np.add.at(blk, (tt[:, None].repeat(d, 1), tt[None, :].repeat(d, 0)), outer)
+                Wf[el, fm.f_moff[f]:fm.f_moff[f] + ds * ds] += blk.ravel()
+                e = F.T @ e
+            Wf[el, off_rho + preps[k] * d: off_rho + (preps[k] + 1) * d] += e
+    return Wf
+
+
+def dprobs_factored(t, fm, Df):
+    """J = Wf . Df   (chain rule through the entries of the small embedded operations)."""
+    return w_matrix_factored(t, fm) @ dense_D(Df)

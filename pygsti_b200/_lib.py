@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200_atom_set_model": (C.c_int, [vp, vp, vp, vp, vp]),
     "b200_atom_set_model_factored": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp, vp, C.c_int64, vp, vp]),
     "b200_atom_set_derivs": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, vp]),
+    "b200_atom_set_derivs_factored": (C.c_int, [vp, vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, vp]),
     "b200_atom_bind_params": (C.c_int, [vp, vp, C.c_int32, vp]),
     "b200_atom_set_params": (C.c_int, [vp, vp, C.c_int32, vp]),
     "b200_atom_set_params_dev": (C.c_int, [vp, vp, C.c_int32, vp]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200fwdsim.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "trie_host.h", "lindblad_core.h", "kernels_lindblad.cuh", "kernels_generic.cuh", "kernels_d16_trie.cuh", "kernels_jtj.cuh", "kernels_gemm.cuh", "kernels_factored.cuh", "kernels_ozaki.cuh", "kernels_levelj.cuh", "kernels_level.cuh", os.path.join("..", "..", "include", "b200_fwdsim.h")]
+HEADERS = ["common.cuh", "trie_host.h", "lindblad_core.h", "kernels_lindblad.cuh", "kernels_generic.cuh", "kernels_d16_trie.cuh", "kernels_jtj.cuh", "kernels_gemm.cuh", "kernels_factored.cuh", "kernels_factoredj.cuh", "kernels_ozaki.cuh", "kernels_levelj.cuh", "kernels_level.cuh", os.path.join("..", "..", "include", "b200_fwdsim.h")]
 
 
 def _nvcc():

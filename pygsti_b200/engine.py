@@ -198,6 +198,15 @@ class Atom:
                                                   int(rows.shape[0]), _ptr(rows), _ptr(cols), _ptr(vals)))
         self.n_params = int(D.n_params)
 
+    def set_derivs_factored(self, Df: DerivMap):
+        """Derivative map in factor space (``packing.pack_derivs_factored``) of the atom's factored model: the Jacobian of
+        d = 64 / 256 atoms is then evaluated from the factor programs themselves.  Call after ``set_model_factored`` and,
+        when a dense map of the same parameter block is also wanted (hprobs, FD mode), after ``set_derivs``."""
+        rows, cols, vals = _i32(Df.rows), _i32(Df.cols), _f64(Df.vals)
+        _lib.check(self._lib.b200_atom_set_derivs_factored(self.ctx._h, self._h, int(Df.n_w), int(Df.n_params),
+                                                           int(rows.shape[0]), _ptr(rows), _ptr(cols), _ptr(vals)))
+        self.n_params = int(Df.n_params)
+
     # ---- on-device model update for members affine in their parameters (SURVEY 8f rank 3) -------
     def bind_params(self, theta0):
         """Fix M_const = M - D theta0 from the model tensors on the device and the parameter vector they came from

@@ -32,6 +32,13 @@ class Case:
             es = z[pre + "element_slice"]
             self.atoms.append(dict(tables=t, G=z[pre + "G"], rho=z[pre + "rho"], E=z[pre + "E"], D=D,
                                    element_slice=slice(int(es[0]), int(es[1]))))
+            if pre + "F_op_fptr" in z:           # gates also as factor programs + the factor-space derivative map
+                from .packing import FactoredModel
+                self.atoms[-1]["fm"] = FactoredModel(n_qubits=int(z[pre + "F_n_qubits"]), op_fptr=z[pre + "F_op_fptr"], f_nq=z[pre + "F_nq"],
+                                                     f_targets=z[pre + "F_targets"], f_moff=z[pre + "F_moff"], mats=z[pre + "F_mats"],
+                                                     rho=z[pre + "rho"], E=z[pre + "E"])
+                self.atoms[-1]["Df"] = DerivMap(int(z[pre + "FD_shape"][0]), int(z[pre + "FD_shape"][1]),
+                                                z[pre + "FD_rows"], z[pre + "FD_cols"], z[pre + "FD_vals"])
 
     def hess_map(self, tag="H2", atom=0):
         """Second-derivative map stored by make_golden.py (`a<atom>_<tag>_*`): full Hessian ("H2") or rectangle i

@@ -472,7 +472,7 @@ def _flatten_factors(op, qubit_labels, out):
         k = len(targets)
         if k < 1 or k > 2 or small.shape != (4 ** k, 4 ** k) or len(set(targets)) != k:
             return False
-        out.append((targets, small))
+        out.append((targets, small, op.embedded_op))
         return True
     return False
 
@@ -497,7 +497,7 @@ def pack_model_factored(model, atom, dim):
         fac = []
         if not _flatten_factors(op, labels, fac):
             return None
-        for targets, small in fac:
+        for targets, small, _ in fac:
             f_nq.append(len(targets)); f_targets.append(list(targets) + [-1] * (4 - len(targets)))
             f_moff.append(off); mats.append(small.ravel()); off += small.size
         fptr.append(len(f_nq))
@@ -509,6 +509,56 @@ def pack_model_factored(model, atom, dim):
     return FactoredModel(n_qubits=nq, op_fptr=np.asarray(fptr, np.int32), f_nq=np.asarray(f_nq, np.int32),
                          f_targets=np.asarray(f_targets, np.int32).reshape(-1, 4), f_moff=np.asarray(f_moff, np.int64),
                          mats=(np.concatenate(mats) if mats else np.zeros(0)), rho=rho, E=E)
+
+
+def pack_derivs_factored(model, atom, dim, fm, param_indices=None):
+    """Derivative map in FACTOR space: rows index [fm.mats | rho | E] -- the entries of the small embedded operations themselves
+    (``embedded_op.deriv_wrt_params()``: 16 x 12 for a 1-qubit full TP gate) instead of the d^2 entries of every dense layer
+    operation -- for ``engine.Atom.set_derivs_factored`` (the Jacobian kernels of csrc/kernels_factoredj.cuh).  ``fm`` is the
+    FactoredModel of the same (model, atom).  None with a parameter interposer (the caller keeps the dense map)."""
+    if getattr(model, '_param_interposer', None) is not None or fm is None:
+        return None
+    ops, rhos, effs = _members(model, atom)
+    d = int(dim)
+    labels = list(model.state_space.sole_tensor_product_block_labels)
+    n_mats = int(fm.mats.size)
+    n_wf = n_mats + (len(rhos) + len(effs)) * d
+    n_model_params = int(model.num_params)
+    rows, cols, vals = [], [], []
+    f = 0
+    for op in ops:
+        fac = []
+        if not _flatten_factors(op, labels, fac):
+            return None
+        for targets, small, eop in fac:
+            gp = _gp_array(eop.gpindices)
+            if gp.size:
+                dM = np.asarray(eop.deriv_wrt_params(), dtype=np.float64).reshape(small.size, gp.size)
+                r, c = np.nonzero(dM)
+                rows.append(int(fm.f_moff[f]) + r); cols.append(gp[c]); vals.append(dM[r, c])
+            f += 1
+    off = n_mats
+    for group in (rhos, effs):
+        for m in group:
+            gp = _gp_array(m.gpindices)
+            if gp.size:
+                dM = np.asarray(m.deriv_wrt_params(), dtype=np.float64).reshape(d, gp.size)
+                r, c = np.nonzero(dM)
+                rows.append(off + r); cols.append(gp[c]); vals.append(dM[r, c])
+            off += d
+    if rows:
+        rows = np.concatenate(rows); cols = np.concatenate(cols); vals = np.concatenate(vals)
+    else:
+        rows = np.zeros(0, np.int64); cols = np.zeros(0, np.int64); vals = np.zeros(0, np.float64)
+    import scipy.sparse as sps
+    D = sps.coo_matrix((vals, (rows, cols)), shape=(n_wf, n_model_params)).tocsr()
+    pidx = param_slice_to_array(param_indices, n_model_params)
+    if not (pidx.size == n_model_params and np.array_equal(pidx, np.arange(n_model_params))):
+        D = D[:, pidx]
+    D = D.tocoo()
+    keep = D.data != 0.0
+    return DerivMap(n_w=n_wf, n_params=int(pidx.size), rows=D.row[keep].astype(np.int32), cols=D.col[keep].astype(np.int32),
+                    vals=D.data[keep].astype(np.float64))
 
 
 def factored_to_dense(fm, dim):

@@ -76,6 +76,14 @@ def build_case(name, model, circuits, num_atoms=None, want_hprobs=False, want_ma
         out[pre + "D_shape"] = np.array([D.n_w, D.n_params])
         es = atom.element_slice
         out[pre + "element_slice"] = np.array([es.start, es.stop])
+        fm = packing.pack_model_factored(mdl, atom, d) if d >= 64 else None
+        if fm is not None:                # layer operations = products of embedded 1-2 qubit operations: factor programs + factor-space D
+            Df = packing.pack_derivs_factored(mdl, atom, d, fm)
+            assert np.max(np.abs(packing.factored_to_dense(fm, d) - mt.G)) < 1e-13
+            out[pre + "F_n_qubits"] = np.array(fm.n_qubits); out[pre + "F_op_fptr"] = fm.op_fptr; out[pre + "F_nq"] = fm.f_nq
+            out[pre + "F_targets"] = fm.f_targets; out[pre + "F_moff"] = fm.f_moff; out[pre + "F_mats"] = fm.mats
+            out[pre + "FD_rows"] = Df.rows; out[pre + "FD_cols"] = Df.cols; out[pre + "FD_vals"] = Df.vals
+            out[pre + "FD_shape"] = np.array([Df.n_w, Df.n_params])
         for tag, (sl1, sl2) in ([("H2", (None, None))] if want_hprobs else []) + \
                 [("H2r%d" % i, r) for i, r in enumerate(hess_rects or [])]:
             H2 = packing.pack_hessians(mdl, atom, d, sl1, sl2)

@@ -370,3 +370,27 @@ def test_jtj_tcgen05_full_size_vs_fp64(gpu_ctx, load_case):
     for mode, tol in ((0, 1e-13), (8, 1e-13), (7, 1e-12)):
         assert np.max(np.abs(res[mode][0][cols] - ref)) <= tol * sc, mode
     at.free()
+
+
+def test_factored_jacobian_golden_c3(gpu_ctx, load_case):
+    """BASELINE config 3's model family (3-qubit crosstalk-free full TP model, d = 64, Np = 775): the reference holds its layers as
+    EmbeddedOps; the engine takes the same factors + the factor-space derivative map (packing.pack_derivs_factored) and must
+    reproduce the reference's Matrix simulator -- with only the factor-space map set, and with both maps set (then the factored
+    kernels run and the dense map stays available to the Hessian paths)."""
+    c = load_case("c3_3q_localnoise_sub")
+    a = c.atoms[0]
+    assert "fm" in a and "Df" in a
+    ref = c["dprobs_matrix"]
+    for both in (False, True):
+        at = gpu_ctx.upload_atom(a["tables"])
+        at.set_model_factored(a["fm"])
+        if both:
+            at.set_derivs(a["D"])
+        at.set_derivs_factored(a["Df"])
+        n0 = gpu_ctx.launch_count
+        J = np.full((c.n_elements, c.num_params), np.nan); p = np.full(c.n_elements, np.nan)
+        at.fill_dprobs(J, p)
+        assert gpu_ctx.launch_count - n0 == 2          # k_fj_forward + k_fj_backward: the factored path ran
+        assert np.max(np.abs(p - c["probs_matrix"])) <= 1e-12
+        assert np.max(np.abs(J - ref)) <= 1e-10 * max(1.0, np.max(np.abs(ref)))
+        at.free()

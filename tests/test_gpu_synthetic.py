@@ -352,3 +352,54 @@ def test_factored_model_embedded_composed(gpu_ctx, dim, n_ops):
     Jo = onp.dprobs_analytic(t, G, rho, E, D)
     assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
     at.free()
+
+
+def _random_factored(dim, n_ops, rng, share=False):
+    from pygsti_b200.packing import FactoredModel
+    nq = {64: 3, 256: 4}[dim]
+    fptr, f_nq, f_t, f_off, mats, off = [0], [], [], [], [], 0
+    for g in range(n_ops):
+        for _ in range(int(rng.integers(0 if g == 0 else 1, 3))):
+            k = int(rng.integers(1, 3))
+            tg = [int(x) for x in rng.choice(nq, size=k, replace=False)]
+            small = np.eye(4 ** k) * 0.8 + 0.3 * rng.standard_normal((4 ** k, 4 ** k)) / 2 ** k
+            if share and f_nq and k == f_nq[0]:                 # this factor re-uses the first factor's matrix (one gate on another qubit)
+                f_nq.append(k); f_t.append(tg + [-1] * (4 - k)); f_off.append(f_off[0])
+                continue
+            f_nq.append(k); f_t.append(tg + [-1] * (4 - k)); f_off.append(off); mats.append(small.ravel()); off += small.size
+        fptr.append(len(f_nq))
+    n_eff = 8
+    rho = rng.standard_normal((2, dim)) / np.sqrt(dim); E = rng.standard_normal((n_eff, dim)) / np.sqrt(dim)
+    return FactoredModel(n_qubits=nq, op_fptr=np.asarray(fptr, np.int32), f_nq=np.asarray(f_nq, np.int32),
+                         f_targets=np.asarray(f_t, np.int32).reshape(-1, 4), f_moff=np.asarray(f_off, np.int64),
+                         mats=np.concatenate(mats), rho=rho, E=E)
+
+
+@pytest.mark.parametrize("dim,n_ops,share", [(64, 7, False), (64, 6, True), (256, 6, False)])
+def test_factored_jacobian_matches_oracle(gpu_ctx, dim, n_ops, share):
+    """The Jacobian straight from the factor programs (b200_atom_set_derivs_factored, kernels_factoredj.cuh: forward states per
+    factor step, backward walk with DMMA chain + accumulate, CSC contraction over factor-space elements) against the numpy
+    restatement (oracle_np.dprobs_factored) on random factor programs: 1- and 2-qubit factors on any qubits in any order, empty
+    products, several factors per layer, shared matrices, a random sparse factor-space map; row scale; probabilities."""
+    from pygsti_b200.packing import DerivMap
+    rng = np.random.default_rng(dim + n_ops)
+    fm = _random_factored(dim, n_ops, rng, share)
+    n_eff = fm.E.shape[0]
+    circs = synth.random_circuits(24, 20, n_ops, 2, n_eff, seed=4)
+    t = synth.make_tables(dim, n_ops, 2, n_eff, circs)
+    n_wf = fm.mats.size + (2 + n_eff) * dim
+    Np = 150
+    nnz = 4000
+    Df = DerivMap(n_wf, Np, rng.integers(0, n_wf, nnz), rng.integers(0, Np, nnz), rng.standard_normal(nnz))
+    at = gpu_ctx.upload_atom(t); at.set_model_factored(fm); at.set_derivs_factored(Df)
+    J = np.full((t.n_elements, Np), np.nan); p = np.full(t.n_elements, np.nan)
+    at.fill_dprobs(J, p)
+    Jo = onp.dprobs_factored(t, fm, Df)
+    from pygsti_b200.packing import factored_to_dense
+    po = onp.mapfill_probs(t, factored_to_dense(fm, dim), fm.rho, fm.E)
+    assert np.max(np.abs(p - po)) <= 1e-12 * max(1.0, np.max(np.abs(po)))
+    assert np.max(np.abs(J - Jo)) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    w = rng.uniform(-2, 2, t.n_elements)
+    Js = np.full((t.n_elements, Np), np.nan); at.fill_dprobs(Js, row_scale=w)
+    assert np.max(np.abs(Js - Jo * w[:, None])) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
+    at.free()

@@ -41,6 +41,19 @@ elif what == "c3":
     import torch
     J = torch.empty((t.n_elements, a["D"].n_params), dtype=torch.float64, device="cuda")
     print("c3 x%d dprobs ms:" % n, wall(lambda: at.fill_dprobs_dev(J.data_ptr(), a["D"].n_params)))
+elif what == "c3f":            # config 3 through the factor programs (kernels_factoredj.cuh) vs the dense level-batched path
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+    c = fx.Case("c3_3q_localnoise_sub"); a = c.atoms[0]
+    t, _ = fx.random_layout(64, a["tables"].n_ops, a["tables"].n_eff, 50000, 256, seed=0, rows=(0, n))
+    Np = a["D"].n_params
+    import torch
+    at = ctx.upload_atom(t); at.set_model_factored(a["fm"]); at.set_derivs(a["D"])
+    Jd = torch.empty((t.n_elements, Np), dtype=torch.float64, device="cuda"); Pd = torch.empty(t.n_elements, dtype=torch.float64, device="cuda")
+    print("c3 x%d dense level path ms:" % n, wall(lambda: at.fill_dprobs_dev(Jd.data_ptr(), Np, Pd.data_ptr())))
+    at.set_derivs_factored(a["Df"])
+    Jf = torch.empty_like(Jd); Pf = torch.empty_like(Pd)
+    print("c3 x%d factored path ms:" % n, wall(lambda: at.fill_dprobs_dev(Jf.data_ptr(), Np, Pf.data_ptr())))
+    print("   max |J_f - J_dense| = %.3e (max |J| %.3e), max |p_f - p_dense| = %.3e" % (float((Jf - Jd).abs().max()), float(Jd.abs().max()), float((Pf - Pd).abs().max())))
 elif what == "c5":
     G, rho, E = fx.random_dense_model(256, 14, 1, 16, seed=1)
     t, _ = fx.random_layout(256, 14, 16, 5000, 128, seed=0)
