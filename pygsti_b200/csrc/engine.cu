@@ -121,7 +121,7 @@ struct b200_atom {
     // factor-space derivative map (b200_atom_set_derivs_factored): the Jacobian straight from the factor programs (kernels_factoredj.cuh)
     bool has_fderivs = false; int32_t fj_n_params = 0; int fj_n_acc = 0, fj_n_frag = 0; uint64_t fj_rows = 0;
     std::vector<FactorRec> fj_fac;                                 // the factor structure the map was built for
-    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval;
+    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval, fj_slots; int fj_slot_fao[FJ64_REG_SLOTS] = {-1, -1, -1, -1};
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -726,7 +726,7 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
     for (int f = 0; f < n_fac; ++f) {
         const FactorRec& r = a->h_fac[f];
         const int ds2 = r.nq == 2 ? 256 : 16;
-        fao[f] = n_acc; ffo[f] = n_frag; n_acc += ds2; n_frag += r.nq == 2 ? 256 : 32;
+        fao[f] = n_acc; ffo[f] = n_frag; n_acc += (r.nq == 1 && d == 64) ? 32 : ds2; n_frag += r.nq == 2 ? 256 : 32;
         const int head = first[r.moff];
         if (head >= 0 && (a->h_fac[head].nq != r.nq)) return fail(B200_E_UNSUPPORTED, "factors of different size share a matrix");
         for (int i = 0; i < ds2; ++i) {
@@ -735,9 +735,19 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
         next[f] = head;
         for (int i = 0; i < ds2; ++i) first[r.moff + i] = f;
     }
+    if (n_acc >= (1 << 16) || n_frag >= (1 << 16)) return fail(B200_E_UNSUPPORTED, "factor programs too large for the factored Jacobian");
+    // d = 64: the accumulators of the first FJ64_REG_SLOTS two-qubit factors live in registers; a 1-qubit factor keeps two partial
+    // 4 x 4 blocks (one per half of the rest index) that the contraction adds
+    std::vector<int32_t> slots((size_t)std::max(n_fac, 1), 0xFF);
+    for (int s2 = 0; s2 < FJ64_REG_SLOTS; ++s2) a->fj_slot_fao[s2] = -1;
+    if (d == 64) {
+        int ns = 0;
+        for (int f = 0; f < n_fac && ns < FJ64_REG_SLOTS; ++f) if (a->h_fac[f].nq == 2) { slots[f] = ns; a->fj_slot_fao[ns] = fao[f]; ++ns; }
+    }
+    const int dup1 = d == 64 ? 2 : 1;
     // CSC with element codes
     std::vector<int32_t> cptr((size_t)n_params + 1, 0);
-    auto n_owner = [&](int64_t w) { int n = 0; for (int f = first[w]; f >= 0; f = next[f]) ++n; return n; };
+    auto n_owner = [&](int64_t w) { int n = 0; for (int f = first[w]; f >= 0; f = next[f]) n += a->h_fac[f].nq == 1 ? dup1 : 1; return n; };
     for (int64_t t = 0; t < nnz; ++t) {
         const int64_t w = rows[t]; const int p = cols[t];
         if (w < 0 || w >= n_wf || p < 0 || p >= n_params) return fail(B200_E_INVALID, "entry %lld out of range", (long long)t);
@@ -755,7 +765,10 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
                 const int e = (int)(w - r.moff);
                 uint32_t code;
                 if (r.nq == 2) { const int ra = e >> 4, cb = e & 15; code = (uint32_t)(fao[f] + ((((ra >> 3) * 2 + (cb >> 3)) * 32 + (((ra & 7) << 2) | ((cb & 7) >> 1))) * 2) + (cb & 1)); }
-                else code = (uint32_t)(fao[f] + e);
+                else {
+                    code = (uint32_t)(fao[f] + e);
+                    if (dup1 == 2) { ccode[fill[p]] = code + 16u; cval[fill[p]++] = vals[t]; }
+                }
                 ccode[fill[p]] = code; cval[fill[p]++] = vals[t];
             }
         } else {
@@ -768,7 +781,7 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
     }
     CU(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = upload_vec(a->fj_fao, fao, ctx->stream)) || (rc = upload_vec(a->fj_ffo, ffo, ctx->stream)) ||
+    if ((rc = upload_vec(a->fj_fao, fao, ctx->stream)) || (rc = upload_vec(a->fj_ffo, ffo, ctx->stream)) || (rc = upload_vec(a->fj_slots, slots, ctx->stream)) ||
         (rc = upload_vec(a->fj_cptr, cptr, ctx->stream)) || (rc = upload_vec(a->fj_ccode, ccode, ctx->stream)) ||
         (rc = upload_vec(a->fj_cval, cval, ctx->stream))) return rc;
     // rows of the forward-state table: one per factor step of every circuit + the initial state
@@ -1541,6 +1554,8 @@ struct PeerSpec { int n = 0; double* J[B200_PEERS_MAX]; double* P[B200_PEERS_MAX
 // factored Jacobian (gates as factor programs + factor-space derivative map): kernels_factoredj.cuh
 // ------------------------------------------------------------------------------------------------
 static size_t fj_smem(b200_atom* a, int warps) {
+    if (a->dim == 64)        // k_fj64_backward: fragment image | index table | fptr | per warp: 3 vectors + accumulators
+        return (size_t)((a->fj_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * 32 * 16 + ((size_t)a->n_ops + 1) * 4 + 16 + (size_t)warps * (3 * 64 + (size_t)a->fj_n_acc) * 8;
     return (size_t)((a->fj_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * sizeof(FactorRec) + ((size_t)a->n_ops + 1 + 2 * (size_t)a->fac_n) * 4 + 16 +
            (size_t)warps * (3 * (size_t)a->dim + a->fj_n_acc) * 8;
 }
@@ -1559,7 +1574,16 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
     CU(c->fj_counter.ensure(16));
     const FactoredDev fd = factored_dev(a);
     const double* M = a->M.as<double>();
-    {
+    FjDev fj;
+    fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
+    fj.n_acc = a->fj_n_acc; fj.n_frag = a->fj_n_frag; fj.cptr = a->fj_cptr.as<int32_t>(); fj.ccode = a->fj_ccode.as<uint32_t>(); fj.cval = a->fj_cval.as<double>();
+    fj.n_params = a->fj_n_params;
+    if (D == 64) {
+        const size_t smem = (size_t)((a->fj_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * 32 * 16 + ((size_t)a->n_ops + 1) * 4 + 16 + (size_t)8 * 2 * 64 * 8;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 7) / 8, (int64_t)c->sm_count * 6));
+        CU(cudaFuncSetAttribute(k_fj64_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fj64_forward<<<grid, 256, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_rho, M + a->off_eff, c->fj_fs.as<double>(), d_probs);
+    } else {
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 4));
         const size_t smem = (size_t)FAC_WARPS * 2 * D * 8 + ((size_t)((a->fac_n_mats + 1) & ~1)) * 8 + (size_t)a->fac_n * sizeof(FactorRec) + ((size_t)a->n_ops + 1) * 4;
         CU(cudaFuncSetAttribute(k_fj_forward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1567,18 +1591,21 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
                                                                 c->fj_fs.as<double>(), d_probs);
     }
     CU(cudaMemsetAsync(c->fj_counter.p, 0, 4, c->stream));
-    FjDev fj;
-    fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
-    fj.n_acc = a->fj_n_acc; fj.n_frag = a->fj_n_frag; fj.cptr = a->fj_cptr.as<int32_t>(); fj.ccode = a->fj_ccode.as<uint32_t>(); fj.cval = a->fj_cval.as<double>();
-    fj.n_params = a->fj_n_params;
     const int warps = fj_warps(c, a);
     const size_t smem = fj_smem(a, warps);
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)227 * 1024) / (smem + 1024)));
     const int64_t n_items = a->n_elements;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_items + warps - 1) / warps, (int64_t)c->sm_count * per_sm));
-    CU(cudaFuncSetAttribute(k_fj_backward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_fj_backward<D><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_eff, c->fj_fs.as<double>(), d_out, ld, d_scale,
-                                                         c->fj_counter.as<unsigned>(), (int)n_items);
+    if (D == 64) {
+        Fj64Slots sl; for (int q = 0; q < FJ64_REG_SLOTS; ++q) sl.fao[q] = a->fj_slot_fao[q];
+        CU(cudaFuncSetAttribute(k_fj64_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fj64_backward<<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, a->fj_slots.as<int32_t>(), sl, M + a->off_eff, c->fj_fs.as<double>(),
+                                                             d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items);
+    } else {
+        CU(cudaFuncSetAttribute(k_fj_backward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fj_backward<D><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_eff, c->fj_fs.as<double>(), d_out, ld, d_scale,
+                                                             c->fj_counter.as<unsigned>(), (int)n_items);
+    }
     c->launches += 2;
     CU(cudaGetLastError());
     return B200_OK;

@@ -122,7 +122,7 @@ k_fj_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __re
     int* fptr = reinterpret_cast<int*>(recs + n_fac);
     int* fao = fptr + (a.n_ops + 1);
     int* ffo = fao + n_fac;
-    double* wbase = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ffo + n_fac) + 15) & ~(uintptr_t)15) + (size_t)warp * (3 * D + fj.n_acc);
+    double* wbase = smj + (((fj.n_frag + 1) & ~1) + n_fac * 2 + ((a.n_ops + 1 + 2 * n_fac + 3) >> 2) * 2) + warp * (3 * D + fj.n_acc);   // (offsets from smj keep the shared address space)
     double* eb0 = wbase; double* eb1 = wbase + D; double* sb = wbase + 2 * D; double* acc = wbase + 3 * D;
 
     for (int i = threadIdx.x; i < n_fac; i += blockDim.x) { recs[i] = fd.fac[i]; fao[i] = fj.fao[i]; ffo[i] = fj.ffo[i]; }
@@ -246,6 +246,273 @@ k_fj_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __re
         }
         // ---- epilogue: cur = e_0 (-> rho block), s_L (-> effect block), accumulators (-> factor blocks) ----
         for (int i = lane; i < D; i += 32) sb[fj_sw((unsigned)i)] = __ldg(srow + (size_t)(fj.base[c + 1] - row0 - 1) * D + i);
+        __syncwarp();
+        const int prep = a.circ_prep[c];
+        const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
+        double* Jrow = J + el * ld;
+        for (int p = lane; p < Np; p += 32) {
+            double v = 0.0;
+            const int t1 = __ldg(fj.cptr + p + 1);
+            for (int q = __ldg(fj.cptr + p); q < t1; ++q) {
+                const uint32_t code = __ldg(fj.ccode + q);
+                const double val = __ldg(fj.cval + q);
+                const uint32_t kind = code >> 30;
+                double x;
+                if (kind == 0u) x = acc[code];
+                else {
+                    const int i = (int)((code >> 16) & 0x3FFFu); const unsigned idx = fj_sw(code & 0xFFFFu);
+                    x = (kind == 1u) ? (i == prep ? cur[idx] : 0.0) : (i == eff ? sb[idx] : 0.0);
+                }
+                v = fma(val, x, v);
+            }
+            Jrow[p] = v * sc;
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================================
+// d = 64 (3 qubits) specialisation.  ncu on the generic backward kernel at BASELINE config 3: 265 issued instructions per factor
+// step, 54 % issue-active, DMMA 27 % -- the lane -> state-index arithmetic (two digit insertions + swizzle per fragment element,
+// ~14 elements per step) was the kernel.  Those indices depend only on (factor, lane), so each CTA builds them ONCE into a
+// shared-memory table: one 16-byte entry per (factor, lane) = the 10 state indices of a step as bytes + the factor's metadata.
+// The accumulators of up to 4 two-qubit factors live in REGISTERS (a warp-uniform switch selects the set), which removes the
+// 16-byte read-modify-write per tile and step that made up half of the shared-memory wavefronts; a 1-qubit accumulate splits
+// the 16 rest values over the two row halves of the 8 x 8 tile (2 DMMA instead of 4, the two diagonal 4 x 4 blocks are summed
+// in the epilogue).  The forward kernel runs the same DMMA chain with the F fragments (the scalar factor application was
+// shared-memory bound: 97 % L1 pipe).
+// =====================================================================================================================
+#define FJ64_REG_SLOTS 4
+
+struct Fj64Tab { uint4* tab; double* frag; };
+
+// table entry of (factor f, lane): x, y, z = indices ix0..ix9 as bytes, z byte 2 = nq, z byte 3 = register slot (0xFF: shared memory),
+// w = accumulator offset | fragment offset << 16
+__device__ __forceinline__ uint4 fj64_entry(const FactorRec fr, int fao, int ffo, int slot, unsigned lg, unsigned lt)
+{
+    unsigned ix[10];
+    if (fr.nq == 2) {
+        const int s0 = fr.shift[0], s1 = fr.shift[1];
+        const int lo = s0 < s1 ? s0 : s1, hi = s0 < s1 ? s1 : s0;
+        ix[0] = fj_idx2(lg, lt, lo, hi, s0, s1); ix[1] = fj_idx2(lg + 8u, lt, lo, hi, s0, s1);
+        for (unsigned kk = 0; kk < 4; ++kk) ix[2 + kk] = fj_idx2(4u * kk + lt, lg & 3u, lo, hi, s0, s1);
+        const unsigned r = 2u * (lt & 1u);
+        ix[6] = fj_idx2(lg, r, lo, hi, s0, s1); ix[7] = fj_idx2(lg, r + 1u, lo, hi, s0, s1);
+        ix[8] = fj_idx2(lg + 8u, r, lo, hi, s0, s1); ix[9] = fj_idx2(lg + 8u, r + 1u, lo, hi, s0, s1);
+    } else {
+        const int sh = fr.shift[0];
+        ix[0] = fj_idx1(lg & 3u, (lg >> 2) * 8u + lt, sh); ix[1] = fj_idx1(lg & 3u, (lg >> 2) * 8u + 4u + lt, sh);
+        ix[2] = ix[3] = 0u;
+        ix[4] = fj_idx1(lt, lg, sh); ix[5] = fj_idx1(lt, 8u + lg, sh);
+        ix[6] = fj_idx1(lg & 3u, 2u * lt, sh); ix[7] = fj_idx1(lg & 3u, 2u * lt + 1u, sh);
+        ix[8] = fj_idx1(lg & 3u, 8u + 2u * lt, sh); ix[9] = fj_idx1(lg & 3u, 9u + 2u * lt, sh);
+    }
+    uint4 e;
+    e.x = ix[0] | (ix[1] << 8) | (ix[2] << 16) | (ix[3] << 24);
+    e.y = ix[4] | (ix[5] << 8) | (ix[6] << 16) | (ix[7] << 24);
+    e.z = ix[8] | (ix[9] << 8) | ((unsigned)fr.nq << 16) | ((unsigned)(slot & 0xFF) << 24);
+    e.w = (unsigned)fao | ((unsigned)ffo << 16);
+    return e;
+}
+
+// chain step through one factor: nxt = (fragment matrix) cur.  fg = this lane's fragments of the factor (F for the forward, F^T
+// for the backward direction): 2 qubits: fg[q * 32], q = mt * 4 + kk; 1 qubit: fg[0].  cur / nxt are addressed as wb[offset + index]
+// with integer offsets: swapping POINTERS made the compiler fall back to generic-space loads and stores (LD.E / ST.E with 64-bit
+// address arithmetic) instead of LDS / STS.
+__device__ __forceinline__ void fj64_chain(const uint4 tb, const double* fg, double* wb, int cur_o, int nxt_o, unsigned lg, unsigned lt)
+{
+    const double* cur = wb + cur_o; double* nxt = wb + nxt_o;
+    if (((tb.z >> 16) & 0xFFu) == 2u) {
+        double2 o0 = make_double2(0.0, 0.0), o1 = make_double2(0.0, 0.0);
+        const double b0 = cur[(tb.x >> 16) & 0xFFu], b1 = cur[tb.x >> 24], b2 = cur[tb.y & 0xFFu], b3 = cur[(tb.y >> 8) & 0xFFu];
+        dmma884(o0.x, o0.y, fg[0 * 32], b0); dmma884(o1.x, o1.y, fg[4 * 32], b0);
+        dmma884(o0.x, o0.y, fg[1 * 32], b1); dmma884(o1.x, o1.y, fg[5 * 32], b1);
+        dmma884(o0.x, o0.y, fg[2 * 32], b2); dmma884(o1.x, o1.y, fg[6 * 32], b2);
+        dmma884(o0.x, o0.y, fg[3 * 32], b3); dmma884(o1.x, o1.y, fg[7 * 32], b3);
+        if (lt < 2u) {
+            nxt[(tb.y >> 16) & 0xFFu] = o0.x; nxt[tb.y >> 24] = o0.y;
+            nxt[tb.z & 0xFFu] = o1.x; nxt[(tb.z >> 8) & 0xFFu] = o1.y;
+        }
+    } else {
+        const double A = fg[0];
+        double2 o0 = make_double2(0.0, 0.0), o1 = make_double2(0.0, 0.0);
+        dmma884(o0.x, o0.y, A, cur[tb.y & 0xFFu]);
+        dmma884(o1.x, o1.y, A, cur[(tb.y >> 8) & 0xFFu]);
+        if (lg < 4u) {
+            nxt[(tb.y >> 16) & 0xFFu] = o0.x; nxt[tb.y >> 24] = o0.y;
+            nxt[tb.z & 0xFFu] = o1.x; nxt[(tb.z >> 8) & 0xFFu] = o1.y;
+        }
+    }
+}
+
+// shared-memory prologue common to both kernels: fragment image (transposed or not), index table, op -> factor ranges
+template <bool TRANSPOSED>
+__device__ __forceinline__ void fj64_stage(const AtomDev& a, const FactoredDev& fd, const FjDev& fj, int n_fac, const int32_t* __restrict__ slots,
+                                           double* frag, uint4* tab, int* fptr)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const unsigned lg = (unsigned)lane >> 2, lt = (unsigned)lane & 3u;
+    for (int i = threadIdx.x; i <= a.n_ops; i += blockDim.x) fptr[i] = fd.op_fptr[i];
+    for (int f = warp; f < n_fac; f += n_warps) {
+        const FactorRec fr = fd.fac[f];
+        const double* m = fd.mats + fr.moff;
+        double* dst = frag + fj.ffo[f];
+        if (fr.nq == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {                         // q = mt * 4 + kk: A[row = 8 mt + lg][col = 4 kk + lt]
+                const int r = 8 * (q >> 2) + (int)lg, cc = 4 * (q & 3) + (int)lt;
+                dst[q * 32 + lane] = TRANSPOSED ? m[cc * 16 + r] : m[r * 16 + cc];
+            }
+        } else {
+            dst[lane] = TRANSPOSED ? m[(int)lt * 4 + (int)(lg & 3u)] : m[(int)(lg & 3u) * 4 + (int)lt];
+        }
+        tab[f * 32 + lane] = fj64_entry(fr, fj.fao[f], fj.ffo[f], slots ? slots[f] : 0xFF, lg, lt);
+    }
+    __syncthreads();
+}
+
+// One warp per circuit.  Shared memory: fragment image [n_frag] | table [n_fac][32] uint4 | fptr [n_ops + 1] | per warp: 2 x 64 doubles.
+__global__ void __launch_bounds__(256)
+k_fj64_forward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __restrict__ rho, const double* __restrict__ E,
+               double* __restrict__ FS, double* __restrict__ probs)
+{
+    constexpr int D = 64;
+    extern __shared__ __align__(16) double smj[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const unsigned lg = (unsigned)lane >> 2, lt = (unsigned)lane & 3u;
+    double* frag = smj;
+    uint4* tab = reinterpret_cast<uint4*>(frag + ((fj.n_frag + 1) & ~1));
+    int* fptr = reinterpret_cast<int*>(tab + (size_t)n_fac * 32);
+    double* wbase = smj + (((fj.n_frag + 1) & ~1) + n_fac * 64 + ((a.n_ops + 4) >> 2) * 2) + warp * 2 * D;     // (plain offsets from smj: keeps the shared address space)
+    fj64_stage<false>(a, fd, fj, n_fac, nullptr, frag, tab, fptr);
+    const unsigned i0 = fj_sw((unsigned)lane), i1 = fj_sw((unsigned)lane + 32u);
+    const int gw = blockIdx.x * n_warps + warp, nw = gridDim.x * n_warps;
+    for (int c = gw; c < a.n_circ; c += nw) {
+        const uint32_t p0 = a.circ_ptr[c], L = a.circ_ptr[c + 1] - p0;
+        const double* r = rho + (size_t)a.circ_prep[c] * D;
+        int cur_o = 0;
+        double* row = FS + (size_t)fj.base[c] * D;
+        { const double v0 = __ldg(r + lane), v1 = __ldg(r + lane + 32); wbase[i0] = v0; wbase[i1] = v1; row[lane] = v0; row[lane + 32] = v1; }
+        __syncwarp();
+        int gch = 0;
+        for (uint32_t k = 0; k < L; ++k) {
+            if ((k & 31u) == 0u) gch = (k + lane < L) ? __ldg(a.circ_ops + p0 + k + lane) : 0;      // 32 gate indices per load
+            const int g = __shfl_sync(0xffffffffu, gch, (int)(k & 31u));
+            const int f1 = fptr[g + 1];
+            for (int f = fptr[g]; f < f1; ++f) {
+                const uint4 tb = tab[f * 32 + lane];
+                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, cur_o, cur_o ^ D, lg, lt);
+                __syncwarp();
+                cur_o ^= D;
+                row += D;
+                row[lane] = wbase[cur_o + i0]; row[lane + 32] = wbase[cur_o + i1];
+            }
+        }
+        if (probs) {
+            for (int qo = a.out_ptr[c]; qo < a.out_ptr[c + 1]; ++qo) {
+                const double* e = E + (size_t)a.out_eff[qo] * D;
+                double part = fma(__ldg(e + lane), wbase[cur_o + i0], __ldg(e + lane + 32) * wbase[cur_o + i1]);
+#pragma unroll
+                for (int mk = 16; mk > 0; mk >>= 1) part += shfl_xor_f64(part, mk);
+                if (lane == 0) probs[a.out_el[qo]] = part;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+#define FJ64_ACC4(C, a0, a1, q0, q1) { dmma884(C[0].x, C[0].y, a0, q0); dmma884(C[1].x, C[1].y, a0, q1); \
+                                       dmma884(C[2].x, C[2].y, a1, q0); dmma884(C[3].x, C[3].y, a1, q1); }
+
+// One warp per (circuit, outcome).  Shared memory: F^T fragment image | table | fptr | per warp: e0, e1, s (64 doubles each), accumulators.
+// slots[f]: register slot of a 2-qubit factor (0 .. FJ64_REG_SLOTS-1) or 0xFF; slot_fao[s]: accumulator offset of slot s or -1.
+struct Fj64Slots { int fao[FJ64_REG_SLOTS]; };
+__global__ void __launch_bounds__(256)
+k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* __restrict__ slots, Fj64Slots sl, const double* __restrict__ E,
+                const double* __restrict__ FS, double* __restrict__ J, int64_t ld, const double* __restrict__ row_scale,
+                unsigned* __restrict__ counter, int n_items)
+{
+    constexpr int D = 64;
+    extern __shared__ __align__(16) double smj[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lg = (unsigned)lane >> 2, lt = (unsigned)lane & 3u;
+    double* frag = smj;
+    uint4* tab = reinterpret_cast<uint4*>(frag + ((fj.n_frag + 1) & ~1));
+    int* fptr = reinterpret_cast<int*>(tab + (size_t)n_fac * 32);
+    double* wbase = smj + (((fj.n_frag + 1) & ~1) + n_fac * 64 + ((a.n_ops + 4) >> 2) * 2) + warp * (3 * D + fj.n_acc);
+    double* sb = wbase + 2 * D; double* acc = wbase + 3 * D;       // wbase: e ping-pong at offsets 0 / 64
+    fj64_stage<true>(a, fd, fj, n_fac, slots, frag, tab, fptr);
+    const unsigned i0 = fj_sw((unsigned)lane), i1 = fj_sw((unsigned)lane + 32u);
+    const int Np = fj.n_params;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int c = fj.out_circ[item];
+        const uint32_t p0 = a.circ_ptr[c];
+        const int L = (int)(a.circ_ptr[c + 1] - p0);
+        const uint32_t row0 = fj.base[c];
+        const uint32_t nst = fj.base[c + 1] - row0 - 1;            // factor steps of the circuit
+        uint32_t t = nst;
+        const int eff = a.out_eff[item];
+        const int64_t el = a.out_el[item];
+        const double* srow = FS + (size_t)row0 * D;
+        int cur_o = 0;
+        for (int i = lane; i < fj.n_acc; i += 32) acc[i] = 0.0;
+        wbase[i0] = __ldg(E + (size_t)eff * D + lane); wbase[i1] = __ldg(E + (size_t)eff * D + lane + 32);
+        double2 R0[4], R1[4], R2[4], R3[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) R0[q] = R1[q] = R2[q] = R3[q] = make_double2(0.0, 0.0);
+        double sr0 = 0.0, sr1 = 0.0;
+        if (t > 0) { sr0 = __ldg(srow + (size_t)(t - 1) * D + lane); sr1 = __ldg(srow + (size_t)(t - 1) * D + lane + 32); }
+        __syncwarp();
+        int gch = 0;
+        for (int k = L - 1; k >= 0; --k) {
+            if ((k & 31) == 31 || k == L - 1) { const int kk0 = k & ~31; gch = (kk0 + lane < L) ? __ldg(a.circ_ops + p0 + kk0 + lane) : 0; }   // 32 gate indices per load
+            const int g = __shfl_sync(0xffffffffu, gch, k & 31);
+            const int f0 = fptr[g];
+            for (int f = fptr[g + 1] - 1; f >= f0; --f) {
+                --t;                                               // this step: factor f between s_t (before) and e (after)
+                sb[i0] = sr0; sb[i1] = sr1;
+                __syncwarp();
+                if (t > 0) { sr0 = __ldg(srow + (size_t)(t - 1) * D + lane); sr1 = __ldg(srow + (size_t)(t - 1) * D + lane + 32); }
+                const uint4 tb = tab[f * 32 + lane];
+                const unsigned j0 = tb.x & 0xFFu, j1 = (tb.x >> 8) & 0xFFu;
+                const double a0 = wbase[cur_o + j0], a1 = wbase[cur_o + j1], q0 = sb[j0], q1 = sb[j1];
+                if (((tb.z >> 16) & 0xFFu) == 2u) {
+                    switch (tb.z >> 24) {
+                    case 0: FJ64_ACC4(R0, a0, a1, q0, q1); break;
+                    case 1: FJ64_ACC4(R1, a0, a1, q0, q1); break;
+                    case 2: FJ64_ACC4(R2, a0, a1, q0, q1); break;
+                    case 3: FJ64_ACC4(R3, a0, a1, q0, q1); break;
+                    default: {
+                        double2* ap = reinterpret_cast<double2*>(acc + (tb.w & 0xFFFFu)) + lane;
+                        double2 C[4] = {ap[0], ap[32], ap[64], ap[96]};
+                        FJ64_ACC4(C, a0, a1, q0, q1);
+                        ap[0] = C[0]; ap[32] = C[1]; ap[64] = C[2]; ap[96] = C[3];
+                    } }
+                } else {
+                    // rows = (rest half h, a), K = 4 rest values of the half per DMMA: the two diagonal 4 x 4 blocks hold the sums
+                    double2 cc = make_double2(0.0, 0.0);
+                    dmma884(cc.x, cc.y, a0, q0); dmma884(cc.x, cc.y, a1, q1);
+                    if ((lg >> 2) == (lt >> 1)) {
+                        double2* ap = reinterpret_cast<double2*>(acc + (tb.w & 0xFFFFu) + (lg >> 2) * 16u + (lg & 3u) * 4u + 2u * (lt & 1u));
+                        double2 v = *ap; v.x += cc.x; v.y += cc.y; *ap = v;
+                    }
+                }
+                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, cur_o, cur_o ^ D, lg, lt);
+                __syncwarp();
+                cur_o ^= D;
+            }
+        }
+        const double* cur = wbase + cur_o;
+        // ---- epilogue: register slots -> accumulator buffer; cur = e_0 (rho block); s_L (effect block) ----
+        if (sl.fao[0] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[0]) + lane; ap[0] = R0[0]; ap[32] = R0[1]; ap[64] = R0[2]; ap[96] = R0[3]; }
+        if (sl.fao[1] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[1]) + lane; ap[0] = R1[0]; ap[32] = R1[1]; ap[64] = R1[2]; ap[96] = R1[3]; }
+        if (sl.fao[2] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[2]) + lane; ap[0] = R2[0]; ap[32] = R2[1]; ap[64] = R2[2]; ap[96] = R2[3]; }
+        if (sl.fao[3] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[3]) + lane; ap[0] = R3[0]; ap[32] = R3[1]; ap[64] = R3[2]; ap[96] = R3[3]; }
+        sb[i0] = __ldg(srow + (size_t)nst * D + lane); sb[i1] = __ldg(srow + (size_t)nst * D + lane + 32);
         __syncwarp();
         const int prep = a.circ_prep[c];
         const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
