@@ -623,7 +623,9 @@ def bench_c3(args, D, engine, stream, ctx):
     n_loc_all = [(hi - lo) * n_eff for lo, hi in blocks]
     slot = -(-max(n_loc_all) // 8) * 8
     nE = n_circ * n_eff
-    atom = ctx.upload_atom(t); atom.set_model(a["G"], a["rho"], a["E"]); atom.set_derivs(a["D"])
+    # the model as pyGSTi holds it: every layer = one operation embedded on 1-2 qubits (factor programs) + the derivative map in
+    # factor space; the dense map is kept as well (Hessian paths) and serves the comparison run of the dense level-batched kernels
+    atom = ctx.upload_atom(t); atom.set_model_factored(a["fm"]); atom.set_derivs(a["D"])
     info = atom.info()
     J = torch.empty((slot * world, Np), dtype=torch.float64, device="cuda"); P = torch.empty(slot * world, dtype=torch.float64, device="cuda")
     Jm, Pm = J[rank * slot:(rank + 1) * slot], P[rank * slot:(rank + 1) * slot]
@@ -637,8 +639,14 @@ def bench_c3(args, D, engine, stream, ctx):
             dist.all_gather_into_tensor(J, Jm); dist.all_gather_into_tensor(P, Pm)
 
     steps = max(3, min(args.steps, 5))
+    ms_dense_fill = timed(D, stream, fill, 2, 1)             # dense d x d gates: k_level_gemm_rows sweeps + k_level_accum3
+    J_dense_head = Jm[:4096].clone()
+    atom.set_derivs_factored(a["Df"])                        # from here on the factored kernels run (k_fj64_forward / k_fj64_backward)
     ms = timed(D, stream, step, steps, 2)
     ms_fill = timed(D, stream, fill, steps, 0) if world > 1 else ms
+    dense_vs_factored = float((Jm[:4096] - J_dense_head).abs().max())
+    assert dense_vs_factored <= 1e-10, dense_vs_factored
+    del J_dense_head
     # parity: first circuits of rank 0's shard against the C oracle (checker only)
     par = None
     if rank == 0:
@@ -649,17 +657,37 @@ def bench_c3(args, D, engine, stream, ctx):
                "probs_max_abs": float(np.max(np.abs(P[:sub.n_elements].cpu().numpy() - po)))}
         assert par["dprobs_max_abs_vs_oracle_first_6_circuits"] <= 1e-10 and par["probs_max_abs"] <= 1e-12, par
     n_prop = sum(len(x) for x in circs)
-    sweep_flops = 2.0 * 64 * 64 * n_prop * (1 + n_eff)                   # forward + one backward sweep per outcome
-    accum_flops = 2.0 * 64 * 64 * n_prop * n_eff                         # W_g = sum_k e_k (x) s_k, every outcome
+    fm = a["fm"]
+    per_op = np.zeros(n_ops)                                             # multiply-adds of one application of op g through its factors
+    for g in range(n_ops):
+        for f in range(fm.op_fptr[g], fm.op_fptr[g + 1]):
+            per_op[g] += 64 * (4 if fm.f_nq[f] == 1 else 16)
+    macs = float(sum(per_op[x].sum() for x in circs))
+    chain_flops = 2.0 * macs * (1 + n_eff)                               # forward chain + one backward chain per outcome
+    accum_flops = 2.0 * macs * n_eff                                     # acc[a][b] += e(a, r) s(b, r), every outcome
+    dense_flops = 2.0 * 64 * 64 * n_prop * (1 + 2 * n_eff)               # the same sweeps and outer products on dense 64 x 64 gates
     alg_bytes = nE * (Np + 1) * 8
+    fs_bytes = (n_prop + n_circ) * 64 * 8                                # forward states of every step, written once
     peak, _ = _peaks()
     out = {"config": "BASELINE configs[2]: 3Q XYCNOT full TP (d=64, Np=775), %d random circuits depth U{1..256}, %d outcomes" % (n_circ, nE),
            "ms": ms, "ms_fill_only": ms_fill, "outcomes_per_s": nE / (ms * 1e-3), "dprobs_elements_per_s": nE * Np / (ms * 1e-3),
            "parallelism": ("shard x%d + ONE ncclAllGather of %.2f GB shards" % (world, slot * (Np + 1) * 8 / 1e9)) if world > 1 else "1 GPU",
-           "algorithmic": {"sweep_flops": sweep_flops, "accumulate_flops": accum_flops, "jacobian_bytes": alg_bytes},
-           "tflops": (sweep_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12,
-           "frac": (sweep_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
-           "bound": "tensor (FP64 DMMA %.1f TFLOP/s measured); HBM floor of the output %.2f ms" % (DMMA_PEAK_TFLOPS, alg_bytes / world / peak / 1e6),
+           "kernel": "k_fj64_forward + k_fj64_backward: gates as factor programs (one 4x4 / 16x16 operation embedded on 1-2 of 3 qubits per layer), "
+                     "DMMA chain + accumulate per factor, derivative map in factor space; no dense 64 x 64 product, no adjoint table",
+           "algorithmic": {"chain_flops": chain_flops, "accumulate_flops": accum_flops, "jacobian_bytes": alg_bytes, "forward_state_bytes": fs_bytes,
+                           "dense_equivalent_flops": dense_flops},
+           "tflops": (chain_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12,
+           "frac": (chain_flops + accum_flops) / world / (ms_fill * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+           "hbm_frac": (alg_bytes + fs_bytes) / world / (ms_fill * 1e-3) / 1e9 / peak,
+           "bound": "latency / issue (dependent 64-vector chain steps of 6-12 DMMA each; ncu: issue-active ~45 %%, DMMA ~34 %%, L1 ~70 %%): "
+                    "frac = algorithmic flops of the factored form / FP64 DMMA %.1f TFLOP/s measured, hbm_frac = (Jacobian + forward states) / "
+                    "measured HBM peak; HBM floor %.2f ms" % (DMMA_PEAK_TFLOPS, (alg_bytes + fs_bytes) / world / peak / 1e6),
+           "dense_level_path": {"ms_fill_only": ms_dense_fill, "tflops": dense_flops / world / (ms_dense_fill * 1e-3) / 1e12,
+                                "frac": dense_flops / world / (ms_dense_fill * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS,
+                                "what": "the same Jacobian with every layer as a dense 64 x 64 matrix (k_level_gemm_rows sweeps + k_level_accum3; round 2's "
+                                        "first path, still used for models that are not factor programs)",
+                                "max_abs_diff_first_4096_rows": dense_vs_factored},
+           "speedup_vs_dense_level_path": ms_dense_fill / ms_fill,
            "atom": {k: int(v) for k, v in info.items()}, "parity": par}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sub, _ = fx.random_layout(64, n_ops, n_eff, n_circ, 256, seed=0, rows=(0, 200))

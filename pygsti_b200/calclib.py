@@ -190,6 +190,7 @@ def _upload_model(fwdsim, layout_atom, ent):
     the parameter vector; the engine evaluates M = M_const + D theta on the device."""
     model = fwdsim.model
     atom = ent["atom"]
+    ent["fm"] = None
     if getattr(fwdsim, "device_model_update", False) and _bound_to(ent, model):
         atom.set_params(model.to_vector())
         return
@@ -199,6 +200,7 @@ def _upload_model(fwdsim, layout_atom, ent):
         fm = packing.pack_model_factored(model, layout_atom, model.dim)
         if fm is not None:
             atom.set_model_factored(fm)
+            ent["fm"] = fm
             return
     atom.set_model(packing.pack_model(model, layout_atom, model.dim))
 
@@ -339,6 +341,12 @@ def _deriv_map(fwdsim, layout_atom, ent, param_indices):
         return pidx
     D = packing.pack_derivs(model, layout_atom, model.dim, pidx)
     ent["atom"].set_derivs(D)
+    if ent.get("fm") is not None and model.dim in (64, 256):
+        # the model went up as factor programs: hand over the derivative map in factor space as well -- the Jacobian is then
+        # evaluated factor by factor (csrc/kernels_factoredj.cuh) instead of through dense d x d sweeps
+        Df = packing.pack_derivs_factored(model, layout_atom, model.dim, ent["fm"], pidx)
+        if Df is not None:
+            ent["atom"].set_derivs_factored(Df)
     ent["deriv_key"] = key
     ent["bound"] = None             # a parameter binding refers to the map it was made with
     return pidx

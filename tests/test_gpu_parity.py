@@ -179,16 +179,23 @@ def test_full_size_config4_cptplnd(gpu_ctx, load_case):
     at.free()
 
 
-def test_full_size_config3_d64(gpu_ctx, load_case):
+@pytest.mark.parametrize("factored", [False, True])
+def test_full_size_config3_d64(gpu_ctx, load_case, factored):
     """BASELINE config 3 on one GPU, 5000 of the 50 000 random circuits of the bench stream (d = 64, Np = 775, depth U{1..256}; model
     tensors from the reference): sampled circuits against the oracle (itself pinned to the reference's Matrix goldens for this
-    model, tests/test_oracle_cpu.py), and for ALL rows the size-independent TP property: sum_j p_j = 1, sum_j dp_j = 0."""
+    model, tests/test_oracle_cpu.py), and for ALL rows the size-independent TP property: sum_j p_j = 1, sum_j dp_j = 0.
+    Both device forms of the model: dense 64 x 64 gates (level-batched sweeps) and factor programs + factor-space map
+    (kernels_factoredj.cuh, the path bench.py times)."""
     from pygsti_b200 import fixtures as fx
     from oracle import oracle_c
     c = load_case("c3_3q_localnoise_sub"); a = c.atoms[0]
     n_ops, n_eff, Np = a["tables"].n_ops, a["tables"].n_eff, a["D"].n_params
     t, circs = fx.random_layout(64, n_ops, n_eff, 50000, 256, seed=0, rows=(0, 5000))
-    at = gpu_ctx.upload_atom(t); at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
+    at = gpu_ctx.upload_atom(t)
+    if factored:
+        at.set_model_factored(a["fm"]); at.set_derivs_factored(a["Df"])
+    else:
+        at.set_model(a["G"], a["rho"], a["E"]); at.set_derivs(a["D"])
     J = engine.pinned_empty((t.n_elements, Np)); p = np.empty(t.n_elements)
     at.fill_dprobs(J, p)
     assert np.max(np.abs(p.reshape(-1, n_eff).sum(axis=1) - 1.0)) <= 1e-12

@@ -220,6 +220,24 @@ def test_three_qubit_local_noise_model_d64():
     _, jmap = _bulk_arrays(model, MapForwardSimulator(), circuits[:6])
     n = jmap.shape[0]
     assert np.max(np.abs(jmap - jb[:n])) <= 2e-5
+    # the simulator handed the layers over as factor programs and the derivative map in factor space: the Jacobian above came from
+    # the factored kernels (csrc/kernels_factoredj.cuh) and must equal the reference's analytic (Matrix) Jacobian to 1e-10
+    from pygsti_b200 import calclib as _cl
+    m = model.copy(); m.sim = B200ForwardSimulator()
+    layout = m.sim.create_layout(circuits[:6], array_types=('e', 'ep'))
+    J = np.empty((layout.num_elements, m.num_params)); m.sim.bulk_fill_dprobs(J, layout)
+    ents = [e for a in layout.atoms for e in _cl._ATOM_CACHE[a].values()]
+    assert ents and all(e.get("fm") is not None for e in ents)
+    mm = model.copy(); mm.sim = MatrixForwardSimulator()
+    lm = mm.sim.create_layout(circuits[:6], array_types=('e', 'ep'))
+    Jm = np.empty((lm.num_elements, mm.num_params)); mm.sim.bulk_fill_dprobs(Jm, lm)
+    for i, c in enumerate(circuits[:6]):
+        ib, ob = layout.indices_and_outcomes_for_index(i); im, om = lm.indices_and_outcomes(c)
+        ib = np.arange(ib.start, ib.stop) if isinstance(ib, slice) else np.asarray(ib)
+        im = np.arange(im.start, im.stop) if isinstance(im, slice) else np.asarray(im)
+        lut = {o: int(k) for o, k in zip(om, im)}
+        for o, k in zip(ob, ib):
+            assert np.max(np.abs(J[int(k)] - Jm[lut[o]])) <= 1e-10
 
 
 def test_four_qubit_cloud_crosstalk_model_d256():
