@@ -121,7 +121,7 @@ struct b200_atom {
     // factor-space derivative map (b200_atom_set_derivs_factored): the Jacobian straight from the factor programs (kernels_factoredj.cuh)
     bool has_fderivs = false; int32_t fj_n_params = 0; int fj_n_acc = 0, fj_n_frag = 0; uint64_t fj_rows = 0;
     std::vector<FactorRec> fj_fac;                                 // the factor structure the map was built for
-    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval, fj_slots; int fj_slot_fao[FJ64_REG_SLOTS] = {-1, -1, -1, -1};
+    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval, fj_slots, fj_steps; int fj_slot_fao[FJ64_REG_SLOTS] = {-1, -1, -1, -1};
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -601,7 +601,8 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
                       &a->t_counters, &a->t_units, &a->t_uidx,
                       &a->cptr, &a->crow, &a->cval, &a->Dd, &a->kt_ptr, &a->kt_idx, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->aff_rptr, &a->aff_rcol, &a->aff_rval, &a->aff_const, &a->aff_theta,
-                      &a->id_colmap, &a->id_spam_col, &a->id_spam_w};
+                      &a->id_colmap, &a->id_spam_col, &a->id_spam_w,
+                      &a->fj_base, &a->fj_out_circ, &a->fj_fao, &a->fj_ffo, &a->fj_cptr, &a->fj_ccode, &a->fj_cval, &a->fj_slots, &a->fj_steps};
     for (DevBuf* b : bufs) b->release();
     delete a;
     return B200_OK;
@@ -801,6 +802,13 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
     cnt[a->n_rows] = (uint32_t)run;
     if (run >= ((uint64_t)1 << 32)) return fail(B200_E_UNSUPPORTED, "forward-state table too large");
     CU(cudaMemcpyAsync(a->fj_base.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(a->fj_steps.ensure(std::max<size_t>((size_t)run * 2, 16)));
+    if (n_fac >= (1 << 16)) return fail(B200_E_UNSUPPORTED, "too many factors");
+    if (a->n_rows > 0) {
+        k_fj_steps<<<(unsigned)std::min<int64_t>((a->n_rows + 255) / 256, 4096), 256, 0, ctx->stream>>>(atom_dev(a), a->fac_ptr.as<int32_t>(), a->fj_base.as<uint32_t>(), a->fj_steps.as<uint16_t>());
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     a->fj_rows = run; a->fj_n_acc = n_acc; a->fj_n_frag = n_frag; a->fj_n_params = n_params; a->fj_fac = a->h_fac;
     a->has_fderivs = true;
@@ -1575,7 +1583,7 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
     const FactoredDev fd = factored_dev(a);
     const double* M = a->M.as<double>();
     FjDev fj;
-    fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
+    fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.step_fac = a->fj_steps.as<uint16_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
     fj.n_acc = a->fj_n_acc; fj.n_frag = a->fj_n_frag; fj.cptr = a->fj_cptr.as<int32_t>(); fj.ccode = a->fj_ccode.as<uint32_t>(); fj.cval = a->fj_cval.as<double>();
     fj.n_params = a->fj_n_params;
     if (D == 64) {

@@ -26,6 +26,7 @@
 struct FjDev {
     const uint32_t* base;      // [n_circ + 1] first FS row of circuit c (steps_c + 1 rows: the state before every factor, and s_L)
     const int32_t* out_circ;   // [n_outcomes] circuit of outcome slot qo
+    const uint16_t* step_fac;  // [rows] factor applied AFTER the state of FS row r (the last row of a circuit: unused)
     const int32_t* fao;        // [n_fac] offset (doubles) of factor f's accumulators in a warp's accumulator buffer
     const int32_t* ffo;        // [n_fac] offset (doubles) of factor f's F^T fragments in the CTA's fragment image
     int n_acc, n_frag;
@@ -42,6 +43,18 @@ __global__ void k_fj_count(AtomDev a, const int32_t* __restrict__ fptr, uint32_t
         for (uint32_t k = a.circ_ptr[c]; k < a.circ_ptr[c + 1]; ++k) { const int g = a.circ_ops[k]; n += (uint32_t)(fptr[g + 1] - fptr[g]); }
         n_rows[c] = n;
         for (int qo = a.out_ptr[c]; qo < a.out_ptr[c + 1]; ++qo) out_circ[qo] = c;
+    }
+}
+
+__global__ void k_fj_steps(AtomDev a, const int32_t* __restrict__ fptr, const uint32_t* __restrict__ base, uint16_t* __restrict__ step_fac)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < a.n_circ; c += gridDim.x * blockDim.x) {
+        uint32_t r = base[c];
+        for (uint32_t k = a.circ_ptr[c]; k < a.circ_ptr[c + 1]; ++k) {
+            const int g = a.circ_ops[k];
+            for (int f = fptr[g]; f < fptr[g + 1]; ++f) step_fac[r++] = (uint16_t)f;
+        }
+        step_fac[r] = 0;
     }
 }
 
@@ -319,9 +332,11 @@ __device__ __forceinline__ uint4 fj64_entry(const FactorRec fr, int fao, int ffo
 // for the backward direction): 2 qubits: fg[q * 32], q = mt * 4 + kk; 1 qubit: fg[0].  cur / nxt are addressed as wb[offset + index]
 // with integer offsets: swapping POINTERS made the compiler fall back to generic-space loads and stores (LD.E / ST.E with 64-bit
 // address arithmetic) instead of LDS / STS.
-__device__ __forceinline__ void fj64_chain(const uint4 tb, const double* fg, double* wb, int cur_o, int nxt_o, unsigned lg, unsigned lt)
+// The update is IN PLACE: a lane's stores depend on its DMMA results, and a (warp-collective) DMMA cannot complete before every lane's
+// operand loads have returned -- no lane can overwrite an element another lane still has to read.
+__device__ __forceinline__ void fj64_chain(const uint4 tb, const double* fg, double* wb, unsigned lg, unsigned lt)
 {
-    const double* cur = wb + cur_o; double* nxt = wb + nxt_o;
+    const double* cur = wb; double* nxt = wb;
     if (((tb.z >> 16) & 0xFFu) == 2u) {
         double2 o0 = make_double2(0.0, 0.0), o1 = make_double2(0.0, 0.0);
         const double b0 = cur[(tb.x >> 16) & 0xFFu], b1 = cur[tb.x >> 24], b2 = cur[tb.y & 0xFFu], b3 = cur[(tb.y >> 8) & 0xFFu];
@@ -390,7 +405,6 @@ k_fj64_forward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __r
     for (int c = gw; c < a.n_circ; c += nw) {
         const uint32_t p0 = a.circ_ptr[c], L = a.circ_ptr[c + 1] - p0;
         const double* r = rho + (size_t)a.circ_prep[c] * D;
-        int cur_o = 0;
         double* row = FS + (size_t)fj.base[c] * D;
         { const double v0 = __ldg(r + lane), v1 = __ldg(r + lane + 32); wbase[i0] = v0; wbase[i1] = v1; row[lane] = v0; row[lane + 32] = v1; }
         __syncwarp();
@@ -401,17 +415,17 @@ k_fj64_forward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __r
             const int f1 = fptr[g + 1];
             for (int f = fptr[g]; f < f1; ++f) {
                 const uint4 tb = tab[f * 32 + lane];
-                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, cur_o, cur_o ^ D, lg, lt);
+                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, lg, lt);
                 __syncwarp();
-                cur_o ^= D;
                 row += D;
-                row[lane] = wbase[cur_o + i0]; row[lane + 32] = wbase[cur_o + i1];
+                row[lane] = wbase[i0]; row[lane + 32] = wbase[i1];
+                __syncwarp();                                      // (the next factor overwrites the state in place)
             }
         }
         if (probs) {
             for (int qo = a.out_ptr[c]; qo < a.out_ptr[c + 1]; ++qo) {
                 const double* e = E + (size_t)a.out_eff[qo] * D;
-                double part = fma(__ldg(e + lane), wbase[cur_o + i0], __ldg(e + lane + 32) * wbase[cur_o + i1]);
+                double part = fma(__ldg(e + lane), wbase[i0], __ldg(e + lane + 32) * wbase[i1]);
 #pragma unroll
                 for (int mk = 16; mk > 0; mk >>= 1) part += shfl_xor_f64(part, mk);
                 if (lane == 0) probs[a.out_el[qo]] = part;
@@ -458,28 +472,29 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         const int eff = a.out_eff[item];
         const int64_t el = a.out_el[item];
         const double* srow = FS + (size_t)row0 * D;
-        int cur_o = 0;
         for (int i = lane; i < fj.n_acc; i += 32) acc[i] = 0.0;
         wbase[i0] = __ldg(E + (size_t)eff * D + lane); wbase[i1] = __ldg(E + (size_t)eff * D + lane + 32);
         double2 R0[4], R1[4], R2[4], R3[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) R0[q] = R1[q] = R2[q] = R3[q] = make_double2(0.0, 0.0);
         double sr0 = 0.0, sr1 = 0.0;
-        if (t > 0) { sr0 = __ldg(srow + (size_t)(t - 1) * D + lane); sr1 = __ldg(srow + (size_t)(t - 1) * D + lane + 32); }
+        const double* sp = srow + (size_t)t * D + lane;           // this lane's element of the row AFTER the one requested next
+        if (t > 0) { sp -= D; sr0 = __ldg(sp); sr1 = __ldg(sp + 32); }
+        const uint16_t* sf = fj.step_fac + row0;
+        int fch = 0;
         __syncwarp();
-        int gch = 0;
-        for (int k = L - 1; k >= 0; --k) {
-            if ((k & 31) == 31 || k == L - 1) { const int kk0 = k & ~31; gch = (kk0 + lane < L) ? __ldg(a.circ_ops + p0 + kk0 + lane) : 0; }   // 32 gate indices per load
-            const int g = __shfl_sync(0xffffffffu, gch, k & 31);
-            const int f0 = fptr[g];
-            for (int f = fptr[g + 1] - 1; f >= f0; --f) {
+        {
+            {
+                while (t > 0) {
                 --t;                                               // this step: factor f between s_t (before) and e (after)
+                if ((t & 31u) == 31u || t == nst - 1u) { const uint32_t t0 = t & ~31u; fch = (t0 + lane < nst) ? (int)__ldg(sf + t0 + lane) : 0; }   // 32 factor ids per load
+                const int f = __shfl_sync(0xffffffffu, fch, (int)(t & 31u));
                 sb[i0] = sr0; sb[i1] = sr1;
                 __syncwarp();
-                if (t > 0) { sr0 = __ldg(srow + (size_t)(t - 1) * D + lane); sr1 = __ldg(srow + (size_t)(t - 1) * D + lane + 32); }
+                if (t > 0) { sp -= D; sr0 = __ldg(sp); sr1 = __ldg(sp + 32); }
                 const uint4 tb = tab[f * 32 + lane];
                 const unsigned j0 = tb.x & 0xFFu, j1 = (tb.x >> 8) & 0xFFu;
-                const double a0 = wbase[cur_o + j0], a1 = wbase[cur_o + j1], q0 = sb[j0], q1 = sb[j1];
+                const double a0 = wbase[j0], a1 = wbase[j1], q0 = sb[j0], q1 = sb[j1];
                 if (((tb.z >> 16) & 0xFFu) == 2u) {
                     switch (tb.z >> 24) {
                     case 0: FJ64_ACC4(R0, a0, a1, q0, q1); break;
@@ -501,12 +516,12 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
                         double2 v = *ap; v.x += cc.x; v.y += cc.y; *ap = v;
                     }
                 }
-                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, cur_o, cur_o ^ D, lg, lt);
+                fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, lg, lt);
                 __syncwarp();
-                cur_o ^= D;
+                }
             }
         }
-        const double* cur = wbase + cur_o;
+        const double* cur = wbase;
         // ---- epilogue: register slots -> accumulator buffer; cur = e_0 (rho block); s_L (effect block) ----
         if (sl.fao[0] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[0]) + lane; ap[0] = R0[0]; ap[32] = R0[1]; ap[64] = R0[2]; ap[96] = R0[3]; }
         if (sl.fao[1] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[1]) + lane; ap[0] = R1[0]; ap[32] = R1[1]; ap[64] = R1[2]; ap[96] = R1[3]; }
