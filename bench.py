@@ -817,6 +817,29 @@ def bench_c4(args, D, engine, stream, ctx):
                                  "what": "b200_hessian_block: analytic hprobs rectangle (first + second derivative terms) evaluated and "
                                          "reduced with w_h / w_d on the device; only 64 x 64 doubles return"},
            "parallelism": "independent rectangles: replica per GPU" if D.world > 1 else "1 GPU"}
+    # on-device model update of the Lindblad members (b200_lindblad_members): synthetic inputs of this config's size -- 7 error generators
+    # (5 gates, prep, POVM) of 240 coefficients / 240 parameters each at d = 16, 10 members -- timed through the C ABI (host buffers)
+    if D.rank == 0:
+        try:
+            from types import SimpleNamespace as NS
+            rng = np.random.default_rng(11)
+            egs = []
+            for _ in range(7):
+                B = (rng.standard_normal((240, 16, 16)) + 1j * rng.standard_normal((240, 16, 16))) / 16
+                egs.append(NS(B_re=np.ascontiguousarray(B.real), B_im=np.ascontiguousarray(B.imag),
+                              c=0.02 * (rng.standard_normal(240) + 1j * rng.standard_normal(240)),
+                              dc=rng.standard_normal((240, 240)) + 1j * rng.standard_normal((240, 240))))
+            mem = [NS(kind="op", errgen=g, static=rng.standard_normal((16, 16))) for g in range(5)] + [NS(kind="rho", errgen=5, static=rng.standard_normal(16))] + \
+                  [NS(kind="eff", errgen=6, static=rng.standard_normal(16)) for _ in range(4)]
+            ctx.lindblad_members(16, egs, mem)
+            ts = []
+            for _ in range(3):
+                t0 = time.time(); ctx.lindblad_members(16, egs, mem); ts.append(time.time() - t0)
+            out["lindblad_members"] = {"e2e_ms": min(ts) * 1e3, "what": "b200_lindblad_members: L, dL, exp(L), Frechet derivatives and composition of 10 members / 7 generators x 240 "
+                                       "parameters (d = 16) incl. H2D of the 6.9 MB term tensors and D2H of values + derivatives; the host path "
+                                       "(pack_model + pack_derivs through the members' own to_dense / deriv_wrt_params) takes 1.0-1.2 s in the build container"}
+        except Exception as e:
+            out["lindblad_members"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if D.rank == 0 and D.world == 1 and not args.no_cpu_baseline:
         orc, kind, _ = _oracle()
         t0 = time.time(); orc.mapfill_probs(a["tables"], a["G"], a["rho"], a["E"]); t_pass = time.time() - t0

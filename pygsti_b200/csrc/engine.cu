@@ -121,7 +121,7 @@ struct b200_atom {
     // factor-space derivative map (b200_atom_set_derivs_factored): the Jacobian straight from the factor programs (kernels_factoredj.cuh)
     bool has_fderivs = false; int32_t fj_n_params = 0; int fj_n_acc = 0, fj_n_frag = 0; uint64_t fj_rows = 0;
     std::vector<FactorRec> fj_fac;                                 // the factor structure the map was built for
-    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval, fj_slots, fj_steps; int fj_slot_fao[FJ64_REG_SLOTS] = {-1, -1, -1, -1};
+    DevBuf fj_base, fj_out_circ, fj_fao, fj_ffo, fj_cptr, fj_ccode, fj_cval, fj_slots, fj_steps; int fj_unit = 0; int fj_slot_fao[FJ64_REG_SLOTS] = {-1, -1, -1, -1};
     // derivative map
     bool has_derivs = false;
     int32_t n_params = 0;
@@ -718,7 +718,7 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
     if (d != 64 && d != 256) return fail(B200_E_UNSUPPORTED, "factor-space derivatives need dim = 64 or 256");
     const int64_t n_mats = a->fac_n_mats;
     if (n_wf != n_mats + (int64_t)(a->n_rho + a->n_eff) * d) return fail(B200_E_INVALID, "n_wf=%lld, expected %lld", (long long)n_wf, (long long)(n_mats + (int64_t)(a->n_rho + a->n_eff) * d));
-    if (a->n_eff >= (1 << 14) || a->n_rho >= (1 << 14)) return fail(B200_E_UNSUPPORTED, "too many preps / effects");
+    if (a->n_eff >= (1 << 13) || a->n_rho >= (1 << 13)) return fail(B200_E_UNSUPPORTED, "too many preps / effects");
     if (a->has_derivs && a->n_params != n_params) return fail(B200_E_INVALID, "factor-space map has %d parameters, the dense map %d", n_params, a->n_params);
     const int n_fac = a->fac_n;
     // accumulator / fragment offsets, owners of every matrix element (factors may share a matrix: their accumulators add up)
@@ -780,6 +780,10 @@ extern "C" int b200_atom_set_derivs_factored(b200_ctx* ctx, b200_atom* a, int64_
             cval[fill[p]++] = vals[t];
         }
     }
+    bool unit = true;                                   // all values +-1 (full / TP members): the sign travels in bit 29 of the code
+    for (int64_t q = 0; q < tot && unit; ++q) unit = cval[q] == 1.0 || cval[q] == -1.0;
+    if (unit) for (int64_t q = 0; q < tot; ++q) if (cval[q] < 0.0) ccode[q] |= 0x20000000u;
+    a->fj_unit = unit ? 1 : 0;
     CU(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = upload_vec(a->fj_fao, fao, ctx->stream)) || (rc = upload_vec(a->fj_ffo, ffo, ctx->stream)) || (rc = upload_vec(a->fj_slots, slots, ctx->stream)) ||
@@ -1585,7 +1589,7 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
     FjDev fj;
     fj.base = a->fj_base.as<uint32_t>(); fj.out_circ = a->fj_out_circ.as<int32_t>(); fj.step_fac = a->fj_steps.as<uint16_t>(); fj.fao = a->fj_fao.as<int32_t>(); fj.ffo = a->fj_ffo.as<int32_t>();
     fj.n_acc = a->fj_n_acc; fj.n_frag = a->fj_n_frag; fj.cptr = a->fj_cptr.as<int32_t>(); fj.ccode = a->fj_ccode.as<uint32_t>(); fj.cval = a->fj_cval.as<double>();
-    fj.n_params = a->fj_n_params;
+    fj.n_params = a->fj_n_params; fj.unit = a->fj_unit;
     if (D == 64) {
         const size_t smem = (size_t)((a->fj_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * 32 * 16 + ((size_t)a->n_ops + 1) * 4 + 16 + (size_t)8 * 2 * 64 * 8;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 7) / 8, (int64_t)c->sm_count * 6));

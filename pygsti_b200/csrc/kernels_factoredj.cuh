@@ -31,9 +31,10 @@ struct FjDev {
     const int32_t* ffo;        // [n_fac] offset (doubles) of factor f's F^T fragments in the CTA's fragment image
     int n_acc, n_frag;
     const int32_t* cptr;       // [n_params + 1]  CSC of the factor-space derivative map
-    const uint32_t* ccode;     // [nnz]  kind << 30 | ...: 0 = accumulator offset; 1 = rho (prep << 16 | index); 2 = effect (effect << 16 | index)
+    const uint32_t* ccode;     // [nnz]  kind << 30 | sign << 29 | ...: 0 = accumulator offset; 1 = rho (prep << 16 | index); 2 = effect (effect << 16 | index)
     const double* cval;        // [nnz]
     int n_params;
+    int unit;                  // all values are +-1: the sign is bit 29 of the code and cval is not read
 };
 
 __global__ void k_fj_count(AtomDev a, const int32_t* __restrict__ fptr, uint32_t* __restrict__ n_rows, int32_t* __restrict__ out_circ)
@@ -271,9 +272,9 @@ k_fj_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __re
                 const double val = __ldg(fj.cval + q);
                 const uint32_t kind = code >> 30;
                 double x;
-                if (kind == 0u) x = acc[code];
+                if (kind == 0u) x = acc[code & 0x1FFFFFFFu];
                 else {
-                    const int i = (int)((code >> 16) & 0x3FFFu); const unsigned idx = fj_sw(code & 0xFFFFu);
+                    const int i = (int)((code >> 16) & 0x1FFFu); const unsigned idx = fj_sw(code & 0xFFFFu);
                     x = (kind == 1u) ? (i == prep ? cur[idx] : 0.0) : (i == eff ? sb[idx] : 0.0);
                 }
                 v = fma(val, x, v);
@@ -294,6 +295,10 @@ k_fj_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __re
 // the 16 rest values over the two row halves of the 8 x 8 tile (2 DMMA instead of 4, the two diagonal 4 x 4 blocks are summed
 // in the epilogue).  The forward kernel runs the same DMMA chain with the F fragments (the scalar factor application was
 // shared-memory bound: 97 % L1 pipe).
+// Measured and NOT kept: two outcomes of a circuit per warp (shared s / F^T fragments and table entry, both backward vectors in one set
+// of 8 chain DMMA with N = (outcome, rest)): 29 % fewer instructions and 26 % fewer shared-memory wavefronts per outcome, but only 10 warps
+// per SM fit (2 x accumulators in registers and shared memory) -- 15.9 vs 14.7 ms at config 3.  The kernel sits on a plateau of issue
+// (44 %), L1 / shared (77 %) and DMMA (36 %) with every instruction of a warp waiting ~9 cycles at 4 warps per scheduler.
 // =====================================================================================================================
 #define FJ64_REG_SLOTS 4
 
@@ -384,6 +389,46 @@ __device__ __forceinline__ void fj64_stage(const AtomDev& a, const FactoredDev& 
         tab[f * 32 + lane] = fj64_entry(fr, fj.fao[f], fj.ffo[f], slots ? slots[f] : 0xFF, lg, lt);
     }
     __syncthreads();
+}
+
+// Jacobian row of one outcome: J[p] = scale * sum over column p of the factor-space map  val * W_f[code]  -- accumulators (acc), e_0
+// (cur, rho block of the circuit's prep) and s_L (sb, block of the outcome's effect).  One lane per parameter, FOUR parameters per lane
+// in flight: the dependent loads cptr -> code -> element are L2 round trips when the CTA's shared memory leaves little L1 (ncu: the
+// one-parameter-at-a-time loop was 25-37 % of the backward kernels' stall samples for 14-20 % of their instructions).
+__device__ __forceinline__ void fj64_row(const FjDev& fj, const double* acc, const double* cur, const double* sb, int prep, int eff,
+                                         double* __restrict__ Jrow, double sc, int lane)
+{
+    const int Np = fj.n_params;
+    for (int p0 = lane; p0 < Np; p0 += 128) {
+        int b[4], n[4]; double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = p0 + 32 * u;
+            b[u] = p < Np ? __ldg(fj.cptr + p) : 0;
+            n[u] = p < Np ? __ldg(fj.cptr + p + 1) - b[u] : 0;
+            v[u] = 0.0;
+        }
+        const int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+        for (int q = 0; q < nmax; ++q) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (q < n[u]) {
+                    const uint32_t code = __ldg(fj.ccode + b[u] + q);
+                    const double val = fj.unit ? ((code & 0x20000000u) ? -1.0 : 1.0) : __ldg(fj.cval + b[u] + q);
+                    const uint32_t kind = code >> 30;
+                    double x;
+                    if (kind == 0u) x = acc[code & 0x1FFFFFFFu];
+                    else {
+                        const int i = (int)((code >> 16) & 0x1FFFu); const unsigned idx = fj_sw(code & 0xFFFFu);
+                        x = (kind == 1u) ? (i == prep ? cur[idx] : 0.0) : (i == eff ? sb[idx] : 0.0);
+                    }
+                    v[u] = fma(val, x, v[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (p0 + 32 * u < Np) Jrow[p0 + 32 * u] = v[u] * sc;
+    }
 }
 
 // One warp per circuit.  Shared memory: fragment image [n_frag] | table [n_fac][32] uint4 | fptr [n_ops + 1] | per warp: 2 x 64 doubles.
@@ -481,18 +526,29 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         const double* sp = srow + (size_t)t * D + lane;           // this lane's element of the row AFTER the one requested next
         if (t > 0) { sp -= D; sr0 = __ldg(sp); sr1 = __ldg(sp + 32); }
         const uint16_t* sf = fj.step_fac + row0;
-        int fch = 0;
+        // factor ids 32 at a time, the NEXT chunk requested when a chunk is entered; the table entry of a step is read during the step before
+        int fch = 0, fnx = 0;
+        uint4 tb = make_uint4(0u, 0u, 0u, 0u);
+        if (t > 0) {
+            const uint32_t ch = (t - 1u) >> 5;
+            fch = (ch * 32u + lane < nst) ? (int)__ldg(sf + ch * 32u + lane) : 0;
+            if (ch > 0u) fnx = (int)__ldg(sf + (ch - 1u) * 32u + lane);
+            tb = tab[__shfl_sync(0xffffffffu, fch, (int)((t - 1u) & 31u)) * 32 + lane];
+        }
         __syncwarp();
         {
             {
                 while (t > 0) {
                 --t;                                               // this step: factor f between s_t (before) and e (after)
-                if ((t & 31u) == 31u || t == nst - 1u) { const uint32_t t0 = t & ~31u; fch = (t0 + lane < nst) ? (int)__ldg(sf + t0 + lane) : 0; }   // 32 factor ids per load
-                const int f = __shfl_sync(0xffffffffu, fch, (int)(t & 31u));
                 sb[i0] = sr0; sb[i1] = sr1;
                 __syncwarp();
-                if (t > 0) { sp -= D; sr0 = __ldg(sp); sr1 = __ldg(sp + 32); }
-                const uint4 tb = tab[f * 32 + lane];
+                uint4 tbn = tb;
+                if (t > 0) {
+                    sp -= D; sr0 = __ldg(sp); sr1 = __ldg(sp + 32);
+                    const uint32_t tn = t - 1u;
+                    if ((tn & 31u) == 31u) { fch = fnx; if ((tn >> 5) > 0u) fnx = (int)__ldg(sf + ((tn >> 5) - 1u) * 32u + lane); }
+                    tbn = tab[__shfl_sync(0xffffffffu, fch, (int)(tn & 31u)) * 32 + lane];
+                }
                 const unsigned j0 = tb.x & 0xFFu, j1 = (tb.x >> 8) & 0xFFu;
                 const double a0 = wbase[j0], a1 = wbase[j1], q0 = sb[j0], q1 = sb[j1];
                 if (((tb.z >> 16) & 0xFFu) == 2u) {
@@ -517,6 +573,7 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
                     }
                 }
                 fj64_chain(tb, frag + (tb.w >> 16) + lane, wbase, lg, lt);
+                tb = tbn;
                 __syncwarp();
                 }
             }
@@ -529,26 +586,7 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         if (sl.fao[3] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[3]) + lane; ap[0] = R3[0]; ap[32] = R3[1]; ap[64] = R3[2]; ap[96] = R3[3]; }
         sb[i0] = __ldg(srow + (size_t)nst * D + lane); sb[i1] = __ldg(srow + (size_t)nst * D + lane + 32);
         __syncwarp();
-        const int prep = a.circ_prep[c];
-        const double sc = row_scale ? __ldg(row_scale + el) : 1.0;
-        double* Jrow = J + el * ld;
-        for (int p = lane; p < Np; p += 32) {
-            double v = 0.0;
-            const int t1 = __ldg(fj.cptr + p + 1);
-            for (int q = __ldg(fj.cptr + p); q < t1; ++q) {
-                const uint32_t code = __ldg(fj.ccode + q);
-                const double val = __ldg(fj.cval + q);
-                const uint32_t kind = code >> 30;
-                double x;
-                if (kind == 0u) x = acc[code];
-                else {
-                    const int i = (int)((code >> 16) & 0x3FFFu); const unsigned idx = fj_sw(code & 0xFFFFu);
-                    x = (kind == 1u) ? (i == prep ? cur[idx] : 0.0) : (i == eff ? sb[idx] : 0.0);
-                }
-                v = fma(val, x, v);
-            }
-            Jrow[p] = v * sc;
-        }
+        fj64_row(fj, acc, cur, sb, a.circ_prep[c], eff, J + el * ld, row_scale ? __ldg(row_scale + el) : 1.0, lane);
         __syncwarp();
     }
 }
