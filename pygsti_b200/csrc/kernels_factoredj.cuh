@@ -499,18 +499,15 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
     uint4* tab = reinterpret_cast<uint4*>(frag + ((fj.n_frag + 1) & ~1));
     int* fptr = reinterpret_cast<int*>(tab + (size_t)n_fac * 32);
     double* wbase = smj + (((fj.n_frag + 1) & ~1) + n_fac * 64 + ((a.n_ops + 4) >> 2) * 2) + warp * (3 * D + fj.n_acc);
-    double* sb = wbase + 2 * D; double* acc = wbase + 3 * D;       // wbase: e ping-pong at offsets 0 / 64
+    double* sb = wbase + 2 * D; double* acc = wbase + 3 * D;       // wbase: e (updated in place) at offset 0
     fj64_stage<true>(a, fd, fj, n_fac, slots, frag, tab, fptr);
     const unsigned i0 = fj_sw((unsigned)lane), i1 = fj_sw((unsigned)lane + 32u);
-    const int Np = fj.n_params;
     for (;;) {
         int item = 0;
         if (lane == 0) item = (int)atomicAdd(counter, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
         const int c = fj.out_circ[item];
-        const uint32_t p0 = a.circ_ptr[c];
-        const int L = (int)(a.circ_ptr[c + 1] - p0);
         const uint32_t row0 = fj.base[c];
         const uint32_t nst = fj.base[c + 1] - row0 - 1;            // factor steps of the circuit
         uint32_t t = nst;
