@@ -118,6 +118,7 @@ struct b200_atom {
     bool has_factored = false;             // gates also held as factor programs (b200_atom_set_model_factored)
     DevBuf fac_ptr, fac_rec, fac_mats; int fac_n_mats = 0, fac_n = 0; bool fac_probs_ok = false;   // (programs small enough for shared memory)
     std::vector<FactorRec> h_fac; std::vector<int32_t> h_fptr;     // host copy of the factor programs
+    DevBuf fac_ffo; int fac_n_frag = 0;                             // DMMA fragment offsets of the factors (k_probs_fdmma)
     // factor-space derivative map (b200_atom_set_derivs_factored): the Jacobian straight from the factor programs (kernels_factoredj.cuh)
     bool has_fderivs = false; int32_t fj_n_params = 0; int fj_n_acc = 0, fj_n_frag = 0; uint64_t fj_rows = 0;
     std::vector<FactorRec> fj_fac;                                 // the factor structure the map was built for
@@ -602,7 +603,7 @@ extern "C" int b200_atom_free(b200_ctx* ctx, b200_atom* a) {
                       &a->cptr, &a->crow, &a->cval, &a->Dd, &a->kt_ptr, &a->kt_idx, &a->colmap, &a->spam_col, &a->spam_w,
                       &a->aff_rptr, &a->aff_rcol, &a->aff_rval, &a->aff_const, &a->aff_theta,
                       &a->id_colmap, &a->id_spam_col, &a->id_spam_w,
-                      &a->fj_base, &a->fj_out_circ, &a->fj_fao, &a->fj_ffo, &a->fj_cptr, &a->fj_ccode, &a->fj_cval, &a->fj_slots, &a->fj_steps};
+                      &a->fj_base, &a->fj_out_circ, &a->fj_fao, &a->fj_ffo, &a->fj_cptr, &a->fj_ccode, &a->fj_cval, &a->fj_slots, &a->fj_steps, &a->fac_ffo};
     for (DevBuf* b : bufs) b->release();
     delete a;
     return B200_OK;
@@ -698,6 +699,13 @@ extern "C" int b200_atom_set_model_factored(b200_ctx* ctx, b200_atom* a, int32_t
     CU(cudaStreamSynchronize(ctx->stream));
     a->has_model = true; a->has_factored = true; a->fac_n_mats = (int)std::min<int64_t>(n_mats, INT_MAX); a->fac_n = n_factors;
     a->h_fac.assign(recs.begin(), recs.begin() + n_factors); a->h_fptr = fptr;
+    {
+        std::vector<int32_t> ffo((size_t)std::max(n_factors, 1), 0); int nf = 0;
+        for (int f = 0; f < n_factors; ++f) { ffo[f] = nf; nf += recs[f].nq == 2 ? 256 : 32; }
+        if ((rc = upload_vec(a->fac_ffo, ffo, ctx->stream))) return rc;
+        CU(cudaStreamSynchronize(ctx->stream));
+        a->fac_n_frag = nf;
+    }
     a->fac_probs_ok = n_mats <= FAC_MATS_MAX && n_factors <= FAC_RECS_MAX && a->n_ops <= 4096;
     return B200_OK;
 }
@@ -1439,6 +1447,23 @@ extern "C" int b200_fill_probs_dev(b200_ctx* c, b200_atom* a, double* d_out) {
         // gates as factor programs (Embedded / Composed reps): no dense d x d products at all
         const FactoredDev fd = factored_dev(a);
         const double* M = a->M.as<double>();
+        {   // the factor chain on the FP64 tensor cores (k_probs_fdmma) when its fragment image and index table fit in shared memory
+            static const bool scalar = getenv("B200_FAC_SCALAR") != nullptr;
+            const size_t smem = (size_t)((a->fac_n_frag + 1) & ~1) * 8 + (size_t)a->fac_n * 1024 + (size_t)(((a->n_ops + 1 + a->fac_n + 3) >> 2) * 2) * 8 + (size_t)8 * a->dim * 8;
+            if (!scalar && smem <= std::min<size_t>(c->smem_optin, (size_t)110 * 1024)) {
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + 7) / 8, (int64_t)c->sm_count * 2));
+                if (a->dim == 64) {
+                    CU(cudaFuncSetAttribute(k_probs_fdmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_probs_fdmma<64><<<grid, 256, smem, c->stream>>>(atom_dev(a), fd, a->fac_ffo.as<int32_t>(), a->fac_n_frag, a->fac_n, M + a->off_rho, M + a->off_eff, d_out, 1);
+                } else {
+                    CU(cudaFuncSetAttribute(k_probs_fdmma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_probs_fdmma<256><<<grid, 256, smem, c->stream>>>(atom_dev(a), fd, a->fac_ffo.as<int32_t>(), a->fac_n_frag, a->fac_n, M + a->off_rho, M + a->off_eff, d_out, 1);
+                }
+                c->launches++;
+                CU(cudaGetLastError());
+                return B200_OK;
+            }
+        }
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a->n_rows + FAC_WARPS - 1) / FAC_WARPS, (int64_t)c->sm_count * 4));
         const int n_ms = a->fac_n_mats, n_fac = a->fac_n;
         const size_t tail = ((size_t)((n_ms + 1) & ~1)) * 8 + (size_t)n_fac * sizeof(FactorRec) + ((size_t)a->n_ops + 1) * 4;

@@ -587,3 +587,144 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         __syncwarp();
     }
 }
+
+// =====================================================================================================================
+// Probabilities from factor programs on the FP64 tensor cores (d = 64 and d = 256): k_probs_factored (kernels_factored.cuh) applies a
+// factor with scalar FMAs whose matrix operands arrive as shared-memory broadcasts -- one LDS per FMA, the L1 pipe at 97 %.  Here a factor
+// is the same DMMA chain step as in the Jacobian kernels: out(a', r) = sum_a F[a'][a] s(a, r), M = K = 4^nq, N = rest in tiles of 8, the
+// state updated in place (a tile's outputs and the next tile's inputs have disjoint rest indices), all state indices of a step from a
+// per-(factor, lane) table of 32 bytes built once per CTA.
+// =====================================================================================================================
+template <int D> struct FpCfg {
+    static constexpr int R2 = D / 16, R1 = D / 4;
+    static constexpr int NT2 = (R2 + 7) / 8, NT1 = R1 / 8;            // N tiles of a 2-qubit / 1-qubit factor
+};
+struct FpEntry { uint32_t w[8]; };    // (stored as two uint4 halves [f][half][lane]: conflict-free 16-byte loads)  bytes: 2 qubits: B[nt * 4 + kk] (NT2 * 4), then stores S[nt * 4 + 0..3]; 1 qubit: B[nt] (NT1), then S[nt * 2 + 0..1]
+
+template <int D>
+__device__ __forceinline__ unsigned fp_byte(const FpEntry& e, int i) { return (e.w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+
+template <int D>
+__device__ __forceinline__ FpEntry fp_entry(const FactorRec fr, unsigned lg, unsigned lt)
+{
+    using C = FpCfg<D>;
+    unsigned char b[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0;
+    if (fr.nq == 2) {
+        const int s0 = fr.shift[0], s1 = fr.shift[1];
+        const int lo = s0 < s1 ? s0 : s1, hi = s0 < s1 ? s1 : s0;
+        for (int nt = 0; nt < C::NT2; ++nt) {
+            const unsigned rB = (8u * nt + lg) & (unsigned)(C::R2 - 1);
+            for (unsigned kk = 0; kk < 4; ++kk) b[nt * 4 + kk] = (unsigned char)fj_idx2(4u * kk + lt, rB, lo, hi, s0, s1);
+            const unsigned rO = (8u * nt + 2u * lt) & (unsigned)(C::R2 - 1);
+            unsigned char* st = b + C::NT2 * 4 + nt * 4;
+            st[0] = (unsigned char)fj_idx2(lg, rO, lo, hi, s0, s1); st[1] = (unsigned char)fj_idx2(lg, rO + 1u, lo, hi, s0, s1);
+            st[2] = (unsigned char)fj_idx2(lg + 8u, rO, lo, hi, s0, s1); st[3] = (unsigned char)fj_idx2(lg + 8u, rO + 1u, lo, hi, s0, s1);
+        }
+    } else {
+        const int sh = fr.shift[0];
+        for (int nt = 0; nt < C::NT1; ++nt) {
+            b[nt] = (unsigned char)fj_idx1(lt, 8u * nt + lg, sh);
+            b[C::NT1 + nt * 2] = (unsigned char)fj_idx1(lg & 3u, 8u * nt + 2u * lt, sh);
+            b[C::NT1 + nt * 2 + 1] = (unsigned char)fj_idx1(lg & 3u, 8u * nt + 2u * lt + 1u, sh);
+        }
+    }
+    FpEntry e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e.w[i] = (unsigned)b[4 * i] | ((unsigned)b[4 * i + 1] << 8) | ((unsigned)b[4 * i + 2] << 16) | ((unsigned)b[4 * i + 3] << 24);
+    return e;
+}
+
+// Shared memory: F fragment image [n_frag] | table [n_fac][32] FpEntry | fptr [n_ops + 1] | nq, fragment offset per factor [2 n_fac] | per warp: D doubles
+template <int D>
+__global__ void __launch_bounds__(256)
+k_probs_fdmma(AtomDev a, FactoredDev fd, const int32_t* __restrict__ ffo_g, int n_frag, int n_fac, const double* __restrict__ rho,
+              const double* __restrict__ E, double* __restrict__ out, int64_t el_stride)
+{
+    using C = FpCfg<D>;
+    extern __shared__ __align__(16) double smj[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const unsigned lg = (unsigned)lane >> 2, lt = (unsigned)lane & 3u;
+    double* frag = smj;
+    uint4* tab = reinterpret_cast<uint4*>(frag + ((n_frag + 1) & ~1));
+    int* fptr = reinterpret_cast<int*>(tab + (size_t)n_fac * 64);
+    int* fmeta = fptr + (a.n_ops + 1);                                 // [f] = nq | fragment offset << 2
+    double* st = smj + (((n_frag + 1) & ~1) + n_fac * 128 + ((a.n_ops + 1 + n_fac + 3) >> 2) * 2) + warp * D;
+    for (int i = threadIdx.x; i <= a.n_ops; i += blockDim.x) fptr[i] = fd.op_fptr[i];
+    for (int f = warp; f < n_fac; f += n_warps) {
+        const FactorRec fr = fd.fac[f];
+        const double* m = fd.mats + fr.moff;
+        double* dst = frag + ffo_g[f];
+        if (fr.nq == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q * 32 + lane] = m[(8 * (q >> 2) + (int)lg) * 16 + 4 * (q & 3) + (int)lt];     // A[row = 8 mt + lg][col = 4 kk + lt]
+        } else {
+            dst[lane] = m[(int)(lg & 3u) * 4 + (int)lt];
+        }
+        const FpEntry en = fp_entry<D>(fr, lg, lt);
+        tab[(f * 2) * 32 + lane] = make_uint4(en.w[0], en.w[1], en.w[2], en.w[3]);
+        tab[(f * 2 + 1) * 32 + lane] = make_uint4(en.w[4], en.w[5], en.w[6], en.w[7]);
+        if (lane == 0) fmeta[f] = fr.nq | (ffo_g[f] << 2);
+    }
+    __syncthreads();
+    const int gw = blockIdx.x * n_warps + warp, nw = gridDim.x * n_warps;
+    for (int c = gw; c < a.n_circ; c += nw) {
+        const uint32_t p0 = a.circ_ptr[c], L = a.circ_ptr[c + 1] - p0;
+        const double* r = rho + (size_t)a.circ_prep[c] * D;
+#pragma unroll
+        for (int j = 0; j < D / 32; ++j) st[fj_sw((unsigned)(lane + 32 * j))] = __ldg(r + lane + 32 * j);
+        __syncwarp();
+        int gch = 0;
+        for (uint32_t k = 0; k < L; ++k) {
+            if ((k & 31u) == 0u) gch = (k + lane < L) ? __ldg(a.circ_ops + p0 + k + lane) : 0;
+            const int g = __shfl_sync(0xffffffffu, gch, (int)(k & 31u));
+            const int f1 = fptr[g + 1];
+            for (int f = fptr[g]; f < f1; ++f) {
+                FpEntry tb;
+                { const uint4 h0 = tab[(f * 2) * 32 + lane], h1 = tab[(f * 2 + 1) * 32 + lane];
+                  tb.w[0] = h0.x; tb.w[1] = h0.y; tb.w[2] = h0.z; tb.w[3] = h0.w; tb.w[4] = h1.x; tb.w[5] = h1.y; tb.w[6] = h1.z; tb.w[7] = h1.w; }
+                const int meta = fmeta[f];
+                const double* fg = frag + (meta >> 2) + lane;
+                if ((meta & 3) == 2) {
+                    double A0[4], A1[4];
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) { A0[kk] = fg[kk * 32]; A1[kk] = fg[(4 + kk) * 32]; }
+#pragma unroll
+                    for (int nt = 0; nt < C::NT2; ++nt) {
+                        double2 o0 = make_double2(0.0, 0.0), o1 = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const double b = st[fp_byte<D>(tb, nt * 4 + kk)];
+                            dmma884(o0.x, o0.y, A0[kk], b); dmma884(o1.x, o1.y, A1[kk], b);
+                        }
+                        if (C::R2 >= 8 || lt < 2u) {
+                            const int s = C::NT2 * 4 + nt * 4;
+                            st[fp_byte<D>(tb, s)] = o0.x; st[fp_byte<D>(tb, s + 1)] = o0.y;
+                            st[fp_byte<D>(tb, s + 2)] = o1.x; st[fp_byte<D>(tb, s + 3)] = o1.y;
+                        }
+                    }
+                } else {
+                    const double A = fg[0];
+#pragma unroll
+                    for (int nt = 0; nt < C::NT1; ++nt) {
+                        double2 o = make_double2(0.0, 0.0);
+                        dmma884(o.x, o.y, A, st[fp_byte<D>(tb, nt)]);
+                        if (lg < 4u) { st[fp_byte<D>(tb, C::NT1 + nt * 2)] = o.x; st[fp_byte<D>(tb, C::NT1 + nt * 2 + 1)] = o.y; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int qo = a.out_ptr[c]; qo < a.out_ptr[c + 1]; ++qo) {
+            const double* e = E + (size_t)a.out_eff[qo] * D;
+            double part = 0.0;
+#pragma unroll
+            for (int j = 0; j < D / 32; ++j) part = fma(__ldg(e + lane + 32 * j), st[fj_sw((unsigned)(lane + 32 * j))], part);
+#pragma unroll
+            for (int mk = 16; mk > 0; mk >>= 1) part += shfl_xor_f64(part, mk);
+            if (lane == 0) out[(int64_t)a.out_el[qo] * el_stride] = part;
+        }
+        __syncwarp();
+    }
+}
