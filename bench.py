@@ -747,8 +747,8 @@ def bench_c5(args, D, engine, stream, ctx):
         err = float((Pf - P).abs().max())
         assert err <= 1e-11, err
         out["embedded_model"] = {"what": "same 5000 circuits, 14 layer labels each = 2 factors embedded on 1-2 of 4 qubits (28 factors): "
-                                         "k_probs_factored (factor programs, no dense matrices) vs the dense level-batched DMMA path on the "
-                                         "densified model", "ms_factored": ms_f, "ms_dense": ms_d, "speedup": ms_d / ms_f,
+                                         "k_probs_fdmma (factor programs applied as DMMA chain steps, no dense matrices) vs the dense "
+                                         "level-batched DMMA path on the densified model", "ms_factored": ms_f, "ms_dense": ms_d, "speedup": ms_d / ms_f,
                                  "outcomes_per_s_factored": D.world * t.n_elements / (ms_f * 1e-3), "max_abs_diff": err}
     except AssertionError:
         raise

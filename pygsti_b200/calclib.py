@@ -358,7 +358,7 @@ def prepare_dprobs_atom(fwdsim, layout_atom, param_indices):
     it walks pyGSTi model objects."""
     model = fwdsim.model
     ctx, ent = _engine_atom(fwdsim, layout_atom)
-    if getattr(fwdsim, "device_lindblad", False) and _lindblad_model_and_derivs(fwdsim, layout_atom, ent, param_indices, ctx):
+    if getattr(fwdsim, "device_lindblad", True) and _lindblad_model_and_derivs(fwdsim, layout_atom, ent, param_indices, ctx):
         pidx = packing.param_slice_to_array(param_indices, model.num_params)
     else:
         _upload_model(fwdsim, layout_atom, ent)

@@ -889,7 +889,7 @@ extern "C" int b200_lindblad_members(b200_ctx* c, int d, int n_eg, const int32_t
         (rc = up(b[I_ST], stat, s_tot))) return rc;
     CU(b[I_L].ensure((size_t)n_eg * n * 8)); CU(b[I_E].ensure((size_t)n_eg * n * 8));
     CU(b[I_DL].ensure(std::max<size_t>((size_t)np_tot * n * 8, 16))); CU(b[I_DE].ensure(std::max<size_t>((size_t)np_tot * n * 8, 16)));
-    CU(b[I_WK].ensure((size_t)n_rows * 7 * n * 8));
+    CU(b[I_WK].ensure(std::max((size_t)n_rows * 7 * n * 8, ((size_t)n_eg * 81 * n + (size_t)n_eg + 16) * 8)));
     // outputs + the two prefix arrays of the members in one buffer: [val | dval | vptr | dptr]
     const long long n_val = vptr[n_mem], n_dval = dptr[n_mem];
     CU(b[I_OUT].ensure(std::max<size_t>((size_t)(n_val + n_dval) * 8 + (size_t)2 * (n_mem + 1) * 8, 16)));
@@ -911,7 +911,14 @@ extern "C" int b200_lindblad_members(b200_ctx* c, int d, int n_eg, const int32_t
     a.stat = b[I_ST].as<double>(); a.val = d_val; a.dval = d_dval;
     const int g1 = (int)std::max<long long>(1, std::min<long long>((n_rows * n + 255) / 256, (long long)c->sm_count * 16));
     k_lind_errgen<<<g1, 256, 0, c->stream>>>(a, n_rows);
-    k_lind_expm<<<(unsigned)((n_rows + 63) / 64), 64, 0, c->stream>>>(a, n_rows);
+    if (d == 16) {              // warp-per-row DMMA recursion (the work area of the per-thread kernel holds T_k, E_q, X, s: 81 d^2 + 1 per generator)
+        const long long n_par_rows = n_rows - n_eg;
+        k_lind_gen16<<<(unsigned)n_eg, 32, 0, c->stream>>>(a);
+        if (n_par_rows > 0) k_lind_dexp16<<<(unsigned)((n_par_rows + LB16_WARPS - 1) / LB16_WARPS), LB16_WARPS * 32, 0, c->stream>>>(a, n_par_rows);
+        c->launches++;
+    } else {
+        k_lind_expm<<<(unsigned)((n_rows + 63) / 64), 64, 0, c->stream>>>(a, n_rows);
+    }
     c->launches += 2;
     if (n_mem > 0) {
         const int g3 = (int)std::max<long long>(1, std::min<long long>((n_val + n_dval + 255) / 256, (long long)c->sm_count * 16));

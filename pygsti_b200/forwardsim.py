@@ -39,6 +39,12 @@ class B200ForwardSimulator(_MapForwardSimulator):
     fused_objective : bool
         True (default): a stock pyGSTi objective function / Levenberg-Marquardt run on this simulator uses the fused row scaling
         and the on-device J^T J / J^T f (``pygsti_b200.objective.install_hooks``); False: pyGSTi's own host-side passes.
+    device_lindblad : bool
+        True (default since round 2): for Lindblad-parameterised members (CPTPLND / H+S / GLND gates, preps, effects) the dense
+        algebra of a model update -- error generators, exponentials, Frechet derivatives, composition with the static parts --
+        runs on the device (``b200_lindblad_members``: 1.2 ms of kernels at BASELINE config 4 instead of 1.0-1.2 s of
+        ``to_dense`` / ``deriv_wrt_params`` on the host); models without such members, or with a parameter interposer, take the
+        host packing path as before.
     analytic_hessian : bool
         True (default): `bulk_fill_hprobs` is fully analytic on the device for every member that provides
         `hessian_wrt_params`.  False: members not linear in their parameters go through the reference's own
@@ -47,7 +53,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
 
     def __init__(self, model=None, max_cache_size=None, num_atoms=None, processor_grid=None, param_blk_sizes=None,
                  derivative_eps=1e-7, hessian_eps=1e-5, derivative_mode='analytic', device=None, devices=None,
-                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False, device_lindblad=False,
+                 analytic_hessian=True, device_model_update=False, host_prefix_cache=False, device_lindblad=True,
                  fused_objective=True):
         if derivative_mode not in ('analytic', 'fd'):
             raise ValueError("derivative_mode must be 'analytic' or 'fd'")
@@ -97,7 +103,7 @@ class B200ForwardSimulator(_MapForwardSimulator):
                    device=state.get('device', None), analytic_hessian=state.get('analytic_hessian', True),
                    device_model_update=state.get('device_model_update', False),
                    host_prefix_cache=state.get('host_prefix_cache', False),
-                   device_lindblad=state.get('device_lindblad', False), fused_objective=state.get('fused_objective', True))
+                   device_lindblad=state.get('device_lindblad', True), fused_objective=state.get('fused_objective', True))
 
     def copy(self, keep_model_attached=True):
         # MapForwardSimulator.copy hard-codes its own class (mapforwardsim.py:190-204) -> must override,

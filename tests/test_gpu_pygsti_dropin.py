@@ -460,8 +460,16 @@ def test_device_lindblad_members_match_host_path():
     model.from_vector(model.to_vector() + 1e-2 * rng.standard_normal(model.num_params))
     circuits = smq1Q_XYI.create_gst_experiment_design(2).all_circuits_needing_data
     res = {}
-    for name, sim in (("dev", B200ForwardSimulator(device_lindblad=True)), ("host", B200ForwardSimulator()),
+    for name, sim in (("dev", B200ForwardSimulator(device_lindblad=True)), ("host", B200ForwardSimulator(device_lindblad=False)),
                       ("matrix", MatrixForwardSimulator())):
         res[name] = _bulk_arrays(model, sim, circuits)
     assert np.max(np.abs(res["dev"][0] - res["host"][0])) <= 1e-12 and np.max(np.abs(res["dev"][0] - res["matrix"][0])) <= 1e-12
     assert np.max(np.abs(res["dev"][1] - res["host"][1])) <= 1e-10 and np.max(np.abs(res["dev"][1] - res["matrix"][1])) <= 1e-10
+    # BASELINE config 4's model family, d = 16: the warp-per-row DMMA recursion (k_lind_gen16 / k_lind_dexp16)
+    m2 = smq2Q_XYCNOT.target_model("CPTPLND")
+    m2.from_vector(m2.to_vector() + 1e-2 * rng.standard_normal(m2.num_params))
+    c2 = smq2Q_XYCNOT.create_gst_experiment_design(1).all_circuits_needing_data[:12]
+    r2 = {name: _bulk_arrays(m2, sim, c2) for name, sim in (("dev", B200ForwardSimulator(device_lindblad=True)),
+                                                             ("host", B200ForwardSimulator(device_lindblad=False)))}
+    assert np.max(np.abs(r2["dev"][0] - r2["host"][0])) <= 1e-12
+    assert np.max(np.abs(r2["dev"][1] - r2["host"][1])) <= 1e-10
