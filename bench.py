@@ -853,6 +853,54 @@ def bench_c4(args, D, engine, stream, ctx):
     return out
 
 
+def bench_plugin(args):
+    """`e2e_plugin`: the call a pyGSTi user makes -- `model.sim.bulk_fill_dprobs(array, layout)` with `model.sim =
+    B200ForwardSimulator()` -- timed by wall clock next to the stock `MapForwardSimulator` (the reference's Cython path, one process,
+    NOT extrapolated) on the same model, circuits and host: smq2Q_XYCNOT `full` (Np = 1360), GST design maxL = 16 (7860 circuits,
+    31 440 outcomes; BASELINE.md's "C2-lite maxL=16" probe, 7.3 s in the build container).  Needs the reference install
+    (baseline/_ref, which travels to the GPU box); rank 0 at N = 1 only."""
+    ref = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "pygsti")):
+        return {"unavailable": "baseline/_ref (reference install) not present"}
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import warnings
+    warnings.filterwarnings("ignore")
+    from pygsti.modelpacks import smq2Q_XYCNOT as mp
+    from pygsti.forwardsims import MapForwardSimulator
+    from pygsti_b200.forwardsim import B200ForwardSimulator
+    base = mp.target_model().depolarize(op_noise=0.01, spam_noise=0.01)
+    circuits = list(mp.create_gst_experiment_design(16).all_circuits_needing_data)
+    out = {"workload": "smq2Q_XYCNOT full (d=16, Np=%d), GST maxL=16: %d circuits; model.sim.bulk_fill_dprobs(J, layout) through pyGSTi, "
+                       "host arrays, wall clock" % (base.num_params, len(circuits))}
+    res = {}
+    for name, sim, reps in (("b200", B200ForwardSimulator(), 4), ("reference", MapForwardSimulator(), 1)):
+        m = base.copy(); m.sim = sim
+        t0 = time.time(); layout = m.sim.create_layout(circuits, array_types=('e', 'ep')); t_layout = time.time() - t0
+        J = np.empty((layout.num_elements, m.num_params))
+        ts = []
+        for _ in range(reps):
+            t0 = time.time(); m.sim.bulk_fill_dprobs(J, layout); ts.append(time.time() - t0)
+        # rows by circuit so that the two layouts can be compared
+        rows = {}
+        for i, c in enumerate(layout.circuits):
+            idx, outc = layout.indices_and_outcomes_for_index(i)
+            idx = np.arange(idx.start, idx.stop) if isinstance(idx, slice) else np.asarray(idx)
+            rows[c] = dict(zip(outc, idx))
+        res[name] = (J, rows)
+        out[name] = {"create_layout_s": t_layout, "first_call_ms": ts[0] * 1e3, "ms": min(ts) * 1e3, "outcomes": int(layout.num_elements)}
+    Jb, rb = res["b200"]; Jr, rr = res["reference"]
+    err = 0.0
+    for c in circuits[::97]:
+        for o, k in rb[c].items():
+            err = max(err, float(np.max(np.abs(Jb[k] - Jr[rr[c][o]]))))
+    out["ratio"] = out["reference"]["ms"] / out["b200"]["ms"]
+    out["max_abs_diff_sampled_circuits"] = err
+    out["note"] = ("reference = the stock Cython MapForwardSimulator: forward differences, eps = 1e-7, one prefix-table pass per parameter on one core "
+                   "(pyGSTi parallelises over MPI ranks only); the difference to the analytic device Jacobian is that FD's truncation error")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -907,6 +955,12 @@ def main():
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_sample(case, os.cpu_count() or 1, core_seconds=20.0)
+            try:
+                line["e2e_plugin"] = bench_plugin(args)
+            except AssertionError:
+                raise
+            except Exception as e:
+                line["e2e_plugin"] = {"error": "%s: %s" % (type(e).__name__, e)}
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
