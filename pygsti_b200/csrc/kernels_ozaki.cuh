@@ -31,6 +31,7 @@
 #define OZ_LBO 128u                    // between the two 16-byte K chunks of a core-matrix row group
 #define OZ_SBO 256u                    // between row groups of 8
 #define OZ_MAX_STAGES_PER_SLICE 2047   // 8 pairs x 65 504 rows x 64^2 < 2^31
+#define OZ_BAD_COLUMN 0x7fffffff       // exponent marker of a column with non-finite entries
 
 // ---- one pass over J: per column the largest magnitude (-> exponent e_p) and, with f, the weighted sum (J^T f)[p] -----------------
 // row slices -> partials [n_slices][Np], reduced in slice order by k_oz_colstats_reduce (deterministic)
@@ -42,15 +43,17 @@ k_oz_colstats(const double* __restrict__ J, int64_t ld, int64_t nE, int Np, cons
     const int64_t k_lo = blockIdx.y * rows_per_slice, k_hi = min(k_lo + rows_per_slice, nE);
     if (c >= Np) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, m0 = 0.0, m1 = 0.0;
+    bool bad = false;
     int64_t k = k_lo;
     for (; k + 3 < k_hi; k += 4) {
         const double v0 = J[k * ld + c], v1 = J[(k + 1) * ld + c], v2 = J[(k + 2) * ld + c], v3 = J[(k + 3) * ld + c];
         if (f) { s0 = fma(f[k], v0, s0); s1 = fma(f[k + 1], v1, s1); s2 = fma(f[k + 2], v2, s2); s3 = fma(f[k + 3], v3, s3); }
         m0 = fmax(m0, fmax(fabs(v0), fabs(v1))); m1 = fmax(m1, fmax(fabs(v2), fabs(v3)));
+        bad |= !(fabs(v0) <= 1.7976931348623157e308) | !(fabs(v1) <= 1.7976931348623157e308) | !(fabs(v2) <= 1.7976931348623157e308) | !(fabs(v3) <= 1.7976931348623157e308);
     }
-    for (; k < k_hi; ++k) { const double v = J[k * ld + c]; if (f) s0 = fma(f[k], v, s0); m0 = fmax(m0, fabs(v)); }
+    for (; k < k_hi; ++k) { const double v = J[k * ld + c]; if (f) s0 = fma(f[k], v, s0); m0 = fmax(m0, fabs(v)); bad |= !(fabs(v) <= 1.7976931348623157e308); }
     part_sum[(size_t)blockIdx.y * Np + c] = (s0 + s1) + (s2 + s3);
-    part_max[(size_t)blockIdx.y * Np + c] = fmax(m0, m1);
+    part_max[(size_t)blockIdx.y * Np + c] = bad ? __longlong_as_double(0x7ff0000000000000LL) : fmax(m0, m1);     // (fmax drops NaN: Inf / NaN entries are flagged explicitly)
 }
 // e_p = smallest e with max_el |J[el][p]| < 2^e  (0 for an all-zero column)
 __global__ void __launch_bounds__(256)
@@ -64,7 +67,9 @@ k_oz_colstats_reduce(const double* __restrict__ part_sum, const double* __restri
     if (jtf) jtf[c] = s;
     int e = 0;
     if (m > 0.0 && isfinite(m)) { frexp(m, &e); }                                  // m = f 2^e, f in [0.5, 1)  =>  |x| 2^-e < 1
-    expo[c] = max(e, -900);
+    // a column holding Inf / NaN (flagged by k_oz_colstats as an infinite maximum) cannot be cut into digits: it is marked, sliced as zeros, and
+    // its row and column of J^T J come out as NaN -- what the FP64 contraction would deliver for it
+    expo[c] = isfinite(m) ? max(e, -900) : OZ_BAD_COLUMN;
 }
 
 // ---- digits, written as the operand image:  S[stage][t][p >> 3][chunk][p & 7][16],  zero padded to P_pad x n_stages ----------
@@ -84,13 +89,14 @@ k_oz_slice(const double* __restrict__ J, int64_t ld, int64_t nE, int Np, const i
     double x[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = (p < Np && el0 + i < nE) ? J[(el0 + i) * ld + p] : 0.0;
-    const double sc = scalbn(1.0, 6 - ((p < Np) ? expo[p] : 0));          // |x| sc < 64
+    const int ex = (p < Np) ? expo[p] : 0;
+    const double sc = ex == OZ_BAD_COLUMN ? 0.0 : scalbn(1.0, 6 - ex);     // |x| sc < 64
     uint32_t w[T][4];
 #pragma unroll
     for (int t = 0; t < T; ++t) { w[t][0] = 0u; w[t][1] = 0u; w[t][2] = 0u; w[t][3] = 0u; }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        double y = x[i] * sc;
+        double y = ex == OZ_BAD_COLUMN ? 0.0 : x[i] * sc;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             const double magic = 6755399441055744.0 / (double)(1ull << (7 * t));     // 1.5 2^(52 - 7t)
@@ -272,7 +278,7 @@ k_oz_reduce(OzArgs p, const int* __restrict__ expo, int Np, double* __restrict__
         if (i >= Np || j > i) continue;
         double s = 0.0;
         for (int sl = 0; sl < p.n_kslices; ++sl) s += p.part[((size_t)sl * p.n_tiles + tile) * (OZ_TM * OZ_TN) + e];
-        s = scalbn(s, expo[i] + expo[j]);
+        s = (expo[i] == OZ_BAD_COLUMN || expo[j] == OZ_BAD_COLUMN) ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(s, expo[i] + expo[j]);
         C[(size_t)i * ldc + j] = s;
         if (j < i) C[(size_t)j * ldc + i] = s;
     }

@@ -403,3 +403,28 @@ def test_factored_jacobian_matches_oracle(gpu_ctx, dim, n_ops, share):
     Js = np.full((t.n_elements, Np), np.nan); at.fill_dprobs(Js, row_scale=w)
     assert np.max(np.abs(Js - Jo * w[:, None])) <= 1e-11 * max(1.0, np.max(np.abs(Jo)))
     at.free()
+
+
+def test_jtj_tcgen05_nonfinite_column(gpu_ctx):
+    """A Jacobian column that holds NaN / Inf cannot be cut into int8 digits: the tcgen05 J^T J must flag it (NaN in that row and
+    column of the result, as an FP64 contraction delivers) and leave every other entry exact."""
+    dim, n_ops, n_eff = 4, 3, 2
+    G, rho, E = synth.random_model(dim, n_ops, 1, n_eff, seed=2)
+    circs = synth.random_circuits(700, 12, n_ops, 1, n_eff, seed=9, subsets=False)
+    t = synth.make_tables(dim, n_ops, 1, n_eff, circs)
+    D = synth.random_derivs(t, 70, density=0.05, seed=3)
+    at = gpu_ctx.upload_atom(t); at.set_model(G, rho, E); at.set_derivs(D)
+    J = np.empty((t.n_elements, 70)); at.fill_dprobs(J)
+    p_bad = int(D.cols[0])
+    vals = D.vals.copy(); vals[0] = np.inf                       # one derivative entry infinite: column p_bad of J becomes Inf / NaN
+    from pygsti_b200.packing import DerivMap
+    at.set_derivs(DerivMap(D.n_w, D.n_params, D.rows, D.cols, vals))
+    try:
+        gpu_ctx.set_jtj_mode(8); X, _ = at.jtj(np.ones(t.n_elements), np.zeros(t.n_elements))
+    finally:
+        gpu_ctx.set_jtj_mode(-1)
+    ok = np.ones(70, bool); ok[p_bad] = False
+    assert np.isnan(X[p_bad]).all() and np.isnan(X[:, p_bad]).all()
+    ref = J[:, ok].T @ J[:, ok]
+    assert np.max(np.abs(X[np.ix_(ok, ok)] - ref)) <= 1e-12 * max(1.0, np.max(np.abs(ref)))
+    at.free()
