@@ -22,6 +22,10 @@ struct LevelTile { uint32_t first; uint16_t count; uint16_t gate; };   // entrie
 // (Round 2 measured two variants of this loop on BASELINE config 5 and reverted both: a four-block register ring for the B
 // fragments, 3.10 vs 2.93 ms, and split-K over two warp groups, 3.32 ms.  The level kernels are not bound by the L2 latency of
 // one warp or by the 64-deep DMMA chain but by how little work one depth level holds: ~0.33 GFLOP = 9 us of the whole GPU.)
+// Also measured and NOT kept (late round 2): ONE persistent launch for all levels -- (tile, output quarter) items from an atomic counter in
+// level-major order, per-circuit arrival counters (release / acquire) instead of the barrier between levels: 3.39 vs 2.90 ms.  With random
+// circuits the 32 circuits of a level-(k+1) tile come from ~14 different level-k gate groups, so an item waits for nearly the whole
+// previous level anyway; the polling and the fences then cost more than the 128 launch gaps they remove.
 // Inner product loop shared by k_level_gemm and k_level_gemm_rows (kernels_levelj.cuh): acc[mt][nt] += A[32 x D] . B[D x 8 NT].
 // A fragments come from shared memory (row stride D + 4), B fragments (rows of G, 32 bytes per row and K step) from L2.  The B
 // loads of the NEXT 16 K (the four sectors of one 128-byte line of each row) are issued before the 4 x 8 DMMA of the current
