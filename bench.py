@@ -408,7 +408,7 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
             fused = {"ms": ms_fused, "outcomes_per_s": nE / (ms_fused * 1e-3), "bitwise_equal_to_nccl_result": same,
                      "bytes_sent_per_rank": (world - 1) * plan.n_local[rank] * (Np + 1) * 8,
                      "what": "b200_fill_dprobs_bcast_dev: k_accum_trie_d16<PEERS> stores every finished Jacobian block into the local array "
-                             "and into the CUDA-IPC-mapped arrays of the %d peers (plain st.global over NVLink), then one 4-byte all-reduce "
+                             "and into the CUDA-IPC-mapped arrays of the %d peers (the unit's 2 KB blocks staged in shared memory and sent as cp.async.bulk stores of the TMA engine over NVLink, one instruction per (outcome, destination) set), then one 4-byte all-reduce "
                              "as the barrier; no separate all-gather pass" % (world - 1)}
             del Jt, Pt
             JP.close(); PP.close()

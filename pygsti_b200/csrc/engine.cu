@@ -1369,8 +1369,9 @@ static int launch_d16(b200_ctx* c, b200_atom* a, const D16Args& args) {
     { int rcP = phase_mark(c); if (rcP) return rcP; }
     const int gB = grid_for(c, ((int64_t)a->n_units + AT_WARPS * AT_CHUNK - 1) / (AT_WARPS * AT_CHUNK), 2);
     if (args.n_peers > 0) {
-        CU(cudaFuncSetAttribute(k_accum_trie_d16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));
-        k_accum_trie_d16<true><<<gB, AT_WARPS * 32, smemB, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
+        const size_t smemP = smemB + 128 + (size_t)AT_WARPS * AT_NO * 256 * 8 + (size_t)a->n_ops * 4;      // + bulk-store staging + per-gate block bases
+        CU(cudaFuncSetAttribute(k_accum_trie_d16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP));
+        k_accum_trie_d16<true><<<gB, AT_WARPS * 32, smemP, c->stream>>>(atom_dev(a), model_dev(a), t, args, a->t_units.as<UnitRec>(), a->n_units,
                                                                        a->t_uidx.as<uint2>(), a->t_counters.as<unsigned>() + 2, AT_CHUNK);
     } else {
         CU(cudaFuncSetAttribute(k_accum_trie_d16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB));

@@ -295,7 +295,19 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
     int2* cm_s = reinterpret_cast<int2*>(spam_stage + AT_WARPS * SPS);  // [n_ops*4][32]
     int* spamc_s = reinterpret_cast<int*>(cm_s + a.n_ops * 4 * 32);     // [SPAM_MAX]
     int* spamw_s = spamc_s + D16_SPAM_MAX;
+    // PEERS: per-warp staging of a unit's NO finished 16 x 16 blocks (2 KB each, in Jacobian-row order) for the bulk stores, and per
+    // gate the first Jacobian column of its block when the block is one contiguous, 16-byte aligned run of 256 columns (else -1)
+    double* bulk_stage = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(spamw_s + D16_SPAM_MAX) + 127) & ~(uintptr_t)127);   // [AT_WARPS][NO * 256]
+    int* gbase_s = reinterpret_cast<int*>(bulk_stage + (PEERS ? AT_WARPS * NO * 256 : 0));                                             // [n_ops]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (PEERS) {
+        for (int g = threadIdx.x; g < a.n_ops; g += blockDim.x) {
+            const int b0 = args.colmap[g * 256];
+            bool ok = b0 >= 0 && (b0 & 1) == 0 && (args.ld & 1) == 0;
+            for (int e = 1; e < 256 && ok; ++e) ok = args.colmap[g * 256 + e] == b0 + e;
+            gbase_s[g] = ok ? b0 : -1;
+        }
+    }
     for (int idx = threadIdx.x; idx < a.n_ops * 4 * 32; idx += blockDim.x) {
         const int g = idx >> 7, tile = (idx >> 5) & 3, l = idx & 31;
         const int i = 8 * (tile >> 1) + (l >> 2), jc = 8 * (tile & 1) + 2 * (l & 3);
@@ -401,6 +413,35 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                     for (int k = 0; k < 8; ++k) acc[o][k] *= sc;
                 }
             }
+            const int gb = PEERS ? gbase_s[g] : -1;
+            if (PEERS && gb >= 0) {
+                // Fused exchange, bulk form: the unit's blocks are staged in shared memory in Jacobian-row order and leave as 2 KB bulk
+                // stores of the TMA engine, ONE instruction for all (outcome, destination) pairs (lane = 8 outcome + destination;
+                // destination 0 = this GPU's array, 1.. = the peers' arrays over NVLink).  The per-lane form below sends every 16-byte
+                // store instruction once per destination: 128 store instructions per unit at 7 peers, and 64-byte NVLink writes.
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous unit's staging has been read
+                __syncwarp();
+                double* stg = bulk_stage + warp * (NO * 256);
+#pragma unroll
+                for (int o = 0; o < NO; ++o)
+#pragma unroll
+                    for (int tile = 0; tile < 4; ++tile)
+                        *reinterpret_cast<double2*>(stg + o * 256 + (8 * (tile >> 1) + (int)mrow) * 16 + 8 * (tile & 1) + 2 * (int)q) =
+                            make_double2(acc[o][tile * 2], acc[o][tile * 2 + 1]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                const int bo = lane >> 3, bd = lane & 7;
+                const int elo = bo == 0 ? els[0] : bo == 1 ? els[1] : bo == 2 ? els[2] : els[3];
+                if (elo >= 0 && bd <= args.n_peers) {
+                    double* Jb = args.J;
+#pragma unroll
+                    for (int r = 0; r < B200_PEERS_MAX; ++r) if (bd == r + 1) Jb = args.peerJ[r];
+                    double* dstp = Jb + (int64_t)elo * args.ld + gb;
+                    const unsigned src = (unsigned)__cvta_generic_to_shared(stg + bo * 256);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstp), "r"(src), "r"(2048u) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            } else {
             const int n_dst = PEERS ? 1 + args.n_peers : 1;
 #pragma unroll 1
             for (int dst = 0; dst < n_dst; ++dst) {
@@ -433,6 +474,7 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
                         }
                     }
                 }
+            }
             }
             if (g == 0) {
                 // SPAM / unmapped columns and probabilities of the group's outcomes.  The rows they come from (s_L and e_0 of every
@@ -485,4 +527,5 @@ k_accum_trie_d16(AtomDev a, ModelDev m, TrieDev t, D16Args args, const UnitRec* 
         }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    if (PEERS) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every bulk store of this thread has completed before the CTA leaves
 }
