@@ -1614,7 +1614,7 @@ static bool factoredj_ok(b200_ctx* c, b200_atom* a) {
            a->fj_n_params == a->n_params && same_factor_structure(a->fj_fac, a->h_fac) && fj_warps(c, a) > 0;
 }
 template <int D>
-static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale) {
+static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld, double* d_probs, const double* d_scale, PeerSpec* ps) {
     CU(c->fj_fs.ensure((size_t)a->fj_rows * D * 8));
     CU(c->fj_counter.ensure(16));
     const FactoredDev fd = factored_dev(a);
@@ -1644,8 +1644,10 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
     if (D == 64) {
         Fj64Slots sl; for (int q = 0; q < FJ64_REG_SLOTS; ++q) sl.fao[q] = a->fj_slot_fao[q];
         CU(cudaFuncSetAttribute(k_fj64_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FjPeers fp; fp.n = 0;
+        if (ps && ps->n > 0) { fp.n = ps->n; for (int r = 0; r < ps->n; ++r) fp.J[r] = ps->J[r]; ps->j_done = true; }      // rows also stored into the peers' arrays
         k_fj64_backward<<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, a->fj_slots.as<int32_t>(), sl, M + a->off_eff, c->fj_fs.as<double>(),
-                                                             d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items);
+                                                             d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items, fp);
     } else {
         CU(cudaFuncSetAttribute(k_fj_backward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_fj_backward<D><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_eff, c->fj_fs.as<double>(), d_out, ld, d_scale,
@@ -1682,7 +1684,7 @@ static int fill_dprobs_device(b200_ctx* c, b200_atom* a, double* d_out, int64_t 
         return launch_d16(c, a, args);
     }
     if (factoredj_ok(c, a)) {
-        return a->dim == 64 ? launch_factoredj<64>(c, a, d_out, ld, d_probs, d_scale) : launch_factoredj<256>(c, a, d_out, ld, d_probs, d_scale);
+        return a->dim == 64 ? launch_factoredj<64>(c, a, d_out, ld, d_probs, d_scale, ps) : launch_factoredj<256>(c, a, d_out, ld, d_probs, d_scale, ps);
     }
     if (!a->has_derivs) return fail(B200_E_STATE, "only a factor-space derivative map is set and the factored Jacobian path is unavailable for this atom");
     if (levelj_ok(c, a)) {

@@ -395,8 +395,9 @@ __device__ __forceinline__ void fj64_stage(const AtomDev& a, const FactoredDev& 
 // (cur, rho block of the circuit's prep) and s_L (sb, block of the outcome's effect).  One lane per parameter, FOUR parameters per lane
 // in flight: the dependent loads cptr -> code -> element are L2 round trips when the CTA's shared memory leaves little L1 (ncu: the
 // one-parameter-at-a-time loop was 25-37 % of the backward kernels' stall samples for 14-20 % of their instructions).
+struct FjPeers { int n; double* J[B200_PEERS_MAX]; };     // fused exchange: the same Jacobian rows also go into the peers' arrays (NVLink)
 __device__ __forceinline__ void fj64_row(const FjDev& fj, const double* acc, const double* cur, const double* sb, int prep, int eff,
-                                         double* __restrict__ Jrow, double sc, int lane)
+                                         double* __restrict__ Jrow, double sc, int lane, const FjPeers& peers, int64_t roff)
 {
     const int Np = fj.n_params;
     for (int p0 = lane; p0 < Np; p0 += 128) {
@@ -428,6 +429,11 @@ __device__ __forceinline__ void fj64_row(const FjDev& fj, const double* acc, con
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) if (p0 + 32 * u < Np) Jrow[p0 + 32 * u] = v[u] * sc;
+        for (int r = 0; r < peers.n; ++r) {                    // 256-byte coalesced runs per warp instruction and destination
+            double* Pr = peers.J[r] + roff;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (p0 + 32 * u < Np) Pr[p0 + 32 * u] = v[u] * sc;
+        }
     }
 }
 
@@ -489,7 +495,7 @@ struct Fj64Slots { int fao[FJ64_REG_SLOTS]; };
 __global__ void __launch_bounds__(256)
 k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* __restrict__ slots, Fj64Slots sl, const double* __restrict__ E,
                 const double* __restrict__ FS, double* __restrict__ J, int64_t ld, const double* __restrict__ row_scale,
-                unsigned* __restrict__ counter, int n_items)
+                unsigned* __restrict__ counter, int n_items, FjPeers peers)
 {
     constexpr int D = 64;
     extern __shared__ __align__(16) double smj[];
@@ -583,7 +589,7 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         if (sl.fao[3] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[3]) + lane; ap[0] = R3[0]; ap[32] = R3[1]; ap[64] = R3[2]; ap[96] = R3[3]; }
         sb[i0] = __ldg(srow + (size_t)nst * D + lane); sb[i1] = __ldg(srow + (size_t)nst * D + lane + 32);
         __syncwarp();
-        fj64_row(fj, acc, cur, sb, a.circ_prep[c], eff, J + el * ld, row_scale ? __ldg(row_scale + el) : 1.0, lane);
+        fj64_row(fj, acc, cur, sb, a.circ_prep[c], eff, J + el * ld, row_scale ? __ldg(row_scale + el) : 1.0, lane, peers, el * ld);
         __syncwarp();
     }
 }
