@@ -1643,11 +1643,17 @@ static int launch_factoredj(b200_ctx* c, b200_atom* a, double* d_out, int64_t ld
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_items + warps - 1) / warps, (int64_t)c->sm_count * per_sm));
     if (D == 64) {
         Fj64Slots sl; for (int q = 0; q < FJ64_REG_SLOTS; ++q) sl.fao[q] = a->fj_slot_fao[q];
-        CU(cudaFuncSetAttribute(k_fj64_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FjPeers fp; fp.n = 0;
         if (ps && ps->n > 0) { fp.n = ps->n; for (int r = 0; r < ps->n; ++r) fp.J[r] = ps->J[r]; ps->j_done = true; }      // rows also stored into the peers' arrays
-        k_fj64_backward<<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, a->fj_slots.as<int32_t>(), sl, M + a->off_eff, c->fj_fs.as<double>(),
-                                                             d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items, fp);
+        if (fp.n > 0) {
+            CU(cudaFuncSetAttribute(k_fj64_backward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fj64_backward<true><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, a->fj_slots.as<int32_t>(), sl, M + a->off_eff, c->fj_fs.as<double>(),
+                                                                       d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items, fp);
+        } else {
+            CU(cudaFuncSetAttribute(k_fj64_backward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_fj64_backward<false><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, a->fj_slots.as<int32_t>(), sl, M + a->off_eff, c->fj_fs.as<double>(),
+                                                                        d_out, ld, d_scale, c->fj_counter.as<unsigned>(), (int)n_items, fp);
+        }
     } else {
         CU(cudaFuncSetAttribute(k_fj_backward<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_fj_backward<D><<<grid, warps * 32, smem, c->stream>>>(atom_dev(a), fd, fj, a->fac_n, M + a->off_eff, c->fj_fs.as<double>(), d_out, ld, d_scale,

@@ -396,6 +396,7 @@ __device__ __forceinline__ void fj64_stage(const AtomDev& a, const FactoredDev& 
 // in flight: the dependent loads cptr -> code -> element are L2 round trips when the CTA's shared memory leaves little L1 (ncu: the
 // one-parameter-at-a-time loop was 25-37 % of the backward kernels' stall samples for 14-20 % of their instructions).
 struct FjPeers { int n; double* J[B200_PEERS_MAX]; };     // fused exchange: the same Jacobian rows also go into the peers' arrays (NVLink)
+template <bool PEERS>
 __device__ __forceinline__ void fj64_row(const FjDev& fj, const double* acc, const double* cur, const double* sb, int prep, int eff,
                                          double* __restrict__ Jrow, double sc, int lane, const FjPeers& peers, int64_t roff)
 {
@@ -429,7 +430,7 @@ __device__ __forceinline__ void fj64_row(const FjDev& fj, const double* acc, con
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) if (p0 + 32 * u < Np) Jrow[p0 + 32 * u] = v[u] * sc;
-        for (int r = 0; r < peers.n; ++r) {                    // 256-byte coalesced runs per warp instruction and destination
+        if (PEERS) for (int r = 0; r < peers.n; ++r) {         // 256-byte coalesced runs per warp instruction and destination
             double* Pr = peers.J[r] + roff;
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (p0 + 32 * u < Np) Pr[p0 + 32 * u] = v[u] * sc;
@@ -492,6 +493,7 @@ k_fj64_forward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const double* __r
 // One warp per (circuit, outcome).  Shared memory: F^T fragment image | table | fptr | per warp: e0, e1, s (64 doubles each), accumulators.
 // slots[f]: register slot of a 2-qubit factor (0 .. FJ64_REG_SLOTS-1) or 0xFF; slot_fao[s]: accumulator offset of slot s or -1.
 struct Fj64Slots { int fao[FJ64_REG_SLOTS]; };
+template <bool PEERS>
 __global__ void __launch_bounds__(256)
 k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* __restrict__ slots, Fj64Slots sl, const double* __restrict__ E,
                 const double* __restrict__ FS, double* __restrict__ J, int64_t ld, const double* __restrict__ row_scale,
@@ -589,7 +591,7 @@ k_fj64_backward(AtomDev a, FactoredDev fd, FjDev fj, int n_fac, const int32_t* _
         if (sl.fao[3] >= 0) { double2* ap = reinterpret_cast<double2*>(acc + sl.fao[3]) + lane; ap[0] = R3[0]; ap[32] = R3[1]; ap[64] = R3[2]; ap[96] = R3[3]; }
         sb[i0] = __ldg(srow + (size_t)nst * D + lane); sb[i1] = __ldg(srow + (size_t)nst * D + lane + 32);
         __syncwarp();
-        fj64_row(fj, acc, cur, sb, a.circ_prep[c], eff, J + el * ld, row_scale ? __ldg(row_scale + el) : 1.0, lane, peers, el * ld);
+        fj64_row<PEERS>(fj, acc, cur, sb, a.circ_prep[c], eff, J + el * ld, row_scale ? __ldg(row_scale + el) : 1.0, lane, peers, el * ld);
         __syncwarp();
     }
 }
