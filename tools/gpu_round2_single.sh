@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 final single-GPU pass: smoke, full -m gpu suite, bench (both arms), launch list of the bench command, ncu captures of the new kernels
+# round 2, one B200 (as run under gpurun): : smoke, full -m gpu suite, bench (both arms), launch list of the bench command, ncu captures of the new kernels
 mkdir -p gpurun_out
 timeout 300 python __graft_entry__.py smoke > gpurun_out/r2z_smoke.log 2>&1; tail -1 gpurun_out/r2z_smoke.log
 timeout 1700 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/r2z_pytest.log; tail -2 gpurun_out/r2z_pytest.log
