@@ -209,6 +209,52 @@ def test_factored_packing_reproduces_to_dense():
     assert packing.pack_model_factored(m1, a1, 4) is None
 
 
+def test_factor_space_derivative_map_equals_dense_map():
+    """packing.pack_derivs_factored (rows = entries of the small embedded operations, what b200_atom_set_derivs_factored takes) is
+    consistent with packing.pack_derivs (rows = entries of the dense layer operations, pinned against the reference): for the
+    3-qubit crosstalk-free model every layer is ONE embedded factor, so  d(dense layer)/d theta = embed(d(factor)/d theta)
+    -- the chain rule the device applies implicitly; SPAM rows are identical."""
+    from pygsti.processors import QubitProcessorSpec
+    from pygsti.models import modelconstruction as mc
+    from pygsti.forwardsims import MapForwardSimulator
+    from pygsti.circuits import Circuit
+    pspec = QubitProcessorSpec(3, ['Gxpi2', 'Gypi2', 'Gcnot'], geometry='line')
+    model = mc.create_crosstalk_free_model(pspec, ideal_gate_type='full TP', ideal_spam_type='full TP')
+    rng = np.random.default_rng(3)
+    model.from_vector(model.to_vector() + 0.01 * rng.standard_normal(model.num_params))
+    prim = list(model.primitive_op_labels)
+    circs = [Circuit([prim[int(rng.integers(len(prim)))] for _ in range(int(rng.integers(1, 7)))], line_labels=(0, 1, 2)) for _ in range(12)]
+    model.sim = MapForwardSimulator()
+    atom = model.sim.create_layout(circs, array_types=('e', 'ep')).atoms[0]
+    d = 64
+    fm = packing.pack_model_factored(model, atom, d)
+    Df = packing.pack_derivs_factored(model, atom, d, fm)
+    Dd = packing.pack_derivs(model, atom, d)
+    assert fm is not None and Df is not None and Df.n_params == Dd.n_params == model.num_params
+    n_ops = fm.op_fptr.size - 1
+    assert np.array_equal(np.diff(fm.op_fptr), np.ones(n_ops, dtype=fm.op_fptr.dtype))      # one factor per layer label
+    dense_f = np.zeros((Df.n_w, Df.n_params)); np.add.at(dense_f, (Df.rows, Df.cols), Df.vals)
+    dense_d = np.zeros((Dd.n_w, Dd.n_params)); np.add.at(dense_d, (Dd.rows, Dd.cols), Dd.vals)
+    n_mats = fm.mats.size
+    assert np.array_equal(dense_f[n_mats:], dense_d[n_ops * d * d:])                        # rho and effect rows
+    idx = np.arange(d)
+    for g in range(n_ops):
+        k = int(fm.f_nq[g]); ds = 4 ** k
+        shifts = [2 * (3 - 1 - int(q)) for q in fm.f_targets[g, :k]]
+        tmask = 0
+        for sh in shifts:
+            tmask |= 3 << sh
+        t = np.zeros(d, dtype=np.int64)
+        for sh in shifts:
+            t = (t << 2) | ((idx >> sh) & 3)
+        rest = idx & ~tmask
+        same_rest = rest[:, None] == rest[None, :]
+        small_rows = int(fm.f_moff[g]) + (t[:, None] * ds + t[None, :])                     # factor-space row feeding dense entry (i, j)
+        emb = np.where(same_rest[:, :, None], dense_f[small_rows], 0.0).reshape(d * d, -1)
+        assert np.max(np.abs(emb - dense_d[g * d * d:(g + 1) * d * d])) <= 1e-14, g
+    assert np.count_nonzero(dense_f) < np.count_nonzero(dense_d)                            # every small entry appears 4 / 16 times in the dense layer
+
+
 def test_stock_objective_hooks_install_and_restore():
     """The simulator installs the objective-function / LM hooks once; they gate on the simulator and the objective (penalty rows,
     omitted outcomes and `derivative_mode='fd'` go to pyGSTi's own methods) and `uninstall_hooks` restores pyGSTi."""
