@@ -52,3 +52,39 @@ def test_reference_arm_line():
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("reference", "port")
     b = _load("r01_bench_n1_final.json")
     assert d["metric"] == b["metric"] and d["unit"] == b["unit"] and d["config"]["workload"] == b["config"]["workload"]
+
+
+@pytest.mark.parametrize("name,n", [("r02_bench_n1_final.json", 1), ("r02_bench_n2_final.json", 2), ("r02_bench_n8_final.json", 8)])
+def test_round2_lines(name, n):
+    """Round 2: ONE layout strong-scaled over the ranks; the jtj section (tcgen05 contraction next to the FP64 DMMA one), the extra
+    configs and -- at N = 1 -- the plug-in level end-to-end figure."""
+    d = _load(name)
+    assert BASE_KEYS <= set(d) and {"roofline", "clocks", "multi_gpu", "jtj", "extra_configs"} <= set(d)
+    assert d["n_gpus"] == n and d["scaling"] == "strong" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["unit"] == "circuit-outcomes/s" and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert abs(d["value"] - 273340 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]          # whole job = the one layout
+    assert not (set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"})
+    mg = d["multi_gpu"]
+    assert sum(mg["shard_outcomes"]) == 273340 and len(mg["shard_outcomes"]) == n
+    if n > 1:
+        assert "shard" in d["config"]["parallelism"] and mg["allgather"]["bytes_received_per_rank"] > 0
+        f = mg["fused_fill_allgather"]
+        assert f["bitwise_equal_to_nccl_result"] is True
+        assert abs(d["ms_per_step"] - min(f["ms"], mg["nccl_step_ms"])) <= 1e-9               # the headline step is the faster, bitwise-equal exchange
+        c3 = d["extra_configs"]["c3_d64_dprobs"]
+        assert c3["fused_fill_allgather"]["bitwise_equal_to_nccl_result"] is True and c3["ms"] <= c3["ms_fill_plus_allgather"]
+    j = d["jtj"]
+    assert j["parity"]["jtj_rel"] <= 1e-11 and j["parity"]["jtf_rel"] <= 1e-11 and j["parity"]["jtj_vs_fp64_dmma_rel"] <= 1e-11
+    assert j["fp64_dmma"]["ms_local"] > j["ms_local"] and 0.0 < j["frac"] < 1.0 and 0.0 < j["fp64_dmma"]["frac"] < 1.0
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) <= 1e-12 and 0.0 < r["frac"] < 1.0
+    x = d["extra_configs"]
+    assert x["c3_d64_dprobs"]["parity"]["dprobs_max_abs_vs_oracle_first_6_circuits"] <= 1e-10
+    assert x["c3_d64_dprobs"]["dense_level_path"]["max_abs_diff_first_4096_rows"] <= 1e-10
+    assert x["c5_d256_probs"]["embedded_model"]["max_abs_diff"] <= 1e-11
+    assert x["c4_cptplnd_hessian"]["hessian_rectangle"]["reduction_rel_err"] <= 1e-10
+    if n == 1:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
+        p = d["e2e_plugin"]
+        assert p["b200"]["outcomes"] == p["reference"]["outcomes"] and p["ratio"] > 50 and p["max_abs_diff_sampled_circuits"] <= 1e-4
+        assert 0 < d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] == 273340 * 1361 * 8
