@@ -1920,8 +1920,8 @@ static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int 
     const int64_t n_stages = ksl * sps;
     if (sps > OZ_MAX_STAGES_PER_SLICE) return fail(B200_E_UNSUPPORTED, "Ozaki J^T J: K slice too long");
     // column statistics: one pass over J for the exponents and J^T f
-    const int ns = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)c->sm_count * 8 * 256 + Np - 1) / Np, (nE + 63) / 64));
-    const int64_t rps = (nE + ns - 1) / ns;
+    const int gy = (int)std::max<int64_t>(1, std::min<int64_t>(128, (nE + 15) / 16));      // block rows of the statistics pass
+    const int ns = 4 * gy;                                                                  // partial slots (row lanes)
     CU(c->oz_S.ensure((size_t)n_stages * T * P_pad * OZ_KS));
     const size_t misc_bytes = (size_t)2 * ns * Np * 8 + (size_t)P_pad * 4 + (size_t)n_tiles * sizeof(int2) + 64;
     CU(c->oz_misc.ensure(misc_bytes));
@@ -1932,7 +1932,7 @@ static int jtj_ozaki(b200_ctx* c, const double* J, int64_t ldj, int64_t nE, int 
     int2* d_tiles = reinterpret_cast<int2*>(d_expo + P_pad);            // P_pad is a multiple of 128: 8-byte aligned
     CU(cudaMemsetAsync(d_expo, 0, (size_t)P_pad * 4, c->stream));
     CU(cudaMemcpyAsync(d_tiles, tiles.data(), (size_t)n_tiles * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
-    k_oz_colstats<<<dim3((unsigned)((Np + 255) / 256), (unsigned)ns), 256, 0, c->stream>>>(J, ldj, nE, Np, d_jtf ? d_f : nullptr, rps, d_psum, d_pmax);
+    k_oz_colstats<<<dim3((unsigned)((Np + 63) / 64), (unsigned)gy), 256, 0, c->stream>>>(J, ldj, nE, Np, d_jtf ? d_f : nullptr, d_psum, d_pmax);
     k_oz_colstats_reduce<<<(unsigned)((Np + 255) / 256), 256, 0, c->stream>>>(d_psum, d_pmax, Np, ns, d_jtf, d_expo);
     k_oz_slice<T><<<dim3((unsigned)(P_pad / 64), (unsigned)((n_stages + 1) / 2)), 256, 0, c->stream>>>(J, ldj, nE, Np, d_expo, c->oz_S.as<int8_t>(), P_pad, n_stages);
     OzArgs p;
