@@ -112,10 +112,17 @@ k_fj_forward(AtomDev a, FactoredDev fd, int n_mats, int n_fac, const uint32_t* _
     }
 }
 
-// swizzle of the backward kernel's shared-memory vectors: the fragment loads walk the state with lanes differing in one or two
-// base-4 digits; folding digits 2 and 3 into digit 1 keeps the 16 lanes of a half-warp on 16 different 8-byte banks for every
-// target-qubit combination of d = 64 and d = 256 (fac_sw folds into digit 0, which collides with the K index of the fragments)
-__device__ __forceinline__ unsigned fj_sw(unsigned i) { return i ^ ((((i >> 4) ^ (i >> 6)) & 3u) << 2); }
+// swizzle of the factored kernels' shared-memory vectors: a fragment load walks the state with the 16 lanes of a half-warp differing in
+// TWO base-4 digits of the index (which two depends on the factor's target qubits).  With the bank (8-byte word of a 128-byte row) a
+// GF(2)-linear function of the digits d0..d3 --  bank = (d0 ^ d2 ^ C d3) | (d1 ^ d2 ^ d3) << 2,  C = [[0,1],[1,1]]  -- every pair of digit
+// columns forms an invertible 4 x 4 matrix, so ANY two digits map the 16 lanes onto 16 different banks (tests/test_factored_fragments_cpu.py
+// checks every target combination of d = 64 and d = 256).  The first swizzle folded digits 2, 3 into digit 1 only and left 4-way conflicts
+// for factors whose first target is the last qubit (ncu: 16 % of the backward kernel's shared-memory wavefronts were conflicts).
+__device__ __forceinline__ unsigned fj_sw(unsigned i) {
+    const unsigned d2 = (i >> 4) & 3u, d3 = (i >> 6) & 3u;
+    const unsigned c3 = (d3 >> 1) | (((d3 ^ (d3 >> 1)) & 1u) << 1);
+    return i ^ (d2 ^ c3) ^ ((d2 ^ d3) << 2);
+}
 __device__ __forceinline__ unsigned fj_idx1(unsigned a, unsigned r, int sh) { return fj_sw(fac_insert2(r, sh) | (a << sh)); }
 __device__ __forceinline__ unsigned fj_idx2(unsigned a, unsigned r, int lo, int hi, int s0, int s1) {
     return fj_sw(fac_insert2(fac_insert2(r, lo), hi) | ((a >> 2) << s0) | ((a & 3u) << s1));
