@@ -45,7 +45,7 @@ WORKLOAD_DESC = ("smq2Q_XYCNOT full model (d=16, Np=1360), GST design maxL=128 l
                  "273340 outcomes; bulk_fill_dprobs + probs")
 METRIC = "circuit-outcomes/sec (bulk_fill_dprobs)"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel k_accum_trie_d16 (ncu --set full,
-# profiles/r01_accum_final_ncu_raw.csv): 0.165 GB read + 2.929 GB written
+# profiles/r02_final_accum_ncu_raw.csv, the round-2 build): 0.176 GB read + 2.919 GB written
 NCU_TRAFFIC_BYTES = 3.094e9
 INT8_PEAK_POPS = 4.5        # nominal dense int8 tensor rate of a B200 (tcgen05.mma kind::i8)
 DMMA_PEAK_TFLOPS = 37.2     # measured on this part with tools/ubench_fp64.cu (mma.sync m8n8k4 f64); DFMA 36.6
@@ -593,8 +593,8 @@ def bench_c2(args, D, engine, stream, ctx, sampler):
                      "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES if world == 1 else None, "peak_source": peak_src,
                      "kernel": "k_accum_trie_d16", "kernel_ms": ms_accum,
                      "algorithmic_bytes_per_launch": shard_bytes,
-                     "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 at N=1 (profiles/r01_accum_final_ncu_raw.csv): dram "
-                                       "read 0.165 GB + write 2.929 GB = 1.04 x the algorithmic bytes",
+                     "traffic_source": "ncu --set full, one launch of k_accum_trie_d16 at N=1 (profiles/r02_final_accum_ncu_raw.csv): dram "
+                                       "read 0.176 GB + write 2.919 GB = 1.04 x the algorithmic bytes",
                      "step": {"ms": ms_per_step, "achieved": achieved_step, "frac": achieved_step / peak,
                               "phases_ms": {"k_trie_prepare": ms_prep, "k_trie_chains": ms_chains,
                                             "k_accum_trie_d16": ms_accum}},
